@@ -1,0 +1,146 @@
+// Shared device/host helpers of the MoPoE-VAE B200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/mopoe_b200.h"
+
+#define MOPOE_THREADS 256
+#define MOPOE_POE_EPS 1e-8f  // mm_div.py:13
+
+namespace mopoe {
+
+// ---------------------------------------------------------------------------------------------
+// host-side error plumbing
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_desc(const mopoe_model_desc* d);
+int cuda_fail(cudaError_t e, const char* what);
+int num_sms();
+
+#define MOPOE_CUDA(call)                                        \
+  do {                                                          \
+    cudaError_t _e = (call);                                    \
+    if (_e != cudaSuccess) return ::mopoe::cuda_fail(_e, #call); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device view of the model (passed by value as a kernel argument)
+// ---------------------------------------------------------------------------------------------
+struct ModView {
+  float* w1;   // (256, D)
+  float* b1;   // (256)
+  float* wh;   // (HC, 256)   HC = 2L + 2S
+  float* bh;   // (HC)
+  float* wd;   // (D, ZD)     ZD = S + L
+  float* bd;   // (D)
+  float* lv;   // (D)
+  int D, S, HC, ZD;
+  int eps_off;  // column of this modality's style block inside an eps row
+};
+
+struct SubsetTable {
+  int n_subsets;                       // 2^M - 1, BaseExperiment.set_subsets order
+  int mask[MOPOE_MAX_SUBSETS];         // member bitmask
+  int n_members[MOPOE_MAX_SUBSETS];
+  int members[MOPOE_MAX_SUBSETS][MOPOE_MAX_MODS];  // fusion order (sorted by modality NAME)
+};
+
+struct ModelView {
+  ModView mod[MOPOE_MAX_MODS];
+  SubsetTable sub;
+  int M, L, E;      // E = eps row width = L + sum S
+  int method;
+  int learn_scale;
+  float beta, beta_style, beta_content;
+};
+
+void build_subsets(const mopoe_model_desc* d, SubsetTable* t);
+void build_view(const mopoe_model_desc* d, const mopoe_param_layout* lay, float* base, ModelView* v);
+
+// ---------------------------------------------------------------------------------------------
+// device utilities
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Grid-wide barrier for cooperative (co-resident) launches.  `bar` is a zero-initialised counter;
+// every CTA keeps its own running `target`.  Same fence/atomic/spin pattern as cooperative groups'
+// grid.sync(): bar.sync orders the CTA's writes before thread 0's gpu-scope fence, the fence after
+// the spin invalidates L1 so later plain loads observe other SMs' writes.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (*((volatile unsigned int*)bar) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// counter-based N(0,1): Philox4x32-10 + Box-Muller (restated in oracle/philox.py)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2,
+                                                       uint32_t& c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+__device__ __forceinline__ float u01(uint32_t x) {
+  return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+}
+
+// the four normals of block `blk` (elements 4*blk .. 4*blk+3) of (seed, stream)
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t stream, uint64_t blk, float out[4]) {
+  uint32_t c0 = (uint32_t)blk, c1 = (uint32_t)(blk >> 32), c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
+  philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+  float r0 = sqrtf(-2.0f * logf(u01(c0)));
+  float r1 = sqrtf(-2.0f * logf(u01(c2)));
+  float s0, q0, s1, q1;
+  sincospif(2.0f * u01(c1), &s0, &q0);
+  sincospif(2.0f * u01(c3), &s1, &q1);
+  out[0] = r0 * q0; out[1] = r0 * s0; out[2] = r1 * q1; out[3] = r1 * s1;
+}
+
+// element `idx` of (seed, stream)
+__device__ __forceinline__ float philox_normal1(uint64_t seed, uint64_t stream, uint64_t idx) {
+  float v[4];
+  philox_normal4(seed, stream, idx >> 2, v);
+  return v[idx & 3];
+}
+
+// noise source: injected tensor or the generator, addressed by the same flat index
+struct Noise {
+  const float* eps;  // NULL => philox
+  uint64_t seed;
+  uint64_t stream;
+  __device__ __forceinline__ float at(uint64_t idx) const {
+    return eps ? eps[idx] : philox_normal1(seed, stream, idx);
+  }
+};
+
+}  // namespace mopoe

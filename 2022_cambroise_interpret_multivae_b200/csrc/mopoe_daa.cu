@@ -1,0 +1,732 @@
+// Digital Avatars Analysis sweep for sm_100a  (workflow.daa_exp, workflow.py:361-537).
+//
+// Launch plan for one shard of validations (all launches on the caller's stream):
+//   1. mopoe_forward(P1+P2) over all n_val*N rows              -> encoder heads (computed ONCE: the
+//      reference re-encodes the unchanged "rois" block in every one of its 41 000 forwards)
+//   2. daa_base_kernel   one CTA per (validation, subject): the M stochastic reconstructions
+//      (workflow.py:388-400; the decoders are affine, so the mean over M passes is taken on z),
+//      loc_hat / scale_hat, the sampled scores (workflow.py:401-405) and rois_reconstructions
+//   3. daa_avatar_kernel persistent, one CTA per SM, work unit = (validation, subject, score):
+//      all n_samples avatars of that unit: perturbed src encoder (rank-1 update of the hidden
+//      pre-activation), class heads, subset PoE / mixture owner, reparameterisation, dst decoder,
+//      optional write of the avatar tile, and the per-subject OLS slope accumulated in fp64 in the
+//      epilogue (stat_utils.py:66-68) -- the avatar tensor never has to be re-read
+//   4. daa_stats_kernel  one thread per (validation, score, roi): second-level t-test
+//      (stat_utils.py:73-75) or the pooled "fixed" regression (stat_utils.py:62-63)
+#include "mopoe_common.cuh"
+#include "mopoe_latent.cuh"
+
+namespace mopoe {
+
+constexpr int RC = 32;          // avatar rows (samples) per chunk
+constexpr int CB = 448;         // decoder output columns per block (2 float4 x 56 lanes)
+constexpr int DEC_THREADS = 224;  // threads that own decoder micro-tiles (4 row groups x 56)
+
+struct DaaWs {
+  float* enc[MOPOE_MAX_MODS];  // (n_val*N, HC_m) encoder heads
+  float* scores;               // (n_val, N, C, J)   sampled scores, J contiguous
+  float* loc_hat;              // (n_val, N, C)
+  double* betas;               // (n_val, C, N, R)  (used when the caller does not want them)
+  double* ybar;                // (n_val, C, N, R)  fixed: mean_j y
+  double* syy;                 // (n_val, C, N, R)  fixed: sum_j (y - ybar)^2
+  double* xstat;               // (n_val, C, N, 2)  xbar, Sxx
+  int* counter;                // work-unit counter of the persistent kernel
+  void* fwd_ws;                // workspace of the encoder forward
+  int64_t fwd_ws_bytes;
+};
+
+static int64_t daa_carve(const mopoe_model_desc* d, const mopoe_daa_desc* q, char* base, DaaWs* w) {
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) { int64_t o = off; off += (bytes + 255) & ~(int64_t)255; return base ? base + o : (char*)nullptr; };
+  const int64_t rows = (int64_t)q->n_val * q->n_subjects;
+  const int C = d->dims[q->src_mod], R = d->dims[q->dst_mod];
+  DaaWs t;
+  memset(&t, 0, sizeof(t));
+  for (int m = 0; m < d->n_mods; ++m) t.enc[m] = (float*)take(rows * (2 * d->latent_dim + 2 * d->style_dims[m]) * 4);
+  t.scores = (float*)take(rows * C * q->n_samples * 4);
+  t.loc_hat = (float*)take(rows * C * 4);
+  t.betas = (double*)take(rows * C * R * 8);
+  if (q->reg_method == 1) {
+    t.ybar = (double*)take(rows * C * R * 8);
+    t.syy = (double*)take(rows * C * R * 8);
+  }
+  t.xstat = (double*)take(rows * C * 2 * 8);
+  t.counter = (int*)take(256);
+  t.fwd_ws_bytes = mopoe_workspace_bytes(d, rows);
+  t.fwd_ws = take(t.fwd_ws_bytes);
+  if (w) *w = t;
+  return off;
+}
+
+struct DaaCtx {
+  mopoe_daa_desc q;
+  mopoe_batch_desc b;   // n_rows = n_subjects, all modalities present
+  const float* x[MOPOE_MAX_MODS];
+  Noise nz_base, nz_score, nz_av;
+  int v_base_off, v_score_off, v_av_off;  // validation index offset inside each noise index space
+  float* avatars; float* sampled_scores; float* recon;
+  double* betas;
+  int C, R, J, N;
+};
+
+// fill dst[0..E) with the noise elements [base, base+E) using `nthr` cooperating threads (rank tid)
+__device__ __forceinline__ void fill_noise_row(const Noise& nz, int64_t base, int E, float* dst, int tid, int nthr) {
+  if (nz.eps) {
+    for (int e = tid; e < E; e += nthr) dst[e] = nz.eps[base + e];
+  } else {
+    const int64_t b0 = base >> 2, b1 = (base + E - 1) >> 2;
+    for (int64_t blk = b0 + tid; blk <= b1; blk += nthr) {
+      float v[4];
+      philox_normal4(nz.seed, nz.stream, (uint64_t)blk, v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t e = blk * 4 + i - base;
+        if (e >= 0 && e < E) dst[e] = v[i];
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// 2. base passes + score sampling: one CTA per (validation, subject)
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MOPOE_THREADS) daa_base_kernel(ModelView mv, DaaCtx cx, DaaWs ws) {
+  extern __shared__ __align__(16) float sm[];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int v = blockIdx.x / cx.N, g = blockIdx.x % cx.N;
+  const int M = mv.M, L = mv.L, E = mv.E;
+  const int64_t row = (int64_t)v * cx.N + g;
+  float* s_mean = sm;                 // [E] mean eps
+  float* s_acc = s_mean + 160;        // [8][E] per-warp sums
+  float* s_row = s_acc + 8 * 160;     // [8][E] per-warp noise row
+  float* s_zz = s_row + 8 * 160;      // [M][64] decoder inputs
+  float* s_loc = s_zz + MOPOE_MAX_MODS * 64;  // [C]
+  for (int i = t; i < 8 * 160; i += MOPOE_THREADS) s_acc[i] = 0.f;
+  __syncthreads();
+  // mean over the n_base passes of the noise row of this subject
+  for (int p = warp; p < cx.q.n_base; p += 8) {
+    const int64_t base = (((int64_t)(cx.v_base_off + v) * cx.q.n_base + p) * cx.N + g) * E;
+    fill_noise_row(cx.nz_base, base, E, s_row + warp * 160, lane, 32);
+    __syncwarp();
+    for (int e = lane; e < E; e += 32) s_acc[warp * 160 + e] += s_row[warp * 160 + e];
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int e = t; e < E; e += MOPOE_THREADS) {
+    float a = 0.f;
+    for (int w = 0; w < 8; ++w) a += s_acc[w * 160 + e];
+    s_mean[e] = a / (float)cx.q.n_base;
+  }
+  __syncthreads();
+  // joint posterior of this row (sampling semantics: the row's mixture owner), mean latent
+  if (t < L) {
+    const int l = t;
+    float mu_e[MOPOE_MAX_MODS], lv_e[MOPOE_MAX_MODS];
+#pragma unroll
+    for (int m = 0; m < MOPOE_MAX_MODS; ++m) {
+      mu_e[m] = m < M ? ws.enc[m][row * mv.mod[m].HC + l] : 0.f;
+      lv_e[m] = m < M ? ws.enc[m][row * mv.mod[m].HC + L + l] : 0.f;
+    }
+    int owner = 0, kidx = 0;
+    for (int k = 0; k < cx.b.n_mix; ++k)
+      if (g >= cx.b.joint_bounds[k] && g < cx.b.joint_bounds[k + 1]) owner = k;
+    float jmu = 0.f, jlv = 0.f;
+    for (int s = 0; s < mv.sub.n_subsets; ++s) {
+      if (!in_mixture(mv, cx.b, s)) continue;
+      if (kidx == owner) { const SubsetEval ev = eval_subset(mv, cx.b, s, g, mu_e, lv_e); jmu = ev.mu; jlv = ev.lv; }
+      ++kidx;
+    }
+    const float z = jmu + expf(0.5f * jlv) * s_mean[l];
+    for (int m = 0; m < M; ++m) s_zz[m * 64 + mv.mod[m].S + l] = z;
+  }
+  for (int m = 0; m < M; ++m) {
+    const ModView& md = mv.mod[m];
+    if (t < md.S) {
+      const float mu = ws.enc[m][row * md.HC + 2 * L + t], lv = ws.enc[m][row * md.HC + 2 * L + md.S + t];
+      s_zz[m * 64 + t] = mu + expf(0.5f * lv) * s_mean[md.eps_off + t];
+    }
+  }
+  __syncthreads();
+  // decode src -> loc_hat, dst -> reconstruction   (affine decoders: mean over passes == decode of mean z)
+  {
+    const ModView& ms = mv.mod[cx.q.src_mod];
+    for (int c = t; c < cx.C; c += MOPOE_THREADS) {
+      float a = ms.bd[c];
+      for (int k = 0; k < ms.ZD; ++k) a = fmaf(s_zz[cx.q.src_mod * 64 + k], ms.wd[(int64_t)c * ms.ZD + k], a);
+      s_loc[c] = a;
+      ws.loc_hat[row * cx.C + c] = a;
+    }
+    const ModView& mdst = mv.mod[cx.q.dst_mod];
+    if (cx.recon)
+      for (int r = t; r < cx.R; r += MOPOE_THREADS) {
+        float a = mdst.bd[r];
+        for (int k = 0; k < mdst.ZD; ++k) a = fmaf(s_zz[cx.q.dst_mod * 64 + k], mdst.wd[(int64_t)r * mdst.ZD + k], a);
+        cx.recon[row * cx.R + r] = a;
+      }
+  }
+  __syncthreads();
+  // scores[j][c] = loc_hat[c] + scale_hat[c] * eps   (Normal(loc_hat, scale_hat).sample, workflow.py:401-405)
+  const ModView& ms = mv.mod[cx.q.src_mod];
+  for (int i = t; i < cx.J * cx.C; i += MOPOE_THREADS) {
+    const int j = i / cx.C, c = i % cx.C;
+    const int64_t idx = (((int64_t)(cx.v_score_off + v) * cx.J + j) * cx.N + g) * cx.C + c;
+    const float s = s_loc[c] + expf(0.5f * ms.lv[c]) * cx.nz_score.at(idx);
+    ws.scores[(row * cx.C + c) * cx.J + j] = s;
+    if (cx.sampled_scores) cx.sampled_scores[(row * cx.J + j) * cx.C + c] = s;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// 3. avatars + per-subject regression: persistent kernel, unit = (validation, subject, score)
+// -------------------------------------------------------------------------------------------
+struct AvSmem {
+  int wdT, bd, whT, bh, w1c, a0, hT, part, zzT, e, eps, sx, oth, misc, total;  // float offsets
+};
+
+__host__ __device__ inline AvSmem av_plan(const ModelView& mv, int src, int dst, int J) {
+  AvSmem p;
+  const int ZD = mv.mod[dst].ZD, HO = 2 * mv.L;
+  int off = 0;
+  auto take = [&](int n) { int o = off; off += (n + 3) & ~3; return o; };
+  p.wdT = take(ZD * CB);
+  p.bd = take(CB);
+  p.whT = take(MOPOE_HIDDEN * HO);
+  p.bh = take(HO);
+  p.w1c = take(MOPOE_HIDDEN);
+  p.a0 = take(MOPOE_HIDDEN);
+  p.hT = take(MOPOE_HIDDEN * RC);
+  const int part = 8 * RC * HO, stat = 2 * 4 * CB * 3;  // partial head sums | fp64 stats reduction
+  p.part = take(part > stat ? part : stat);
+  p.zzT = take(ZD * RC);
+  p.e = take(RC * HO);
+  p.eps = take(RC * mv.E);
+  p.sx = take(J);
+  p.oth = take(MOPOE_MAX_MODS * 2 * 32 + 2 * 32);  // other experts (mu, lv)[L], dst style (mu, lv)[S]
+  p.misc = take(64);
+  p.total = off;
+  return p;
+}
+
+template <bool FIXED>
+__global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_kernel(ModelView mv, DaaCtx cx, DaaWs ws, int col0) {
+  extern __shared__ __align__(16) float sm[];
+  const AvSmem pl = av_plan(mv, cx.q.src_mod, cx.q.dst_mod, cx.J);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int src = cx.q.src_mod, dst = cx.q.dst_mod;
+  const ModView& ms = mv.mod[src];
+  const ModView& mdst = mv.mod[dst];
+  const int L = mv.L, M = mv.M, E = mv.E, HO = 2 * L, ZD = mdst.ZD, Sd = mdst.S;
+  const int C = cx.C, R = cx.R, J = cx.J, N = cx.N;
+  const int ncol = min(CB, R - col0);
+  float* s_wdT = sm + pl.wdT;
+  float* s_bd = sm + pl.bd;
+  float* s_whT = sm + pl.whT;
+  float* s_bh = sm + pl.bh;
+  float* s_w1c = sm + pl.w1c;
+  float* s_a0 = sm + pl.a0;
+  float* s_hT = sm + pl.hT;
+  float* s_part = sm + pl.part;
+  float* s_zzT = sm + pl.zzT;
+  float* s_e = sm + pl.e;
+  float* s_eps = sm + pl.eps;
+  float* s_sx = sm + pl.sx;
+  float* s_oth = sm + pl.oth;
+  float* s_dsty = s_oth + MOPOE_MAX_MODS * 2 * 32;
+  double* s_d = reinterpret_cast<double*>(sm + pl.misc);  // [0] xbar [1] Sxx
+  int* s_i = reinterpret_cast<int*>(sm + pl.misc + 8);    // [0] unit
+  // ---- weights resident in shared memory for the whole launch ----
+  for (int i = t; i < ZD * CB; i += MOPOE_THREADS) {
+    const int k = i / CB, c = i % CB;
+    s_wdT[i] = c < ncol ? mdst.wd[(int64_t)(col0 + c) * ZD + k] : 0.f;
+  }
+  for (int i = t; i < CB; i += MOPOE_THREADS) s_bd[i] = i < ncol ? mdst.bd[col0 + i] : 0.f;
+  for (int i = t; i < MOPOE_HIDDEN * HO; i += MOPOE_THREADS) {
+    const int o = i / MOPOE_HIDDEN, k = i % MOPOE_HIDDEN;  // coalesced read of wh rows
+    s_whT[k * HO + o] = ms.wh[(int64_t)o * MOPOE_HIDDEN + k];
+  }
+  for (int i = t; i < HO; i += MOPOE_THREADS) s_bh[i] = ms.bh[i];
+  const int present = (1 << M) - 1;
+  const int n_units = cx.q.n_val * N * C;
+  const int rg = t / 56, cg = t % 56;  // decoder micro-tile owner (t < 224)
+  while (true) {
+    __syncthreads();
+    if (t == 0) s_i[0] = atomicAdd(ws.counter, 1);
+    __syncthreads();
+    const int unit = s_i[0];
+    if (unit >= n_units) break;
+    const int c = unit % C, g = (unit / C) % N, v = unit / (C * N);
+    const int64_t row = (int64_t)v * N + g;
+    // ---- per-unit setup ----
+    int owner = 0;
+    for (int k = 0; k < cx.b.n_mix; ++k)
+      if (g >= cx.b.joint_bounds[k] && g < cx.b.joint_bounds[k + 1]) owner = k;
+    int s_own = 0, kidx = 0;
+    bool need_src = !cx.q.sample_latents;
+    for (int s = 0; s < mv.sub.n_subsets; ++s) {
+      if (!in_mixture(mv, cx.b, s)) continue;
+      if (kidx == owner) s_own = s;
+      ++kidx;
+    }
+    if (cx.q.sample_latents) {
+      need_src = (mv.sub.mask[s_own] >> src) & 1;
+      if (mv.method == MOPOE_METHOD_MOE && mv.sub.n_members[s_own] > 1) need_src = true;
+    }
+    {  // hidden pre-activation without the perturbed column, and that column of W1
+      const float* w = ms.w1 + (int64_t)t * C;
+      const float* xr = cx.x[src] + row * C;
+      float a = ms.b1[t];
+      for (int i = 0; i < C; ++i) a = (i == c) ? a : fmaf(w[i], xr[i], a);
+      s_a0[t] = a;
+      s_w1c[t] = w[c];
+    }
+    for (int j = t; j < J; j += MOPOE_THREADS) s_sx[j] = ws.scores[(row * C + c) * J + j];
+    for (int i = t; i < M * L; i += MOPOE_THREADS) {
+      const int m = i / L, l = i % L;
+      s_oth[(m * 2 + 0) * 32 + l] = ws.enc[m][row * mv.mod[m].HC + l];
+      s_oth[(m * 2 + 1) * 32 + l] = ws.enc[m][row * mv.mod[m].HC + L + l];
+    }
+    if (t < Sd) {
+      s_dsty[t] = ws.enc[dst][row * mdst.HC + 2 * L + t];
+      s_dsty[32 + t] = expf(0.5f * ws.enc[dst][row * mdst.HC + 2 * L + Sd + t]);
+    }
+    __syncthreads();
+    if (warp == 0) {  // xbar, Sxx in fp64 (centred: stat_utils OLS slope = Sxy / Sxx)
+      double sx = 0.0;
+      for (int j = lane; j < J; j += 32) sx += (double)s_sx[j];
+      sx = warp_sum(sx);
+      const double xb = sx / (double)J;
+      double sxx = 0.0;
+      for (int j = lane; j < J; j += 32) { const double d = (double)s_sx[j] - xb; sxx += d * d; }
+      sxx = warp_sum(sxx);
+      if (lane == 0) { s_d[0] = xb; s_d[1] = sxx; ws.xstat[(((int64_t)v * C + c) * N + g) * 2] = xb; ws.xstat[(((int64_t)v * C + c) * N + g) * 2 + 1] = sxx; }
+    }
+    __syncthreads();
+    const double xbar = s_d[0], sxx_d = s_d[1];
+    double st_xy[8], st_y[8], st_yy[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st_xy[i] = st_y[i] = st_yy[i] = 0.0;
+
+    for (int j0 = 0; j0 < J; j0 += RC) {
+      const int nrow = min(RC, J - j0);
+      // noise rows of this chunk
+      if (cx.q.sample_latents) {
+        const int jj = t >> 3, sub = t & 7;  // 8 threads per row
+        if (jj < nrow) {
+          const int64_t base = ((((int64_t)(cx.v_av_off + v) * J + j0 + jj) * C + c) * N + g) * E;
+          fill_noise_row(cx.nz_av, base, E, s_eps + jj * E, sub, 8);
+        }
+      }
+      if (need_src) {
+        // B1: hidden layer of the perturbed src row:  h = relu(a0 + W1[:,c] * score)
+        {  // warp w owns hidden units 32w..32w+31, lanes walk the rows (conflict-free stores)
+          const float sc = lane < nrow ? s_sx[j0 + lane] : 0.f;
+#pragma unroll 8
+          for (int kk = 0; kk < 32; ++kk) {
+            const int k = warp * 32 + kk;
+            s_hT[k * RC + lane] = fmaxf(fmaf(s_w1c[k], sc, s_a0[k]), 0.f);
+          }
+        }
+        __syncthreads();
+        // B2: class heads, K split over the 8 warps (32 hidden units each); lane = 4 row groups x 8 col groups
+        {
+          const int hrg = lane >> 3, hcg = lane & 7;
+          const int cpl = (HO + 7) >> 3;  // columns per lane (<= 8)
+          float acc[8][8];
+#pragma unroll
+          for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int bq = 0; bq < 8; ++bq) acc[a][bq] = 0.f;
+          for (int kk = 0; kk < 32; ++kk) {
+            const int k = warp * 32 + kk;
+            const float4 h0 = *reinterpret_cast<const float4*>(s_hT + k * RC + hrg * 8);
+            const float4 h1 = *reinterpret_cast<const float4*>(s_hT + k * RC + hrg * 8 + 4);
+            const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+            for (int bq = 0; bq < 8; ++bq) {
+              if (bq < cpl) {
+                const int o = hcg * cpl + bq;
+                const float w = o < HO ? s_whT[k * HO + o] : 0.f;
+#pragma unroll
+                for (int a = 0; a < 8; ++a) acc[a][bq] = fmaf(hv[a], w, acc[a][bq]);
+              }
+            }
+          }
+#pragma unroll
+          for (int bq = 0; bq < 8; ++bq) {
+            if (bq < cpl) {
+              const int o = hcg * cpl + bq;
+              if (o < HO)
+#pragma unroll
+                for (int a = 0; a < 8; ++a) s_part[(warp * RC + hrg * 8 + a) * HO + o] = acc[a][bq];
+            }
+          }
+        }
+        __syncthreads();
+        for (int i = t; i < RC * HO; i += MOPOE_THREADS) {
+          float a = s_bh[i % HO];
+#pragma unroll
+          for (int w = 0; w < 8; ++w) a += s_part[w * RC * HO + i];
+          s_e[i] = a;
+        }
+      }
+      __syncthreads();
+      // B3: subset posterior of the row's mixture owner (or the mixture mean), reparameterise
+      for (int i = t; i < RC * L; i += MOPOE_THREADS) {
+        const int jj = i / L, l = i % L;
+        float mu_e[MOPOE_MAX_MODS], lv_e[MOPOE_MAX_MODS];
+#pragma unroll
+        for (int m = 0; m < MOPOE_MAX_MODS; ++m) {
+          mu_e[m] = m < M ? s_oth[(m * 2 + 0) * 32 + l] : 0.f;
+          lv_e[m] = m < M ? s_oth[(m * 2 + 1) * 32 + l] : 0.f;
+        }
+        if (need_src) { mu_e[src] = s_e[jj * HO + l]; lv_e[src] = s_e[jj * HO + L + l]; }
+        float z;
+        if (cx.q.sample_latents) {
+          const SubsetEval ev = eval_subset(mv, cx.b, s_own, g, mu_e, lv_e);
+          z = s_eps[jj * E + l] * expf(0.5f * ev.lv) + ev.mu;
+        } else {
+          float jmu = 0.f;
+          for (int s = 0; s < mv.sub.n_subsets; ++s)
+            if (in_mixture(mv, cx.b, s)) jmu += eval_subset(mv, cx.b, s, g, mu_e, lv_e).mu;
+          z = jmu / (float)cx.b.n_mix;
+        }
+        s_zzT[(Sd + l) * RC + jj] = z;
+      }
+      for (int i = t; i < RC * Sd; i += MOPOE_THREADS) {
+        const int jj = i / Sd, s = i % Sd;
+        const float e0 = cx.q.sample_latents ? s_eps[jj * E + mdst.eps_off + s] : 0.f;
+        s_zzT[s * RC + jj] = s_dsty[s] + s_dsty[32 + s] * e0;
+      }
+      __syncthreads();
+      // B4: dst decoder, 8 rows x 8 columns per thread (224 threads), fp64 regression epilogue
+      if (t < DEC_THREADS) {
+        float acc[8][8];
+        const float4 b0 = *reinterpret_cast<const float4*>(s_bd + cg * 4);
+        const float4 b1 = *reinterpret_cast<const float4*>(s_bd + 224 + cg * 4);
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          acc[a][0] = b0.x; acc[a][1] = b0.y; acc[a][2] = b0.z; acc[a][3] = b0.w;
+          acc[a][4] = b1.x; acc[a][5] = b1.y; acc[a][6] = b1.z; acc[a][7] = b1.w;
+        }
+#pragma unroll 4
+        for (int k = 0; k < ZD; ++k) {
+          const float4 z0 = *reinterpret_cast<const float4*>(s_zzT + k * RC + rg * 8);
+          const float4 z1 = *reinterpret_cast<const float4*>(s_zzT + k * RC + rg * 8 + 4);
+          const float4 w0 = *reinterpret_cast<const float4*>(s_wdT + k * CB + cg * 4);
+          const float4 w1 = *reinterpret_cast<const float4*>(s_wdT + k * CB + 224 + cg * 4);
+          const float zv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int bq = 0; bq < 8; ++bq) acc[a][bq] = fmaf(zv[a], wv[bq], acc[a][bq]);
+        }
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          const int jj = rg * 8 + a;
+          if (jj < nrow) {
+            const int j = j0 + jj;
+            const double xc = (double)s_sx[j] - xbar;
+#pragma unroll
+            for (int bq = 0; bq < 8; ++bq) {
+              const double y = (double)acc[a][bq];
+              st_xy[bq] = fma(xc, y, st_xy[bq]);
+              if (FIXED) { st_y[bq] += y; st_yy[bq] = fma(y, y, st_yy[bq]); }
+            }
+            if (cx.avatars) {
+              float* o = cx.avatars + ((((int64_t)v * N + g) * C + c) * J + j) * (int64_t)R + col0;
+              const int ca = cg * 4, cb = 224 + cg * 4;
+              if ((R & 3) == 0 && ca + 4 <= ncol) *reinterpret_cast<float4*>(o + ca) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+              else for (int q = 0; q < 4; ++q) if (ca + q < ncol) o[ca + q] = acc[a][q];
+              if ((R & 3) == 0 && cb + 4 <= ncol) *reinterpret_cast<float4*>(o + cb) = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
+              else for (int q = 0; q < 4; ++q) if (cb + q < ncol) o[cb + q] = acc[a][4 + q];
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // ---- unit epilogue: combine the 4 row groups, slope per ROI ----
+    double* red = reinterpret_cast<double*>(s_part);  // [3][4][CB]
+    if (t < DEC_THREADS) {
+#pragma unroll
+      for (int bq = 0; bq < 8; ++bq) {
+        const int col = (bq < 4 ? cg * 4 + bq : 224 + cg * 4 + bq - 4);
+        red[(0 * 4 + rg) * CB + col] = st_xy[bq];
+        if (FIXED) { red[(1 * 4 + rg) * CB + col] = st_y[bq]; red[(2 * 4 + rg) * CB + col] = st_yy[bq]; }
+      }
+    }
+    __syncthreads();
+    for (int col = t; col < ncol; col += MOPOE_THREADS) {
+      const double sxy = red[0 * CB + col] + red[1 * CB + col] + red[2 * CB + col] + red[3 * CB + col];
+      const int64_t o = (((int64_t)v * C + c) * N + g) * R + col0 + col;
+      const double beta = sxy / sxx_d;
+      ws.betas[o] = beta;
+      if (FIXED) {
+        const double sy = red[(4 + 0) * CB + col] + red[(4 + 1) * CB + col] + red[(4 + 2) * CB + col] + red[(4 + 3) * CB + col];
+        const double syy = red[(8 + 0) * CB + col] + red[(8 + 1) * CB + col] + red[(8 + 2) * CB + col] + red[(8 + 3) * CB + col];
+        const double yb = sy / (double)J;
+        ws.ybar[o] = yb;
+        ws.syy[o] = syy - (double)J * yb * yb;
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// statistics on a materialised avatar tensor (mopoe_daa_regression): CTA per (v, g, c)
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MOPOE_THREADS) daa_moments_kernel(int N, int C, int J, int R, const float* avatars,
+                                                                    const float* scores /*(v,N,J,C)*/, double* betas,
+                                                                    double* ybar, double* syy, double* xstat) {
+  const int unit = blockIdx.x;
+  const int c = unit % C, g = (unit / C) % N, v = unit / (C * N);
+  const int t = threadIdx.x, lane = t & 31;
+  __shared__ double s_d[2];
+  extern __shared__ __align__(16) float s_sx[];
+  const int64_t row = (int64_t)v * N + g;
+  for (int j = t; j < J; j += MOPOE_THREADS) s_sx[j] = scores[(row * J + j) * C + c];
+  __syncthreads();
+  if (t < 32) {
+    double sx = 0.0;
+    for (int j = lane; j < J; j += 32) sx += (double)s_sx[j];
+    sx = warp_sum(sx);
+    const double xb = sx / (double)J;
+    double sxx = 0.0;
+    for (int j = lane; j < J; j += 32) { const double d = (double)s_sx[j] - xb; sxx += d * d; }
+    sxx = warp_sum(sxx);
+    if (lane == 0) { s_d[0] = xb; s_d[1] = sxx; xstat[(((int64_t)v * C + c) * N + g) * 2] = xb; xstat[(((int64_t)v * C + c) * N + g) * 2 + 1] = sxx; }
+  }
+  __syncthreads();
+  const double xb = s_d[0], sxx = s_d[1];
+  const float* a = avatars + ((row * C + c) * (int64_t)J) * R;
+  for (int r = t; r < R; r += MOPOE_THREADS) {
+    double sxy = 0.0, sy = 0.0, syy_ = 0.0;
+    for (int j = 0; j < J; ++j) {
+      const double y = (double)a[(int64_t)j * R + r];
+      sxy = fma((double)s_sx[j] - xb, y, sxy);
+      sy += y; syy_ = fma(y, y, syy_);
+    }
+    const int64_t o = (((int64_t)v * C + c) * N + g) * R + r;
+    betas[o] = sxy / sxx;
+    if (ybar) { const double yb = sy / (double)J; ybar[o] = yb; syy[o] = syy_ - (double)J * yb * yb; }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// Student-t survival function in fp64: 2*sf(|t|, nu) = I_x(nu/2, 1/2), x = nu / (nu + t^2)
+// (regularised incomplete beta by Lentz's continued fraction)
+// -------------------------------------------------------------------------------------------
+__device__ double betacf(double a, double b, double x) {
+  const double FPMIN = 1e-300, EPS = 1e-16;
+  const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+  double c = 1.0, d = 1.0 - qab * x / qap;
+  if (fabs(d) < FPMIN) d = FPMIN;
+  d = 1.0 / d;
+  double h = d;
+  for (int m = 1; m <= 500; ++m) {
+    const int m2 = 2 * m;
+    double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+    d = 1.0 + aa * d; if (fabs(d) < FPMIN) d = FPMIN;
+    c = 1.0 + aa / c; if (fabs(c) < FPMIN) c = FPMIN;
+    d = 1.0 / d; h *= d * c;
+    aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+    d = 1.0 + aa * d; if (fabs(d) < FPMIN) d = FPMIN;
+    c = 1.0 + aa / c; if (fabs(c) < FPMIN) c = FPMIN;
+    d = 1.0 / d;
+    const double del = d * c;
+    h *= del;
+    if (fabs(del - 1.0) < EPS) break;
+  }
+  return h;
+}
+
+__device__ double betai(double a, double b, double x, double xc /* 1 - x, accurate */) {
+  if (x <= 0.0) return 0.0;
+  if (xc <= 0.0) return 1.0;
+  const double bt = exp(lgamma(a + b) - lgamma(a) - lgamma(b) + a * log(x) + b * log(xc));
+  if (x < (a + 1.0) / (a + b + 2.0)) return bt * betacf(a, b, x) / a;
+  return 1.0 - bt * betacf(b, a, xc) / b;
+}
+
+__device__ double two_sided_t_pvalue(double tval, double nu) {
+  if (isnan(tval)) return tval;
+  if (isinf(tval)) return 0.0;
+  const double t2 = tval * tval;
+  const double x = nu / (nu + t2), xc = t2 / (nu + t2);
+  return betai(0.5 * nu, 0.5, x, xc);
+}
+
+// 4. second-level statistics: one thread per (validation, score, roi)
+__global__ void daa_stats_kernel(int n_val, int N, int C, int J, int R, int reg_method, const double* betas,
+                                 const double* ybar, const double* syy, const double* xstat,
+                                 const float* recon, double* coefs, double* pvalues) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n_val * C * R) return;
+  const int r = (int)(i % R), c = (int)((i / R) % C), v = (int)(i / ((int64_t)R * C));
+  const int64_t base = ((int64_t)v * C + c) * N;
+  if (reg_method == 0) {
+    // hierarchical (stat_utils.py:66-75): OLS "beta ~ 1" == one-sample t-test of the subject slopes
+    double mean = 0.0;
+    for (int g = 0; g < N; ++g) mean += betas[(base + g) * R + r];
+    mean /= (double)N;
+    double ss = 0.0;
+    for (int g = 0; g < N; ++g) { const double d = betas[(base + g) * R + r] - mean; ss += d * d; }
+    const double sd = sqrt(ss / (double)(N - 1));
+    const double tval = mean / (sd / sqrt((double)N));
+    coefs[i] = mean;
+    pvalues[i] = two_sided_t_pvalue(tval, (double)(N - 1));
+  } else {
+    // fixed (stat_utils.py:62-63, workflow.py:489-492): pooled OLS of (avatar - reconstruction) ~ score
+    double xm = 0.0, ym = 0.0;
+    for (int g = 0; g < N; ++g) {
+      xm += xstat[(base + g) * 2];
+      ym += ybar[(base + g) * R + r] - (double)recon[((int64_t)v * N + g) * R + r];
+    }
+    xm /= (double)N; ym /= (double)N;
+    double sxx = 0.0, sxy = 0.0, syy_ = 0.0;
+    for (int g = 0; g < N; ++g) {
+      const double xb = xstat[(base + g) * 2], sxx_g = xstat[(base + g) * 2 + 1];
+      const double yb = ybar[(base + g) * R + r] - (double)recon[((int64_t)v * N + g) * R + r];
+      const double sxy_g = betas[(base + g) * R + r] * sxx_g;
+      sxx += sxx_g + (double)J * (xb - xm) * (xb - xm);
+      sxy += sxy_g + (double)J * (xb - xm) * (yb - ym);
+      syy_ += syy[(base + g) * R + r] + (double)J * (yb - ym) * (yb - ym);
+    }
+    const double n = (double)N * (double)J;
+    const double beta = sxy / sxx;
+    const double rss = syy_ - beta * sxy;
+    const double se = sqrt(rss / (n - 2.0) / sxx);
+    coefs[i] = beta;
+    pvalues[i] = two_sided_t_pvalue(beta / se, n - 2.0);
+  }
+}
+
+}  // namespace mopoe
+
+using namespace mopoe;
+
+extern "C" {
+
+int64_t mopoe_daa_workspace_bytes(const mopoe_model_desc* desc, const mopoe_daa_desc* daa) {
+  if (check_desc(desc)) return MOPOE_EINVAL;
+  if (!daa) { set_error("daa is NULL"); return MOPOE_EINVAL; }
+  return daa_carve(desc, daa, nullptr, nullptr);
+}
+
+static int check_daa(const mopoe_model_desc* d, const mopoe_daa_desc* q) {
+  if (q->n_val < 1 || q->n_subjects < 2 || q->n_samples < 3 || q->n_base < 1) {
+    set_error("daa sizes invalid (n_val=%d n_subjects=%d n_samples=%d n_base=%d)", q->n_val, q->n_subjects, q->n_samples, q->n_base);
+    return MOPOE_EINVAL; }
+  if (q->src_mod < 0 || q->src_mod >= d->n_mods || q->dst_mod < 0 || q->dst_mod >= d->n_mods || q->src_mod == q->dst_mod) {
+    set_error("src_mod=%d dst_mod=%d invalid", q->src_mod, q->dst_mod); return MOPOE_EINVAL; }
+  if (q->reg_method < 0 || q->reg_method > 1) { set_error("reg_method=%d unsupported (hierarchical, fixed; mixed is not on this path)", q->reg_method); return MOPOE_EINVAL; }
+  if (d->dims[q->src_mod] > 64) { set_error("src modality wider than 64 columns is unsupported in the DAA kernel"); return MOPOE_EINVAL; }
+  int E = d->latent_dim;
+  for (int m = 0; m < d->n_mods; ++m) E += d->style_dims[m];
+  if (E > 160) { set_error("noise row wider than 160"); return MOPOE_EINVAL; }
+  return MOPOE_OK;
+}
+
+int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mopoe_daa_desc* daa,
+                    const mopoe_batch_desc* batch, const float* const* x, const float* eps_base,
+                    const float* eps_score, const float* eps_av, uint64_t seed, float* avatars,
+                    float* sampled_scores, float* reconstructions, double* betas, double* coefs, double* pvalues,
+                    void* workspace, int64_t workspace_bytes, void* stream_) {
+  int rc = check_desc(desc);
+  if (rc) return rc;
+  if (mopoe_device_count() == 0) { set_error("no CUDA device: the DAA path has no CPU fallback"); return MOPOE_ENODEV; }
+  if (!params || !daa || !batch || !x || !coefs || !pvalues || !workspace) { set_error("NULL argument"); return MOPOE_EINVAL; }
+  if ((rc = check_daa(desc, daa))) return rc;
+  const int M = desc->n_mods, N = daa->n_subjects;
+  if (batch->n_rows != N || batch->present_mask != (1 << M) - 1) { set_error("batch desc must describe n_subjects rows with every modality present"); return MOPOE_EINVAL; }
+  if (daa->reg_method == 1 && !reconstructions) { set_error("reg_method fixed needs the reconstructions buffer"); return MOPOE_EINVAL; }
+  const int64_t need = daa_carve(desc, daa, nullptr, nullptr);
+  if (workspace_bytes < need) { set_error("workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need); return MOPOE_ENOSPC; }
+  DaaWs ws;
+  daa_carve(desc, daa, (char*)workspace, &ws);
+  if (betas) ws.betas = betas;  // caller wants the per-subject slopes: write them in place
+  cudaStream_t stream = (cudaStream_t)stream_;
+  mopoe_param_layout lay;
+  mopoe_param_layout_of(desc, &lay);
+  ModelView mv;
+  build_view(desc, &lay, const_cast<float*>(params), &mv);
+  // 1. encoder heads of every (validation, subject) row
+  {
+    mopoe_batch_desc fb;
+    memset(&fb, 0, sizeof(fb));
+    fb.n_rows = daa->n_val * N; fb.present_mask = (1 << M) - 1; fb.n_mix = 1;
+    fb.joint_bounds[0] = 0; fb.joint_bounds[1] = fb.n_rows;
+    for (int k = 1; k <= M; ++k) { fb.moe_bounds[k][0] = 0; for (int i = 1; i <= k; ++i) fb.moe_bounds[k][i] = fb.n_rows; }
+    mopoe_forward_out fo;
+    memset(&fo, 0, sizeof(fo));
+    for (int m = 0; m < M; ++m) fo.enc_heads[m] = ws.enc[m];
+    rc = mopoe_forward(desc, params, &fb, x, nullptr, seed, 0, -1, 0, &fo, ws.fwd_ws, ws.fwd_ws_bytes, stream_);
+    if (rc) return rc;
+  }
+  DaaCtx cx;
+  memset(&cx, 0, sizeof(cx));
+  cx.q = *daa; cx.b = *batch;
+  for (int m = 0; m < M; ++m) cx.x[m] = x[m];
+  cx.nz_base = Noise{eps_base, seed, MOPOE_STREAM_DAA_BASE};
+  cx.nz_score = Noise{eps_score, seed, MOPOE_STREAM_DAA_SCORE};
+  cx.nz_av = Noise{eps_av, seed, MOPOE_STREAM_DAA_AVATAR};
+  cx.v_base_off = eps_base ? 0 : daa->val_begin;
+  cx.v_score_off = eps_score ? 0 : daa->val_begin;
+  cx.v_av_off = eps_av ? 0 : daa->val_begin;
+  cx.avatars = avatars; cx.sampled_scores = sampled_scores; cx.recon = reconstructions; cx.betas = betas;
+  cx.C = desc->dims[daa->src_mod]; cx.R = desc->dims[daa->dst_mod]; cx.J = daa->n_samples; cx.N = N;
+  // 2. base passes
+  const int base_smem = (160 + 16 * 160 + MOPOE_MAX_MODS * 64 + 64) * 4;
+  daa_base_kernel<<<daa->n_val * N, MOPOE_THREADS, base_smem, stream>>>(mv, cx, ws);
+  MOPOE_CUDA(cudaGetLastError());
+  // 3. avatars + first-level regression
+  const AvSmem pl = av_plan(mv, daa->src_mod, daa->dst_mod, cx.J);
+  const int av_smem = pl.total * 4;
+  if (av_smem > 227 * 1024) { set_error("DAA avatar kernel needs %d bytes of shared memory (> 227 KB): latent/style dims too large", av_smem); return MOPOE_EINVAL; }
+  void* fn = daa->reg_method == 1 ? (void*)daa_avatar_kernel<true> : (void*)daa_avatar_kernel<false>;
+  MOPOE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, av_smem));
+  const int n_units = daa->n_val * N * cx.C;
+  const int grid = n_units < num_sms() ? n_units : num_sms();
+  for (int col0 = 0; col0 < cx.R; col0 += CB) {
+    MOPOE_CUDA(cudaMemsetAsync(ws.counter, 0, sizeof(int), stream));
+    if (daa->reg_method == 1) daa_avatar_kernel<true><<<grid, MOPOE_THREADS, av_smem, stream>>>(mv, cx, ws, col0);
+    else daa_avatar_kernel<false><<<grid, MOPOE_THREADS, av_smem, stream>>>(mv, cx, ws, col0);
+    MOPOE_CUDA(cudaGetLastError());
+  }
+  // 4. second level
+  const int64_t nstat = (int64_t)daa->n_val * cx.C * cx.R;
+  daa_stats_kernel<<<(unsigned)((nstat + 127) / 128), 128, 0, stream>>>(daa->n_val, N, cx.C, cx.J, cx.R, daa->reg_method, ws.betas,
+                                                                       ws.ybar, ws.syy, ws.xstat, reconstructions, coefs, pvalues);
+  MOPOE_CUDA(cudaGetLastError());
+  return MOPOE_OK;
+}
+
+int mopoe_daa_regression(int32_t n_val, int32_t n_subjects, int32_t n_scores, int32_t n_samples, int32_t n_rois,
+                         int32_t reg_method, const float* avatars, const float* sampled_scores,
+                         const float* reconstructions, double* betas, double* coefs, double* pvalues, void* stream_) {
+  if (mopoe_device_count() == 0) { set_error("no CUDA device: the DAA path has no CPU fallback"); return MOPOE_ENODEV; }
+  if (!avatars || !sampled_scores || !betas || !coefs || !pvalues) { set_error("NULL argument"); return MOPOE_EINVAL; }
+  if (reg_method < 0 || reg_method > 1) { set_error("reg_method=%d unsupported", reg_method); return MOPOE_EINVAL; }
+  if (reg_method == 1 && !reconstructions) { set_error("reg_method fixed needs reconstructions"); return MOPOE_EINVAL; }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int64_t nb = (int64_t)n_val * n_scores * n_subjects * n_rois;
+  double* scratch = nullptr;
+  // ybar | syy | xstat live in one stream-ordered allocation
+  const int64_t bytes = (reg_method == 1 ? 2 * nb : 0) * 8 + (int64_t)n_val * n_scores * n_subjects * 2 * 8;
+  MOPOE_CUDA(cudaMallocAsync((void**)&scratch, bytes, stream));
+  double* ybar = reg_method == 1 ? scratch : nullptr;
+  double* syy = reg_method == 1 ? scratch + nb : nullptr;
+  double* xstat = scratch + (reg_method == 1 ? 2 * nb : 0);
+  daa_moments_kernel<<<n_val * n_subjects * n_scores, MOPOE_THREADS, n_samples * 4, stream>>>(
+      n_subjects, n_scores, n_samples, n_rois, avatars, sampled_scores, betas, ybar, syy, xstat);
+  MOPOE_CUDA(cudaGetLastError());
+  const int64_t nstat = (int64_t)n_val * n_scores * n_rois;
+  daa_stats_kernel<<<(unsigned)((nstat + 127) / 128), 128, 0, stream>>>(n_val, n_subjects, n_scores, n_samples, n_rois, reg_method,
+                                                                       betas, ybar, syy, xstat, reconstructions, coefs, pvalues);
+  MOPOE_CUDA(cudaGetLastError());
+  MOPOE_CUDA(cudaFreeAsync(scratch, stream));
+  return MOPOE_OK;
+}
+
+}  // extern "C"

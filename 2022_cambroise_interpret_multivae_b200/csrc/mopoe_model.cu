@@ -1,0 +1,1015 @@
+// MoPoE-VAE forward / ELBO / backward / Adam kernels for sm_100a.
+//
+// One batch of the path is processed in three phases (DESIGN.md section "kernels"):
+//   P1  h_m = relu(x_m W1_m^T + b1_m)                     32x32 register-tiled NT GEMM tiles
+//   P2  per row tile: heads -> subset PoE / MoE -> mixture selection -> reparameterise -> decoders
+//       -> NLL / KL reductions -> (backward) d z, d heads, d pre-activations      (no cross-row deps)
+//   P3  weight gradients as output-stationary TN GEMM tiles (deterministic, no atomics) with the
+//       Adam update applied in the tile epilogue
+// `mopoe_forward` runs P1 + P2(forward only) as two launches; `mopoe_train_steps` runs
+// P1 | grid barrier | P2 | grid barrier | P3 for n_steps batches inside ONE cooperative persistent
+// launch (weights never leave L2, no host round trips, logging scalars written per step).
+//
+// Reference semantics restated here (paths relative to <reference>/experiments):
+//   networks.py:30-36,66-77 (Encoder/Decoder), BaseMMVae.py:137-239 (forward/inference),
+//   mm_div.py:13-20 (poe), utils.py:63-85 (mixture_component_selection), kl_div.py:7-14,
+//   modality.py:42-45 (calc_log_prob), run_epochs.py:73-135 (basic_routine_epoch),
+//   utils.py:88-112 (calc_elbo), experiment.py:268-271 (Adam).
+#include <cooperative_groups.h>
+
+#include "mopoe_common.cuh"
+#include "mopoe_latent.cuh"
+
+namespace mopoe {
+
+constexpr int TILE = 32;      // GEMM tile edge (P1/P3)
+constexpr int TLD = 34;       // padded leading dimension of a staged chunk
+constexpr float HALF_LOG_2PI = 0.91893853320467274178f;
+
+// -------------------------------------------------------------------------------------------
+// workspace
+// -------------------------------------------------------------------------------------------
+struct Workspace {
+  float* h[MOPOE_MAX_MODS];    // (N, 256)      post-ReLU hidden
+  float* dA[MOPOE_MAX_MODS];   // (N, 256)      d loss / d pre-activation
+  float* de[MOPOE_MAX_MODS];   // (N, HC)       d loss / d heads
+  float* zz[MOPOE_MAX_MODS];   // (2, N, ZD)    decoder inputs [style | content], pass 0 / unimodal
+  float* dx[MOPOE_MAX_MODS];   // (2, N, D)     d loss / d x_hat
+  double* acc;                 // (MOPOE_N_SCALARS) scalar accumulators of the current step
+  unsigned int* bar;           // grid barrier counter
+  int64_t max_rows;
+};
+
+static int64_t carve(const mopoe_model_desc* d, int64_t N, char* base, Workspace* w) {
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) { int64_t o = off; off += (bytes + 255) & ~(int64_t)255; return base ? base + o : (char*)nullptr; };
+  const int L = d->latent_dim;
+  Workspace tmp;
+  tmp.acc = (double*)take(MOPOE_N_SCALARS * sizeof(double));
+  tmp.bar = (unsigned int*)take(256);
+  for (int m = 0; m < d->n_mods; ++m) {
+    const int S = d->style_dims[m], D = d->dims[m];
+    tmp.h[m] = (float*)take(N * MOPOE_HIDDEN * 4);
+    tmp.dA[m] = (float*)take(N * MOPOE_HIDDEN * 4);
+    tmp.de[m] = (float*)take(N * (2 * L + 2 * S) * 4);
+    tmp.zz[m] = (float*)take(2 * N * (S + L) * 4);
+    tmp.dx[m] = (float*)take(2 * N * D * 4);
+  }
+  tmp.max_rows = N;
+  if (w) *w = tmp;
+  return off;
+}
+
+// -------------------------------------------------------------------------------------------
+// per-step context (kernel argument)
+// -------------------------------------------------------------------------------------------
+struct StepCtx {
+  const float* x[MOPOE_MAX_MODS];          // data blocks
+  const int32_t* row_index[MOPOE_MAX_MODS];  // optional gather lists
+  Noise noise;
+  int64_t eps_step_stride;                 // n_pass * max_rows * E   (0 for the forward API)
+  int64_t eps_pass_stride;                 // max_rows * E
+  int sample_latents, use_expert, with_nll, uni_pass, mode;
+  mopoe_forward_out out;                   // forward API outputs (NULLs in training)
+  float lr, b1, b2, adam_eps;
+  float* adam_m; float* adam_v; int32_t* adam_t; float* grads; float* params;
+  mopoe_param_layout lay;
+};
+
+__device__ __forceinline__ int64_t src_row(const StepCtx& cx, const mopoe_batch_desc& b, int m, int n) {
+  return cx.row_index[m] ? (int64_t)cx.row_index[m][b.row_offset + n] : (int64_t)n;
+}
+
+// -------------------------------------------------------------------------------------------
+// 32x32 register-tiled GEMM tile:  acc[i][j] = sum_k A(i,k) * B(j,k), 256 threads, 2x2 per thread,
+// K streamed in chunks of 32 through shared memory with register double buffering.
+// FA/FB: (row-in-tile, k) -> float (0 outside the matrix).  *_KC: operand is contiguous along k
+// in memory (lanes walk k) else contiguous along the tile row index (lanes walk i).
+// -------------------------------------------------------------------------------------------
+template <bool A_KC, bool B_KC, class FA, class FB>
+__device__ __forceinline__ void tile_gemm(FA fa, FB fb, int K, float acc[2][2], float* sm) {
+  float* As = sm;                   // [2][TILE][TLD]
+  float* Bs = sm + 2 * TILE * TLD;  // [2][TILE][TLD]
+  const int t = threadIdx.x;
+  const int lo = t & 31, hi = t >> 5;
+  const int ty = t >> 4, tx = t & 15;
+  float ra[4], rb[4];
+  acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = 0.f;
+  const int nchunk = (K + TILE - 1) / TILE;
+  auto fetch = [&](int c) {
+    const int k0 = c * TILE;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int kk_a = A_KC ? lo : hi + 8 * q, ii_a = A_KC ? hi + 8 * q : lo;
+      const int kk_b = B_KC ? lo : hi + 8 * q, ii_b = B_KC ? hi + 8 * q : lo;
+      ra[q] = fa(ii_a, k0 + kk_a);
+      rb[q] = fb(ii_b, k0 + kk_b);
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int kk_a = A_KC ? lo : hi + 8 * q, ii_a = A_KC ? hi + 8 * q : lo;
+      const int kk_b = B_KC ? lo : hi + 8 * q, ii_b = B_KC ? hi + 8 * q : lo;
+      As[(buf * TILE + kk_a) * TLD + ii_a] = ra[q];
+      Bs[(buf * TILE + kk_b) * TLD + ii_b] = rb[q];
+    }
+  };
+  __syncthreads();  // previous users of `sm` are done
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int c = 0; c < nchunk; ++c) {
+    const int buf = c & 1;
+    if (c + 1 < nchunk) fetch(c + 1);
+    const float* a = As + buf * TILE * TLD + 2 * ty;
+    const float* b = Bs + buf * TILE * TLD + 2 * tx;
+#pragma unroll 8
+    for (int kk = 0; kk < TILE; ++kk) {
+      const float2 av = *reinterpret_cast<const float2*>(a + kk * TLD);
+      const float2 bv = *reinterpret_cast<const float2*>(b + kk * TLD);
+      acc[0][0] = fmaf(av.x, bv.x, acc[0][0]);
+      acc[0][1] = fmaf(av.x, bv.y, acc[0][1]);
+      acc[1][0] = fmaf(av.y, bv.x, acc[1][0]);
+      acc[1][1] = fmaf(av.y, bv.y, acc[1][1]);
+    }
+    if (c + 1 < nchunk) stash(buf ^ 1);
+    __syncthreads();
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// P1: encoder first layer.  Work unit = (present modality, 32-row tile, 32-column tile).
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ int p1_units(const ModelView& mv, const mopoe_batch_desc& b) {
+  const int tn = (b.n_rows + TILE - 1) / TILE;
+  return __popc(b.present_mask) * tn * (MOPOE_HIDDEN / TILE);
+}
+
+__device__ void p1_unit(const ModelView& mv, const StepCtx& cx, const mopoe_batch_desc& b,
+                        const Workspace& ws, int u, float* sm) {
+  const int tn = (b.n_rows + TILE - 1) / TILE;
+  const int per_mod = tn * (MOPOE_HIDDEN / TILE);
+  int slot = u / per_mod, rem = u % per_mod, m = 0;
+  for (int mm = 0; mm < mv.M; ++mm)
+    if (b.present_mask >> mm & 1) { if (slot == 0) { m = mm; break; } --slot; }
+  const int n0 = (rem / (MOPOE_HIDDEN / TILE)) * TILE, j0 = (rem % (MOPOE_HIDDEN / TILE)) * TILE;
+  const ModView& md = mv.mod[m];
+  const int D = md.D, N = b.n_rows;
+  const float* x = cx.x[m];
+  const float* w1 = md.w1;
+  // this thread always fetches the same rows: resolve the gather once
+  const int t = threadIdx.x, hi = t >> 5;
+  int64_t rows[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int n = n0 + hi + 8 * q;
+    rows[q] = n < N ? src_row(cx, b, m, n) : -1;
+  }
+  auto fa = [&](int i, int k) -> float {
+    const int64_t r = rows[(i - hi) >> 3];
+    return (r >= 0 && k < D) ? x[r * D + k] : 0.f;
+  };
+  auto fb = [&](int j, int k) -> float { return k < D ? w1[(int64_t)(j0 + j) * D + k] : 0.f; };
+  float acc[2][2];
+  tile_gemm<true, true>(fa, fb, D, acc, sm);
+  const int ty = t >> 4, tx = t & 15;
+  const int j = j0 + 2 * tx;
+  const float bj0 = md.b1[j], bj1 = md.b1[j + 1];
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int n = n0 + 2 * ty + a;
+    if (n < N) {
+      float2 o = make_float2(fmaxf(acc[a][0] + bj0, 0.f), fmaxf(acc[a][1] + bj1, 0.f));
+      *reinterpret_cast<float2*>(ws.h[m] + (int64_t)n * MOPOE_HIDDEN + j) = o;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// P2 shared-memory plan
+// -------------------------------------------------------------------------------------------
+struct P2Smem {
+  int h, e, de, zz, dzz, rp, rps, dx, part, red, total;  // offsets in floats
+  int hc_max, zd_max, s_max;
+};
+
+__host__ __device__ inline P2Smem p2_plan(const ModelView& mv, int R) {
+  P2Smem p;
+  int hc = 0, zd = 0, s = 1;
+  for (int m = 0; m < mv.M; ++m) {
+    hc = mv.mod[m].HC > hc ? mv.mod[m].HC : hc;
+    zd = mv.mod[m].ZD > zd ? mv.mod[m].ZD : zd;
+    s = mv.mod[m].S > s ? mv.mod[m].S : s;
+  }
+  p.hc_max = hc; p.zd_max = zd; p.s_max = s;
+  int off = 0;
+  auto take = [&](int n) { int o = off; off += (n + 3) & ~3; return o; };
+  p.h = take(mv.M * R * MOPOE_HIDDEN);
+  p.e = take(mv.M * R * hc);
+  p.de = take(mv.M * R * hc);
+  p.zz = take(mv.M * 2 * R * zd);
+  p.dzz = take(mv.M * 2 * R * zd);
+  p.rp = take((1 + mv.M) * R * mv.L);
+  p.rps = take(mv.M * 2 * R * s);
+  p.dx = take(R * MOPOE_THREADS);
+  p.part = take(R * zd > MOPOE_THREADS ? R * zd : MOPOE_THREADS);
+  p.red = take(MOPOE_N_SCALARS);
+  p.total = off;
+  return p;
+}
+
+__device__ __forceinline__ void block_add(float* red, int slot, float v) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(red + slot, v);
+}
+
+// -------------------------------------------------------------------------------------------
+// P2: one tile of R rows, everything between the hidden layer and the per-row gradients.
+// -------------------------------------------------------------------------------------------
+template <int R, bool BWD>
+__device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batch_desc& b,
+                        const Workspace& ws, int64_t eps_base, int r0, float* sm) {
+  const P2Smem pl = p2_plan(mv, R);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int N = b.n_rows, L = mv.L, M = mv.M, present = b.present_mask;
+  const int nr = min(R, N - r0);
+  const float invN = 1.f / (float)N;
+  float* sh_h = sm + pl.h;
+  float* sh_e = sm + pl.e;
+  float* sh_de = sm + pl.de;
+  float* sh_zz = sm + pl.zz;
+  float* sh_dzz = sm + pl.dzz;
+  float* sh_rp = sm + pl.rp;
+  float* sh_rps = sm + pl.rps;
+  float* sh_dx = sm + pl.dx;
+  float* sh_part = sm + pl.part;
+  float* sh_red = sm + pl.red;
+  const int HCM = pl.hc_max, ZDM = pl.zd_max, SM_ = pl.s_max;
+  const bool uni = cx.uni_pass != 0;
+
+  __syncthreads();
+  if (t < MOPOE_N_SCALARS) sh_red[t] = 0.f;
+  for (int i = t; i < M * 2 * R * ZDM; i += MOPOE_THREADS) sh_dzz[i] = 0.f;
+  // ---- hidden rows -> smem ----
+  for (int m = 0; m < M; ++m) {
+    if (!(present >> m & 1)) continue;
+    for (int i = t; i < R * (MOPOE_HIDDEN / 4); i += MOPOE_THREADS) {
+      const int r = i / (MOPOE_HIDDEN / 4), c = i % (MOPOE_HIDDEN / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nr) v = *reinterpret_cast<const float4*>(ws.h[m] + (int64_t)(r0 + r) * MOPOE_HIDDEN + 4 * c);
+      *reinterpret_cast<float4*>(sh_h + (m * R + r) * MOPOE_HIDDEN + 4 * c) = v;
+    }
+  }
+  __syncthreads();
+  // ---- heads: e[r][j] = bh[j] + h[r] . wh[j]   (warp per output, lanes split k) ----
+  for (int m = 0; m < M; ++m) {
+    if (!(present >> m & 1)) continue;
+    const ModView& md = mv.mod[m];
+    for (int j = warp; j < md.HC; j += MOPOE_THREADS / 32) {
+      const float4* wrow = reinterpret_cast<const float4*>(md.wh + (int64_t)j * MOPOE_HIDDEN);
+      const float4 wa = wrow[lane], wb = wrow[lane + 32];
+      float acc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4* hr = reinterpret_cast<const float4*>(sh_h + (m * R + r) * MOPOE_HIDDEN);
+        const float4 ha = hr[lane], hb = hr[lane + 32];
+        acc[r] = wa.x * ha.x + wa.y * ha.y + wa.z * ha.z + wa.w * ha.w + wb.x * hb.x + wb.y * hb.y +
+                 wb.z * hb.z + wb.w * hb.w;
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
+      const float bj = md.bh[j];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (lane == r % 32) sh_e[(m * R + r) * HCM + j] = acc[r] + bj;
+    }
+  }
+  __syncthreads();
+  if (cx.out.enc_heads[0] || cx.out.enc_heads[1] || cx.out.enc_heads[2] || cx.out.enc_heads[3]) {
+    for (int m = 0; m < M; ++m) {
+      if (!(present >> m & 1) || !cx.out.enc_heads[m]) continue;
+      const int HC = mv.mod[m].HC;
+      for (int i = t; i < nr * HC; i += MOPOE_THREADS)
+        cx.out.enc_heads[m][(int64_t)(r0 + i / HC) * HC + i % HC] = sh_e[(m * R + i / HC) * HCM + i % HC];
+    }
+  }
+  // ---- latent element-wise forward: thread per (row, latent dim) ----
+  const int nsub = mv.sub.n_subsets;
+  const float wmix = 1.f / (float)b.n_mix;  // uniform mixture weights (BaseMMVae.py:225, :64-78)
+  for (int base = 0; base < R * L; base += MOPOE_THREADS) {
+    const int idx = base + t;
+    const int r = idx / L, l = idx % L;
+    const bool valid = idx < R * L && r < nr;
+    const int n = r0 + r;
+    float mu_e[MOPOE_MAX_MODS], lv_e[MOPOE_MAX_MODS];
+#pragma unroll
+    for (int m = 0; m < MOPOE_MAX_MODS; ++m) {
+      const bool on = valid && m < M && (present >> m & 1);
+      mu_e[m] = on ? sh_e[(m * R + r) * HCM + l] : 0.f;
+      lv_e[m] = on ? sh_e[(m * R + r) * HCM + L + l] : 0.f;
+    }
+    for (int m = 0; m < M; ++m) {
+      if (!(present >> m & 1)) continue;
+      block_add(sh_red, MOPOE_S_MEAN_HEAD + 4 * m + 0, valid ? mu_e[m] : 0.f);
+      block_add(sh_red, MOPOE_S_MEAN_HEAD + 4 * m + 1, valid ? lv_e[m] : 0.f);
+    }
+    float jmu = 0.f, jlv = 0.f;
+    float smu[MOPOE_MAX_MODS], slv[MOPOE_MAX_MODS];  // singleton posteriors (poe unimodal passes)
+#pragma unroll
+    for (int m = 0; m < MOPOE_MAX_MODS; ++m) smu[m] = slv[m] = 0.f;
+    int kidx = 0, owner = 0;
+    for (int k = 0; k < b.n_mix; ++k)
+      if (n >= b.joint_bounds[k] && n < b.joint_bounds[k + 1]) owner = k;
+    for (int s = 0; s < nsub; ++s) {
+      if ((mv.sub.mask[s] & present) != mv.sub.mask[s]) continue;
+      const SubsetEval ev = eval_subset(mv, b, s, n, mu_e, lv_e);
+      if (valid) {
+        if (cx.out.subset_mu) cx.out.subset_mu[((int64_t)s * N + n) * L + l] = ev.mu;
+        if (cx.out.subset_logvar) cx.out.subset_logvar[((int64_t)s * N + n) * L + l] = ev.lv;
+      }
+      const float kl = valid ? -0.5f * (1.f - expf(ev.lv) - ev.mu * ev.mu + ev.lv) : 0.f;
+      block_add(sh_red, MOPOE_S_KLD_SUBSET + s, kl);
+      if (mv.sub.n_members[s] == 1) { smu[mv.sub.members[s][0]] = ev.mu; slv[mv.sub.members[s][0]] = ev.lv; }
+      if (in_mixture(mv, b, s)) {
+        if (cx.use_expert < 0) {
+          if (cx.sample_latents) { if (kidx == owner) { jmu = ev.mu; jlv = ev.lv; } }
+          else { jmu += ev.mu; jlv += ev.lv; }
+        }
+        ++kidx;
+      }
+      if (cx.use_expert == s) { jmu = ev.mu; jlv = ev.lv; }
+    }
+    if (cx.use_expert < 0 && !cx.sample_latents) { jmu /= (float)b.n_mix; jlv /= (float)b.n_mix; }
+    if (valid) {
+      float z = jmu, rp = 0.f;
+      if (cx.sample_latents) {
+        const float e0 = cx.noise.at(eps_base + (int64_t)n * mv.E + l);
+        const float sd = expf(0.5f * jlv);
+        z = e0 * sd + jmu;
+        rp = 0.5f * e0 * sd;
+      }
+      sh_rp[r * L + l] = rp;
+      for (int m = 0; m < M; ++m)
+        if (present >> m & 1) sh_zz[((m * 2 + 0) * R + r) * ZDM + mv.mod[m].S + l] = z;
+      if (cx.out.joint_mu) cx.out.joint_mu[(int64_t)n * L + l] = jmu;
+      if (cx.out.joint_logvar) cx.out.joint_logvar[(int64_t)n * L + l] = jlv;
+      if (cx.out.z) cx.out.z[(int64_t)n * L + l] = z;
+      if (uni) {
+        for (int m = 0; m < M; ++m) {
+          if (!(present >> m & 1)) continue;
+          const float e1 = cx.noise.at(eps_base + (1 + m) * cx.eps_pass_stride + (int64_t)n * mv.E + l);
+          const float sd = expf(0.5f * slv[m]);
+          sh_zz[((m * 2 + 1) * R + r) * ZDM + mv.mod[m].S + l] = e1 * sd + smu[m];
+          sh_rp[((1 + m) * R + r) * L + l] = 0.5f * e1 * sd;
+        }
+      }
+    }
+  }
+  // ---- style element-wise forward ----
+  for (int m = 0; m < M; ++m) {
+    if (!(present >> m & 1)) continue;
+    const ModView& md = mv.mod[m];
+    const int S = md.S;
+    if (S == 0) continue;
+    for (int base = 0; base < R * S; base += MOPOE_THREADS) {
+      const int idx = base + t;
+      const int r = idx / S, s = idx % S;
+      const bool valid = idx < R * S && r < nr;
+      const int n = r0 + r;
+      float klv = 0.f, mu = 0.f, lv = 0.f;
+      if (valid) {
+        mu = sh_e[(m * R + r) * HCM + 2 * L + s];
+        lv = sh_e[(m * R + r) * HCM + 2 * L + S + s];
+        klv = -0.5f * (1.f - expf(lv) - mu * mu + lv);
+        const float sd = expf(0.5f * lv);
+        float zs = mu, rp = 0.f;
+        if (cx.sample_latents) {
+          const float e0 = cx.noise.at(eps_base + (int64_t)n * mv.E + md.eps_off + s);
+          zs = e0 * sd + mu; rp = 0.5f * e0 * sd;
+        }
+        sh_zz[((m * 2 + 0) * R + r) * ZDM + s] = zs;
+        sh_rps[((m * 2 + 0) * R + r) * SM_ + s] = rp;
+        if (cx.out.z_style[m]) cx.out.z_style[m][(int64_t)n * S + s] = zs;
+        if (uni) {
+          const float e1 = cx.noise.at(eps_base + (1 + m) * cx.eps_pass_stride + (int64_t)n * mv.E + md.eps_off + s);
+          sh_zz[((m * 2 + 1) * R + r) * ZDM + s] = e1 * sd + mu;
+          sh_rps[((m * 2 + 1) * R + r) * SM_ + s] = 0.5f * e1 * sd;
+        }
+      }
+      block_add(sh_red, MOPOE_S_KLD_STYLE + m, klv);
+      block_add(sh_red, MOPOE_S_MEAN_HEAD + 4 * m + 2, mu);
+      block_add(sh_red, MOPOE_S_MEAN_HEAD + 4 * m + 3, lv);
+    }
+  }
+  __syncthreads();
+  // ---- decoders (+ NLL, d x_hat, d z) : thread per output feature, 256 features at a time ----
+  const int npass = uni ? 2 : 1;
+  for (int m = 0; m < M; ++m) {
+    if (!(present >> m & 1)) continue;
+    const ModView& md = mv.mod[m];
+    const int D = md.D, ZD = md.ZD;
+    if (BWD) {  // decoder inputs -> workspace for the weight-gradient phase
+      for (int p = 0; p < npass; ++p)
+        for (int i = t; i < nr * ZD; i += MOPOE_THREADS)
+          ws.zz[m][((int64_t)p * ws.max_rows + r0 + i / ZD) * ZD + i % ZD] = sh_zz[((m * 2 + p) * R + i / ZD) * ZDM + i % ZD];
+    }
+    for (int p = 0; p < npass; ++p) {
+      const float* zrow = sh_zz + (m * 2 + p) * R * ZDM;
+      for (int d0 = 0; d0 < D; d0 += MOPOE_THREADS) {
+        const int d = d0 + t;
+        const int dlen = min(MOPOE_THREADS, D - d0);
+        float nll = 0.f;
+        if (d < D) {
+          float acc[R];
+          const float bd = md.bd[d];
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = bd;
+          const float* w = md.wd + (int64_t)d * ZD;
+          for (int k = 0; k < ZD; ++k) {
+            const float wk = w[k];
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = fmaf(zrow[r * ZDM + k], wk, acc[r]);
+          }
+          const float lam = md.lv[d];
+          const float iv = expf(-lam);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            if (r < nr) {
+              const int n = r0 + r;
+              if (p == 0 && cx.out.rec_loc[m]) cx.out.rec_loc[m][(int64_t)n * D + d] = acc[r];
+              if (cx.with_nll) {
+                const float xv = cx.x[m][src_row(cx, b, m, n) * D + d];
+                const float diff = xv - acc[r];
+                nll += 0.5f * diff * diff * iv + 0.5f * lam + HALF_LOG_2PI;
+                if (BWD) {
+                  const float g = -diff * iv * invN;
+                  sh_dx[r * MOPOE_THREADS + t] = g;
+                  ws.dx[m][((int64_t)p * ws.max_rows + n) * D + d] = g;
+                }
+              }
+            } else if (BWD) {
+              sh_dx[r * MOPOE_THREADS + t] = 0.f;
+            }
+          }
+        }
+        if (cx.with_nll) block_add(sh_red, (p == 0 ? MOPOE_S_NLL : MOPOE_S_NLL_UNI) + m, nll);
+        if (BWD) {
+          __syncthreads();
+          // d zz[r][k] += sum_d dx[r][d] * wd[d][k]
+          const int P = R * ZD;
+          const int nsplit = P >= MOPOE_THREADS ? 1 : MOPOE_THREADS / P;
+          for (int q0 = 0; q0 < P * nsplit; q0 += MOPOE_THREADS) {
+            const int q = q0 + t;
+            if (q < P * nsplit) {
+              const int pr = q % P, sp = q / P;
+              const int r = pr / ZD, k = pr % ZD;
+              float a = 0.f;
+              for (int dd = sp; dd < dlen; dd += nsplit)
+                a = fmaf(sh_dx[r * MOPOE_THREADS + dd], md.wd[(int64_t)(d0 + dd) * ZD + k], a);
+              if (nsplit == 1) sh_dzz[((m * 2 + p) * R + r) * ZDM + k] += a;
+              else sh_part[sp * P + pr] = a;
+            }
+          }
+          if (nsplit > 1) {
+            __syncthreads();
+            if (t < P) {
+              float a = 0.f;
+              for (int sp = 0; sp < nsplit; ++sp) a += sh_part[sp * P + t];
+              sh_dzz[((m * 2 + p) * R + t / ZD) * ZDM + t % ZD] += a;
+            }
+          }
+          __syncthreads();
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (BWD) {
+    // ---- latent element-wise backward ----
+    const float ckl = mv.beta * mv.beta_content * invN;
+    for (int base = 0; base < R * L; base += MOPOE_THREADS) {
+      const int idx = base + t;
+      const int r = idx / L, l = idx % L;
+      if (idx < R * L && r < nr) {
+        const int n = r0 + r;
+        float mu_e[MOPOE_MAX_MODS], lv_e[MOPOE_MAX_MODS], dmu[MOPOE_MAX_MODS], dlv[MOPOE_MAX_MODS];
+#pragma unroll
+        for (int m = 0; m < MOPOE_MAX_MODS; ++m) {
+          const bool on = m < M && (present >> m & 1);
+          mu_e[m] = on ? sh_e[(m * R + r) * HCM + l] : 0.f;
+          lv_e[m] = on ? sh_e[(m * R + r) * HCM + L + l] : 0.f;
+          dmu[m] = dlv[m] = 0.f;
+        }
+        float gz = 0.f;
+        for (int m = 0; m < M; ++m)
+          if (present >> m & 1) gz += sh_dzz[((m * 2 + 0) * R + r) * ZDM + mv.mod[m].S + l];
+        int kidx = 0, owner = 0;
+        for (int k = 0; k < b.n_mix; ++k)
+          if (n >= b.joint_bounds[k] && n < b.joint_bounds[k + 1]) owner = k;
+        for (int s = 0; s < nsub; ++s) {
+          if ((mv.sub.mask[s] & present) != mv.sub.mask[s]) continue;
+          const SubsetEval ev = eval_subset(mv, b, s, n, mu_e, lv_e);
+          const int nm = mv.sub.n_members[s];
+          float umu = 0.f, ulv = 0.f;
+          const float dkl_lv = 0.5f * (expf(ev.lv) - 1.f);
+          if (in_mixture(mv, b, s)) {
+            umu += ckl * wmix * ev.mu;
+            ulv += ckl * wmix * dkl_lv;
+            if (kidx == owner) { umu += gz; ulv += gz * sh_rp[r * L + l]; }
+            ++kidx;
+          }
+          if (mv.method == MOPOE_METHOD_POE && nm == 1) {  // unimodal ELBO of modality m (run_epochs.py:115-125)
+            const int m = mv.sub.members[s][0];
+            umu += ckl * ev.mu;
+            ulv += ckl * dkl_lv;
+            if (uni) {
+              const float g1 = sh_dzz[((m * 2 + 1) * R + r) * ZDM + mv.mod[m].S + l];
+              umu += g1; ulv += g1 * sh_rp[((1 + m) * R + r) * L + l];
+            }
+          }
+          if (umu == 0.f && ulv == 0.f) continue;
+          if (mv.method == MOPOE_METHOD_MOE) {
+            const int m = mv.sub.members[s][ev.sel];
+            dmu[m] += umu; dlv[m] += ulv;
+          } else {
+            const float invP = 1.f / ev.sumT;
+            for (int i = 0; i < nm; ++i) {
+              const int m = mv.sub.members[s][i];
+              const float ex = expf(lv_e[m]);
+              const float T = 1.f / (ex + MOPOE_POE_EPS);
+              dmu[m] += umu * T * invP;
+              const float dT = umu * (mu_e[m] - ev.mu) * invP - ulv * invP;
+              dlv[m] += dT * (-T * T * ex);
+            }
+          }
+        }
+        for (int m = 0; m < M; ++m)
+          if (present >> m & 1) {
+            sh_de[(m * R + r) * HCM + l] = dmu[m];
+            sh_de[(m * R + r) * HCM + L + l] = dlv[m];
+          }
+      }
+    }
+    // ---- style element-wise backward ----
+    for (int m = 0; m < M; ++m) {
+      if (!(present >> m & 1)) continue;
+      const int S = mv.mod[m].S;
+      // style KL enters the joint ELBO and (poe) the unimodal ELBO of m, each with beta*beta_style^2
+      const float cks = mv.beta * mv.beta_style * mv.beta_style * invN * (mv.method == MOPOE_METHOD_POE ? 2.f : 1.f);
+      for (int idx = t; idx < R * S; idx += MOPOE_THREADS) {
+        const int r = idx / S, s = idx % S;
+        if (r >= nr) continue;
+        const float mu = sh_e[(m * R + r) * HCM + 2 * L + s];
+        const float lv = sh_e[(m * R + r) * HCM + 2 * L + S + s];
+        const float g0 = sh_dzz[((m * 2 + 0) * R + r) * ZDM + s];
+        float gmu = g0 + cks * mu;
+        float glv = g0 * sh_rps[((m * 2 + 0) * R + r) * SM_ + s] + cks * 0.5f * (expf(lv) - 1.f);
+        if (uni) {
+          const float g1 = sh_dzz[((m * 2 + 1) * R + r) * ZDM + s];
+          gmu += g1; glv += g1 * sh_rps[((m * 2 + 1) * R + r) * SM_ + s];
+        }
+        sh_de[(m * R + r) * HCM + 2 * L + s] = gmu;
+        sh_de[(m * R + r) * HCM + 2 * L + S + s] = glv;
+      }
+    }
+    __syncthreads();
+    // ---- d heads -> workspace; d pre-activation = (W_h^T d heads) * relu' ----
+    for (int m = 0; m < M; ++m) {
+      if (!(present >> m & 1)) continue;
+      const ModView& md = mv.mod[m];
+      const int HC = md.HC;
+      for (int i = t; i < nr * HC; i += MOPOE_THREADS)
+        ws.de[m][(int64_t)(r0 + i / HC) * HC + i % HC] = sh_de[(m * R + i / HC) * HCM + i % HC];
+      float acc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = 0.f;
+      for (int j = 0; j < HC; ++j) {
+        const float w = md.wh[(int64_t)j * MOPOE_HIDDEN + t];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = fmaf(sh_de[(m * R + r) * HCM + j], w, acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (r < nr) ws.dA[m][(int64_t)(r0 + r) * MOPOE_HIDDEN + t] = sh_h[(m * R + r) * MOPOE_HIDDEN + t] > 0.f ? acc[r] : 0.f;
+    }
+  }
+  __syncthreads();
+  if (t < MOPOE_N_SCALARS && sh_red[t] != 0.f) atomicAdd(ws.acc + t, (double)sh_red[t]);
+}
+
+// -------------------------------------------------------------------------------------------
+// scalars of one step from the accumulated sums (one thread)
+// -------------------------------------------------------------------------------------------
+__device__ void finalize_scalars(const ModelView& mv, const StepCtx& cx, const mopoe_batch_desc& b,
+                                 const double* acc, float* out) {
+  const int M = mv.M, L = mv.L, present = b.present_mask;
+  const double N = (double)b.n_rows;
+  float s[MOPOE_N_SCALARS];
+  for (int i = 0; i < MOPOE_N_SCALARS; ++i) s[i] = 0.f;
+  double jd = 0.0, nll = 0.0, kls = 0.0, uni = 0.0;
+  for (int q = 0; q < mv.sub.n_subsets; ++q) {
+    if ((mv.sub.mask[q] & present) != mv.sub.mask[q]) continue;
+    const double kl = acc[MOPOE_S_KLD_SUBSET + q] / N;
+    s[MOPOE_S_KLD_SUBSET + q] = (float)kl;
+    if (in_mixture(mv, b, q)) jd += kl / (double)b.n_mix;
+  }
+  for (int m = 0; m < M; ++m) {
+    if (!(present >> m & 1)) continue;
+    const int S = mv.mod[m].S;
+    const double nm = acc[MOPOE_S_NLL + m] / N, nu = acc[MOPOE_S_NLL_UNI + m] / N;
+    const double ks = acc[MOPOE_S_KLD_STYLE + m] / N;
+    s[MOPOE_S_NLL + m] = (float)nm;
+    s[MOPOE_S_NLL_UNI + m] = (float)nu;
+    s[MOPOE_S_KLD_STYLE + m] = (float)ks;
+    s[MOPOE_S_MEAN_HEAD + 4 * m + 0] = (float)(acc[MOPOE_S_MEAN_HEAD + 4 * m + 0] / (N * L));
+    s[MOPOE_S_MEAN_HEAD + 4 * m + 1] = (float)(acc[MOPOE_S_MEAN_HEAD + 4 * m + 1] / (N * L));
+    if (S > 0) {
+      s[MOPOE_S_MEAN_HEAD + 4 * m + 2] = (float)(acc[MOPOE_S_MEAN_HEAD + 4 * m + 2] / (N * S));
+      s[MOPOE_S_MEAN_HEAD + 4 * m + 3] = (float)(acc[MOPOE_S_MEAN_HEAD + 4 * m + 3] / (N * S));
+    }
+    nll += nm;
+    kls += mv.beta_style * ks;  // calc_style_kld: style_weights[m] = beta_style
+    if (mv.method == MOPOE_METHOD_POE)  // unimodal ELBO (utils.calc_elbo, modality != 'joint')
+      uni += nu + mv.beta * (mv.beta_content * (acc[MOPOE_S_KLD_SUBSET + m] / N) + mv.beta_style * (mv.beta_style * ks));
+  }
+  s[MOPOE_S_JOINT_DIV] = (float)jd;
+  s[MOPOE_S_TOTAL_LOSS] = (float)(nll + mv.beta * (mv.beta_style * kls + mv.beta_content * jd) + uni);
+  s[MOPOE_S_N_ROWS] = (float)b.n_rows;
+  s[MOPOE_S_PRESENT] = (float)present;
+  for (int i = 0; i < MOPOE_N_SCALARS; ++i) out[i] = s[i];
+}
+
+// -------------------------------------------------------------------------------------------
+// P3: weight gradients (+ Adam).  Work units:
+//   kind 0  dW1_m[j][d]  = sum_n dA_m[n][j] x_m[n][d]            (256 x D)
+//   kind 1  dWh_m[j][k]  = sum_n de_m[n][j] h_m[n][k]            (HC x 256)
+//   kind 2  dWd_m[d][z]  = sum_{p,n} dx_m[p][n][d] zz_m[p][n][z] (D x ZD)
+//   kind 3  column sums: db1 (256), dbh (HC), dbd (D), d logvar (D), 32 columns per unit
+// -------------------------------------------------------------------------------------------
+struct P3Unit { int m, kind, ti, tj; };
+
+__device__ __forceinline__ int p3_units_of(const ModView& md, int kind) {
+  auto c = [](int v) { return (v + TILE - 1) / TILE; };
+  switch (kind) {
+    case 0: return (MOPOE_HIDDEN / TILE) * c(md.D);
+    case 1: return c(md.HC) * (MOPOE_HIDDEN / TILE);
+    case 2: return c(md.D) * c(md.ZD);
+    default: return (MOPOE_HIDDEN / TILE) + c(md.HC) + 2 * c(md.D);
+  }
+}
+
+__device__ int p3_total(const ModelView& mv, int present) {
+  int n = 0;
+  for (int m = 0; m < mv.M; ++m)
+    if (present >> m & 1)
+      for (int k = 0; k < 4; ++k) n += p3_units_of(mv.mod[m], k);
+  return n;
+}
+
+__device__ P3Unit p3_decode(const ModelView& mv, int present, int u) {
+  P3Unit r = {0, 0, 0, 0};
+  auto c = [](int v) { return (v + TILE - 1) / TILE; };
+  for (int m = 0; m < mv.M; ++m) {
+    if (!(present >> m & 1)) continue;
+    for (int k = 0; k < 4; ++k) {
+      const int cnt = p3_units_of(mv.mod[m], k);
+      if (u < cnt) {
+        r.m = m; r.kind = k;
+        const int tjn = k == 0 ? c(mv.mod[m].D) : k == 1 ? MOPOE_HIDDEN / TILE : k == 2 ? c(mv.mod[m].ZD) : 1;
+        r.ti = u / tjn; r.tj = u % tjn;
+        return r;
+      }
+      u -= cnt;
+    }
+  }
+  return r;
+}
+
+// Adam update / gradient store of one scalar parameter (torch.optim.Adam, no amsgrad / decay)
+__device__ __forceinline__ void apply_grad(const StepCtx& cx, int64_t idx, float g, float bc1, float bc2s) {
+  if (cx.mode == 1) { cx.grads[idx] = g; return; }
+  const float m = cx.b1 * cx.adam_m[idx] + (1.f - cx.b1) * g;
+  const float v = cx.b2 * cx.adam_v[idx] + (1.f - cx.b2) * g * g;
+  cx.adam_m[idx] = m;
+  cx.adam_v[idx] = v;
+  const float denom = sqrtf(v) / bc2s + cx.adam_eps;
+  cx.params[idx] -= (cx.lr / bc1) * (m / denom);
+}
+
+__device__ void p3_unit(const ModelView& mv, const StepCtx& cx, const mopoe_batch_desc& b,
+                        const Workspace& ws, int u, float* sm) {
+  const P3Unit pu = p3_decode(mv, b.present_mask, u);
+  const int m = pu.m;
+  const ModView& md = mv.mod[m];
+  const int N = b.n_rows, D = md.D, HC = md.HC, ZD = md.ZD, t = threadIdx.x;
+  const int npass = cx.uni_pass ? 2 : 1;
+  // bias corrections of this modality's parameter group (step count t_m incremented by the caller)
+  float bc1 = 1.f, bc2s = 1.f;
+  if (cx.mode == 2) {
+    const float tt = (float)(cx.adam_t[m] + 1);
+    bc1 = 1.f - powf(cx.b1, tt);
+    bc2s = sqrtf(1.f - powf(cx.b2, tt));
+  }
+  const int ty = t >> 4, tx = t & 15;
+  float acc[2][2];
+  if (pu.kind == 0) {
+    const int i0 = pu.ti * TILE, j0 = pu.tj * TILE;
+    const float* dA = ws.dA[m];
+    const float* x = cx.x[m];
+    // B operand walks j (feature) fastest: each thread resolves its 4 gathered rows per chunk
+    auto fa = [&](int i, int k) -> float { return k < N ? dA[(int64_t)k * MOPOE_HIDDEN + i0 + i] : 0.f; };
+    auto fb = [&](int j, int k) -> float {
+      return (k < N && j0 + j < D) ? x[src_row(cx, b, m, k) * D + j0 + j] : 0.f;
+    };
+    tile_gemm<false, false>(fa, fb, N, acc, sm);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int i = i0 + 2 * ty + a, j = j0 + 2 * tx + c;
+        if (j < D) apply_grad(cx, cx.lay.enc_w1[m] + (int64_t)i * D + j, acc[a][c], bc1, bc2s);
+      }
+  } else if (pu.kind == 1) {
+    const int i0 = pu.ti * TILE, j0 = pu.tj * TILE;
+    const float* de = ws.de[m];
+    const float* h = ws.h[m];
+    auto fa = [&](int i, int k) -> float { return (k < N && i0 + i < HC) ? de[(int64_t)k * HC + i0 + i] : 0.f; };
+    auto fb = [&](int j, int k) -> float { return k < N ? h[(int64_t)k * MOPOE_HIDDEN + j0 + j] : 0.f; };
+    tile_gemm<false, false>(fa, fb, N, acc, sm);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int i = i0 + 2 * ty + a, j = j0 + 2 * tx + c;
+        if (i < HC) apply_grad(cx, cx.lay.enc_wh[m] + (int64_t)i * MOPOE_HIDDEN + j, acc[a][c], bc1, bc2s);
+      }
+  } else if (pu.kind == 2) {
+    const int i0 = pu.ti * TILE, j0 = pu.tj * TILE;
+    const float* dx = ws.dx[m];
+    const float* zz = ws.zz[m];
+    const int64_t mr = ws.max_rows;
+    const int K = npass * N;
+    auto fa = [&](int i, int k) -> float {
+      if (k >= K || i0 + i >= D) return 0.f;
+      const int p = k / N, n = k - p * N;
+      return dx[((int64_t)p * mr + n) * D + i0 + i];
+    };
+    auto fb = [&](int j, int k) -> float {
+      if (k >= K || j0 + j >= ZD) return 0.f;
+      const int p = k / N, n = k - p * N;
+      return zz[((int64_t)p * mr + n) * ZD + j0 + j];
+    };
+    tile_gemm<false, false>(fa, fb, K, acc, sm);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int i = i0 + 2 * ty + a, j = j0 + 2 * tx + c;
+        if (i < D && j < ZD) apply_grad(cx, cx.lay.dec_w[m] + (int64_t)i * ZD + j, acc[a][c], bc1, bc2s);
+      }
+  } else {
+    // column sums: which vector does this unit belong to?
+    auto c32 = [](int v) { return (v + TILE - 1) / TILE; };
+    int q = pu.ti, which = 0;
+    if (q >= MOPOE_HIDDEN / TILE) { q -= MOPOE_HIDDEN / TILE; which = 1;
+      if (q >= c32(HC)) { q -= c32(HC); which = 2; if (q >= c32(D)) { q -= c32(D); which = 3; } } }
+    const int c0 = q * TILE, col = c0 + (t & 31), grp = t >> 5;
+    const int width = which == 0 ? MOPOE_HIDDEN : which == 1 ? HC : D;
+    float sum = 0.f;
+    if (col < width) {
+      if (which == 0) {
+        for (int n = grp; n < N; n += 8) sum += ws.dA[m][(int64_t)n * MOPOE_HIDDEN + col];
+      } else if (which == 1) {
+        for (int n = grp; n < N; n += 8) sum += ws.de[m][(int64_t)n * HC + col];
+      } else {
+        const float var = which == 3 ? expf(md.lv[col]) : 0.f;
+        const float fN = (float)N;
+        for (int p = 0; p < npass; ++p)
+          for (int n = grp; n < N; n += 8) {
+            const float g = ws.dx[m][((int64_t)p * ws.max_rows + n) * D + col];
+            // d nll / d logvar_d = (1/N) sum_n 0.5 (1 - diff^2/var),  diff = -g var N
+            sum += which == 2 ? g : 0.5f / fN - 0.5f * fN * var * g * g;
+          }
+      }
+    }
+    __syncthreads();
+    sm[grp * 32 + (t & 31)] = sum;
+    __syncthreads();
+    if (t < 32 && c0 + t < width) {
+      float tot = 0.f;
+      for (int g = 0; g < 8; ++g) tot += sm[g * 32 + t];
+      const int64_t base = which == 0 ? cx.lay.enc_b1[m] : which == 1 ? cx.lay.enc_bh[m]
+                           : which == 2 ? cx.lay.dec_b[m] : cx.lay.dec_lv[m];
+      if (which != 3 || mv.learn_scale) apply_grad(cx, base + c0 + t, tot, bc1, bc2s);
+      else if (cx.mode == 1) cx.grads[base + c0 + t] = 0.f;
+    }
+    __syncthreads();
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// kernels
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MOPOE_THREADS) p1_kernel(ModelView mv, StepCtx cx, mopoe_batch_desc b, Workspace ws) {
+  extern __shared__ __align__(16) float sm[];
+  const int nu = p1_units(mv, b);
+  for (int u = blockIdx.x; u < nu; u += gridDim.x) p1_unit(mv, cx, b, ws, u, sm);
+}
+
+template <int R>
+__global__ void __launch_bounds__(MOPOE_THREADS) p2_forward_kernel(ModelView mv, StepCtx cx, mopoe_batch_desc b, Workspace ws) {
+  extern __shared__ __align__(16) float sm[];
+  const int nt = (b.n_rows + R - 1) / R;
+  for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) p2_tile<R, false>(mv, cx, b, ws, 0, tile * R, sm);
+}
+
+__global__ void finalize_kernel(ModelView mv, StepCtx cx, mopoe_batch_desc b, Workspace ws) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && cx.out.scalars) finalize_scalars(mv, cx, b, ws.acc, cx.out.scalars);
+}
+
+// the fused persistent training kernel: n_steps x (P1 | barrier | P2 | barrier | P3 | barrier)
+template <int R>
+__global__ void __launch_bounds__(MOPOE_THREADS) train_kernel(ModelView mv, StepCtx cx, const mopoe_batch_desc* batches,
+                                                              int n_steps, float* scalars, Workspace ws) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ mopoe_batch_desc sb;
+  unsigned int target = 0;
+  for (int step = 0; step < n_steps; ++step) {
+    __syncthreads();
+    if (threadIdx.x == 0) sb = batches[step];
+    __syncthreads();
+    const mopoe_batch_desc& b = sb;
+    if (blockIdx.x == 0 && threadIdx.x < MOPOE_N_SCALARS) ws.acc[threadIdx.x] = 0.0;
+    const int nu1 = p1_units(mv, b);
+    for (int u = blockIdx.x; u < nu1; u += gridDim.x) p1_unit(mv, cx, b, ws, u, sm);
+    grid_barrier(ws.bar, target);
+    const int nt = (b.n_rows + R - 1) / R;
+    const int64_t eps_base = (int64_t)step * cx.eps_step_stride;
+    for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+      if (cx.mode == 0) p2_tile<R, false>(mv, cx, b, ws, eps_base, tile * R, sm);
+      else p2_tile<R, true>(mv, cx, b, ws, eps_base, tile * R, sm);
+    }
+    grid_barrier(ws.bar, target);
+    if (blockIdx.x == 0 && threadIdx.x == 0) finalize_scalars(mv, cx, b, ws.acc, scalars + (int64_t)step * MOPOE_N_SCALARS);
+    if (cx.mode != 0) {
+      const int nu3 = p3_total(mv, b.present_mask);
+      for (int u = blockIdx.x; u < nu3; u += gridDim.x) p3_unit(mv, cx, b, ws, u, sm);
+      grid_barrier(ws.bar, target);
+      if (cx.mode == 2 && blockIdx.x == 0 && threadIdx.x < mv.M && (b.present_mask >> threadIdx.x & 1))
+        cx.adam_t[threadIdx.x] += 1;
+      // adam_t is next read in P3 of the following step, two barriers away
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// host launchers
+// -------------------------------------------------------------------------------------------
+static int pick_rows(const ModelView& mv, int64_t n_rows, int* smem_bytes) {
+  int R = n_rows > 2048 ? 16 : 4;
+  int bytes = p2_plan(mv, R).total * 4;
+  if (bytes > 220 * 1024) { R = 4; bytes = p2_plan(mv, R).total * 4; }
+  const int gemm = 4 * TILE * TLD * 4;
+  *smem_bytes = bytes > gemm ? bytes : gemm;
+  return R;
+}
+
+static int validate_batch(const mopoe_model_desc* d, const mopoe_batch_desc* b) {
+  if (b->n_rows < 1) { set_error("n_rows=%d", b->n_rows); return MOPOE_EINVAL; }
+  if (b->present_mask <= 0 || b->present_mask >= (1 << d->n_mods)) { set_error("present_mask=%d invalid", b->present_mask); return MOPOE_EINVAL; }
+  if (b->n_mix < 1 || b->n_mix > MOPOE_MAX_SUBSETS) { set_error("n_mix=%d invalid", b->n_mix); return MOPOE_EINVAL; }
+  if (b->joint_bounds[0] != 0 || b->joint_bounds[b->n_mix] != b->n_rows) { set_error("joint_bounds do not span the batch"); return MOPOE_EINVAL; }
+  return MOPOE_OK;
+}
+
+}  // namespace mopoe
+
+using namespace mopoe;
+
+extern "C" {
+
+int64_t mopoe_workspace_bytes(const mopoe_model_desc* desc, int64_t max_rows) {
+  if (check_desc(desc)) return MOPOE_EINVAL;
+  if (max_rows < 1) { set_error("max_rows=%lld", (long long)max_rows); return MOPOE_EINVAL; }
+  return carve(desc, max_rows, nullptr, nullptr);
+}
+
+int mopoe_forward(const mopoe_model_desc* desc, const float* params, const mopoe_batch_desc* batch,
+                  const float* const* x, const float* eps, uint64_t seed, int sample_latents, int use_expert,
+                  int with_nll, const mopoe_forward_out* out, void* workspace, int64_t workspace_bytes, void* stream_) {
+  int rc = check_desc(desc);
+  if (rc) return rc;
+  if (mopoe_device_count() == 0) { set_error("no CUDA device: the MoPoE path has no CPU fallback"); return MOPOE_ENODEV; }
+  if (!params || !batch || !x || !out || !workspace) { set_error("NULL argument"); return MOPOE_EINVAL; }
+  if ((rc = validate_batch(desc, batch))) return rc;
+  mopoe_param_layout lay;
+  mopoe_param_layout_of(desc, &lay);
+  ModelView mv;
+  build_view(desc, &lay, const_cast<float*>(params), &mv);
+  if (use_expert >= mv.sub.n_subsets) { set_error("use_expert=%d out of range", use_expert); return MOPOE_EINVAL; }
+  if (use_expert >= 0 && (mv.sub.mask[use_expert] & batch->present_mask) != mv.sub.mask[use_expert]) {
+    set_error("use_expert subset %d is not available in this batch", use_expert); return MOPOE_EINVAL; }
+  const int64_t need = carve(desc, batch->n_rows, nullptr, nullptr);
+  if (workspace_bytes < need) { set_error("workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need); return MOPOE_ENOSPC; }
+  Workspace ws;
+  carve(desc, batch->n_rows, (char*)workspace, &ws);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  StepCtx cx;
+  memset(&cx, 0, sizeof(cx));
+  for (int m = 0; m < desc->n_mods; ++m) {
+    cx.x[m] = (batch->present_mask >> m & 1) ? x[m] : nullptr;
+    if ((batch->present_mask >> m & 1) && !x[m]) { set_error("x[%d] is NULL but modality is present", m); return MOPOE_EINVAL; }
+  }
+  cx.noise.eps = eps; cx.noise.seed = seed; cx.noise.stream = MOPOE_STREAM_FORWARD;
+  cx.eps_pass_stride = (int64_t)batch->n_rows * mv.E;
+  cx.sample_latents = sample_latents; cx.use_expert = use_expert < 0 ? -1 : use_expert;
+  cx.with_nll = with_nll; cx.uni_pass = 0; cx.mode = 0;
+  cx.out = *out;
+  cx.lay = lay;
+  mopoe_batch_desc b = *batch;
+  b.row_offset = 0;
+  MOPOE_CUDA(cudaMemsetAsync(ws.acc, 0, MOPOE_N_SCALARS * sizeof(double), stream));
+  const int tn = (b.n_rows + TILE - 1) / TILE;
+  int present_n = 0;
+  for (int m = 0; m < desc->n_mods; ++m) present_n += b.present_mask >> m & 1;
+  const int nu1 = present_n * tn * (MOPOE_HIDDEN / TILE);
+  const int sms = num_sms();
+  p1_kernel<<<nu1 < 8 * sms ? nu1 : 8 * sms, MOPOE_THREADS, 4 * TILE * TLD * 4, stream>>>(mv, cx, b, ws);
+  MOPOE_CUDA(cudaGetLastError());
+  int smem = 0;
+  const int R = pick_rows(mv, b.n_rows, &smem);
+  const int nt = (b.n_rows + R - 1) / R;
+  if (R == 4) {
+    MOPOE_CUDA(cudaFuncSetAttribute(p2_forward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    p2_forward_kernel<4><<<nt < 4 * sms ? nt : 4 * sms, MOPOE_THREADS, smem, stream>>>(mv, cx, b, ws);
+  } else {
+    MOPOE_CUDA(cudaFuncSetAttribute(p2_forward_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    p2_forward_kernel<16><<<nt < 2 * sms ? nt : 2 * sms, MOPOE_THREADS, smem, stream>>>(mv, cx, b, ws);
+  }
+  MOPOE_CUDA(cudaGetLastError());
+  if (out->scalars) {
+    finalize_kernel<<<1, 32, 0, stream>>>(mv, cx, b, ws);
+    MOPOE_CUDA(cudaGetLastError());
+  }
+  return MOPOE_OK;
+}
+
+int mopoe_train_steps(const mopoe_model_desc* desc, float* params, float* adam_m, float* adam_v, int32_t* adam_t,
+                      float* grads, const float* const* data, const int32_t* const* row_index,
+                      const mopoe_batch_desc* batches, int32_t n_steps, int64_t max_rows, const float* eps,
+                      uint64_t seed, int mode, float lr, float b1, float b2, float adam_eps, float* scalars,
+                      const mopoe_forward_out* out, void* workspace, int64_t workspace_bytes, void* stream_) {
+  int rc = check_desc(desc);
+  if (rc) return rc;
+  if (mopoe_device_count() == 0) { set_error("no CUDA device: the MoPoE path has no CPU fallback"); return MOPOE_ENODEV; }
+  if (!params || !data || !batches || !scalars || !workspace) { set_error("NULL argument"); return MOPOE_EINVAL; }
+  if (mode < 0 || mode > 2) { set_error("mode=%d", mode); return MOPOE_EINVAL; }
+  if (mode == 1 && (!grads || n_steps != 1)) { set_error("mode 1 needs grads and n_steps == 1"); return MOPOE_EINVAL; }
+  if (mode == 2 && (!adam_m || !adam_v || !adam_t)) { set_error("mode 2 needs Adam state"); return MOPOE_EINVAL; }
+  if (out && n_steps != 1) { set_error("forward outputs need n_steps == 1"); return MOPOE_EINVAL; }
+  if (n_steps < 1 || max_rows < 1) { set_error("n_steps=%d max_rows=%lld", n_steps, (long long)max_rows); return MOPOE_EINVAL; }
+  const int64_t need = carve(desc, max_rows, nullptr, nullptr);
+  if (workspace_bytes < need) { set_error("workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need); return MOPOE_ENOSPC; }
+  mopoe_param_layout lay;
+  mopoe_param_layout_of(desc, &lay);
+  ModelView mv;
+  build_view(desc, &lay, params, &mv);
+  Workspace ws;
+  carve(desc, max_rows, (char*)workspace, &ws);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  StepCtx cx;
+  memset(&cx, 0, sizeof(cx));
+  for (int m = 0; m < desc->n_mods; ++m) {
+    cx.x[m] = data[m];
+    cx.row_index[m] = row_index ? row_index[m] : nullptr;
+  }
+  const int n_pass = desc->method == MOPOE_METHOD_POE ? 1 + desc->n_mods : 1;
+  cx.noise.eps = eps; cx.noise.seed = seed; cx.noise.stream = MOPOE_STREAM_TRAIN;
+  cx.eps_pass_stride = max_rows * mv.E;
+  cx.eps_step_stride = (int64_t)n_pass * max_rows * mv.E;
+  cx.sample_latents = 1; cx.use_expert = -1; cx.with_nll = 1;
+  cx.uni_pass = desc->method == MOPOE_METHOD_POE; cx.mode = mode;
+  cx.lr = lr; cx.b1 = b1; cx.b2 = b2; cx.adam_eps = adam_eps;
+  cx.adam_m = adam_m; cx.adam_v = adam_v; cx.adam_t = adam_t; cx.grads = grads; cx.params = params;
+  cx.lay = lay;
+  if (out) { cx.out = *out; cx.out.scalars = nullptr; }
+  if (mode == 1) MOPOE_CUDA(cudaMemsetAsync(grads, 0, lay.total * sizeof(float), stream));
+  MOPOE_CUDA(cudaMemsetAsync(ws.bar, 0, sizeof(unsigned int), stream));
+  int smem = 0;
+  const int R = pick_rows(mv, max_rows, &smem);
+  void* fn = R == 4 ? (void*)train_kernel<4> : (void*)train_kernel<16>;
+  MOPOE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int per_sm = 0;
+  MOPOE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, MOPOE_THREADS, smem));
+  if (per_sm < 1) { set_error("train kernel does not fit on an SM (smem %d)", smem); return MOPOE_EINVAL; }
+  // one CTA per SM: the phases are tile loops, extra co-resident CTAs only lengthen the barriers
+  const int grid = num_sms();
+  const mopoe_batch_desc* bptr = batches;
+  float* sptr = scalars;
+  void* args[] = {&mv, &cx, &bptr, &n_steps, &sptr, &ws};
+  MOPOE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(MOPOE_THREADS), args, smem, stream));
+  return MOPOE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,131 @@
+"""Digital Avatars Analysis on the GPU: the device half of workflow.daa_exp
+(experiments/workflow.py:361-537) behind one call, plus its multi-GPU sharding.
+
+`daa_sweep` runs the avatar generation AND the association statistics for a block of validations;
+`shard_validations` / `gather_tables` implement SURVEY.md 8e: validations are independent given the
+weights, so they are split over ranks with no data-path collective and only the final
+(n_val, n_scores, n_rois) fp64 tables are gathered."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import Workspace, _f32, _ptr, _require_cuda, _stream
+from .spec import PathSpec
+
+REG_METHODS = {"hierarchical": 0, "fixed": 1}
+
+
+class DaaResult:
+    pass
+
+
+def daa_sweep(spec: PathSpec, flat_params, src, dst, n_samples, n_base, *, src_mod=0, dst_mod=1,
+              sample_latents=True, reg_method="hierarchical", seed=1037, val_begin=0, n_val_total=None,
+              eps_base=None, eps_score=None, eps_av=None, materialize=True, want_betas=True,
+              others=None, workspace=None, out=None):
+    """src: (n_val, N, C) drawn test batches of the perturbed modality, dst: (n_val, N, R).
+    others: optional {modality index: (n_val, N, D_m)} for models with more than two modalities.
+    Returns a DaaResult with CUDA tensors avatars (or None), sampled_scores, reconstructions,
+    betas (or None), coefs, pvalues."""
+    if reg_method not in REG_METHODS:
+        raise NotImplementedError("reg_method=%r is not on the B200 path (hierarchical, fixed)" % (reg_method,))
+    _require_cuda(flat_params, "parameters")
+    device = flat_params.device
+    src, dst = _f32(src), _f32(dst)
+    _require_cuda(src, "src")
+    _require_cuda(dst, "dst")
+    n_val, N, Cc = src.shape
+    R = dst.shape[2]
+    assert Cc == spec.dims[src_mod] and R == spec.dims[dst_mod] and dst.shape[:2] == (n_val, N)
+    xs = [None] * spec.n_mods
+    xs[src_mod], xs[dst_mod] = src, dst
+    for m in range(spec.n_mods):
+        if xs[m] is None:
+            if others is None or m not in others:
+                raise ValueError("DAA needs every modality present (missing %s)" % spec.mod_names[m])
+            xs[m] = _f32(others[m])
+    E = spec.eps_width
+    if eps_base is not None:
+        eps_base = _f32(eps_base); assert eps_base.shape == (n_val, n_base, N, E)
+    if eps_score is not None:
+        eps_score = _f32(eps_score); assert eps_score.shape == (n_val, n_samples, N, Cc)
+    if eps_av is not None:
+        eps_av = _f32(eps_av); assert eps_av.shape == (n_val, n_samples, Cc, N, E)
+    q = _lib.DaaDesc(n_val=n_val, val_begin=val_begin, n_val_total=n_val_total or n_val, n_subjects=N,
+                     n_samples=n_samples, n_base=n_base, src_mod=src_mod, dst_mod=dst_mod,
+                     sample_latents=int(bool(sample_latents)), reg_method=REG_METHODS[reg_method])
+    bd = spec.batch_desc(N, (1 << spec.n_mods) - 1)
+    lib = _lib.lib()
+    nbytes = lib.mopoe_daa_workspace_bytes(C.byref(spec.desc), C.byref(q))
+    if nbytes < 0:
+        _lib.check(int(nbytes))
+    ws = (workspace or Workspace()).get(nbytes, device)
+    r = out or DaaResult()
+    if out is None:
+        f = lambda dt, *s: torch.empty(*s, dtype=dt, device=device)
+        r.avatars = f(torch.float32, n_val, N, Cc, n_samples, R) if materialize else None
+        r.sampled_scores = f(torch.float32, n_val, N, n_samples, Cc)
+        r.reconstructions = f(torch.float32, n_val, N, R)
+        r.betas = f(torch.float64, n_val, Cc, N, R) if want_betas else None
+        r.coefs = f(torch.float64, n_val, Cc, R)
+        r.pvalues = f(torch.float64, n_val, Cc, R)
+    xp = (C.c_void_p * _lib.MAX_MODS)(*[_ptr(x).value for x in xs] + [None] * (_lib.MAX_MODS - spec.n_mods))
+    _lib.check(lib.mopoe_daa_sweep(C.byref(spec.desc), _ptr(flat_params), C.byref(q), C.byref(bd), xp,
+                                   _ptr(eps_base), _ptr(eps_score), _ptr(eps_av), seed, _ptr(r.avatars),
+                                   _ptr(r.sampled_scores), _ptr(r.reconstructions), _ptr(r.betas), _ptr(r.coefs),
+                                   _ptr(r.pvalues), _ptr(ws), ws.numel(), _stream()))
+    r._keep = (xs, eps_base, eps_score, eps_av, ws)
+    return r
+
+
+def daa_regression(avatars, sampled_scores, reconstructions=None, reg_method="hierarchical"):
+    """stat_utils.make_regression for every (validation, score, roi) of a materialised avatar tensor
+    (workflow.py:466-505).  avatars (n_val,N,C,J,R) fp32 CUDA, sampled_scores (n_val,N,J,C)."""
+    if reg_method not in REG_METHODS:
+        raise NotImplementedError("reg_method=%r is not on the B200 path (hierarchical, fixed)" % (reg_method,))
+    avatars, sampled_scores = _f32(avatars), _f32(sampled_scores)
+    _require_cuda(avatars, "avatars")
+    n_val, N, Cc, J, R = avatars.shape
+    device = avatars.device
+    betas = torch.empty(n_val, Cc, N, R, dtype=torch.float64, device=device)
+    coefs = torch.empty(n_val, Cc, R, dtype=torch.float64, device=device)
+    pvalues = torch.empty(n_val, Cc, R, dtype=torch.float64, device=device)
+    rec = _f32(reconstructions) if reconstructions is not None else None
+    _lib.check(_lib.lib().mopoe_daa_regression(n_val, N, Cc, J, R, REG_METHODS[reg_method], _ptr(avatars),
+                                               _ptr(sampled_scores), _ptr(rec), _ptr(betas), _ptr(coefs),
+                                               _ptr(pvalues), _stream()))
+    return pvalues, coefs, betas
+
+
+def significant(pvalues, trust_level):
+    """workflow.py:517-523.  pvalues (n_val, n_scores, n_rois) numpy/torch -> bool (n_scores, n_rois)."""
+    p = pvalues.detach().cpu().numpy() if torch.is_tensor(pvalues) else np.asarray(pvalues)
+    n_val, Cc, R = p.shape
+    thr = 0.05 / R / Cc
+    return (p < thr).sum(axis=0) >= trust_level * n_val
+
+
+# ---- multi-GPU: validations are independent units --------------------------------
+def shard_validations(n_validation, rank, world_size):
+    """Contiguous block split of range(n_validation): -> (begin, end) of this rank."""
+    base, rem = divmod(n_validation, world_size)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def gather_tables(local, n_validation, group=None):
+    """all_gather the per-validation fp64 tables of every rank into the full (n_validation, ...) table.
+    `local` is this rank's (n_local, ...) block; ranks may own different counts (padded to the max)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    counts = [shard_validations(n_validation, r, world) for r in range(world)]
+    n_max = max(e - b for b, e in counts)
+    pad = torch.zeros((n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([bufs[r][: e - b] for r, (b, e) in enumerate(counts)], dim=0)

@@ -1,0 +1,205 @@
+"""Host-side description of the hot path: the fields of the reference `flags` namespace
+(experiments/workflow.py:98-149) that the MoPoE path reads, the subset table
+(experiments/utils/BaseExperiment.py:58-79) and the bit-faithful selection boundaries
+(experiments/utils/utils.py:63-85)."""
+import ctypes as C
+from itertools import chain, combinations
+
+import torch
+
+from . import _lib
+
+
+def selection_bounds(n_rows, n_comp):
+    """Row boundaries of utils.mixture_component_selection for the uniform weights the model uses,
+    evaluated with the reference's own fp32 torch expression (BaseMMVae.py:225,99; utils.py:71-82):
+    N=256,K=3 -> 85/85/86, N=50,K=3 -> 16/16/18."""
+    w = (1 / float(n_comp)) * torch.ones(n_comp)
+    w = w / w.sum()
+    bounds = [0]
+    for k in range(n_comp):
+        if k == n_comp - 1:
+            bounds.append(n_rows)
+        else:
+            bounds.append(bounds[-1] + int(torch.floor(n_rows * w[k])))
+    bounds[-1] = n_rows
+    return bounds
+
+
+class PathSpec:
+    def __init__(self, dims, style_dims, latent_dim=20, method="joint_elbo", mod_names=None,
+                 learn_output_scale=True, beta=1.0, beta_style=1.0, beta_content=1.0,
+                 num_hidden_layer_encoder=1, num_hidden_layer_decoder=0, likelihood="normal",
+                 learn_output_sample_scale=False, initial_out_logvar=-3.0, dropout_rate=0.0):
+        self.dims = [int(d) for d in dims]
+        self.style_dims = [int(s) for s in style_dims]
+        self.latent_dim = int(latent_dim)
+        self.method = method
+        names = list(mod_names) if mod_names is not None else ["clinical", "rois", "modc", "modd"]
+        self.mod_names = names[: len(self.dims)]
+        self.learn_output_scale = bool(learn_output_scale)
+        self.beta, self.beta_style, self.beta_content = float(beta), float(beta_style), float(beta_content)
+        self.n_hidden_enc = int(num_hidden_layer_encoder)
+        self.n_hidden_dec = int(num_hidden_layer_decoder)
+        self.likelihood = likelihood
+        self.learn_output_sample_scale = bool(learn_output_sample_scale)
+        self.initial_out_logvar = float(initial_out_logvar)
+        if method not in _lib.METHODS:
+            raise NotImplementedError("method=%r is not on the B200 path (poe, moe, joint_elbo)" % (method,))
+        if likelihood != "normal":
+            raise NotImplementedError("likelihood=%r is not on the B200 path (normal only)" % (likelihood,))
+        if dropout_rate:
+            raise NotImplementedError("dropout_rate != 0 is not on the B200 path")
+        if len(self.style_dims) != len(self.dims) or len(self.mod_names) != len(self.dims):
+            raise ValueError("dims / style_dims / mod_names length mismatch")
+        self._desc = self._make_desc()
+        self._layout = _lib.ParamLayout()
+        # validation + layout arithmetic are pure host code: this works without a GPU
+        _lib.check(_lib.lib().mopoe_param_layout_of(C.byref(self._desc), C.byref(self._layout)))
+
+    @classmethod
+    def from_flags(cls, flags, mod_names=None):
+        """flags: the SimpleNamespace train_exp builds (workflow.py:98-149)."""
+        method = ("poe" if getattr(flags, "modality_poe", False) else
+                  "moe" if getattr(flags, "modality_moe", False) else
+                  "jsd" if getattr(flags, "modality_jsd", False) else
+                  "joint_elbo" if getattr(flags, "joint_elbo", False) else getattr(flags, "method", None))
+        style = list(flags.style_dim) if not isinstance(flags.style_dim, int) else [flags.style_dim] * len(flags.input_dim)
+        if len(style) != len(flags.input_dim):                       # experiment.py:133-136
+            style = [style[0]] * len(flags.input_dim)
+        if not flags.factorized_representation:
+            style = [0] * len(flags.input_dim)
+        return cls(flags.input_dim, style, flags.class_dim, method, mod_names,
+                   learn_output_scale=flags.learn_output_scale, beta=flags.beta,
+                   beta_style=flags.beta_style, beta_content=flags.beta_content,
+                   num_hidden_layer_encoder=flags.num_hidden_layer_encoder,
+                   num_hidden_layer_decoder=flags.num_hidden_layer_decoder, likelihood=flags.likelihood,
+                   learn_output_sample_scale=getattr(flags, "learn_output_sample_scale", False),
+                   initial_out_logvar=flags.initial_out_logvar,
+                   dropout_rate=getattr(flags, "dropout_rate", 0.0))
+
+    # ---- derived -------------------------------------------------------------------------
+    @property
+    def n_mods(self):
+        return len(self.dims)
+
+    @property
+    def eps_width(self):
+        return self.latent_dim + sum(self.style_dims)
+
+    @property
+    def n_pass(self):
+        return 1 + self.n_mods if self.method == "poe" else 1
+
+    def style_offset(self, m):
+        return self.latent_dim + sum(self.style_dims[:m])
+
+    def head_cols(self, m):
+        return 2 * self.latent_dim + 2 * self.style_dims[m]
+
+    def subsets(self):
+        """[(key, [member modality indices in fusion order])] in set_subsets order, '' excluded."""
+        out = []
+        idx = list(range(self.n_mods))
+        for combo in chain.from_iterable(combinations(idx, n) for n in range(1, len(idx) + 1)):
+            names = sorted(self.mod_names[i] for i in combo)
+            out.append(("_".join(names), [self.mod_names.index(n) for n in names]))
+        return out
+
+    def present_mask(self, keys):
+        mask = 0
+        for m, n in enumerate(self.mod_names):
+            if n in keys:
+                mask |= 1 << m
+        if mask == 0:
+            raise ValueError("input batch holds none of the modalities %s" % self.mod_names)
+        return mask
+
+    def mixture_subsets(self, present_mask):
+        """indices (into subsets()) of the subsets that enter the mixture for this batch
+        (fusion_condition_*, BaseMMVae.py:125-134) and of all available ones."""
+        avail, mix = [], []
+        n_present = bin(present_mask).count("1")
+        for s, (_, members) in enumerate(self.subsets()):
+            if any(not (present_mask >> m & 1) for m in members):
+                continue
+            avail.append(s)
+            if self.method == "moe":
+                cond = len(members) == 1
+            elif self.method == "poe":
+                cond = len(members) == n_present
+            else:
+                cond = True
+            if cond:
+                mix.append(s)
+        return avail, mix
+
+    def _make_desc(self):
+        d = _lib.ModelDesc()
+        d.n_mods = self.n_mods
+        order = sorted(range(self.n_mods), key=lambda m: self.mod_names[m])
+        for m in range(self.n_mods):
+            d.dims[m] = self.dims[m]
+            d.style_dims[m] = self.style_dims[m]
+            d.name_rank[m] = order.index(m)
+        d.latent_dim = self.latent_dim
+        d.hidden = _lib.HIDDEN
+        d.n_hidden_enc = self.n_hidden_enc
+        d.n_hidden_dec = self.n_hidden_dec
+        d.method = _lib.METHODS[self.method]
+        d.likelihood = 0
+        d.scale_mode = 1 if self.learn_output_sample_scale else 0
+        d.learn_output_scale = int(self.learn_output_scale)
+        d.beta, d.beta_style, d.beta_content = self.beta, self.beta_style, self.beta_content
+        return d
+
+    @property
+    def desc(self):
+        return self._desc
+
+    @property
+    def layout(self):
+        return self._layout
+
+    def batch_desc(self, n_rows, present_mask, row_offset=0):
+        b = _lib.BatchDesc()
+        b.n_rows = int(n_rows)
+        b.present_mask = int(present_mask)
+        _, mix = self.mixture_subsets(present_mask)
+        b.n_mix = len(mix)
+        for i, v in enumerate(selection_bounds(n_rows, len(mix))):
+            b.joint_bounds[i] = v
+        for k in range(1, self.n_mods + 1):
+            for i, v in enumerate(selection_bounds(n_rows, k)):
+                b.moe_bounds[k][i] = v
+        b.row_offset = int(row_offset)
+        return b
+
+    def param_slices(self):
+        """state-dict name -> (offset, shape) inside the flat parameter buffer."""
+        lay, L, out = self._layout, self.latent_dim, {}
+        for m, name in enumerate(self.mod_names):
+            D, S = self.dims[m], self.style_dims[m]
+            e = "encoders.%s." % name
+            out[e + "shared_encoder.0.weight"] = (lay.enc_w1[m], (_lib.HIDDEN, D))
+            out[e + "shared_encoder.0.bias"] = (lay.enc_b1[m], (_lib.HIDDEN,))
+            wh, bh = lay.enc_wh[m], lay.enc_bh[m]
+            out[e + "class_mu.weight"] = (wh, (L, _lib.HIDDEN))
+            out[e + "class_mu.bias"] = (bh, (L,))
+            out[e + "class_logvar.weight"] = (wh + L * _lib.HIDDEN, (L, _lib.HIDDEN))
+            out[e + "class_logvar.bias"] = (bh + L, (L,))
+            if S > 0:
+                out[e + "style_mu.weight"] = (wh + 2 * L * _lib.HIDDEN, (S, _lib.HIDDEN))
+                out[e + "style_mu.bias"] = (bh + 2 * L, (S,))
+                out[e + "style_logvar.weight"] = (wh + (2 * L + S) * _lib.HIDDEN, (S, _lib.HIDDEN))
+                out[e + "style_logvar.bias"] = (bh + 2 * L + S, (S,))
+        for m, name in enumerate(self.mod_names):
+            D, S = self.dims[m], self.style_dims[m]
+            d = "decoders.%s." % name
+            out[d + "logvar"] = (lay.dec_lv[m], (1, D))
+            out[d + "out_mu.weight"] = (lay.dec_w[m], (D, S + L))
+            out[d + "out_mu.bias"] = (lay.dec_b[m], (D,))
+        return out
+
+    def modality_of_param(self, name):
+        return self.mod_names.index(name.split(".")[1])

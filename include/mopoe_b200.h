@@ -1,0 +1,241 @@
+/*
+ * mopoe_b200.h -- C-ABI of the B200-native MoPoE-VAE hot path.
+ *
+ * Drop-in boundary for the one data-parallel hot path of
+ * neurospin-projects/2022_cambroise_interpret_multivae: the joint-ELBO step of the MoPoE-VAE and the
+ * Digital Avatars Analysis (DAA) sweep that re-runs its forward pass.  The reference has no FFI of
+ * its own (it is pure Python / eager PyTorch); the seams this library replaces are the Python
+ * functions cited on each entry point (paths relative to <reference>/experiments).  The host-side
+ * mirror of those functions (same names / arguments / return structure) lives in the Python package
+ * `2022_cambroise_interpret_multivae_b200` and binds this header through ctypes
+ * (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in
+ *     `_host`; all buffers are caller-owned and pre-allocated, the library never allocates on the
+ *     data path (scratch comes in through `workspace`, sized by mopoe_workspace_bytes).
+ *   - every call enqueues on `stream` (a cudaStream_t passed as void*) and returns without
+ *     synchronising; 0 = success, negative = MOPOE_E* (message via mopoe_last_error()).
+ *   - float tensors are fp32 row-major contiguous; statistics tables are fp64.
+ *   - noise: `eps` tensors are INJECTED standard-normal draws laid out as documented per call.
+ *     A NULL eps pointer selects the built-in counter-based generator
+ *     eps[i] = philox_normal(seed, stream_id, i)  (i = flat index into the same layout), so results
+ *     do not depend on how a sweep is sharded over GPUs (oracle/philox.py restates it).
+ *   - no CPU fallback: with no CUDA device every compute entry point returns MOPOE_ENODEV.
+ */
+#ifndef MOPOE_B200_H
+#define MOPOE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOPOE_MAX_MODS 4
+#define MOPOE_MAX_SUBSETS 15 /* 2^4 - 1 */
+#define MOPOE_HIDDEN 256     /* networks.py:15,50 hard-code the hidden width */
+#define MOPOE_N_SCALARS 64
+
+enum { MOPOE_METHOD_POE = 0, MOPOE_METHOD_MOE = 1, MOPOE_METHOD_JOINT_ELBO = 2 };
+
+enum {
+  MOPOE_OK = 0,
+  MOPOE_EINVAL = -1,   /* bad argument / unsupported configuration (message says which) */
+  MOPOE_ENODEV = -2,   /* no CUDA device */
+  MOPOE_ECUDA = -3,    /* CUDA runtime error (message carries cudaGetErrorString) */
+  MOPOE_ENOSPC = -4    /* workspace too small */
+};
+
+/* Model description: the subset of the reference `flags` namespace (workflow.py:98-149) that the
+ * hot path reads.  Unsupported values are rejected with MOPOE_EINVAL, never silently ignored. */
+typedef struct mopoe_model_desc {
+  int32_t n_mods;                       /* len(flags.input_dim), 1..4 */
+  int32_t dims[MOPOE_MAX_MODS];         /* flags.input_dim */
+  int32_t style_dims[MOPOE_MAX_MODS];   /* flags.style_dim, zeros when not factorised (workflow.py:148) */
+  int32_t latent_dim;                   /* flags.class_dim, 1..32 */
+  int32_t hidden;                       /* must be 256 */
+  int32_t n_hidden_enc;                 /* flags.num_hidden_layer_encoder, must be 1 */
+  int32_t n_hidden_dec;                 /* flags.num_hidden_layer_decoder, must be 0 */
+  int32_t method;                       /* MOPOE_METHOD_* (flags.modality_poe/moe/joint_elbo) */
+  int32_t likelihood;                   /* 0 = normal (modality.py:18-30); others rejected */
+  int32_t scale_mode;                   /* 0 = per-feature logvar Parameter (networks.py:61-64) */
+  int32_t learn_output_scale;           /* flags.learn_output_scale */
+  int32_t name_rank[MOPOE_MAX_MODS];    /* rank of modality m's NAME in sorted order: fusion order
+                                           inside a subset (BaseExperiment.py:72-77) */
+  float beta, beta_style, beta_content; /* flags.beta, beta_style, beta_content */
+} mopoe_model_desc;
+
+/* Offsets (in floats) of every parameter block inside the flat parameter buffer.  Each block keeps
+ * torch's own [out, in] row-major layout so that nn.Parameters can be views of the buffer and the
+ * reference's state-dict keys/shapes are preserved:
+ *   enc_w1  = encoders.<m>.shared_encoder.0.weight (256, D)      enc_b1 = ....bias (256)
+ *   enc_wh  = rows [class_mu (L); class_logvar (L); style_mu (S); style_logvar (S)] x 256
+ *   enc_bh  = the matching biases (2L + 2S)
+ *   dec_w   = decoders.<m>.out_mu.weight (D, S + L)              dec_b = ....bias (D)
+ *   dec_lv  = decoders.<m>.logvar (1, D)
+ * Adam moments and gradient buffers use the same layout. */
+typedef struct mopoe_param_layout {
+  int64_t enc_w1[MOPOE_MAX_MODS], enc_b1[MOPOE_MAX_MODS];
+  int64_t enc_wh[MOPOE_MAX_MODS], enc_bh[MOPOE_MAX_MODS];
+  int64_t dec_w[MOPOE_MAX_MODS], dec_b[MOPOE_MAX_MODS], dec_lv[MOPOE_MAX_MODS];
+  int64_t total; /* floats */
+} mopoe_param_layout;
+
+/* One batch of the path.  A batch is homogeneous in its set of present modalities
+ * (MissingModalitySampler, dataset.py:295-354); absent modalities are neither encoded nor decoded
+ * (BaseMMVae.py:156,167-178).  `joint_bounds`/`moe_bounds` are the row boundaries of
+ * utils.mixture_component_selection (utils/utils.py:63-85), computed ON THE HOST with the
+ * reference's own fp32 expression int(floor(N * w_k)) so they are bit-faithful. */
+typedef struct mopoe_batch_desc {
+  int32_t n_rows;
+  int32_t present_mask;                     /* bit m set <=> modality m is a key of input_batch */
+  int32_t n_mix;                            /* K = number of subsets entering the mixture */
+  int32_t joint_bounds[MOPOE_MAX_SUBSETS + 1]; /* K + 1 boundaries of the joint selection */
+  int32_t moe_bounds[MOPOE_MAX_MODS + 1][MOPOE_MAX_MODS + 1]; /* [k][0..k]: selection inside a
+                                               k-member subset (method = moe only) */
+  int64_t row_offset;                       /* first entry of this batch in `row_index` */
+} mopoe_batch_desc;
+
+/* Outputs of one forward pass == the `results` dict of BaseMMVae.forward (BaseMMVae.py:137-165).
+ * Any pointer may be NULL (that output is skipped).  Subset arrays are indexed by the subset's
+ * position in BaseExperiment.set_subsets order without the empty set; rows of unavailable subsets
+ * are left untouched. */
+typedef struct mopoe_forward_out {
+  float* enc_heads[MOPOE_MAX_MODS]; /* (N, 2L+2S_m): [class_mu | class_logvar | style_mu | style_logvar] */
+  float* subset_mu;                 /* (n_subsets, N, L)   latents['subsets'][key][0] */
+  float* subset_logvar;             /* (n_subsets, N, L) */
+  float* joint_mu;                  /* (N, L)              latents['joint'][0] */
+  float* joint_logvar;              /* (N, L) */
+  float* z;                         /* (N, L)              class_embeddings */
+  float* z_style[MOPOE_MAX_MODS];   /* (N, S_m) */
+  float* rec_loc[MOPOE_MAX_MODS];   /* (N, D_m)            results['rec'][m].loc  (scale = exp(.5*logvar)) */
+  float* scalars;                   /* (MOPOE_N_SCALARS)   see mopoe_scalar_index */
+} mopoe_forward_out;
+
+/* Index of each entry of a `scalars` row (all are means over rows, exactly the numbers
+ * basic_routine_epoch returns and TBLogger.add_basic_logs logs, TBLogger.py:84-91). */
+enum mopoe_scalar_index {
+  MOPOE_S_TOTAL_LOSS = 0,   /* total_loss                       run_epochs.py:103,128 */
+  MOPOE_S_JOINT_DIV = 1,    /* results['joint_divergence']      BaseMMVae.py:147-149 */
+  MOPOE_S_NLL = 2,          /* +m: log_probs[m]                 run_epochs.py:27-38 */
+  MOPOE_S_NLL_UNI = 6,      /* +m: unimodal-pass -log p (poe)   run_epochs.py:117-119 */
+  MOPOE_S_KLD_SUBSET = 10,  /* +s: klds[subset s]               run_epochs.py:41-48 */
+  MOPOE_S_KLD_STYLE = 25,   /* +m: klds_style[m]                run_epochs.py:51-59 */
+  MOPOE_S_MEAN_HEAD = 29,   /* +4m+{0,1,2,3}: mean class_mu, class_logvar, style_mu, style_logvar */
+  MOPOE_S_N_ROWS = 45,
+  MOPOE_S_PRESENT = 46
+};
+
+const char* mopoe_last_error(void);
+int mopoe_version(void);
+/* Number of CUDA devices visible (0 => every compute call returns MOPOE_ENODEV). */
+int mopoe_device_count(void);
+
+/* Validate `desc` and fill the parameter layout. */
+int mopoe_param_layout_of(const mopoe_model_desc* desc, mopoe_param_layout* out);
+
+/* Bytes of scratch the model calls need for batches of up to `max_rows` rows
+ * (`n_pass` = 1, or 1 + n_mods when method = poe trains with its unimodal passes). */
+int64_t mopoe_workspace_bytes(const mopoe_model_desc* desc, int64_t max_rows);
+
+/* BaseMMVae.forward(input_batch, sample_latents, use_expert)           BaseMMVae.py:137-165
+ * (encode :167-178, inference :181-239, poe mm_div.py:13-20, mixture_component_selection
+ * utils.py:63-85, reparameterize :37-40, Decoder.forward networks.py:66-77).
+ *   x[m]        (N, D_m) rows of modality m, NULL/ignored when absent from present_mask
+ *   eps         (N, E) injected noise, E = L + sum_m S_m: cols [0,L) joint content, then the style
+ *               block of each modality in order; NULL => philox(seed, MOPOE_STREAM_FORWARD)
+ *   use_expert  subset index whose posterior becomes the joint (BaseMMVae.py:230-231), -1 = none
+ *   with_nll    also fill the NLL scalars (needs x as target; run_epochs.calc_log_probs) */
+int mopoe_forward(const mopoe_model_desc* desc, const float* params, const mopoe_batch_desc* batch_host,
+                  const float* const* x_host_ptrs, const float* eps, uint64_t seed, int sample_latents,
+                  int use_expert, int with_nll, const mopoe_forward_out* out_host, void* workspace,
+                  int64_t workspace_bytes, void* stream);
+
+/* run_epochs.basic_routine_epoch + loss.backward() [+ Adam.step()]   run_epochs.py:73-135,180-182
+ * executed for `n_steps` consecutive batches inside ONE cooperative persistent kernel launch.
+ *   mode 0: losses only (run_epochs.test under no_grad, :187-219)
+ *   mode 1: losses + gradients of total_loss w.r.t. every parameter into `grads` (flat layout;
+ *           n_steps must be 1) -- backs the torch.autograd.Function of the Python mirror
+ *   mode 2: losses + gradients + in-kernel Adam update of `params`, `adam_m`, `adam_v`
+ *           (torch.optim.Adam as configured by experiment.py:268-271: betas (b1,b2), eps, no weight
+ *           decay; parameters of absent modalities are skipped entirely like torch skips grad=None)
+ *   data[m]       (n_data_rows_m, D_m) resident dataset block of modality m
+ *   row_index     int32 rows of each step's batch (batches[s].row_offset .. +n_rows), one list per
+ *                 modality (row_index[m]); NULL => rows 0..n_rows-1
+ *   eps           (n_steps, n_pass, max_rows, E) injected noise or NULL => philox(seed, TRAIN)
+ *   adam_t        int32 (n_mods) per-modality step counters (device), updated in mode 2
+ *   scalars       (n_steps, MOPOE_N_SCALARS) fp32
+ *   batches       device array of n_steps mopoe_batch_desc
+ *   out_host      optional forward outputs of the (single) step, n_steps must be 1: lets
+ *                 basic_routine_epoch return its `results` dict from the same launch */
+int mopoe_train_steps(const mopoe_model_desc* desc, float* params, float* adam_m, float* adam_v,
+                      int32_t* adam_t, float* grads, const float* const* data_host_ptrs,
+                      const int32_t* const* row_index_host_ptrs, const mopoe_batch_desc* batches,
+                      int32_t n_steps, int64_t max_rows, const float* eps, uint64_t seed, int mode,
+                      float lr, float b1, float b2, float adam_eps, float* scalars,
+                      const mopoe_forward_out* out_host, void* workspace, int64_t workspace_bytes,
+                      void* stream);
+
+/* ---- Digital Avatars Analysis  (workflow.daa_exp, workflow.py:361-537) ----------------------- */
+
+typedef struct mopoe_daa_desc {
+  int32_t n_val;        /* validations handled by THIS call (a shard of params.n_validation) */
+  int32_t val_begin;    /* global index of the first one (keys the philox streams) */
+  int32_t n_val_total;  /* params.n_validation (sizes the philox index space) */
+  int32_t n_subjects;   /* rows per validation batch (params.n_subjects) */
+  int32_t n_samples;    /* params.n_samples */
+  int32_t n_base;       /* params.M stochastic reconstructions */
+  int32_t src_mod;      /* perturbed modality ("clinical") */
+  int32_t dst_mod;      /* read-out modality ("rois") */
+  int32_t sample_latents;
+  int32_t reg_method;   /* 0 = hierarchical (stat_utils.py:66-75), 1 = fixed (:62-63) */
+} mopoe_daa_desc;
+
+/* Bytes of scratch mopoe_daa_sweep needs. */
+int64_t mopoe_daa_workspace_bytes(const mopoe_model_desc* desc, const mopoe_daa_desc* daa);
+
+/* The whole DAA sweep for `n_val` validations (all modalities present):
+ *   workflow.py:388-400  M stochastic reconstructions -> mean src loc/scale, mean dst loc
+ *   workflow.py:401-405  scores ~ Normal(loc_hat, scale_hat)          (sampling = "likelihood")
+ *   workflow.py:406-419  one forward per (sample, score) with ONE src column overwritten -> dst loc
+ *   workflow.py:466-505  make_regression per (validation, score, roi)  (stat_utils.py:55-79)
+ * inputs
+ *   x[m]        (n_val, n_subjects, D_m) the drawn test batches (every modality)
+ *   eps_base    (n_val, n_base, N, E), eps_score (n_val, n_samples, N, C), eps_av
+ *               (n_val, n_samples, C, N, E); each NULL => philox(seed, MOPOE_STREAM_DAA_*)
+ * outputs (each may be NULL except coefs/pvalues)
+ *   avatars         fp32 (n_val, N, C, n_samples, R)  rois_digital_avatars.npy (workflow.py:280-288)
+ *   sampled_scores  fp32 (n_val, N, n_samples, C)     sampled_scores.npy       (workflow.py:435)
+ *   reconstructions fp32 (n_val, N, R)                rois_reconstructions.npy (workflow.py:437)
+ *   betas           fp64 (n_val, C, N, R)             per-subject slopes -> all_coefs.npy (:499-505)
+ *   coefs, pvalues  fp64 (n_val, C, R)                coefs.npy / pvalues.npy  (workflow.py:510-511)
+ * C = dims[src_mod], R = dims[dst_mod], N = n_subjects. */
+int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mopoe_daa_desc* daa,
+                    const mopoe_batch_desc* batch_host, const float* const* x_host_ptrs,
+                    const float* eps_base, const float* eps_score, const float* eps_av, uint64_t seed,
+                    float* avatars, float* sampled_scores, float* reconstructions, double* betas,
+                    double* coefs, double* pvalues, void* workspace, int64_t workspace_bytes,
+                    void* stream);
+
+/* stat_utils.make_regression(method="hierarchical"|"fixed") on an avatar tensor that is already in
+ * device memory (same layouts as above) -- the statistics stage alone (workflow.py:466-505). */
+int mopoe_daa_regression(int32_t n_val, int32_t n_subjects, int32_t n_scores, int32_t n_samples,
+                         int32_t n_rois, int32_t reg_method, const float* avatars,
+                         const float* sampled_scores, const float* reconstructions, double* betas,
+                         double* coefs, double* pvalues, void* stream);
+
+/* Fill `out[0..n)` with philox_normal(seed, stream_id, start + i): the production noise generator,
+ * exposed so hosts/tests can materialise exactly what the kernels draw. */
+int mopoe_philox_normal(uint64_t seed, uint64_t stream_id, int64_t start, int64_t n, float* out,
+                        void* stream);
+
+enum {
+  MOPOE_STREAM_DAA_BASE = 1, MOPOE_STREAM_DAA_SCORE = 2, MOPOE_STREAM_DAA_AVATAR = 3,
+  MOPOE_STREAM_TRAIN = 4, MOPOE_STREAM_FORWARD = 5
+};
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOPOE_B200_H */

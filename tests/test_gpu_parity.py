@@ -1,0 +1,218 @@
+"""Parity of the CUDA path (through the C-ABI) with the CPU oracle and with the golden vectors
+recorded from the unmodified reference.  Tolerance: 1e-4 relative (BASELINE.json north_star),
+measured against each tensor's own scale (max |value|)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, daa_oracle, mopoe_oracle as mo, philox
+from helpers import GOLDEN, RTOL, assert_digest_close, digest, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = load_golden()
+
+
+def _setup(case):
+    import mopoe_b200
+    from mopoe_b200 import engine
+    ospec = cases.spec_of(case)
+    spec = mopoe_b200.PathSpec(ospec.dims, ospec.style_dims, ospec.latent_dim, ospec.method, ospec.mod_names,
+                               learn_output_scale=ospec.learn_output_scale)
+    params = mo.init_params(ospec, seed=case["seed"])
+    flat = engine.pack_params(spec, params, torch.device("cuda"))
+    return ospec, spec, params, flat
+
+
+def _close(got, want, what, rtol=RTOL):
+    got = got.detach().double().cpu().numpy() if torch.is_tensor(got) else np.asarray(got, np.float64)
+    want = want.detach().double().cpu().numpy() if torch.is_tensor(want) else np.asarray(want, np.float64)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    scale = max(np.abs(want).max(), 1e-30)
+    err = np.abs(got - want).max() / scale
+    assert err <= rtol, (what, err)
+
+
+@pytest.mark.parametrize("name", sorted(cases.FORWARD_CASES))
+def test_forward(name):
+    from mopoe_b200 import engine
+    case = cases.FORWARD_CASES[name]
+    ospec, spec, params, flat = _setup(case)
+    batch, eps = cases.inputs_of(case, ospec)
+    sample = case.get("sample_latents", True)
+    res = engine.forward(spec, flat, {k: v.cuda() for k, v in batch.items()}, eps=eps[0].cuda(),
+                         sample_latents=sample, use_expert=case.get("use_expert"), with_nll=True)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        want = mo.forward(params, ospec, batch, eps[0], sample_latents=sample, use_expert=case.get("use_expert"))
+    _close(res.joint_mu, want["latents"]["joint"][0], "joint_mu")
+    _close(res.joint_logvar, want["latents"]["joint"][1], "joint_logvar")
+    _close(res.z, want["z"], "z")
+    keys = [k for k, _ in spec.subsets()]
+    for k, (mu, lv) in want["latents"]["subsets"].items():
+        _close(res.subset_mu[keys.index(k)], mu, "subset mu " + k)
+        _close(res.subset_logvar[keys.index(k)], lv, "subset lv " + k)
+    for m, n in enumerate(spec.mod_names):
+        if n in batch:
+            _close(res.rec_loc[m], want["rec"][n][0], "loc " + n)
+            smu, slv, mu, lv = mo.encoder(params, ospec, m, batch[n])
+            _close(res.enc_heads[m][:, :spec.latent_dim], mu, "class_mu " + n)
+            _close(res.enc_heads[m][:, spec.latent_dim:2 * spec.latent_dim], lv, "class_logvar " + n)
+    sc = res.scalars.cpu().numpy()
+    assert abs(sc[1] - float(want["joint_divergence"])) <= RTOL * abs(float(want["joint_divergence"]))
+    # and against the reference's own numbers
+    g = GOLD["forward"][name]
+    assert_digest_close(digest(res.joint_mu), g["joint_mu"])
+    for k, v in g["rec_loc"].items():
+        assert_digest_close(digest(res.rec_loc[spec.mod_names.index(k)]), v, what=k)
+    assert abs(sc[1] - g["joint_divergence"]) <= RTOL * abs(g["joint_divergence"])
+
+
+def _run_step(spec, flat, batch, eps, mode, **kw):
+    from mopoe_b200 import engine
+    dev = flat.device
+    n_rows = next(iter(batch.values())).shape[0]
+    mask = spec.present_mask(batch.keys())
+    data = [batch[n].cuda().contiguous() if n in batch else None for n in spec.mod_names]
+    bdev = engine.make_batches(spec, [(n_rows, mask, 0)], dev)
+    return engine.train_steps(spec, flat, data, bdev, 1, n_rows, mode, eps=eps.cuda().contiguous()[None], **kw)
+
+
+@pytest.mark.parametrize("name", sorted(cases.ELBO_CASES))
+def test_elbo_terms_and_gradients(name):
+    from mopoe_b200 import engine
+    case = cases.ELBO_CASES[name]
+    ospec, spec, params, flat = _setup(case)
+    batch, eps = cases.inputs_of(case, ospec)
+    grads = torch.zeros_like(flat)
+    sc = _run_step(spec, flat, batch, eps, 1, grads=grads)[0].cpu().numpy()
+    torch.cuda.synchronize()
+    out, g, used = mo.elbo_and_grads(params, ospec, batch, eps)
+    want = GOLD["elbo"][name]
+    from mopoe_b200 import _lib
+    assert abs(sc[_lib.S_TOTAL_LOSS] - float(out["total_loss"])) <= RTOL * abs(float(out["total_loss"]))
+    assert abs(sc[_lib.S_TOTAL_LOSS] - want["total_loss"]) <= RTOL * abs(want["total_loss"])
+    assert abs(sc[_lib.S_JOINT_DIV] - want["joint_divergence"]) <= RTOL * abs(want["joint_divergence"])
+    keys = [k for k, _ in spec.subsets()]
+    for k, v in want["klds"].items():
+        assert abs(sc[_lib.S_KLD_SUBSET + keys.index(k)] - v) <= RTOL * abs(v), k
+    for k, v in want["log_probs"].items():
+        assert abs(sc[_lib.S_NLL + spec.mod_names.index(k)] - v) <= RTOL * abs(v), k
+    got = engine.unpack_params(spec, grads)
+    for k in g:
+        if used[k]:
+            _close(got[k], g[k], "grad " + k)
+            assert_digest_close(digest(got[k]), want["grads"][k], what=k)
+        else:
+            assert float(got[k].abs().max()) == 0.0, k
+
+
+@pytest.mark.parametrize("name", ["hbn_joint_elbo_fact_01", "hbn_poe_fact_01", "hbn_moe_nofact_1",
+                                  "stress_joint_elbo_13", "hbn_joint_elbo_fact_01_fixedscale"])
+def test_fused_adam_steps(name):
+    """3 x (fwd + bwd + Adam) inside ONE launch == oracle (torch.optim.Adam semantics), with
+    different present-sets across steps to exercise the per-modality step counters."""
+    from mopoe_b200 import engine
+    case = cases.ELBO_CASES[name]
+    ospec, spec, params, flat = _setup(case)
+    dev = flat.device
+    steps, batches, eps_l = 3, [], []
+    for s in range(steps):
+        b, e = cases.inputs_of(dict(case, data_seed=case["data_seed"] + s), ospec)
+        if s == 1 and len(b) > 1:      # drop one modality in the middle step
+            b = {k: v for k, v in list(b.items())[:1]}
+        batches.append(b)
+        eps_l.append(e)
+    new, opt, losses = mo.train_steps(params, ospec, batches, eps_l, lr=0.002)
+    N = case["n_rows"]
+    # resident dataset = the three batches stacked; row_index picks each step's rows
+    data, row_index = [], []
+    for m, n in enumerate(spec.mod_names):
+        blocks = [b[n] if n in b else torch.zeros(N, spec.dims[m]) for b in batches]
+        data.append(torch.cat(blocks).cuda().contiguous())
+        row_index.append(torch.arange(steps * N, dtype=torch.int32, device=dev))
+    bdev = engine.make_batches(spec, [(N, spec.present_mask(b.keys()), s * N) for s, b in enumerate(batches)], dev)
+    eps = torch.stack(eps_l).cuda().contiguous()
+    m_ = torch.zeros_like(flat); v_ = torch.zeros_like(flat)
+    t_ = torch.zeros(4, dtype=torch.int32, device=dev)
+    sc = engine.train_steps(spec, flat, data, bdev, steps, N, 2, row_index=row_index, eps=eps, adam_m=m_,
+                            adam_v=v_, adam_t=t_, lr=0.002).cpu().numpy()
+    torch.cuda.synchronize()
+    for s in range(steps):
+        assert abs(sc[s, 0] - float(losses[s]["total_loss"])) <= 2 * RTOL * abs(float(losses[s]["total_loss"])), s
+    got = engine.unpack_params(spec, flat)
+    for k in new:
+        _close(got[k], new[k], "param " + k, rtol=2 * RTOL)
+
+
+@pytest.mark.parametrize("name", sorted(cases.DAA_CASES))
+def test_daa_sweep_injected(name):
+    from mopoe_b200 import daa
+    case = cases.DAA_CASES[name]
+    ospec, spec, params, flat = _setup(case)
+    src, dst, eb, es, ea = cases.daa_inputs_of(case, ospec)
+    r = daa.daa_sweep(spec, flat, src.cuda(), dst.cuda(), case["n_samples"], case["n_base"],
+                      sample_latents=case["sample_latents"], eps_base=eb.cuda(), eps_score=es.cuda(),
+                      eps_av=ea.cuda())
+    torch.cuda.synchronize()
+    gold = np.load(os.path.join(GOLDEN, "reference_daa_%s.npz" % name))
+    _close(r.sampled_scores, gold["sampled_scores"], "sampled_scores")
+    _close(r.reconstructions, gold["reconstructions"], "reconstructions")
+    _close(r.avatars[..., ::cases.DAA_ROI_STRIDE], gold["avatars_sub"], "avatars vs reference")
+    av, sc, rc = daa_oracle.daa_generate(params, ospec, src, dst, eb, es, ea, sample_latents=case["sample_latents"])
+    _close(r.avatars, av, "avatars vs oracle")
+    # statistics: oracle closed form evaluated on the GPU's own avatars/scores (fp64)
+    p, coef, betas = daa_oracle.hierarchical_regression(r.avatars.cpu().numpy(), r.sampled_scores.cpu().numpy())
+    _close(r.betas, betas, "betas", rtol=1e-9)
+    _close(r.coefs, coef, "coefs", rtol=1e-9)
+    gp = r.pvalues.cpu().numpy()
+    assert np.all(np.abs(np.log(gp) - np.log(p)) <= 1e-8 * np.maximum(1.0, np.abs(np.log(p))))
+
+
+def test_daa_fixed_regression_and_standalone():
+    from mopoe_b200 import daa
+    case = cases.DAA_CASES["joint_elbo"]
+    ospec, spec, params, flat = _setup(case)
+    src, dst, eb, es, ea = cases.daa_inputs_of(case, ospec)
+    r = daa.daa_sweep(spec, flat, src.cuda(), dst.cuda(), case["n_samples"], case["n_base"], reg_method="fixed",
+                      eps_base=eb.cuda(), eps_score=es.cuda(), eps_av=ea.cuda())
+    torch.cuda.synchronize()
+    av, sc, rc = r.avatars.cpu().numpy(), r.sampled_scores.cpu().numpy(), r.reconstructions.cpu().numpy()
+    p, coef = daa_oracle.fixed_regression(av, sc, rc)
+    _close(r.coefs, coef, "fixed coefs", rtol=1e-8)
+    assert np.all(np.abs(np.log(r.pvalues.cpu().numpy()) - np.log(p)) <= 1e-7 * np.maximum(1.0, np.abs(np.log(p))))
+    # stand-alone statistics stage on a materialised tensor (make_regression mirror)
+    for method, fn in (("hierarchical", lambda: daa_oracle.hierarchical_regression(av, sc)[:2]),
+                       ("fixed", lambda: daa_oracle.fixed_regression(av, sc, rc))):
+        pv, cf, _ = daa.daa_regression(r.avatars, r.sampled_scores, r.reconstructions, reg_method=method)
+        p, coef = fn()
+        _close(cf, coef, method + " coefs", rtol=1e-8)
+        assert np.all(np.abs(np.log(pv.cpu().numpy()) - np.log(p)) <= 1e-7 * np.maximum(1.0, np.abs(np.log(p))))
+
+
+def test_philox_device_matches_numpy():
+    from mopoe_b200 import engine
+    got = engine.philox_normal(1037, philox.STREAM_DAA_AVATAR, 100000, torch.device("cuda"), start=777).cpu().numpy()
+    want = philox.philox_normal(1037, philox.STREAM_DAA_AVATAR, 100000, start=777)
+    assert np.abs(got - want).max() <= 2e-6 * max(1.0, np.abs(want).max())
+
+
+def test_daa_production_noise_is_shard_invariant_and_matches_oracle():
+    """NULL eps => in-kernel philox; the oracle is fed the same draws materialised with numpy."""
+    from mopoe_b200 import daa
+    case = dict(cases.DAA_CASES["joint_elbo"], n_val=3)
+    ospec, spec, params, flat = _setup(case)
+    src, dst, _, _, _ = cases.daa_inputs_of(case, ospec)
+    J, Mb, N, C_, E = case["n_samples"], case["n_base"], case["n_rows"], ospec.dims[0], ospec.eps_width
+    seed = 1037
+    full = daa.daa_sweep(spec, flat, src.cuda(), dst.cuda(), J, Mb, seed=seed, n_val_total=3)
+    part = daa.daa_sweep(spec, flat, src[1:].cuda(), dst[1:].cuda(), J, Mb, seed=seed, val_begin=1, n_val_total=3)
+    torch.cuda.synchronize()
+    assert torch.equal(full.avatars[1:], part.avatars) and torch.equal(full.pvalues[1:], part.pvalues)
+    eb = torch.from_numpy(philox.philox_normal(seed, philox.STREAM_DAA_BASE, 3 * Mb * N * E)).view(3, Mb, N, E)
+    es = torch.from_numpy(philox.philox_normal(seed, philox.STREAM_DAA_SCORE, 3 * J * N * C_)).view(3, J, N, C_)
+    ea = torch.from_numpy(philox.philox_normal(seed, philox.STREAM_DAA_AVATAR, 3 * J * C_ * N * E)).view(3, J, C_, N, E)
+    av, sc, rc = daa_oracle.daa_generate(params, ospec, src, dst, eb, es, ea)
+    _close(full.avatars, av, "avatars (philox)")
+    _close(full.sampled_scores, sc, "scores (philox)")
