@@ -111,20 +111,29 @@ def test_elbo_terms_and_gradients(name):
 @pytest.mark.parametrize("name", ["hbn_joint_elbo_fact_01", "hbn_poe_fact_01", "hbn_moe_nofact_1",
                                   "stress_joint_elbo_13", "hbn_joint_elbo_fact_01_fixedscale"])
 def test_fused_adam_steps(name):
-    """3 x (fwd + bwd + Adam) inside ONE launch == oracle (torch.optim.Adam semantics), with
-    different present-sets across steps to exercise the per-modality step counters."""
+    """3 x (fwd + bwd + Adam) inside ONE launch, with different present-sets across steps to
+    exercise the per-modality step counters.
+
+    Adam divides by sqrt(v): an element whose gradient is ~1e-8 turns a 1e-7 relative gradient
+    difference into an O(lr) parameter difference, so element-wise parity of the parameters
+    against an independent trajectory is ill-posed.  The test therefore checks
+      (a) EXACTNESS of the in-kernel Adam: replay the same 3 steps with the kernel's own gradients
+          (mode 1) pushed through the oracle's torch.optim.Adam restatement -> parameters equal to
+          1e-5 of their scale;
+      (b) the trajectory against the pure-CPU oracle: per-step losses within 2e-4, 99.9 % of the
+          parameters within 1e-4 of their tensor's scale and none further than 2*lr*steps."""
     from mopoe_b200 import engine
     case = cases.ELBO_CASES[name]
     ospec, spec, params, flat = _setup(case)
     dev = flat.device
-    steps, batches, eps_l = 3, [], []
+    lr, steps, batches, eps_l = 0.002, 3, [], []
     for s in range(steps):
         b, e = cases.inputs_of(dict(case, data_seed=case["data_seed"] + s), ospec)
         if s == 1 and len(b) > 1:      # drop one modality in the middle step
             b = {k: v for k, v in list(b.items())[:1]}
         batches.append(b)
         eps_l.append(e)
-    new, opt, losses = mo.train_steps(params, ospec, batches, eps_l, lr=0.002)
+    new, opt, losses = mo.train_steps(params, ospec, batches, eps_l, lr=lr)
     N = case["n_rows"]
     # resident dataset = the three batches stacked; row_index picks each step's rows
     data, row_index = [], []
@@ -134,16 +143,36 @@ def test_fused_adam_steps(name):
         row_index.append(torch.arange(steps * N, dtype=torch.int32, device=dev))
     bdev = engine.make_batches(spec, [(N, spec.present_mask(b.keys()), s * N) for s, b in enumerate(batches)], dev)
     eps = torch.stack(eps_l).cuda().contiguous()
+    flat0 = flat.clone()
     m_ = torch.zeros_like(flat); v_ = torch.zeros_like(flat)
     t_ = torch.zeros(4, dtype=torch.int32, device=dev)
     sc = engine.train_steps(spec, flat, data, bdev, steps, N, 2, row_index=row_index, eps=eps, adam_m=m_,
-                            adam_v=v_, adam_t=t_, lr=0.002).cpu().numpy()
+                            adam_v=v_, adam_t=t_, lr=lr).cpu().numpy()
     torch.cuda.synchronize()
+    got = engine.unpack_params(spec, flat)
+    # (a) replay with the kernel's own gradients through the oracle Adam
+    cur = flat0.clone()
+    oparams = {k: v.clone() for k, v in params.items()}
+    oadam = mo.Adam(oparams, lr=lr)
+    for s in range(steps):
+        g = torch.zeros_like(cur)
+        _run_step(spec, cur, batches[s], eps_l[s], 1, grads=g)
+        torch.cuda.synchronize()
+        gd = {k: v.cpu() for k, v in engine.unpack_params(spec, g).items()}
+        used = {k: (spec.mod_names[spec.modality_of_param(k)] in batches[s]) and mo.trainable(ospec, k) for k in oparams}
+        oparams = oadam.step(oparams, gd, used)
+        cur = engine.pack_params(spec, oparams, dev)
+    for k in oparams:
+        _close(got[k], oparams[k], "adam replay " + k, rtol=1e-5)
+    assert t_.cpu().tolist()[:spec.n_mods] == [sum(n in b for b in batches) for n in spec.mod_names]
+    # (b) independent oracle trajectory
     for s in range(steps):
         assert abs(sc[s, 0] - float(losses[s]["total_loss"])) <= 2 * RTOL * abs(float(losses[s]["total_loss"])), s
-    got = engine.unpack_params(spec, flat)
     for k in new:
-        _close(got[k], new[k], "param " + k, rtol=2 * RTOL)
+        a, w = got[k].cpu().double().numpy(), new[k].double().numpy()
+        err = np.abs(a - w) / max(np.abs(w).max(), 1e-30)
+        assert np.mean(err <= RTOL) >= 0.999, (k, float(np.mean(err <= RTOL)))
+        assert np.abs(a - w).max() <= 2 * lr * steps, k
 
 
 @pytest.mark.parametrize("name", sorted(cases.DAA_CASES))
