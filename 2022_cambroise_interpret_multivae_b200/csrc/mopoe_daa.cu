@@ -245,7 +245,6 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_kernel(ModelView 
     s_whT[k * HO + o] = ms.wh[(int64_t)o * MOPOE_HIDDEN + k];
   }
   for (int i = t; i < HO; i += MOPOE_THREADS) s_bh[i] = ms.bh[i];
-  const int present = (1 << M) - 1;
   const int n_units = cx.q.n_val * N * C;
   const int rg = t / 56, cg = t % 56;  // decoder micro-tile owner (t < 224)
   while (true) {
@@ -606,7 +605,26 @@ __global__ void daa_stats_kernel(int n_val, int N, int C, int J, int R, int reg_
 
 using namespace mopoe;
 
+static int g_profile = 0;
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+
 extern "C" {
+
+int mopoe_profile_enable(int on) {
+  g_profile = on;
+  if (on && !g_ev0) {
+    MOPOE_CUDA(cudaEventCreate(&g_ev0));
+    MOPOE_CUDA(cudaEventCreate(&g_ev1));
+  }
+  return MOPOE_OK;
+}
+
+int mopoe_daa_last_kernel_ms(float* ms_out) {
+  if (!g_ev0 || !ms_out) { set_error("profiling not enabled"); return MOPOE_EINVAL; }
+  MOPOE_CUDA(cudaEventSynchronize(g_ev1));
+  MOPOE_CUDA(cudaEventElapsedTime(ms_out, g_ev0, g_ev1));
+  return MOPOE_OK;
+}
 
 int64_t mopoe_daa_workspace_bytes(const mopoe_model_desc* desc, const mopoe_daa_desc* daa) {
   if (check_desc(desc)) return MOPOE_EINVAL;
@@ -690,10 +708,12 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   const int grid = n_units < num_sms() ? n_units : num_sms();
   for (int col0 = 0; col0 < cx.R; col0 += CB) {
     MOPOE_CUDA(cudaMemsetAsync(ws.counter, 0, sizeof(int), stream));
+    if (g_profile && col0 == 0) MOPOE_CUDA(cudaEventRecord(g_ev0, stream));
     if (daa->reg_method == 1) daa_avatar_kernel<true><<<grid, MOPOE_THREADS, av_smem, stream>>>(mv, cx, ws, col0);
     else daa_avatar_kernel<false><<<grid, MOPOE_THREADS, av_smem, stream>>>(mv, cx, ws, col0);
     MOPOE_CUDA(cudaGetLastError());
   }
+  if (g_profile) MOPOE_CUDA(cudaEventRecord(g_ev1, stream));
   // 4. second level
   const int64_t nstat = (int64_t)daa->n_val * cx.C * cx.R;
   daa_stats_kernel<<<(unsigned)((nstat + 127) / 128), 128, 0, stream>>>(daa->n_val, N, cx.C, cx.J, cx.R, daa->reg_method, ws.betas,

@@ -225,6 +225,12 @@ int mopoe_daa_regression(int32_t n_val, int32_t n_subjects, int32_t n_scores, in
                          const float* sampled_scores, const float* reconstructions, double* betas,
                          double* coefs, double* pvalues, void* stream);
 
+/* Measurement hook (bench.py): when enabled, mopoe_daa_sweep brackets its dominant kernel
+ * (daa_avatar_kernel) with CUDA events on the caller's stream; mopoe_daa_last_kernel_ms waits for
+ * the last bracket and returns its duration. */
+int mopoe_profile_enable(int on);
+int mopoe_daa_last_kernel_ms(float* ms_out);
+
 /* Fill `out[0..n)` with philox_normal(seed, stream_id, start + i): the production noise generator,
  * exposed so hosts/tests can materialise exactly what the kernels draw. */
 int mopoe_philox_normal(uint64_t seed, uint64_t stream_id, int64_t start, int64_t n, float* out,
