@@ -1,0 +1,206 @@
+"""Drop-in for the reference model class `multimodal_cohort.networks.VAE.VAE`
+(experiments/multimodal_cohort/networks/VAE.py:6-8 -> experiments/utils/BaseMMVae.py).
+
+Same constructor `VAE(flags, modalities, subsets)`, same state-dict keys and shapes
+(`encoders.<m>.shared_encoder.0.weight` ... `decoders.<m>.out_mu.bias`), same
+`forward(input_batch, sample_latents=True, use_expert=None) -> results` structure
+(BaseMMVae.py:137-165) -- but the arithmetic runs in the sm_100a kernels behind
+include/mopoe_b200.h.  Parameters are nn.Parameters whose storage is ONE flat fp32 buffer in the
+C-ABI layout, so torch optimisers / checkpoints keep working and the fused Adam kernel can update
+them in place.  The tensors in `results` are detached: training goes through
+`run_epochs.basic_routine_epoch`, whose `total_loss` carries the kernel-computed gradients.
+There is no CPU fallback: calling the model with CPU tensors raises.
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib, engine
+from .spec import PathSpec
+
+
+class Encoder(nn.Module):
+    """Parameter container mirroring networks.py:9-28 (the math lives in the CUDA kernels)."""
+
+    def __init__(self, spec: PathSpec, m):
+        super().__init__()
+        D, S, L = spec.dims[m], spec.style_dims[m], spec.latent_dim
+        self.shared_encoder = nn.Sequential(nn.Linear(D, _lib.HIDDEN), nn.ReLU(), nn.Dropout(0.0))
+        self.style_dim = S
+        self.class_mu = nn.Linear(_lib.HIDDEN, L)
+        self.class_logvar = nn.Linear(_lib.HIDDEN, L)
+        if S > 0:
+            self.style_mu = nn.Linear(_lib.HIDDEN, S)
+            self.style_logvar = nn.Linear(_lib.HIDDEN, S)
+
+
+class Decoder(nn.Module):
+    """Parameter container mirroring networks.py:44-64."""
+
+    def __init__(self, spec: PathSpec, m):
+        super().__init__()
+        D, S, L = spec.dims[m], spec.style_dims[m], spec.latent_dim
+        self.style_dim = S
+        self.out_mu = nn.Linear(S + L, D)
+        self.logvar = nn.Parameter(torch.full((1, D), spec.initial_out_logvar), requires_grad=spec.learn_output_scale)
+
+
+class VAE(nn.Module):
+    def __init__(self, flags, modalities, subsets=None):
+        super().__init__()
+        self.flags = flags
+        self.modalities = modalities
+        self.num_modalities = len(modalities)
+        self.spec = PathSpec.from_flags(flags, mod_names=list(modalities.keys()))
+        self.subsets = subsets if subsets is not None else {k: None for k, _ in self.spec.subsets()}
+        encoders, decoders = nn.ModuleDict(), nn.ModuleDict()
+        for m, key in enumerate(modalities.keys()):   # same construction order as BaseMMVae.py:28-31
+            encoders[key] = Encoder(self.spec, m)
+            decoders[key] = Decoder(self.spec, m)
+        self.encoders, self.decoders = encoders, decoders
+        self.lhoods = {k: torch.distributions.Normal for k in modalities}
+        self._flat = None
+        self._noise = None
+        self._ws = engine.Workspace()
+        self.philox_seed = None      # set to an int to use the in-kernel generator instead of torch.randn
+
+    # ---- flat parameter storage -------------------------------------------------------------
+    def flat_parameters(self):
+        """The flat fp32 parameter buffer (C-ABI layout) that every nn.Parameter is a view of."""
+        named = dict(self.named_parameters())
+        slices = self.spec.param_slices()
+        dev = next(iter(named.values())).device
+        if dev.type != "cuda":
+            raise _lib.MopoeError("the model must be on a CUDA device: the MoPoE B200 path has no CPU fallback")
+        ok = self._flat is not None and self._flat.device == dev
+        if ok:
+            base = self._flat.data_ptr()
+            ok = all(named[k].data_ptr() == base + 4 * off and named[k].dtype == torch.float32 for k, (off, _) in slices.items())
+        if not ok:
+            flat = torch.zeros(self.spec.layout.total, dtype=torch.float32, device=dev)
+            for k, (off, shape) in slices.items():
+                n = named[k].numel()
+                flat[off:off + n].copy_(named[k].detach().reshape(-1).float())
+                named[k].data = flat[off:off + n].view(shape)
+            self._flat = flat
+        return self._flat
+
+    def inject_noise(self, eps):
+        """Next forward/step consumes this (N, E) [or (n_pass, N, E)] tensor instead of fresh draws."""
+        self._noise = eps
+
+    def _draw(self, n_pass, n_rows, device):
+        if self._noise is not None:
+            eps, self._noise = self._noise, None
+            return eps.to(device=device, dtype=torch.float32).reshape(n_pass, n_rows, self.spec.eps_width).contiguous()
+        if self.philox_seed is not None:
+            return None
+        return torch.randn(n_pass, n_rows, self.spec.eps_width, device=device)   # global torch generator
+
+    # ---- reference API ----------------------------------------------------------------------
+    def reparameterize(self, mu, logvar):
+        std = logvar.mul(0.5).exp()
+        return torch.randn_like(std).mul(std).add(mu)            # BaseMMVae.py:37-40
+
+    def _results(self, res, batch, scale_only_present=True):
+        spec, L = self.spec, self.spec.latent_dim
+        keys = [k for k, _ in spec.subsets()]
+        avail, mix = spec.mixture_subsets(res.present_mask)
+        enc = {}
+        for m, name in enumerate(spec.mod_names):
+            if res.enc_heads[m] is None:
+                enc[name + "_style"] = [None, None]
+                enc[name] = [None, None]
+                continue
+            h, S = res.enc_heads[m], spec.style_dims[m]
+            enc[name] = [h[:, :L], h[:, L:2 * L]]
+            enc[name + "_style"] = [h[:, 2 * L:2 * L + S], h[:, 2 * L + S:]] if S > 0 else [None, None]
+        idx = torch.tensor(mix, device=res.subset_mu.device)
+        latents = {"modalities": enc, "mus": res.subset_mu.index_select(0, idx),
+                   "logvars": res.subset_logvar.index_select(0, idx),
+                   "weights": (1 / float(len(mix))) * torch.ones(len(mix), device=idx.device),
+                   "joint": [res.joint_mu, res.joint_logvar],
+                   "subsets": {keys[s]: [res.subset_mu[s], res.subset_logvar[s]] for s in avail}}
+        sc = res.scalars
+        results = {"latents": latents, "group_distr": latents["joint"], "joint_divergence": sc[_lib.S_JOINT_DIV],
+                   "individual_divs": sc[_lib.S_KLD_SUBSET:_lib.S_KLD_SUBSET + len(keys)].index_select(0, idx),
+                   "dyn_prior": None}
+        rec = {}
+        for m, name in enumerate(spec.mod_names):
+            if res.rec_loc[m] is not None:
+                scale = (self.decoders[name].logvar.detach() * 0.5).exp()
+                rec[name] = torch.distributions.Normal(res.rec_loc[m], scale)
+        results["rec"] = rec
+        results["class_embeddings"] = res.z
+        return results
+
+    def _forward_raw(self, input_batch, sample_latents=True, use_expert=None, with_nll=False):
+        flat = self.flat_parameters()
+        n_rows = len(next(iter(input_batch.values())))
+        eps = self._draw(1, n_rows, flat.device) if sample_latents else None
+        seed = self.philox_seed or 0
+        return engine.forward(self.spec, flat, input_batch, eps=None if eps is None else eps[0], seed=seed,
+                              sample_latents=sample_latents, use_expert=use_expert, with_nll=with_nll,
+                              workspace=self._ws)
+
+    @torch.no_grad()
+    def forward(self, input_batch, sample_latents=True, use_expert=None):
+        return self._results(self._forward_raw(input_batch, sample_latents, use_expert), input_batch)
+
+    @torch.no_grad()
+    def inference(self, input_batch, num_samples=None, sample=True, use_expert=None):
+        return self.forward(input_batch, sample_latents=sample, use_expert=use_expert)["latents"]
+
+    @torch.no_grad()
+    def encode(self, input_batch):
+        return self.forward(input_batch, sample_latents=False)["latents"]["modalities"]
+
+    def save_networks(self):                                   # BaseMMVae.py:315-322
+        for key in self.modalities:
+            torch.save(self.encoders[key].state_dict(), os.path.join(self.flags.dir_checkpoints, "enc_" + key))
+            torch.save(self.decoders[key].state_dict(), os.path.join(self.flags.dir_checkpoints, "dec_" + key))
+
+
+class _ElboFunction(torch.autograd.Function):
+    """total_loss with kernel-computed gradients: backward hands each nn.Parameter its slice of the
+    flat gradient buffer (None for the parameters of absent modalities, as autograd would)."""
+
+    @staticmethod
+    def forward(ctx, loss, grads, *params):
+        ctx.g = grads
+        return loss.detach().clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        return (None, None) + tuple((None if g is None else g * gout) for g in ctx.g)
+
+
+def elbo_step(model: VAE, input_batch, need_grad=True):
+    """One basic_routine_epoch on the GPU (single cooperative launch): returns
+    (scalars row, ForwardResult, total_loss tensor wired to the parameters)."""
+    spec = model.spec
+    flat = model.flat_parameters()
+    dev = flat.device
+    mask = spec.present_mask(input_batch.keys())
+    data = [engine._f32(input_batch[n]) if n in input_batch else None for n in spec.mod_names]
+    for x in data:
+        if x is not None:
+            engine._require_cuda(x, "input batch")
+    n_rows = next(x for x in data if x is not None).shape[0]
+    eps = model._draw(spec.n_pass, n_rows, dev)
+    res = engine.ForwardResult(spec, n_rows, mask, dev)
+    bdev = engine.make_batches(spec, [(n_rows, mask, 0)], dev)
+    grads = torch.zeros_like(flat) if need_grad else None
+    sc = engine.train_steps(spec, flat, data, bdev, 1, n_rows, 1 if need_grad else 0,
+                            eps=None if eps is None else eps[None].contiguous(), seed=model.philox_seed or 0,
+                            grads=grads, forward_result=res, workspace=model._ws)[0]
+    res.scalars = sc
+    loss = sc[_lib.S_TOTAL_LOSS]
+    if need_grad:
+        named = dict(model.named_parameters())
+        names = [k for k in spec.param_slices() if named[k].requires_grad]
+        gviews = engine.unpack_params(spec, grads)
+        glist = [gviews[k] if (mask >> spec.modality_of_param(k) & 1) else None for k in names]
+        loss = _ElboFunction.apply(loss, glist, *[named[k] for k in names])
+    return sc, res, loss

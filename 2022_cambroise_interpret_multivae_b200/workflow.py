@@ -1,0 +1,298 @@
+"""Mirror of the two hot-path workflows of experiments/workflow.py on the B200 path.
+
+  train_exp(dataset, datasetdir, outdir, input_dims, ...)      workflow.py:41-182
+  daa_exp(dataset, datasetdir, outdir, run, ...)               workflow.py:185-539
+
+Same keyword arguments, same run-directory layout, same output files (names, dtypes, axis order):
+  <outdir>/<dataset>_<YYYY_MM_DD_HH_MM>/flags.rar, checkpoints/<epoch:04d>/model, checkpoints/enc_*,
+  <run>/daa/<params>/rois_digital_avatars.npy (float32 (n_val, n_subj, n_scores, n_samples, n_rois)),
+  sampled_scores.npy, metadatas.npy, rois_reconstructions.npy, coefs.npy, pvalues.npy,
+  all_coefs.npy, significant_rois.tsv.
+What differs (documented in DESIGN.md): the cohort is standardised once and kept resident in HBM
+(no DataLoader workers), an epoch is one persistent launch, the DAA statistics are computed on the
+GPU in fp64 in closed form, and the train/test split is our own seeded split (the reference's
+iterstrat-based fetcher is out of scope; only subjects with every block go to the test set, as in
+multiblock_fetcher.py:102-119).  With torch.distributed initialised, daa_exp shards validations
+over the ranks and all-gathers the result tables.
+"""
+import glob
+import os
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import daa, run_epochs as re_
+from .model import VAE
+
+MODALITIES = ["clinical", "rois"]
+
+
+class _Mod:
+    def __init__(self, name):
+        self.name = name
+
+
+class Experiment:
+    """What MultimodalExperiment provides to the hot path (experiment.py:64-91), with the cohort
+    standardised once (StandardScaler on the train rows, experiment.py:146-166) and resident in HBM."""
+
+    def __init__(self, flags, device=None):
+        self.flags = flags
+        self.device = device or torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.modalities = {n: _Mod(n) for n in MODALITIES[: len(flags.input_dim)]}
+        self.mod_names = list(self.modalities)
+        self.rng = np.random.RandomState(None if flags.data_seed == "defaults" else int(flags.data_seed))
+        self._seed = int(self.rng.randint(1, 2 ** 31 - 1))
+        self._load(flags.datasetdir)
+        torch_state = None
+        self.models = VAE(flags, self.modalities).to(self.device)
+        self.optimizers = None
+        self.adam_state = None
+        self.rec_weights = {n: 1.0 for n in self.mod_names}
+        self.style_weights = {n: flags.beta_style for n in self.mod_names}
+
+    def next_seed(self):
+        self._seed += 1
+        return self._seed
+
+    def _load(self, datasetdir):
+        meta = pd.read_table(os.path.join(datasetdir, "metadata.tsv"))
+        subjects = meta["participant_id"].to_numpy()
+        pos = {s: i for i, s in enumerate(subjects)}
+        n = len(subjects)
+        blocks, has = [], []
+        for mod in self.mod_names:
+            x = np.load(os.path.join(datasetdir, mod + "_data.npy"), mmap_mode="r")
+            subj = np.load(os.path.join(datasetdir, mod + "_subjects.npy"), allow_pickle=True)
+            full = np.zeros((n, x.shape[1]), np.float32)
+            h = np.zeros(n, bool)
+            idx = np.array([pos[s] for s in subj])
+            full[idx] = np.asarray(x, np.float32)
+            h[idx] = True
+            blocks.append(full)
+            has.append(h)
+        has = np.stack(has)
+        complete = np.flatnonzero(has.all(0))
+        split = np.random.RandomState(42)                       # fetchers/hbn.py:20 seed
+        perm = split.permutation(complete)
+        n_test = int(round(0.2 * len(complete)))                # experiment.py:203 test_size
+        test_idx = np.sort(perm[:n_test])
+        train_mask = np.ones(n, bool)
+        train_mask[test_idx] = False
+        if not self.flags.allow_missing_blocks:
+            train_mask &= has.all(0)
+        train_idx = np.flatnonzero(train_mask & has.any(0))
+        self.scalers = []
+        for m in range(len(blocks)):
+            rows = blocks[m][train_idx][has[m][train_idx]]
+            mean, std = rows.mean(0), rows.std(0)
+            std[std == 0] = 1.0
+            self.scalers.append((mean, std))
+            blocks[m] = ((blocks[m] - mean) / std).astype(np.float32)
+        dev = self.device
+        self.metadata = meta
+        self.train_idx, self.test_idx = train_idx, test_idx
+        self.resident = {"train": [torch.from_numpy(b[train_idx]).to(dev) for b in blocks],
+                         "test": [torch.from_numpy(b[test_idx]).to(dev) for b in blocks],
+                         "has_train": has[:, train_idx], "n_test": len(test_idx)}
+
+    def set_optimizers(self):
+        flat = self.models.flat_parameters()
+        self.adam_state = {"m": torch.zeros_like(flat), "v": torch.zeros_like(flat),
+                           "t": torch.zeros(4, dtype=torch.int32, device=flat.device)}
+        print("num parameters: %d" % sum(p.numel() for p in self.models.parameters()))
+
+    @classmethod
+    def get_experiment(cls, flags_file, checkpoints_dir, load_epoch=None):
+        """experiment.py:93-121 (torch >= 2.6 needs weights_only=False to unpickle the namespace)."""
+        flags = torch.load(flags_file, weights_only=False)
+        if "num_models" not in vars(flags):
+            flags.num_models = 1
+        flags.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        exp = cls(flags)
+        cp_files = glob.glob(os.path.join(checkpoints_dir, "*", flags.model_save))
+        if len(cp_files) == 0:
+            raise ValueError("You need first to train the model.")
+        cp_files = sorted(cp_files, key=lambda p: int(p.split(os.sep)[-2]))
+        cp_file = cp_files[-1]
+        if load_epoch is not None:
+            epochs = np.array([int(p.split(os.sep)[-2]) for p in cp_files])
+            cp_file = cp_files[int(np.argmin(epochs >= load_epoch))]
+        print(cp_file)
+        exp.models.load_state_dict(torch.load(cp_file, map_location=flags.device))
+        return exp, flags
+
+
+def _make_flags(dataset, datasetdir, outdir, input_dims, num_models, latent_dim, style_dim, data_seed,
+                num_hidden_layer_encoder, num_hidden_layer_decoder, allow_missing_blocks,
+                factorized_representation, likelihood, learning_rate, batch_size, num_epochs, eval_freq,
+                eval_freq_fid, beta, data_multiplications, dropout_rate, initial_out_logvar, learn_output_scale,
+                out_scale_per_subject, method, grad_scaling):
+    flags = SimpleNamespace(   # workflow.py:98-121, hot-path fields + the ones downstream tools read
+        dataset=dataset, datasetdir=datasetdir, num_models=num_models, allow_missing_blocks=allow_missing_blocks,
+        batch_size=batch_size, beta=beta, beta_1=0.9, beta_2=0.999, beta_content=1.0, beta_style=1.0,
+        calc_nll=False, calc_prd=False, class_dim=latent_dim, data_multiplications=data_multiplications,
+        dir_experiment=outdir, div_weight=None, div_weight_uniform_content=None, end_epoch=num_epochs,
+        eval_freq=eval_freq, eval_freq_fid=eval_freq_fid, factorized_representation=factorized_representation,
+        initial_learning_rate=learning_rate, initial_out_logvar=initial_out_logvar, input_dim=list(input_dims),
+        joint_elbo=False, kl_annealing=0, include_prior_expert=False, learn_output_scale=learn_output_scale,
+        learn_output_sample_scale=out_scale_per_subject, likelihood=likelihood, load_saved=False, method=method,
+        model_save="model", modality_jsd=False, modality_moe=False, modality_poe=False,
+        num_hidden_layer_encoder=num_hidden_layer_encoder, num_hidden_layer_decoder=num_hidden_layer_decoder,
+        dropout_rate=dropout_rate, poe_unimodal_elbos=True, start_epoch=0, style_dim=list(style_dim),
+        data_seed=data_seed, grad_scaling=grad_scaling)
+    flags.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    if method == "poe":
+        flags.modality_poe = True
+    elif method == "moe":
+        flags.modality_moe = True
+    elif method == "joint_elbo":
+        flags.joint_elbo = True
+    elif method == "jsd":
+        raise NotImplementedError("method='jsd' is not on the B200 path")
+    else:
+        print("Method not implemented...exit!")                  # workflow.py:134-136
+        return None
+    flags.num_mods = len(flags.input_dim)
+    flags.div_weight_uniform_content = 1 / (flags.num_mods + 1)
+    flags.alpha_modalities = [flags.div_weight_uniform_content] + [1 / (flags.num_mods + 1)] * flags.num_mods
+    if not flags.factorized_representation:
+        flags.style_dim = [0] * len(flags.style_dim)
+    return flags
+
+
+def _create_dir_structure(flags):
+    """utils/filehandling.py:13-17,29-94: <outdir>/<dataset>_<YYYY_MM_DD_HH_MM>/{checkpoints,logs}."""
+    name = flags.dataset + "_" + time.strftime("%Y_%m_%d_%H_%M")
+    flags.str_experiment = name
+    flags.dir_experiment_run = os.path.join(flags.dir_experiment, name)
+    flags.dir_checkpoints = os.path.join(flags.dir_experiment_run, "checkpoints")
+    flags.dir_logs = os.path.join(flags.dir_experiment_run, "logs")
+    for d in (flags.dir_experiment_run, flags.dir_checkpoints, flags.dir_logs):
+        os.makedirs(d, exist_ok=True)
+    return flags
+
+
+def train_exp(dataset, datasetdir, outdir, input_dims, num_models=1, latent_dim=20, style_dim=[3, 20],
+              data_seed="defaults", num_hidden_layer_encoder=1, num_hidden_layer_decoder=0,
+              allow_missing_blocks=True, factorized_representation=True, likelihood="normal",
+              learning_rate=0.002, batch_size=256, num_epochs=1500, eval_freq=25, eval_freq_fid=100, beta=1.,
+              data_multiplications=1, dropout_rate=0., initial_out_logvar=-3., learn_output_scale=True,
+              out_scale_per_subject=False, method="joint_elbo", grad_scaling=False):
+    """Train the model (workflow.py:41-182).  Returns the run name."""
+    if num_models != 1:
+        raise NotImplementedError("num_models > 1 (k-fold ensembles) is not on the B200 path")
+    flags = _make_flags(dataset, datasetdir, outdir, input_dims, num_models, latent_dim, style_dim, data_seed,
+                        num_hidden_layer_encoder, num_hidden_layer_decoder, allow_missing_blocks,
+                        factorized_representation, likelihood, learning_rate, batch_size, num_epochs, eval_freq,
+                        eval_freq_fid, beta, data_multiplications, dropout_rate, initial_out_logvar,
+                        learn_output_scale, out_scale_per_subject, method, grad_scaling)
+    if flags is None:
+        return None
+    _create_dir_structure(flags)
+    exp = Experiment(flags)
+    exp.set_optimizers()
+    exp.logs = re_.run_epochs(exp)
+    runs_file = os.path.join(flags.dir_experiment, "runs.tsv")     # workflow.py:155-182
+    row = pd.DataFrame(dict(name=[flags.str_experiment], dataset=[flags.dataset],
+                            out_scale_per_subject=[flags.learn_output_sample_scale],
+                            n_hidden_layer_encoder=[flags.num_hidden_layer_encoder],
+                            n_hidden_layer_decoder=[flags.num_hidden_layer_decoder],
+                            allow_missing_blocks=[flags.allow_missing_blocks]))
+    if os.path.exists(runs_file):
+        row = pd.concat((pd.read_table(runs_file), row))
+    row.to_csv(runs_file, index=False, sep="\t")
+    return flags.str_experiment
+
+
+def daa_exp(dataset, datasetdir, outdir, run, sampling_strategy="likelihood", n_validation=5, n_samples=200,
+            n_subjects=50, M=1000, trust_level=0.75, seed=1037, reg_method="hierarchical", sample_latents=True,
+            vote_prop=1, materialize_avatars=True):
+    """Digital avatars analysis (workflow.py:185-539).  Returns the results directory."""
+    if sampling_strategy != "likelihood":
+        raise NotImplementedError("sampling_strategy=%r is not on the B200 path (likelihood)" % (sampling_strategy,))
+    import torch.distributed as dist
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+    expdir = os.path.join(outdir, run)
+    daadir = os.path.join(expdir, "daa")
+    flags_file = os.path.join(expdir, "flags.rar")
+    if not os.path.isfile(flags_file):
+        raise ValueError("You need first to train the model.")
+    exp, flags = Experiment.get_experiment(flags_file, os.path.join(expdir, "checkpoints"))
+    clinical_names = np.load(os.path.join(datasetdir, "clinical_names.npy"), allow_pickle=True)
+    rois_names = np.load(os.path.join(datasetdir, "rois_names.npy"), allow_pickle=True)
+    n_scores, n_rois = len(clinical_names), len(rois_names)
+    params = SimpleNamespace(n_validation=n_validation, n_subjects=n_subjects, M=M, n_samples=n_samples,
+                             reg_method=reg_method, sampling=sampling_strategy, sample_latents=sample_latents, seed=seed)
+    name = "_".join(["_".join([k, str(v)]) for k, v in params.__dict__.items()])     # workflow.py:261-262
+    resdir = os.path.join(daadir, name)
+    if rank == 0:
+        os.makedirs(resdir, exist_ok=True)
+    model = exp.models
+    model.eval()
+    flat = model.flat_parameters()
+    # draw n_validation batches of test subjects on the host (workflow.py:362-372), seeded
+    rs = np.random.RandomState(seed)
+    n_test = exp.resident["n_test"]
+    draws = np.stack([rs.permutation(n_test)[:n_subjects] for _ in range(n_validation)])
+    begin, end = daa.shard_validations(n_validation, rank, world)
+    idx = torch.from_numpy(draws[begin:end]).to(flat.device)
+    src = exp.resident["test"][0][idx]
+    dst = exp.resident["test"][1][idx]
+    r = daa.daa_sweep(model.spec, flat, src, dst, n_samples, M, sample_latents=sample_latents, reg_method=reg_method,
+                      seed=0 if seed is None else seed, val_begin=begin, n_val_total=n_validation,
+                      materialize=materialize_avatars, workspace=model._ws)
+    coefs = daa.gather_tables(r.coefs, n_validation)
+    pvalues = daa.gather_tables(r.pvalues, n_validation)
+    betas = daa.gather_tables(r.betas, n_validation)
+    scores = daa.gather_tables(r.sampled_scores, n_validation)
+    recons = daa.gather_tables(r.reconstructions, n_validation)
+    torch.cuda.synchronize()
+    meta = exp.metadata.iloc[exp.test_idx].reset_index(drop=True)
+    meta_cols = list(meta.columns)
+    if materialize_avatars:
+        from numpy.lib.format import open_memmap
+        da_file = os.path.join(resdir, "rois_digital_avatars.npy")
+        if world > 1:
+            dist.barrier()
+        mode = "w+" if rank == 0 else "r+"
+        if rank == 0:
+            mm = open_memmap(da_file, dtype="float32", mode="w+", shape=(n_validation, n_subjects, n_scores, n_samples, n_rois))
+            del mm
+        if world > 1:
+            dist.barrier()
+        mm = np.load(da_file, mmap_mode="r+")
+        mm[begin:end] = r.avatars.cpu().numpy()                 # disjoint slices per rank
+        mm.flush()
+        del mm
+    if rank == 0:
+        np.save(os.path.join(resdir, "sampled_scores.npy"), scores.cpu().numpy())
+        np.save(os.path.join(resdir, "metadatas.npy"), np.stack([meta.iloc[d].to_numpy() for d in draws]))
+        np.save(os.path.join(resdir, "rois_reconstructions.npy"), recons.cpu().numpy())
+        np.save(os.path.join(resdir, "pvalues.npy"), pvalues.cpu().numpy())
+        np.save(os.path.join(resdir, "coefs.npy"), coefs.cpu().numpy())
+        if reg_method == "hierarchical":                        # workflow.py:476-505: per-subject betas
+            b = betas.cpu().numpy()
+            cols = [str(n).replace("&", "_").replace("-", "_") for n in rois_names]
+            pid, site = meta_cols.index("participant_id"), meta_cols.index("site")
+            all_coefs = []
+            for v in range(n_validation):
+                all_coefs.append([])
+                m = meta.iloc[draws[v]].to_numpy()[:, [pid, site]]
+                for c in range(n_scores):
+                    df = pd.DataFrame(m, columns=["participant_id", "site"])
+                    all_coefs[v].append(pd.concat([df, pd.DataFrame(b[v, c], columns=cols)], axis=1))
+            np.save(os.path.join(resdir, "all_coefs.npy"), np.array(all_coefs, dtype=object), allow_pickle=True)
+        idx_sign = daa.significant(pvalues, trust_level)        # workflow.py:517-523
+        rows = {"metric": [], "roi": [], "score": []}
+        for i, score in enumerate(clinical_names):
+            for nm in rois_names[np.where(idx_sign[i])]:
+                roi, metric = nm.rsplit("_", 1)
+                rows["score"].append(score); rows["metric"].append(metric); rows["roi"].append(roi)
+        pd.DataFrame.from_dict(rows).to_csv(os.path.join(resdir, "significant_rois.tsv"), sep="\t", index=False)
+    if world > 1:
+        dist.barrier()
+    return resdir

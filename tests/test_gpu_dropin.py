@@ -1,0 +1,157 @@
+"""The reference-interface mirrors on the GPU: VAE drop-in, basic_routine_epoch, make_regression,
+train_exp / daa_exp end to end on a small synthetic cohort."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, daa_oracle, mopoe_oracle as mo
+from helpers import RTOL, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _flags(method="joint_elbo", factorized=True):
+    f = SimpleNamespace(input_dim=[7, 444], style_dim=[3, 20], class_dim=20, factorized_representation=factorized,
+                        modality_poe=method == "poe", modality_moe=method == "moe", modality_jsd=False,
+                        joint_elbo=method == "joint_elbo", learn_output_scale=True, learn_output_sample_scale=False,
+                        beta=1.0, beta_style=1.0, beta_content=1.0, num_hidden_layer_encoder=1,
+                        num_hidden_layer_decoder=0, likelihood="normal", initial_out_logvar=-3.0, dropout_rate=0.0,
+                        num_models=1, dir_checkpoints="")
+    return f
+
+
+def _model(method="joint_elbo", seed=11):
+    from mopoe_b200.model import VAE
+    flags = _flags(method)
+    mods = {"clinical": SimpleNamespace(name="clinical"), "rois": SimpleNamespace(name="rois")}
+    model = VAE(flags, mods).cuda()
+    ospec = mo.ModelSpec(method=method)
+    params = mo.init_params(ospec, seed=seed)
+    model.load_state_dict(params, strict=True)
+    return model, ospec, params
+
+
+def test_state_dict_keys_match_reference():
+    model, ospec, params = _model()
+    assert list(model.state_dict().keys()) == list(mo.param_shapes(ospec).keys())
+    assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == mo.param_shapes(ospec)
+    # same construction order as the reference => same default init under the same torch seed
+    gold = load_golden()
+    assert sum(p.numel() for p in model.parameters()) == 167173
+
+
+def test_forward_results_structure_and_values():
+    model, ospec, params = _model()
+    g = torch.Generator().manual_seed(3)
+    batch = {"clinical": torch.randn(50, 7, generator=g), "rois": torch.randn(50, 444, generator=g)}
+    eps = torch.randn(50, ospec.eps_width, generator=g)
+    model.inject_noise(eps)
+    res = model({k: v.cuda() for k, v in batch.items()}, sample_latents=True)
+    with torch.no_grad():
+        want = mo.forward(params, ospec, batch, eps)
+    assert set(res) >= {"latents", "group_distr", "joint_divergence", "individual_divs", "dyn_prior", "rec"}
+    assert set(res["latents"]) == {"modalities", "mus", "logvars", "weights", "joint", "subsets"}
+    assert list(res["latents"]["subsets"]) == ["clinical", "rois", "clinical_rois"]
+    assert res["latents"]["mus"].shape == (3, 50, 20)
+    for k in ("clinical", "rois"):
+        assert isinstance(res["rec"][k], torch.distributions.Normal)
+        assert torch.allclose(res["rec"][k].loc.cpu(), want["rec"][k][0], rtol=0, atol=RTOL * float(want["rec"][k][0].abs().max()))
+        assert torch.allclose(res["rec"][k].scale.cpu()[0], want["rec"][k][1][0], rtol=1e-6)
+    assert torch.allclose(res["latents"]["mus"].cpu(), want["latents"]["mus"], atol=RTOL * float(want["latents"]["mus"].abs().max()))
+    assert abs(float(res["joint_divergence"]) - float(want["joint_divergence"])) <= RTOL * abs(float(want["joint_divergence"]))
+    # missing block: absent modality is neither encoded nor decoded
+    res1 = model({"rois": batch["rois"].cuda()})
+    assert list(res1["rec"]) == ["rois"] and res1["latents"]["modalities"]["clinical"] == [None, None]
+    with pytest.raises(Exception):
+        model(batch)          # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("method", ["joint_elbo", "poe", "moe"])
+def test_basic_routine_epoch_backward_and_torch_adam(method):
+    from mopoe_b200 import run_epochs
+    model, ospec, params = _model(method)
+    exp = SimpleNamespace(models=model, flags=model.flags)
+    g = torch.Generator().manual_seed(5)
+    batch = {"clinical": torch.randn(96, 7, generator=g), "rois": torch.randn(96, 444, generator=g)}
+    eps = torch.randn(3 if method == "poe" else 1, 96, ospec.eps_width, generator=g)
+    model.inject_noise(eps)
+    opt = torch.optim.Adam(model.parameters(), lr=0.002, betas=(0.9, 0.999))
+    out = run_epochs.basic_routine_epoch(exp, 0, ({k: v.clone() for k, v in batch.items()}, None, None))
+    assert set(out) == {"results", "log_probs", "total_loss", "klds"}
+    opt.zero_grad()
+    out["total_loss"].backward()
+    want, grads, used = mo.elbo_and_grads(params, ospec, batch, eps)
+    assert abs(float(out["total_loss"]) - float(want["total_loss"])) <= RTOL * abs(float(want["total_loss"]))
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        err = float((p.grad.cpu() - grads[k]).abs().max() / (grads[k].abs().max() + 1e-30))
+        assert err <= RTOL, (k, err)
+    for k, v in want["klds"].items():
+        assert abs(float(out["klds"][k]) - float(v)) <= RTOL * abs(float(v))
+    before = model.state_dict()["encoders.rois.class_mu.weight"].clone()
+    opt.step()                                  # stock torch optimiser works on the flat-buffer views
+    assert not torch.equal(before, model.state_dict()["encoders.rois.class_mu.weight"])
+    # missing block: gradients of the absent modality stay None (torch.optim.Adam then skips them)
+    opt.zero_grad(set_to_none=True)
+    out = run_epochs.basic_routine_epoch(exp, 0, ({"rois": batch["rois"].clone()}, None, None))
+    out["total_loss"].backward()
+    assert model.encoders["clinical"].class_mu.weight.grad is None
+    assert model.encoders["rois"].class_mu.weight.grad is not None
+
+
+def test_make_regression_mirror():
+    import pandas as pd
+    from mopoe_b200 import stat_utils
+    rng = np.random.default_rng(0)
+    G, J = 9, 40
+    x = rng.standard_normal((G, J)).astype(np.float32)
+    y = (0.3 * x + 0.1 * rng.standard_normal((G, J)) + rng.standard_normal((G, 1))).astype(np.float32)
+    df = pd.DataFrame({"participant_id": np.repeat(np.arange(G), J), "sampled_score": x.reshape(-1), "roi_avatar": y.reshape(-1)})
+    p, coef, betas = stat_utils.make_regression(df, "sampled_score", "roi_avatar", groups_name="participant_id", method="hierarchical")
+    pw, cw, bw = daa_oracle.hierarchical_regression(y[None, :, None, :, None], x[None, :, :, None])
+    assert abs(coef - cw[0, 0, 0]) <= 1e-9 and abs(np.log(p) - np.log(pw[0, 0, 0])) <= 1e-7
+    assert np.allclose(betas["beta"].to_numpy(), bw[0, 0, :, 0], rtol=1e-9)
+    p, coef, _ = stat_utils.make_regression(df, "sampled_score", "roi_avatar", method="fixed")
+    from scipy import stats as sps
+    lr = sps.linregress(x.reshape(-1).astype(np.float64), y.reshape(-1).astype(np.float64))
+    assert abs(coef - lr.slope) <= 1e-9 and abs(np.log(p) - np.log(lr.pvalue)) <= 1e-6
+    with pytest.raises(NotImplementedError):
+        stat_utils.make_regression(df, "sampled_score", "roi_avatar", groups_name="participant_id", method="mixed")
+
+
+def test_train_exp_then_daa_exp_end_to_end(tmp_path):
+    from mopoe_b200 import data, workflow, daa
+    ds, out = str(tmp_path / "data"), str(tmp_path / "out")
+    os.makedirs(out)
+    data.write_dataset(ds, data.make_cohort(n_both=640, n_clinical_only=128, n_rois_only=64, standardize=False))
+    run = workflow.train_exp("hbn", ds, out, [7, 444], num_epochs=6, batch_size=128, method="joint_elbo", data_seed=3)
+    rundir = os.path.join(out, run)
+    assert os.path.isfile(os.path.join(rundir, "flags.rar"))
+    assert os.path.isfile(os.path.join(rundir, "checkpoints", "0004", "model"))
+    assert os.path.isfile(os.path.join(rundir, "checkpoints", "0005", "model"))
+    assert os.path.isfile(os.path.join(rundir, "checkpoints", "enc_rois"))
+    sd = torch.load(os.path.join(rundir, "checkpoints", "0005", "model"))
+    assert list(sd.keys()) == list(mo.param_shapes(mo.ModelSpec()).keys())
+    tr = np.load(os.path.join(rundir, "logs", "scalars_train_model0.npy"))
+    assert np.isfinite(tr).all() and tr[-1, 0] < tr[0, 0]          # the loss goes down
+    resdir = workflow.daa_exp("hbn", ds, out, run, n_validation=3, n_samples=12, n_subjects=20, M=30, trust_level=0.7)
+    av = np.load(os.path.join(resdir, "rois_digital_avatars.npy"))
+    sc = np.load(os.path.join(resdir, "sampled_scores.npy"))
+    assert av.shape == (3, 20, 7, 12, 444) and av.dtype == np.float32 and sc.shape == (3, 20, 12, 7)
+    assert np.load(os.path.join(resdir, "rois_reconstructions.npy")).shape == (3, 20, 444)
+    p = np.load(os.path.join(resdir, "pvalues.npy")); c = np.load(os.path.join(resdir, "coefs.npy"))
+    assert p.shape == c.shape == (3, 7, 444) and p.dtype == np.float64
+    pw, cw, _ = daa_oracle.hierarchical_regression(av, sc)          # statistics recomputed from the files
+    assert np.allclose(c, cw, rtol=1e-9, atol=1e-12)
+    assert np.all(np.abs(np.log(p) - np.log(pw)) <= 1e-7 * np.maximum(1.0, np.abs(np.log(pw))))
+    allc = np.load(os.path.join(resdir, "all_coefs.npy"), allow_pickle=True)
+    assert allc.shape[:2] == (3, 7)
+    sig = open(os.path.join(resdir, "significant_rois.tsv")).read().splitlines()
+    assert sig[0].split("\t") == ["metric", "roi", "score"]
+    want = daa_oracle.significant(pw, 0.7)
+    assert len(sig) - 1 == int(want.sum())
+    meta = np.load(os.path.join(resdir, "metadatas.npy"), allow_pickle=True)
+    assert meta.shape[:2] == (3, 20)

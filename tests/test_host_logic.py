@@ -1,0 +1,129 @@
+"""CPU tests of the host side: C-ABI exports, model description, subset order, selection
+boundaries, parameter layout, epoch planner, sharding and the world_size-2 gather (gloo)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import mopoe_b200
+from mopoe_b200 import _lib, daa, data
+from oracle import mopoe_oracle as mo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "mopoe_b200.h")).read()
+    declared = set(re.findall(r"\b(mopoe_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert set(_lib.EXPORTED) == declared
+
+
+def test_no_device_is_a_loud_error():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mopoe_b200 import engine
+    spec = mopoe_b200.PathSpec([7, 444], [3, 20])
+    with pytest.raises(_lib.MopoeError):
+        engine.forward(spec, torch.zeros(spec.layout.total), {"clinical": torch.zeros(4, 7)})
+    assert _lib.lib().mopoe_philox_normal(1, 1, 0, 4, None, None) == -2      # MOPOE_ENODEV
+    assert b"no CUDA device" in _lib.lib().mopoe_last_error()
+
+
+@pytest.mark.parametrize("kw", [dict(num_hidden_layer_decoder=1), dict(num_hidden_layer_encoder=2),
+                                dict(learn_output_sample_scale=True), dict(latent_dim=64)])
+def test_unsupported_configurations_are_rejected(kw):
+    with pytest.raises(_lib.MopoeError):
+        mopoe_b200.PathSpec([7, 444], [3, 20], **kw)
+
+
+def test_unsupported_method_and_likelihood():
+    with pytest.raises(NotImplementedError):
+        mopoe_b200.PathSpec([7, 444], [3, 20], method="jsd")
+    with pytest.raises(NotImplementedError):
+        mopoe_b200.PathSpec([7, 444], [3, 20], likelihood="laplace")
+
+
+@pytest.mark.parametrize("names", [["clinical", "rois"], ["clinical", "rois", "modc", "modd"], ["zeta", "alpha", "mid"]])
+def test_subset_table_matches_oracle_order(names):
+    dims, style = [5 + i for i in range(len(names))], [2] * len(names)
+    spec = mopoe_b200.PathSpec(dims, style, mod_names=names)
+    ospec = mo.ModelSpec(dims=dims, style_dims=style, mod_names=names)
+    assert spec.subsets() == ospec.subsets()
+    assert len(spec.subsets()) == 2 ** len(names) - 1
+
+
+def test_selection_bounds_are_the_reference_expression():
+    for n, k in [(256, 3), (50, 3), (37, 2), (65536, 15), (7, 3), (1, 1)]:
+        assert mopoe_b200.selection_bounds(n, k) == mo.selection_bounds(n, k)
+    b = mopoe_b200.PathSpec([7, 444], [3, 20]).batch_desc(50, 3)
+    assert list(b.joint_bounds)[:4] == [0, 16, 32, 50] and b.n_mix == 3
+
+
+def test_param_layout_is_disjoint_and_named_like_the_reference():
+    spec = mopoe_b200.PathSpec([7, 444], [3, 20])
+    ospec = mo.ModelSpec()
+    sl = spec.param_slices()
+    assert {k: v[1] for k, v in sl.items()} == mo.param_shapes(ospec)
+    spans = sorted((off, off + int(np.prod(shape))) for off, shape in sl.values())
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 <= b0
+    assert spans[-1][1] <= spec.layout.total
+    assert sum(int(np.prod(s)) for _, s in sl.values()) == 167173      # factorised default
+
+
+def test_epoch_plan_is_homogeneous_and_complete():
+    c = data.make_cohort(n_both=300, n_clinical_only=70, n_rois_only=40)
+    has = np.stack([c["has_clinical"], c["has_rois"]])
+    plan = data.epoch_plan(has, 64, np.random.RandomState(0))
+    seen = np.concatenate([ix for _, ix in plan])
+    assert sorted(seen.tolist()) == list(range(410))
+    sizes = [len(ix) for _, ix in plan]
+    first_incomplete = next(i for i, s in enumerate(sizes) if s < 64)
+    assert all(s == 64 for s in sizes[:first_incomplete]) and all(s < 64 for s in sizes[first_incomplete:])
+    for mask, ix in plan:
+        assert np.all(has[0][ix] == bool(mask & 1)) and np.all(has[1][ix] == bool(mask & 2))
+
+
+def test_shard_validations_partition():
+    for n, w in [(20, 1), (20, 8), (5, 2), (3, 4)]:
+        spans = [daa.shard_validations(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+
+
+_GLOO = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+import mopoe_b200
+from mopoe_b200 import daa
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n_val = 5
+b, e = daa.shard_validations(n_val, rank, world)
+local = torch.arange(b, e, dtype=torch.float64).view(-1, 1, 1).expand(-1, 7, 11).contiguous() + 0.5
+full = daa.gather_tables(local, n_val)
+want = torch.arange(n_val, dtype=torch.float64).view(-1, 1, 1).expand(-1, 7, 11) + 0.5
+assert full.shape == (n_val, 7, 11) and torch.equal(full, want), (rank, full[:, 0, 0])
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_gather_tables_world_size_2_gloo(tmp_path):
+    script = tmp_path / "g.py"
+    script.write_text(_GLOO % ROOT)
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count("ok") == 2
