@@ -93,6 +93,9 @@ def lib():
                                   vp, vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     L.mopoe_daa_regression.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.mopoe_philox_normal.argtypes = [u64, u64, i64, i64, vp, vp]
+    L.mopoe_umma_selftest.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
+    L.mopoe_umma_selftest.restype = C.c_int
+    L.mopoe_daa_last_impl.restype = C.c_int
     L.mopoe_profile_enable.argtypes = [C.c_int]
     L.mopoe_profile_enable.restype = C.c_int
     L.mopoe_daa_last_kernel_ms.argtypes = [C.POINTER(C.c_float)]
@@ -112,4 +115,4 @@ def check(rc):
 EXPORTED = ["mopoe_last_error", "mopoe_version", "mopoe_device_count", "mopoe_param_layout_of",
             "mopoe_workspace_bytes", "mopoe_forward", "mopoe_train_steps", "mopoe_daa_workspace_bytes",
             "mopoe_daa_sweep", "mopoe_daa_regression", "mopoe_philox_normal", "mopoe_profile_enable",
-            "mopoe_daa_last_kernel_ms"]
+            "mopoe_daa_last_kernel_ms", "mopoe_umma_selftest", "mopoe_daa_last_impl"]

@@ -13,8 +13,11 @@
 //      epilogue (stat_utils.py:66-68) -- the avatar tensor never has to be re-read
 //   4. daa_stats_kernel  one thread per (validation, score, roi): second-level t-test
 //      (stat_utils.py:73-75) or the pooled "fixed" regression (stat_utils.py:62-63)
+#include <stdlib.h>
+
 #include "mopoe_common.cuh"
 #include "mopoe_latent.cuh"
+#include "mopoe_umma.cuh"
 
 namespace mopoe {
 
@@ -31,6 +34,8 @@ struct DaaWs {
   double* syy;                 // (n_val, C, N, R)  fixed: sum_j (y - ybar)^2
   double* xstat;               // (n_val, C, N, 2)  xbar, Sxx
   int* counter;                // work-unit counter of the persistent kernel
+  int* err;                    // device error flag (tcgen05 barrier time-out)
+  unsigned char* bsplit;       // fp16 hi/lo operand planes of the decoder / class-head weights (UMMA layout)
   void* fwd_ws;                // workspace of the encoder forward
   int64_t fwd_ws_bytes;
 };
@@ -52,6 +57,8 @@ static int64_t daa_carve(const mopoe_model_desc* d, const mopoe_daa_desc* q, cha
   }
   t.xstat = (double*)take(rows * C * 2 * 8);
   t.counter = (int*)take(256);
+  t.err = (int*)take(256);
+  t.bsplit = (unsigned char*)take(2 * (448 * 64 * 2) + 2 * (64 * 256 * 2));
   t.fwd_ws_bytes = mopoe_workspace_bytes(d, rows);
   t.fwd_ws = take(t.fwd_ws_bytes);
   if (w) *w = t;
@@ -173,6 +180,22 @@ __global__ void __launch_bounds__(MOPOE_THREADS) daa_base_kernel(ModelView mv, D
     const float s = s_loc[c] + expf(0.5f * ms.lv[c]) * cx.nz_score.at(idx);
     ws.scores[(row * cx.C + c) * cx.J + j] = s;
     if (cx.sampled_scores) cx.sampled_scores[(row * cx.J + j) * cx.C + c] = s;
+  }
+  __syncthreads();
+  // xbar, Sxx of every (subject, score) series in fp64 (centred OLS: slope = Sxy / Sxx)
+  for (int c = warp; c < cx.C; c += 8) {
+    const float* sx = ws.scores + (row * cx.C + c) * cx.J;
+    double a = 0.0;
+    for (int j = lane; j < cx.J; j += 32) a += (double)sx[j];
+    a = warp_sum(a);
+    const double xb = a / (double)cx.J;
+    double q = 0.0;
+    for (int j = lane; j < cx.J; j += 32) { const double d = (double)sx[j] - xb; q += d * d; }
+    q = warp_sum(q);
+    if (lane == 0) {
+      const int64_t o = (((int64_t)v * cx.C + c) * cx.N + g) * 2;
+      ws.xstat[o] = xb; ws.xstat[o + 1] = q;
+    }
   }
 }
 
@@ -472,6 +495,19 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_kernel(ModelView 
   }
 }
 
+}  // namespace mopoe
+#include "mopoe_daa_umma.cuh"
+namespace mopoe {
+
+// poison the result tables when a tcgen05 barrier wait timed out (never silently wrong)
+__global__ void daa_poison_kernel(const int* err, double* coefs, double* pvalues, int64_t n) {
+  if (*err == 0) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    coefs[i] = __longlong_as_double(0x7ff8000000000000LL);
+    pvalues[i] = __longlong_as_double(0x7ff8000000000000LL);
+  }
+}
+
 // -------------------------------------------------------------------------------------------
 // statistics on a materialised avatar tensor (mopoe_daa_regression): CTA per (v, g, c)
 // -------------------------------------------------------------------------------------------
@@ -606,6 +642,7 @@ __global__ void daa_stats_kernel(int n_val, int N, int C, int J, int R, int reg_
 using namespace mopoe;
 
 static int g_profile = 0;
+static int g_last_impl = 0;
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 
 extern "C" {
@@ -702,16 +739,40 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   const AvSmem pl = av_plan(mv, daa->src_mod, daa->dst_mod, cx.J);
   const int av_smem = pl.total * 4;
   if (av_smem > 227 * 1024) { set_error("DAA avatar kernel needs %d bytes of shared memory (> 227 KB): latent/style dims too large", av_smem); return MOPOE_EINVAL; }
-  void* fn = daa->reg_method == 1 ? (void*)daa_avatar_kernel<true> : (void*)daa_avatar_kernel<false>;
-  MOPOE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, av_smem));
   const int n_units = daa->n_val * N * cx.C;
   const int grid = n_units < num_sms() ? n_units : num_sms();
-  for (int col0 = 0; col0 < cx.R; col0 += CB) {
-    MOPOE_CUDA(cudaMemsetAsync(ws.counter, 0, sizeof(int), stream));
-    if (g_profile && col0 == 0) MOPOE_CUDA(cudaEventRecord(g_ev0, stream));
-    if (daa->reg_method == 1) daa_avatar_kernel<true><<<grid, MOPOE_THREADS, av_smem, stream>>>(mv, cx, ws, col0);
-    else daa_avatar_kernel<false><<<grid, MOPOE_THREADS, av_smem, stream>>>(mv, cx, ws, col0);
-    MOPOE_CUDA(cudaGetLastError());
+  // implementation choice: tensor cores (tcgen05, 3xFP16 split) when the shapes fit its tiling,
+  // else the CUDA-core kernel; MOPOE_DAA_IMPL=ffma|umma forces one (tests cross-check both)
+  const UmmaDims ud0 = umma_dims(mv, daa->src_mod, daa->dst_mod, CB);
+  const int um_smem = umma_plan(mv, daa->src_mod, ud0).total;
+  bool use_umma = cx.J >= UM_ROWS && cx.C <= UM_MAXC && ud0.NH <= 48 && ud0.KZ <= 64 && um_smem <= 227 * 1024;
+  const char* force = getenv("MOPOE_DAA_IMPL");
+  if (force && !strcmp(force, "ffma")) use_umma = false;
+  if (force && !strcmp(force, "umma") && !use_umma) { set_error("MOPOE_DAA_IMPL=umma but the shapes do not fit the tcgen05 tiling"); return MOPOE_EINVAL; }
+  g_last_impl = use_umma ? 1 : 0;
+  MOPOE_CUDA(cudaMemsetAsync(ws.err, 0, sizeof(int), stream));
+  if (use_umma) {
+    void* ufn = daa->reg_method == 1 ? (void*)daa_avatar_umma_kernel<true> : (void*)daa_avatar_umma_kernel<false>;
+    MOPOE_CUDA(cudaFuncSetAttribute(ufn, cudaFuncAttributeMaxDynamicSharedMemorySize, um_smem));
+    for (int col0 = 0; col0 < cx.R; col0 += CB) {
+      const UmmaDims ud = umma_dims(mv, daa->src_mod, daa->dst_mod, cx.R - col0 < CB ? cx.R - col0 : CB);
+      daa_umma_prep_kernel<<<64, 256, 0, stream>>>(mv, daa->src_mod, daa->dst_mod, col0, ud, ws.bsplit);
+      MOPOE_CUDA(cudaGetLastError());
+      if (g_profile && col0 == 0) MOPOE_CUDA(cudaEventRecord(g_ev0, stream));
+      if (daa->reg_method == 1) daa_avatar_umma_kernel<true><<<grid, MOPOE_THREADS, um_smem, stream>>>(mv, cx, ws, col0);
+      else daa_avatar_umma_kernel<false><<<grid, MOPOE_THREADS, um_smem, stream>>>(mv, cx, ws, col0);
+      MOPOE_CUDA(cudaGetLastError());
+    }
+  } else {
+    void* fn = daa->reg_method == 1 ? (void*)daa_avatar_kernel<true> : (void*)daa_avatar_kernel<false>;
+    MOPOE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, av_smem));
+    for (int col0 = 0; col0 < cx.R; col0 += CB) {
+      MOPOE_CUDA(cudaMemsetAsync(ws.counter, 0, sizeof(int), stream));
+      if (g_profile && col0 == 0) MOPOE_CUDA(cudaEventRecord(g_ev0, stream));
+      if (daa->reg_method == 1) daa_avatar_kernel<true><<<grid, MOPOE_THREADS, av_smem, stream>>>(mv, cx, ws, col0);
+      else daa_avatar_kernel<false><<<grid, MOPOE_THREADS, av_smem, stream>>>(mv, cx, ws, col0);
+      MOPOE_CUDA(cudaGetLastError());
+    }
   }
   if (g_profile) MOPOE_CUDA(cudaEventRecord(g_ev1, stream));
   // 4. second level
@@ -719,8 +780,14 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   daa_stats_kernel<<<(unsigned)((nstat + 127) / 128), 128, 0, stream>>>(daa->n_val, N, cx.C, cx.J, cx.R, daa->reg_method, ws.betas,
                                                                        ws.ybar, ws.syy, ws.xstat, reconstructions, coefs, pvalues);
   MOPOE_CUDA(cudaGetLastError());
+  if (use_umma) {
+    daa_poison_kernel<<<32, 256, 0, stream>>>(ws.err, coefs, pvalues, nstat);
+    MOPOE_CUDA(cudaGetLastError());
+  }
   return MOPOE_OK;
 }
+
+int mopoe_daa_last_impl(void) { return g_last_impl; }
 
 int mopoe_daa_regression(int32_t n_val, int32_t n_subjects, int32_t n_scores, int32_t n_samples, int32_t n_rois,
                          int32_t reg_method, const float* avatars, const float* sampled_scores,

@@ -1,0 +1,88 @@
+// Self-test of the tcgen05 building blocks (mopoe_umma.cuh): one CTA computes
+// D[128][N] = A[128][K] * B[N][K]^T with the 3xFP16 split on the tensor cores.
+#include "mopoe_common.cuh"
+#include "mopoe_umma.cuh"
+
+namespace mopoe {
+
+__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* A, const float* B, float* D, int N, int K,
+                                                               int variant, int* err) {
+  extern __shared__ __align__(1024) unsigned char smraw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  using namespace umma;
+  const int t = threadIdx.x, warp = t >> 5;
+  unsigned char* a_hi = smraw;
+  unsigned char* a_lo = a_hi + 128 * K * 2;
+  unsigned char* b_hi = a_lo + 128 * K * 2;
+  unsigned char* b_lo = b_hi + N * K * 2;
+  const int k8n = K / 8;
+  for (int i = t; i < 128 * k8n; i += 128) {
+    const int row = i % 128, k8 = i / 128;
+    float x[8];
+    for (int q = 0; q < 8; ++q) x[q] = A[row * K + k8 * 8 + q];
+    store_split8(a_hi, a_lo, core_off(row, k8, 128), x);
+  }
+  for (int i = t; i < N * k8n; i += 128) {
+    const int row = i % N, k8 = i / N;
+    float x[8];
+    for (int q = 0; q < 8; ++q) x[q] = B[row * K + k8 * 8 + q];
+    store_split8(b_hi, b_lo, core_off(row, k8, N), x);
+  }
+  uint32_t ncols = 32;
+  while ((int)ncols < N) ncols <<= 1;
+  if (t == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_slot, ncols);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (t == 0) {
+    const uint32_t lbo_a = (128 / 8) * 128, lbo_b = (N / 8) * 128, sbo = 128;
+    const uint32_t idesc = idesc_f16(128, N);
+    uint32_t acc = 0;
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint32_t offa = ks * 2 * lbo_a, offb = ks * 2 * lbo_b;
+      uint64_t dah, dal, dbh, dbl;
+      if (variant == 0) {
+        dah = smem_desc(smem_u32(a_hi) + offa, lbo_a, sbo); dal = smem_desc(smem_u32(a_lo) + offa, lbo_a, sbo);
+        dbh = smem_desc(smem_u32(b_hi) + offb, lbo_b, sbo); dbl = smem_desc(smem_u32(b_lo) + offb, lbo_b, sbo);
+      } else {
+        dah = smem_desc(smem_u32(a_hi) + offa, sbo, lbo_a); dal = smem_desc(smem_u32(a_lo) + offa, sbo, lbo_a);
+        dbh = smem_desc(smem_u32(b_hi) + offb, sbo, lbo_b); dbl = smem_desc(smem_u32(b_lo) + offb, sbo, lbo_b);
+      }
+      mma_f16(tmem, dah, dbh, idesc, acc); acc = 1;
+      mma_f16(tmem, dah, dbl, idesc, 1);
+      mma_f16(tmem, dal, dbh, idesc, 1);
+    }
+    mma_commit(&bar);
+  }
+  if (!mbar_wait(&bar, 0)) { if (t == 0) *err = 1; }
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    for (int q = 0; q < 16; ++q) D[(warp * 32 + (t & 31)) * N + c0 + q] = v[q];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, ncols);
+}
+
+}  // namespace mopoe
+
+using namespace mopoe;
+
+extern "C" int mopoe_umma_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t variant,
+                                   int32_t* err_flag, void* stream) {
+  if (mopoe_device_count() == 0) { set_error("no CUDA device"); return MOPOE_ENODEV; }
+  if (N % 16 || N < 16 || N > 256 || K % 16 || K < 16) { set_error("selftest needs N%%16==0 (16..256), K%%16==0"); return MOPOE_EINVAL; }
+  const int smem = (128 + N) * K * 2 * 2;
+  if (smem > 200 * 1024) { set_error("selftest operands too large"); return MOPOE_EINVAL; }
+  MOPOE_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, K, variant, err_flag);
+  MOPOE_CUDA(cudaGetLastError());
+  return MOPOE_OK;
+}

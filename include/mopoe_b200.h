@@ -229,12 +229,20 @@ int mopoe_daa_regression(int32_t n_val, int32_t n_subjects, int32_t n_scores, in
  * (daa_avatar_kernel) with CUDA events on the caller's stream; mopoe_daa_last_kernel_ms waits for
  * the last bracket and returns its duration. */
 int mopoe_profile_enable(int on);
+/* which avatar kernel the last mopoe_daa_sweep used: 1 = tcgen05 tensor cores, 0 = CUDA cores
+ * (shapes outside the tcgen05 tiling, or MOPOE_DAA_IMPL=ffma in the environment) */
+int mopoe_daa_last_impl(void);
 int mopoe_daa_last_kernel_ms(float* ms_out);
 
 /* Fill `out[0..n)` with philox_normal(seed, stream_id, start + i): the production noise generator,
  * exposed so hosts/tests can materialise exactly what the kernels draw. */
 int mopoe_philox_normal(uint64_t seed, uint64_t stream_id, int64_t start, int64_t n, float* out,
                         void* stream);
+
+/* Self-test of the tcgen05 building blocks: one CTA computes D[128][N] = A[128][K] * B[N][K]^T on
+ * the tensor cores with the 3xFP16 split the DAA kernel uses (N%16==0, K%16==0). */
+int mopoe_umma_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t variant,
+                        int32_t* err_flag, void* stream);
 
 enum {
   MOPOE_STREAM_DAA_BASE = 1, MOPOE_STREAM_DAA_SCORE = 2, MOPOE_STREAM_DAA_AVATAR = 3,

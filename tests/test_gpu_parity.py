@@ -245,3 +245,60 @@ def test_daa_production_noise_is_shard_invariant_and_matches_oracle():
     av, sc, rc = daa_oracle.daa_generate(params, ospec, src, dst, eb, es, ea)
     _close(full.avatars, av, "avatars (philox)")
     _close(full.sampled_scores, sc, "scores (philox)")
+
+
+# ---- tensor-core (tcgen05) avatar kernel ------------------------------------------------------
+def _daa_case(method="joint_elbo", factorized=True, dims=(7, 444), n_rows=12, n_val=2, n_samples=150, n_base=6,
+              sample_latents=True, seed=80):
+    base = dict(cases.HBN, dims=list(dims))
+    return dict(cases._case(base, method, factorized, (0, 1), n_rows, seed, seed + 100), n_val=n_val, n_base=n_base,
+                n_samples=n_samples, sample_latents=sample_latents)
+
+
+def _sweep(spec, flat, src, dst, case, impl, monkeypatch, **kw):
+    from mopoe_b200 import _lib, daa
+    monkeypatch.setenv("MOPOE_DAA_IMPL", impl)
+    r = daa.daa_sweep(spec, flat, src.cuda(), dst.cuda(), case["n_samples"], case["n_base"],
+                      sample_latents=case["sample_latents"], **kw)
+    torch.cuda.synchronize()
+    assert _lib.lib().mopoe_daa_last_impl() == (1 if impl == "umma" else 0)
+    return r
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(method="moe", factorized=False), dict(method="poe", n_samples=131),
+                                dict(sample_latents=False, n_samples=128), dict(dims=(7, 445), n_rows=9),
+                                dict(dims=(5, 900), n_rows=7, n_val=1, n_samples=140)])
+def test_daa_tensor_core_kernel_vs_oracle_and_cuda_core_kernel(kw, monkeypatch):
+    case = _daa_case(**kw)
+    ospec, spec, params, flat = _setup(case)
+    src, dst, eb, es, ea = cases.daa_inputs_of(case, ospec)
+    inj = dict(eps_base=eb.cuda(), eps_score=es.cuda(), eps_av=ea.cuda())
+    um = _sweep(spec, flat, src, dst, case, "umma", monkeypatch, **inj)
+    ff = _sweep(spec, flat, src, dst, case, "ffma", monkeypatch, **inj)
+    av, sc, rc = daa_oracle.daa_generate(params, ospec, src, dst, eb, es, ea, sample_latents=case["sample_latents"])
+    _close(um.avatars, av, "tensor-core avatars vs oracle")
+    _close(ff.avatars, av, "cuda-core avatars vs oracle")
+    _close(um.avatars, ff.avatars, "tensor-core vs cuda-core avatars", rtol=2e-5)
+    assert torch.equal(um.sampled_scores, ff.sampled_scores)
+    # statistics: closed-form oracle on the kernel's own avatars (fp64), and the two kernels agree
+    p, coef, betas = daa_oracle.hierarchical_regression(um.avatars.cpu().numpy(), um.sampled_scores.cpu().numpy())
+    _close(um.betas, betas, "betas", rtol=1e-9)
+    _close(um.coefs, coef, "coefs", rtol=1e-9)
+    assert np.all(np.abs(np.log(um.pvalues.cpu().numpy()) - np.log(p)) <= 1e-8 * np.maximum(1.0, np.abs(np.log(p))))
+    _close(um.coefs, ff.coefs, "coefs tensor-core vs cuda-core", rtol=1e-3)
+
+
+def test_daa_tensor_core_fixed_regression_and_philox(monkeypatch):
+    case = _daa_case(n_rows=10, n_val=2)
+    ospec, spec, params, flat = _setup(case)
+    src, dst, _, _, _ = cases.daa_inputs_of(case, ospec)
+    um = _sweep(spec, flat, src, dst, case, "umma", monkeypatch, reg_method="fixed", seed=5)
+    ff = _sweep(spec, flat, src, dst, case, "ffma", monkeypatch, reg_method="fixed", seed=5)
+    _close(um.avatars, ff.avatars, "philox avatars tensor-core vs cuda-core", rtol=2e-5)
+    av, sc, rc = um.avatars.cpu().numpy(), um.sampled_scores.cpu().numpy(), um.reconstructions.cpu().numpy()
+    p, coef = daa_oracle.fixed_regression(av, sc, rc)
+    _close(um.coefs, coef, "fixed coefs", rtol=1e-8)
+    assert np.all(np.abs(np.log(um.pvalues.cpu().numpy()) - np.log(p)) <= 1e-7 * np.maximum(1.0, np.abs(np.log(p))))
+    # no materialisation: same tables
+    nm = _sweep(spec, flat, src, dst, case, "umma", monkeypatch, reg_method="fixed", seed=5, materialize=False)
+    assert nm.avatars is None and torch.equal(nm.coefs, um.coefs) and torch.equal(nm.pvalues, um.pvalues)
