@@ -22,6 +22,13 @@ constexpr int UM_ROWS = 128;
 constexpr int UM_HCHUNK = 64;      // hidden columns produced per T1 step
 constexpr int UM_STAGE_LD = 36;    // floats per staged row (16-byte aligned, conflict-free for .128 access)
 constexpr int UM_MAXC = 16;        // max src width handled in registers
+constexpr int UM_HEAD_LD = 49;     // staged heads row stride (odd: conflict-free thread-per-row access)
+
+__device__ __noinline__ float4 philox_normal4_call(uint64_t seed, uint64_t stream, uint64_t blk) {
+  float v[4];
+  philox_normal4(seed, stream, blk, v);
+  return make_float4(v[0], v[1], v[2], v[3]);
+}
 
 struct UmmaDims {
   int KC, KS, KZ;     // content / style / total K of the decoder GEMM (multiples of 8 / 8 / 16)
@@ -30,7 +37,7 @@ struct UmmaDims {
 };
 
 struct UmmaSmem {
-  int bd_hi, bd_lo, bh_hi, bh_lo, az_hi, az_lo, ah, w1, b1, biasd, biash, score, xc, rowu, need, cache, bars, total;
+  int bd_hi, bd_lo, bh_hi, bh_lo, az_hi, az_lo, ah, a0, biasd, biash, score, xc, need, cache, bars, total;
 };
 
 __host__ __device__ inline UmmaDims umma_dims(const ModelView& mv, int src, int dst, int ncol) {
@@ -52,15 +59,13 @@ __host__ __device__ inline UmmaSmem umma_plan(const ModelView& mv, int src, cons
   p.az_hi = take(UM_ROWS * d.KZ * 2); p.az_lo = take(UM_ROWS * d.KZ * 2);   // also: fp64 reduction scratch
   const int ah = 2 * UM_ROWS * UM_HCHUNK * 2, stage = 8 * 32 * UM_STAGE_LD * 4;
   p.ah = take(ah > stage ? ah : stage);                                        // A_h chunk | epilogue staging
-  p.w1 = take(MOPOE_HIDDEN * mv.mod[src].D * 4);
-  p.b1 = take(MOPOE_HIDDEN * 4);
+  p.a0 = take(2 * 2 * MOPOE_HIDDEN * 4);   // per slot: hidden pre-activation without the perturbed column | that W1 column
   p.biasd = take(CB * 4);
   p.biash = take(d.NH * 4);
   p.score = take(UM_ROWS * 4);
   p.xc = take(UM_ROWS * 8);
-  p.rowu = take(UM_ROWS * 4);
   p.need = take(UM_ROWS * 4);
-  p.cache = take(2 * (MOPOE_MAX_MODS * 2 * 32 + 64) * 4);
+  p.cache = take(2 * 128 * 4);
   p.bars = take(64);
   p.total = off;
   return p;
@@ -122,19 +127,21 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
   unsigned char* s_ah_hi = smem + pl.ah;
   unsigned char* s_ah_lo = s_ah_hi + UM_ROWS * UM_HCHUNK * 2;
   float* s_stage = reinterpret_cast<float*>(smem + pl.ah) + warp * 32 * UM_STAGE_LD;
-  double* s_red = reinterpret_cast<double*>(smem + pl.az_hi);   // [3][4][CB] needs <= 2 * 128 * KZ * 2 bytes? checked on host
-  float* s_w1 = reinterpret_cast<float*>(smem + pl.w1);
-  float* s_b1 = reinterpret_cast<float*>(smem + pl.b1);
+  float* s_heads = reinterpret_cast<float*>(smem + pl.ah);      // [128][UM_HEAD_LD], free between T1 and T4
+  // fp64 reduction scratch [3][4][CB]: spans az_hi, az_lo and (FIXED) the head of the ah region, all idle then
+  double* s_red = reinterpret_cast<double*>(smem + pl.az_hi);
+  float* s_a0 = reinterpret_cast<float*>(smem + pl.a0);         // [2 slots][256] pre-activation w/o perturbed column
+  float* s_w1c = s_a0 + 2 * MOPOE_HIDDEN;                       // [2 slots][256] perturbed column of W1
   float* s_biasd = reinterpret_cast<float*>(smem + pl.biasd);
   float* s_biash = reinterpret_cast<float*>(smem + pl.biash);
   float* s_score = reinterpret_cast<float*>(smem + pl.score);
   double* s_xc = reinterpret_cast<double*>(smem + pl.xc);
-  int* s_rowu = reinterpret_cast<int*>(smem + pl.rowu);
   int* s_need = reinterpret_cast<int*>(smem + pl.need);
-  float* s_cache = reinterpret_cast<float*>(smem + pl.cache);   // [2 slots][M][2][32] + [2][32] dst style (mu, sd)
+  // per slot: [0..31] A, [32..63] B (posterior partials, see T0), [64..95] dst style mu, [96..127] dst style sd
+  float* s_cache = reinterpret_cast<float*>(smem + pl.cache);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + pl.bars);   // [0] heads, [1] decoder
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + pl.bars + 32);
-  constexpr int CSLOT = MOPOE_MAX_MODS * 2 * 32 + 64;
+  constexpr int CSLOT = 128;
 
   // ---- launch-lifetime state: operands, biases, barriers, TMEM ----
   {
@@ -148,8 +155,6 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
       reinterpret_cast<uint4*>(s_bh_hi)[i] = g[2 * nbd + i];
       reinterpret_cast<uint4*>(s_bh_lo)[i] = g[2 * nbd + nbh + i];
     }
-    for (int i = t; i < MOPOE_HIDDEN * C; i += MOPOE_THREADS) s_w1[i] = ms.w1[i];
-    s_b1[t] = ms.b1[t];
     for (int i = t; i < CB; i += MOPOE_THREADS) s_biasd[i] = i < ncol ? mdst.bd[col0 + i] : 0.f;
     for (int i = t; i < NH; i += MOPOE_THREADS) s_biash[i] = i < 2 * L ? ms.bh[i] : 0.f;
   }
@@ -166,6 +171,7 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
   const uint32_t LBO_A = (UM_ROWS / 8) * 128, LBO_BH = (NH / 8) * 128, LBO_BD = (CB / 8) * 128;
   uint32_t ph_h = 0, ph_d = 0;
   bool timed_out = false;
+  const bool fast_post = cx.q.sample_latents != 0;    // posterior of the row's mixture owner from cached partial sums
 
   // ---- this CTA's contiguous range of (validation, subject, score) series ----
   const int n_units = cx.q.n_val * N * C;
@@ -180,7 +186,7 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
     accA[i] = accB[i] = 0.0;
     if (FIXED) { syA[i] = syB[i] = syyA[i] = syyB[i] = 0.0; }
   }
-  // mixture owner per subject row index g is launch-invariant: evaluate on the fly
+  // mixture owner of subject row g (launch-invariant table lookups)
   auto owner_subset = [&](int g, bool& need_src) -> int {
     int owner = 0, kidx = 0, s_own = 0;
     for (int k = 0; k < cx.b.n_mix; ++k)
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
   };
 
   for (int64_t tile_row = row_begin; tile_row < row_end; tile_row += UM_ROWS) {
-    // ================= T0: row metadata =================
+    // ================= T0: row metadata, per-series caches =================
     const int r = t & 127;
     const int64_t rho = tile_row + r;
     const bool valid = rho < row_end;
@@ -210,53 +216,79 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
     if (t < UM_ROWS) {
       s_score[r] = score;
       s_xc[r] = (double)score - ws.xstat[(((int64_t)v * C + c) * N + g) * 2];
-      s_rowu[r] = u;
       s_need[r] = need;
     }
-    const int tile_need = __syncthreads_or(need ? 1 : 0);
-    // unit boundary inside the tile (at most one: series are longer than a tile only if J >= 128;
-    // shorter series are handled by the FFMA kernel, see the host-side dispatch)
+    // at most one series boundary per tile (J >= 128, enforced by the host dispatch)
     const int64_t bnd = (int64_t)(cur_unit + 1) * J - tile_row;
     const int rb = bnd < UM_ROWS ? (int)bnd : UM_ROWS;
-    // cached experts / dst style of the (<= 2) subjects of the tile: slot 0 = current unit, 1 = next
-    for (int i = t; i < 2 * (M * L + Sd); i += MOPOE_THREADS) {
-      const int slot = i / (M * L + Sd), k = i % (M * L + Sd);
+    // slot 0 = current series, slot 1 = next series.  Thread k owns hidden unit k.
+#pragma unroll 1
+    for (int slot = 0; slot < 2; ++slot) {
       const int uu = min(cur_unit + slot, n_units - 1);
-      const int64_t row = (int64_t)(uu / (C * N)) * N + (uu / C) % N;
+      const int uc = uu % C;
+      const float* xs = cx.x[src] + ((int64_t)(uu / (C * N)) * N + (uu / C) % N) * C;
+      const float* w = ms.w1 + (int64_t)t * C;
+      float a = ms.b1[t];
+      for (int i = 0; i < C; ++i) a = (i == uc) ? a : fmaf(w[i], xs[i], a);
+      s_a0[slot * MOPOE_HIDDEN + t] = a;
+      s_w1c[slot * MOPOE_HIDDEN + t] = w[uc];
+    }
+    // posterior partial sums of the mixture owner and dst style of both series
+    for (int i = t; i < 2 * (L + Sd); i += MOPOE_THREADS) {
+      const int slot = i / (L + Sd), k = i % (L + Sd);
+      const int uu = min(cur_unit + slot, n_units - 1);
+      const int ug = (uu / C) % N;
+      const int64_t row = (int64_t)(uu / (C * N)) * N + ug;
       float* cs = s_cache + slot * CSLOT;
-      if (k < M * L) {
-        const int m = k / L, l = k % L;
-        cs[(m * 2 + 0) * 32 + l] = ws.enc[m][row * mv.mod[m].HC + l];
-        cs[(m * 2 + 1) * 32 + l] = ws.enc[m][row * mv.mod[m].HC + L + l];
+      if (k < L) {
+        bool nd;
+        const int so = owner_subset(ug, nd);
+        float A = 0.f, B = 0.f;
+        if (mv.method == MOPOE_METHOD_MOE) {
+          // singleton owner: the member's own posterior (copy); multi-member subsets never own rows
+          const int m = mv.sub.members[so][0];
+          A = ws.enc[m][row * mv.mod[m].HC + k];
+          B = expf(0.5f * ws.enc[m][row * mv.mod[m].HC + L + k]);
+        } else {
+          // sum of precisions / precision-weighted means over every expert of the owner but src
+          const int nm = mv.sub.n_members[so];
+          for (int q = 0; q < nm; ++q) {
+            const int m = mv.sub.members[so][q];
+            if (m == src) continue;
+            const float T = 1.f / (expf(ws.enc[m][row * mv.mod[m].HC + L + k]) + MOPOE_POE_EPS);
+            A += T; B += ws.enc[m][row * mv.mod[m].HC + k] * T;
+          }
+          if (mv.method == MOPOE_METHOD_POE || nm == M) A += 1.f / (1.f + MOPOE_POE_EPS);
+          if (!((mv.sub.mask[so] >> src) & 1)) {   // owner without src: finished posterior (mu, sd)
+            const float mu = B / A, lv = logf(1.f / A);
+            A = mu; B = expf(0.5f * lv);
+          }
+        }
+        cs[k] = A; cs[32 + k] = B;
       } else {
-        const int s = k - M * L;
-        cs[MOPOE_MAX_MODS * 64 + s] = ws.enc[dst][row * mdst.HC + 2 * L + s];
-        cs[MOPOE_MAX_MODS * 64 + 32 + s] = expf(0.5f * ws.enc[dst][row * mdst.HC + 2 * L + Sd + s]);
+        const int s = k - L;
+        cs[64 + s] = ws.enc[dst][row * mdst.HC + 2 * L + s];
+        cs[96 + s] = expf(0.5f * ws.enc[dst][row * mdst.HC + 2 * L + Sd + s]);
       }
     }
+    const int tile_need = __syncthreads_or(need ? 1 : 0);
+    const int slot = (r < rb) ? 0 : 1;
     // ================= T1: class heads of the perturbed src rows =================
     if (tile_need) {
-      float xr[UM_MAXC];
-      {
-        const float* xs = cx.x[src] + ((int64_t)v * N + g) * C;
-#pragma unroll
-        for (int i = 0; i < UM_MAXC; ++i) xr[i] = (i < C && valid) ? (i == c ? score : xs[i]) : 0.f;
-      }
       const int half = t >> 7;
-      for (int kc = 0; kc < MOPOE_HIDDEN / UM_HCHUNK; ++kc) {
+      const float4* a0p = reinterpret_cast<const float4*>(s_a0 + slot * MOPOE_HIDDEN);
+      const float4* wcp = reinterpret_cast<const float4*>(s_w1c + slot * MOPOE_HIDDEN);
 #pragma unroll 1
+      for (int kc = 0; kc < MOPOE_HIDDEN / UM_HCHUNK; ++kc) {
+#pragma unroll
         for (int i8 = 0; i8 < 4; ++i8) {
+          const int k4 = (kc * UM_HCHUNK + half * 32 + i8 * 8) >> 2;
+          const float4 a0 = a0p[k4], a1 = a0p[k4 + 1], w0 = wcp[k4], w1 = wcp[k4 + 1];
           float hv[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int k = kc * UM_HCHUNK + half * 32 + i8 * 8 + q;
-            float a = s_b1[k];
-            const float* w = s_w1 + k * C;
-#pragma unroll
-            for (int i = 0; i < UM_MAXC; ++i)
-              if (i < C) a = fmaf(w[i], xr[i], a);
-            hv[q] = fmaxf(a, 0.f);
-          }
+          hv[0] = fmaxf(fmaf(w0.x, score, a0.x), 0.f); hv[1] = fmaxf(fmaf(w0.y, score, a0.y), 0.f);
+          hv[2] = fmaxf(fmaf(w0.z, score, a0.z), 0.f); hv[3] = fmaxf(fmaf(w0.w, score, a0.w), 0.f);
+          hv[4] = fmaxf(fmaf(w1.x, score, a1.x), 0.f); hv[5] = fmaxf(fmaf(w1.y, score, a1.y), 0.f);
+          hv[6] = fmaxf(fmaf(w1.z, score, a1.z), 0.f); hv[7] = fmaxf(fmaf(w1.w, score, a1.w), 0.f);
           store_split8(s_ah_hi, s_ah_lo, core_off(r, half * 4 + i8, UM_ROWS), hv);
         }
         fence_proxy_async();
@@ -277,90 +309,83 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
         if (!mbar_wait(&s_bar[0], ph_h)) timed_out = true;
         ph_h ^= 1;
       }
-    } else {
-      __syncthreads();   // cache / metadata visible
+      tc_fence_after();
+      if (t < UM_ROWS) {   // heads (+bias) of this thread's row -> smem, so both thread halves can use them
+        float hd[48];
+        tmem_ld32(tmem_heads + lane_base, hd);
+        if (NH > 32) tmem_ld16(tmem_heads + lane_base + 32, hd + 32);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 48; ++i)
+          if (i < 2 * L) s_heads[r * UM_HEAD_LD + i] = hd[i] + s_biash[i];
+      }
+      __syncthreads();
     }
-    tc_fence_after();
     // ================= T2: posterior, reparameterisation, z -> A operand =================
     {
-      const int slot = (r < rb) ? 0 : 1;
       const float* cs = s_cache + slot * CSLOT;
       const int64_t ebase = ((((int64_t)(cx.v_av_off + v) * J + j) * C + c) * N + g) * (int64_t)E;
-      if (t < UM_ROWS) {
-        float hd[48];
-        if (tile_need) {
-          tmem_ld32(tmem_heads + lane_base, hd);
-          if (NH > 32) tmem_ld16(tmem_heads + lane_base + 32, hd + 32);
-          tmem_ld_wait();
-        }
+      const bool my_need = need;
+      const int nq = KZ / 8, nqc = dm.KC / 8;
+      const int nq0 = nqc < 2 ? nqc : 2;                 // thread half 0: first content chunks, half 1: the rest
+      const int qbeg = (t < UM_ROWS) ? 0 : nq0, qend = (t < UM_ROWS) ? nq0 : nq;
+      float4 nv = make_float4(0.f, 0.f, 0.f, 0.f);
+      int64_t blk_have = -1;
+#pragma unroll 1
+      for (int q = qbeg; q < qend; ++q) {
         float zb[8];
-        float nv[4];
-        int64_t blk_have = -1;
-        const bool my_need = s_need[r] != 0;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          if (q >= dm.KC / 8) break;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int l = q * 8 + i;
-            float z = 0.f;
-            if (l < L && valid) {
+        for (int i = 0; i < 8; ++i) {
+          const int kz = q * 8 + i;
+          float z = 0.f;
+          const bool content = kz < dm.KC;
+          const int l = content ? kz : kz - dm.KC;
+          if (valid && l < (content ? L : Sd)) {
+            float e0 = 0.f;
+            if (cx.q.sample_latents) {
+              const int64_t idx = ebase + (content ? 0 : mdst.eps_off) + l;
+              if (cx.nz_av.eps) e0 = cx.nz_av.eps[idx];
+              else {
+                if ((idx >> 2) != blk_have) { blk_have = idx >> 2; nv = philox_normal4_call(cx.nz_av.seed, cx.nz_av.stream, (uint64_t)blk_have); }
+                const int w = (int)(idx & 3);
+                e0 = w == 0 ? nv.x : w == 1 ? nv.y : w == 2 ? nv.z : nv.w;
+              }
+            }
+            if (!content) {
+              z = cs[64 + l] + cs[96 + l] * e0;
+            } else if (fast_post) {
+              float mu = cs[l], sd = cs[32 + l];
+              if (my_need) {
+                const float hm = s_heads[r * UM_HEAD_LD + l], hl = s_heads[r * UM_HEAD_LD + L + l];
+                if (mv.method == MOPOE_METHOD_MOE) { mu = hm; sd = expf(0.5f * hl); }
+                else {
+                  const float T = 1.f / (expf(hl) + MOPOE_POE_EPS);
+                  const float sT = mu + T;                 // cs[l] = sum of the other precisions
+                  mu = (sd + hm * T) / sT;                 // cs[32+l] = sum of the other mu*T
+                  sd = expf(0.5f * logf(1.f / sT));
+                }
+              }
+              z = e0 * sd + mu;
+            } else {
+              // sample_latents = False: mean of the mixture components' means (BaseMMVae.py:228-229)
               float mu_e[MOPOE_MAX_MODS], lv_e[MOPOE_MAX_MODS];
+              const int64_t row = (int64_t)v * N + g;
 #pragma unroll
               for (int m = 0; m < MOPOE_MAX_MODS; ++m) {
-                mu_e[m] = m < M ? cs[(m * 2 + 0) * 32 + l] : 0.f;
-                lv_e[m] = m < M ? cs[(m * 2 + 1) * 32 + l] : 0.f;
+                mu_e[m] = m < M ? ws.enc[m][row * mv.mod[m].HC + l] : 0.f;
+                lv_e[m] = m < M ? ws.enc[m][row * mv.mod[m].HC + L + l] : 0.f;
               }
-              if (my_need) { mu_e[src] = hd[l] + s_biash[l]; lv_e[src] = hd[L + l] + s_biash[L + l]; }
-              if (cx.q.sample_latents) {
-                const SubsetEval ev = eval_subset(mv, cx.b, s_own, g, mu_e, lv_e);
-                float e0;
-                if (cx.nz_av.eps) e0 = cx.nz_av.eps[ebase + l];
-                else {
-                  const int64_t idx = ebase + l;
-                  if ((idx >> 2) != blk_have) { blk_have = idx >> 2; philox_normal4(cx.nz_av.seed, cx.nz_av.stream, (uint64_t)blk_have, nv); }
-                  const int w = (int)(idx & 3);
-                  e0 = w == 0 ? nv[0] : w == 1 ? nv[1] : w == 2 ? nv[2] : nv[3];
-                }
-                z = e0 * expf(0.5f * ev.lv) + ev.mu;
-              } else {
-                float jmu = 0.f;
-                for (int s = 0; s < mv.sub.n_subsets; ++s)
-                  if (in_mixture(mv, cx.b, s)) jmu += eval_subset(mv, cx.b, s, g, mu_e, lv_e).mu;
-                z = jmu / (float)cx.b.n_mix;
-              }
-            }
-            zb[i] = z;
-          }
-          store_split8(s_az_hi, s_az_lo, core_off(r, q, UM_ROWS), zb);
-        }
-      } else {
-        float zb[8];
-        float nv[4];
-        int64_t blk_have = -1;
+              mu_e[src] = s_heads[r * UM_HEAD_LD + l]; lv_e[src] = s_heads[r * UM_HEAD_LD + L + l];
+              float jmu = 0.f;
 #pragma unroll 1
-        for (int q = 0; q < (KZ - dm.KC) / 8; ++q) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int s = q * 8 + i;
-            float z = 0.f;
-            if (s < Sd && valid) {
-              float e0 = 0.f;
-              if (cx.q.sample_latents) {
-                const int64_t idx = ebase + mdst.eps_off + s;
-                if (cx.nz_av.eps) e0 = cx.nz_av.eps[idx];
-                else {
-                  if ((idx >> 2) != blk_have) { blk_have = idx >> 2; philox_normal4(cx.nz_av.seed, cx.nz_av.stream, (uint64_t)blk_have, nv); }
-                  const int w = (int)(idx & 3);
-                  e0 = w == 0 ? nv[0] : w == 1 ? nv[1] : w == 2 ? nv[2] : nv[3];
-                }
-              }
-              z = cs[MOPOE_MAX_MODS * 64 + s] + cs[MOPOE_MAX_MODS * 64 + 32 + s] * e0;
+              for (int s = 0; s < mv.sub.n_subsets; ++s)
+                if (in_mixture(mv, cx.b, s)) jmu += eval_subset(mv, cx.b, s, g, mu_e, lv_e).mu;
+              z = jmu / (float)cx.b.n_mix;
             }
-            zb[i] = z;
           }
-          store_split8(s_az_hi, s_az_lo, core_off(r, dm.KC / 8 + q, UM_ROWS), zb);
+          zb[i] = z;
         }
+        store_split8(s_az_hi, s_az_lo, core_off(r, q, UM_ROWS), zb);
       }
     }
     fence_proxy_async();
@@ -390,7 +415,8 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
     // ================= T4: epilogue =================
     {
       const int q4 = warp & 3, hh = warp >> 2;
-      const int rows_left = (int)min((int64_t)32, row_end - (tile_row + q4 * 32));   // valid rows of this quarter
+      const int rows_left = (int)max((int64_t)0, min((int64_t)32, row_end - (tile_row + q4 * 32)));   // valid rows of this quarter
+      const int rowsA = max(0, min(rows_left, rb - q4 * 32));   // rows of the current series; the rest belong to the next
 #pragma unroll
       for (int ci = 0; ci < NCH; ++ci) {
         const int cb0 = (hh * NCH + ci) * 32;
@@ -399,10 +425,9 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float4 o;
-          o.x = vv[4 * i + 0] + s_biasd[cb0 + 4 * i + 0]; o.y = vv[4 * i + 1] + s_biasd[cb0 + 4 * i + 1];
-          o.z = vv[4 * i + 2] + s_biasd[cb0 + 4 * i + 2]; o.w = vv[4 * i + 3] + s_biasd[cb0 + 4 * i + 3];
-          *reinterpret_cast<float4*>(s_stage + lane * UM_STAGE_LD + 4 * i) = o;
+          const float4 bb = *reinterpret_cast<const float4*>(s_biasd + cb0 + 4 * i);
+          *reinterpret_cast<float4*>(s_stage + lane * UM_STAGE_LD + 4 * i) =
+              make_float4(vv[4 * i] + bb.x, vv[4 * i + 1] + bb.y, vv[4 * i + 2] + bb.z, vv[4 * i + 3] + bb.w);
         }
         __syncwarp();
         if (cx.avatars && cb0 < ncol) {
@@ -424,12 +449,29 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
           }
         }
         // first-level regression sums, lane = ROI column cb0 + lane
-        for (int rr = 0; rr < rows_left; ++rr) {
-          const int rt = q4 * 32 + rr;
-          const double y = (double)s_stage[rr * UM_STAGE_LD + lane];
-          const double xcr = s_xc[rt];
-          if (rt < rb) { accA[ci] = fma(xcr, y, accA[ci]); if (FIXED) { syA[ci] += y; syyA[ci] = fma(y, y, syyA[ci]); } }
-          else         { accB[ci] = fma(xcr, y, accB[ci]); if (FIXED) { syB[ci] += y; syyB[ci] = fma(y, y, syyB[ci]); } }
+        {
+          const float* sp = s_stage + lane;
+          const double* xp = s_xc + q4 * 32;
+          double a = accA[ci], sy = FIXED ? syA[ci] : 0.0, syy = FIXED ? syyA[ci] : 0.0;
+#pragma unroll 4
+          for (int rr = 0; rr < rowsA; ++rr) {
+            const double y = (double)sp[rr * UM_STAGE_LD];
+            a = fma(xp[rr], y, a);
+            if (FIXED) { sy += y; syy = fma(y, y, syy); }
+          }
+          accA[ci] = a;
+          if (FIXED) { syA[ci] = sy; syyA[ci] = syy; }
+          if (rowsA < rows_left) {
+            double b = accB[ci], ty = FIXED ? syB[ci] : 0.0, tyy = FIXED ? syyB[ci] : 0.0;
+#pragma unroll 4
+            for (int rr = rowsA; rr < rows_left; ++rr) {
+              const double y = (double)sp[rr * UM_STAGE_LD];
+              b = fma(xp[rr], y, b);
+              if (FIXED) { ty += y; tyy = fma(y, y, tyy); }
+            }
+            accB[ci] = b;
+            if (FIXED) { syB[ci] = ty; syyB[ci] = tyy; }
+          }
         }
         __syncwarp();
       }

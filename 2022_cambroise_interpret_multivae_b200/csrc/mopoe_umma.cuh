@@ -29,6 +29,7 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // hanging the GPU).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
     uint32_t ok;
     asm volatile(
