@@ -114,16 +114,25 @@ __device__ __forceinline__ float u01(uint32_t x) {
   return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);
 }
 
-// the four normals of block `blk` (elements 4*blk .. 4*blk+3) of (seed, stream)
+// -ln(u) for u in (0,1): MUFU.LG2 away from 1, the log1p series next to 1 (where lg2's absolute error
+// would dominate); both evaluated, selected branch-free
+__device__ __forceinline__ float neg_log_u(float u) {
+  const float t = 1.0f - u;   // exact
+  const float series = t * (1.0f + t * (0.5f + t * (0.33333334f + t * 0.25f)));
+  return u > 0.99f ? series : -0.69314718f * __log2f(u);
+}
+
+// the four normals of block `blk` (elements 4*blk .. 4*blk+3) of (seed, stream):
+// Box-Muller with sin/cos evaluated on [-pi, pi) (MUFU range of full accuracy) and negated
 __device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t stream, uint64_t blk, float out[4]) {
   uint32_t c0 = (uint32_t)blk, c1 = (uint32_t)(blk >> 32), c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
   philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
-  float r0 = sqrtf(-2.0f * logf(u01(c0)));
-  float r1 = sqrtf(-2.0f * logf(u01(c2)));
+  const float r0 = sqrtf(2.0f * neg_log_u(u01(c0)));
+  const float r1 = sqrtf(2.0f * neg_log_u(u01(c2)));
   float s0, q0, s1, q1;
-  sincospif(2.0f * u01(c1), &s0, &q0);
-  sincospif(2.0f * u01(c3), &s1, &q1);
-  out[0] = r0 * q0; out[1] = r0 * s0; out[2] = r1 * q1; out[3] = r1 * s1;
+  __sincosf(6.28318530718f * (u01(c1) - 0.5f), &s0, &q0);
+  __sincosf(6.28318530718f * (u01(c3) - 0.5f), &s1, &q1);
+  out[0] = -r0 * q0; out[1] = -r0 * s0; out[2] = -r1 * q1; out[3] = -r1 * s1;
 }
 
 // element `idx` of (seed, stream)

@@ -35,6 +35,7 @@ struct DaaWs {
   double* xstat;               // (n_val, C, N, 2)  xbar, Sxx
   int* counter;                // work-unit counter of the persistent kernel
   int* err;                    // device error flag (tcgen05 barrier time-out)
+  long long* phase;            // [grid][8] per-phase cycle counters of the tcgen05 kernel (profiling runs)
   unsigned char* bsplit;       // fp16 hi/lo operand planes of the decoder / class-head weights (UMMA layout)
   void* fwd_ws;                // workspace of the encoder forward
   int64_t fwd_ws_bytes;
@@ -58,6 +59,7 @@ static int64_t daa_carve(const mopoe_model_desc* d, const mopoe_daa_desc* q, cha
   t.xstat = (double*)take(rows * C * 2 * 8);
   t.counter = (int*)take(256);
   t.err = (int*)take(256);
+  t.phase = (long long*)take(256 * 8 * 8);
   t.bsplit = (unsigned char*)take(2 * (448 * 64 * 2) + 2 * (64 * 256 * 2));
   t.fwd_ws_bytes = mopoe_workspace_bytes(d, rows);
   t.fwd_ws = take(t.fwd_ws_bytes);
@@ -788,6 +790,17 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
 }
 
 int mopoe_daa_last_impl(void) { return g_last_impl; }
+
+int mopoe_daa_read_phases(const mopoe_model_desc* desc, const mopoe_daa_desc* daa, void* workspace, int64_t* out8_host) {
+  if (check_desc(desc)) return MOPOE_EINVAL;
+  DaaWs ws;
+  daa_carve(desc, daa, (char*)workspace, &ws);
+  long long h[256 * 8];
+  MOPOE_CUDA(cudaMemcpy(h, ws.phase, sizeof(h), cudaMemcpyDeviceToHost));
+  const int grid = num_sms();
+  for (int i = 0; i < 8; ++i) { long long mx = 0; for (int b = 0; b < grid && b < 256; ++b) mx = h[b * 8 + i] > mx ? h[b * 8 + i] : mx; out8_host[i] = mx; }
+  return MOPOE_OK;
+}
 
 int mopoe_daa_regression(int32_t n_val, int32_t n_subjects, int32_t n_scores, int32_t n_samples, int32_t n_rois,
                          int32_t reg_method, const float* avatars, const float* sampled_scores,

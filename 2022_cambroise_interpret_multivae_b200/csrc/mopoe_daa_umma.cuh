@@ -34,10 +34,11 @@ struct UmmaDims {
   int KC, KS, KZ;     // content / style / total K of the decoder GEMM (multiples of 8 / 8 / 16)
   int NH;             // N of the heads GEMM (2L rounded to 16)
   int ncol;           // valid decoder columns of this block (<= 448)
+  int bias_slot;      // K slot carrying a constant 1 in z and the decoder bias in B (-1: no free pad slot)
 };
 
 struct UmmaSmem {
-  int bd_hi, bd_lo, bh_hi, bh_lo, az_hi, az_lo, ah, a0, biasd, biash, score, xc, need, cache, bars, total;
+  int bd_hi, bd_lo, bh_hi, bh_lo, az_hi, az_lo, ah, a0, biasd, biash, score, xc, need, cache, spart, sacc, bars, total;
 };
 
 __host__ __device__ inline UmmaDims umma_dims(const ModelView& mv, int src, int dst, int ncol) {
@@ -47,6 +48,7 @@ __host__ __device__ inline UmmaDims umma_dims(const ModelView& mv, int src, int 
   d.KZ = (d.KC + d.KS + 15) & ~15;
   d.NH = (2 * mv.L + 15) & ~15;
   d.ncol = ncol;
+  d.bias_slot = d.KC > mv.L ? mv.L : (d.KS > mv.mod[dst].S ? d.KC + mv.mod[dst].S : (d.KZ > d.KC + d.KS ? d.KC + d.KS : -1));
   return d;
 }
 
@@ -66,6 +68,8 @@ __host__ __device__ inline UmmaSmem umma_plan(const ModelView& mv, int src, cons
   p.xc = take(UM_ROWS * 8);
   p.need = take(UM_ROWS * 4);
   p.cache = take(2 * 128 * 4);
+  p.spart = take(4 * 2 * 64 * 8);   // [row group][slot][k] partial sums of xc * z
+  p.sacc = take(2 * 64 * 8);        // [slot][k] running sums of the current / next series
   p.bars = take(64);
   p.total = off;
   return p;
@@ -92,6 +96,7 @@ __global__ void daa_umma_prep_kernel(ModelView mv, int src, int dst, int col0, U
         if (n < d.ncol) {
           if (kz < d.KC) { if (kz < mv.L) w = md.wd[(int64_t)(col0 + n) * md.ZD + md.S + kz]; }
           else if (kz - d.KC < md.S) w = md.wd[(int64_t)(col0 + n) * md.ZD + (kz - d.KC)];
+          if (kz == d.bias_slot) w = md.bd[col0 + n];
         }
         x[q] = w;
       }
@@ -139,6 +144,8 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
   int* s_need = reinterpret_cast<int*>(smem + pl.need);
   // per slot: [0..31] A, [32..63] B (posterior partials, see T0), [64..95] dst style mu, [96..127] dst style sd
   float* s_cache = reinterpret_cast<float*>(smem + pl.cache);
+  double* s_spart = reinterpret_cast<double*>(smem + pl.spart);
+  double* s_sacc = reinterpret_cast<double*>(smem + pl.sacc);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + pl.bars);   // [0] heads, [1] decoder
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + pl.bars + 32);
   constexpr int CSLOT = 128;
@@ -158,6 +165,7 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
     for (int i = t; i < CB; i += MOPOE_THREADS) s_biasd[i] = i < ncol ? mdst.bd[col0 + i] : 0.f;
     for (int i = t; i < NH; i += MOPOE_THREADS) s_biash[i] = i < 2 * L ? ms.bh[i] : 0.f;
   }
+  if (t < 128) s_sacc[t] = 0.0;
   if (t == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(s_tmem, 512);
   fence_proxy_async();
@@ -171,6 +179,9 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
   const uint32_t LBO_A = (UM_ROWS / 8) * 128, LBO_BH = (NH / 8) * 128, LBO_BD = (CB / 8) * 128;
   uint32_t ph_h = 0, ph_d = 0;
   bool timed_out = false;
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tprev = clock64();
+#define MOPOE_PHASE(i) do { if (t == 0) { const long long _n = clock64(); pc[i] += _n - tprev; tprev = _n; } } while (0)
   const bool fast_post = cx.q.sample_latents != 0;    // posterior of the row's mixture owner from cached partial sums
 
   // ---- this CTA's contiguous range of (validation, subject, score) series ----
@@ -273,6 +284,7 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
     }
     const int tile_need = __syncthreads_or(need ? 1 : 0);
     const int slot = (r < rb) ? 0 : 1;
+    MOPOE_PHASE(0);
     // ================= T1: class heads of the perturbed src rows =================
     if (tile_need) {
       const int half = t >> 7;
@@ -321,6 +333,7 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
       }
       __syncthreads();
     }
+    MOPOE_PHASE(1);
     // ================= T2: posterior, reparameterisation, z -> A operand =================
     {
       const float* cs = s_cache + slot * CSLOT;
@@ -340,6 +353,7 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
           float z = 0.f;
           const bool content = kz < dm.KC;
           const int l = content ? kz : kz - dm.KC;
+          if (valid && kz == dm.bias_slot) z = 1.0f;
           if (valid && l < (content ? L : Sd)) {
             float e0 = 0.f;
             if (cx.q.sample_latents) {
@@ -391,6 +405,7 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    MOPOE_PHASE(2);
     // ================= T3: dst decoder GEMM =================
     if (t == 0) {
       tc_fence_after();
@@ -409,9 +424,31 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
       }
       mma_commit(&s_bar[1]);
     }
+    if (!FIXED) {
+      // First-level regression by linearity, while the tensor cores run:  sum_rows xc * y[:, col] =
+      // sum_k Wd[col][k] * (sum_rows xc * z[:, k])  (+ bias * sum xc through the constant-1 slot), so only
+      // KZ running sums per series are needed instead of one fp64 FMA per avatar element.
+      // z is read back exactly as the tensor cores see it (fp16 hi + lo planes).
+      if (t < 4 * KZ) {
+        const int k = t % KZ, rg = t / KZ;
+        const unsigned char* ph = s_az_hi + (k >> 3) * LBO_A + (k & 7) * 2;
+        const unsigned char* plo = s_az_lo + (k >> 3) * LBO_A + (k & 7) * 2;
+        double a = 0.0, b = 0.0;
+        const int rlo = rg * 32, rhi = min(rg * 32 + 32, (int)min((int64_t)UM_ROWS, row_end - tile_row));
+        for (int rr = rlo; rr < rhi; ++rr) {
+          const uint32_t o = (rr >> 3) * 128u + (rr & 7) * 16u;
+          const float zv = __half2float(*reinterpret_cast<const __half*>(ph + o)) + __half2float(*reinterpret_cast<const __half*>(plo + o));
+          const double p = s_xc[rr] * (double)zv;
+          if (rr < rb) a += p; else b += p;
+        }
+        s_spart[(rg * 2 + 0) * 64 + k] = a;
+        s_spart[(rg * 2 + 1) * 64 + k] = b;
+      }
+    }
     if (!mbar_wait(&s_bar[1], ph_d)) timed_out = true;
     ph_d ^= 1;
     tc_fence_after();
+    MOPOE_PHASE(3);
     // ================= T4: epilogue =================
     {
       const int q4 = warp & 3, hh = warp >> 2;
@@ -423,12 +460,13 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
         float vv[32];
         tmem_ld32(tmem + lane_base + cb0, vv);
         tmem_ld_wait();
+        if (dm.bias_slot < 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 bb = *reinterpret_cast<const float4*>(s_biasd + cb0 + 4 * i);
-          *reinterpret_cast<float4*>(s_stage + lane * UM_STAGE_LD + 4 * i) =
-              make_float4(vv[4 * i] + bb.x, vv[4 * i + 1] + bb.y, vv[4 * i + 2] + bb.z, vv[4 * i + 3] + bb.w);
+          for (int i = 0; i < 32; ++i) vv[i] += s_biasd[cb0 + i];
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(s_stage + lane * UM_STAGE_LD + 4 * i) = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
         __syncwarp();
         if (cx.avatars && cb0 < ncol) {
           const int rr0 = lane >> 3, cg = (lane & 7) * 4;
@@ -448,8 +486,8 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
             }
           }
         }
-        // first-level regression sums, lane = ROI column cb0 + lane
-        {
+        // pooled ("fixed") regression needs sum y and sum y^2 per element: lane = ROI column cb0 + lane
+        if (FIXED) {
           const float* sp = s_stage + lane;
           const double* xp = s_xc + q4 * 32;
           double a = accA[ci], sy = FIXED ? syA[ci] : 0.0, syy = FIXED ? syyA[ci] : 0.0;
@@ -478,8 +516,32 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
     }
     tc_fence_before();
     __syncthreads();
+    MOPOE_PHASE(4);
     // ================= series finished inside this tile: reduce the 4 row quarters, emit slopes =================
-    if ((int64_t)(cur_unit + 1) * J <= min(tile_row + UM_ROWS, row_end)) {
+    if (!FIXED && t < 2 * KZ) {   // fold this tile's partial sums into the running sums of both series
+      const int sl = t / KZ, k = t % KZ;
+      s_sacc[sl * 64 + k] += s_spart[(0 * 2 + sl) * 64 + k] + s_spart[(1 * 2 + sl) * 64 + k] +
+                             s_spart[(2 * 2 + sl) * 64 + k] + s_spart[(3 * 2 + sl) * 64 + k];
+    }
+    if (!FIXED) __syncthreads();
+    if (!FIXED && (int64_t)(cur_unit + 1) * J <= min(tile_row + UM_ROWS, row_end)) {
+      const int uc = cur_unit % C, ug = (cur_unit / C) % N, uv = cur_unit / (C * N);
+      const int64_t obase = (((int64_t)uv * C + uc) * N + ug);
+      const double sxx = ws.xstat[obase * 2 + 1];
+      for (int col = t; col < ncol; col += MOPOE_THREADS) {
+        const float* wrow = mdst.wd + (int64_t)(col0 + col) * mdst.ZD;
+        double sxy = 0.0;
+        for (int k = 0; k < L; ++k) sxy = fma(s_sacc[k], (double)wrow[Sd + k], sxy);
+        for (int k = 0; k < Sd; ++k) sxy = fma(s_sacc[dm.KC + k], (double)wrow[k], sxy);
+        if (dm.bias_slot >= 0) sxy = fma(s_sacc[dm.bias_slot], (double)mdst.bd[col0 + col], sxy);
+        ws.betas[obase * R + col0 + col] = sxy / sxx;
+      }
+      __syncthreads();
+      if (t < KZ) { s_sacc[t] = s_sacc[64 + t]; s_sacc[64 + t] = 0.0; }
+      ++cur_unit;
+      __syncthreads();
+    }
+    if (FIXED && (int64_t)(cur_unit + 1) * J <= min(tile_row + UM_ROWS, row_end)) {
       const int q4 = warp & 3, hh = warp >> 2;
 #pragma unroll
       for (int ci = 0; ci < NCH; ++ci) {
@@ -511,7 +573,10 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
       ++cur_unit;
       __syncthreads();
     }
+
+    MOPOE_PHASE(5);
   }
+  if (t == 0 && ws.phase) for (int i = 0; i < 8; ++i) ws.phase[blockIdx.x * 8 + i] = pc[i];
   if (timed_out && t == 0) atomicExch(ws.err, 1);
   tc_fence_before();
   __syncthreads();

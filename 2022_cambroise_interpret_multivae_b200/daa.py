@@ -77,7 +77,16 @@ def daa_sweep(spec: PathSpec, flat_params, src, dst, n_samples, n_base, *, src_m
                                    _ptr(r.sampled_scores), _ptr(r.reconstructions), _ptr(r.betas), _ptr(r.coefs),
                                    _ptr(r.pvalues), _ptr(ws), ws.numel(), _stream()))
     r._keep = (xs, eps_base, eps_score, eps_av, ws)
+    r._desc = q
     return r
+
+
+def phase_cycles(spec: PathSpec, result):
+    """Per-phase cycle counters of the tcgen05 avatar kernel of `result`'s sweep (profiling aid)."""
+    out = (C.c_int64 * 8)()
+    torch.cuda.synchronize()
+    _lib.check(_lib.lib().mopoe_daa_read_phases(C.byref(spec.desc), C.byref(result._desc), _ptr(result._keep[-1]), out))
+    return list(out)
 
 
 def daa_regression(avatars, sampled_scores, reconstructions=None, reg_method="hierarchical"):

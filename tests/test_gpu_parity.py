@@ -224,7 +224,7 @@ def test_philox_device_matches_numpy():
     from mopoe_b200 import engine
     got = engine.philox_normal(1037, philox.STREAM_DAA_AVATAR, 100000, torch.device("cuda"), start=777).cpu().numpy()
     want = philox.philox_normal(1037, philox.STREAM_DAA_AVATAR, 100000, start=777)
-    assert np.abs(got - want).max() <= 2e-6 * max(1.0, np.abs(want).max())
+    assert np.abs(got - want).max() <= 4e-6     # MUFU-based Box-Muller vs float64 numpy
 
 
 def test_daa_production_noise_is_shard_invariant_and_matches_oracle():
@@ -280,12 +280,18 @@ def test_daa_tensor_core_kernel_vs_oracle_and_cuda_core_kernel(kw, monkeypatch):
     _close(ff.avatars, av, "cuda-core avatars vs oracle")
     _close(um.avatars, ff.avatars, "tensor-core vs cuda-core avatars", rtol=2e-5)
     assert torch.equal(um.sampled_scores, ff.sampled_scores)
-    # statistics: closed-form oracle on the kernel's own avatars (fp64), and the two kernels agree
+    # statistics: closed-form oracle on the kernel's own avatars (fp64).  The tensor-core kernel gets the
+    # first-level sums by linearity from z (exact algebra; differs from summing the stored fp32 avatars
+    # by their fp32 rounding only), the cuda-core kernel sums the stored values themselves.
     p, coef, betas = daa_oracle.hierarchical_regression(um.avatars.cpu().numpy(), um.sampled_scores.cpu().numpy())
-    _close(um.betas, betas, "betas", rtol=1e-9)
-    _close(um.coefs, coef, "coefs", rtol=1e-9)
-    assert np.all(np.abs(np.log(um.pvalues.cpu().numpy()) - np.log(p)) <= 1e-8 * np.maximum(1.0, np.abs(np.log(p))))
+    # (bound: |y| * 2^-24 * sqrt(J / Sxx) per slope; SURVEY 8d asks for coefs <= 1e-4 relative)
+    _close(um.betas, betas, "betas", rtol=1e-5)
+    _close(um.coefs, coef, "coefs", rtol=1e-5)
+    assert np.all(np.abs(np.log(um.pvalues.cpu().numpy()) - np.log(p)) <= 1e-4 * np.maximum(1.0, np.abs(np.log(p))))
+    pf, cf, bf = daa_oracle.hierarchical_regression(ff.avatars.cpu().numpy(), ff.sampled_scores.cpu().numpy())
+    _close(ff.betas, bf, "betas (cuda-core)", rtol=1e-9)
     _close(um.coefs, ff.coefs, "coefs tensor-core vs cuda-core", rtol=1e-3)
+    assert np.array_equal(daa_oracle.significant(um.pvalues.cpu().numpy(), 0.7), daa_oracle.significant(pf, 0.7))
 
 
 def test_daa_tensor_core_fixed_regression_and_philox(monkeypatch):
