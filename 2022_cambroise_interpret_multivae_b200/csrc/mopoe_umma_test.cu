@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* A, c
   unsigned char* b_hi = a_lo + 128 * K * 2;
   unsigned char* b_lo = b_hi + N * K * 2;
   const int k8n = K / 8;
+  if (variant != 2)
   for (int i = t; i < 128 * k8n; i += 128) {
     const int row = i % 128, k8 = i / 128;
     float x[8];
@@ -30,7 +31,8 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* A, c
     store_split8(b_hi, b_lo, core_off(row, k8, N), x);
   }
   uint32_t ncols = 32;
-  while ((int)ncols < N) ncols <<= 1;
+  const int a_col = (N + 31) & ~31;   // variant 2: A planes in TMEM behind the accumulator
+  while ((int)ncols < (variant == 2 ? a_col + K : N)) ncols <<= 1;
   if (t == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(&tmem_slot, ncols);
   fence_proxy_async();
@@ -38,7 +40,34 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* A, c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (t == 0) {
+  if (variant == 2) {   // thread = row: split the row and park both planes in TMEM
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int k0 = 0; k0 < K; k0 += 32) {
+      uint32_t hi[16], lo[16];
+      for (int q = 0; q < 16; ++q) split_pack2(A[t * K + k0 + 2 * q], A[t * K + k0 + 2 * q + 1], hi[q], lo[q]);
+      tmem_st16(lane_addr + a_col + k0 / 2, hi);
+      tmem_st16(lane_addr + a_col + K / 2 + k0 / 2, lo);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  if (t == 0 && variant == 2) {
+    const uint32_t lbo_b = (N / 8) * 128, sbo = 128;
+    const uint32_t idesc = idesc_f16(128, N);
+    uint32_t acc = 0;
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint32_t offb = ks * 2 * lbo_b;
+      const uint64_t dbh = smem_desc(smem_u32(b_hi) + offb, lbo_b, sbo), dbl = smem_desc(smem_u32(b_lo) + offb, lbo_b, sbo);
+      const uint32_t ah = tmem + a_col + ks * 8, al = tmem + a_col + K / 2 + ks * 8;
+      mma_f16_ts(tmem, ah, dbh, idesc, acc); acc = 1;
+      mma_f16_ts(tmem, ah, dbl, idesc, 1);
+      mma_f16_ts(tmem, al, dbh, idesc, 1);
+    }
+    mma_commit(&bar);
+  }
+  if (t == 0 && variant != 2) {
     const uint32_t lbo_a = (128 / 8) * 128, lbo_b = (N / 8) * 128, sbo = 128;
     const uint32_t idesc = idesc_f16(128, N);
     uint32_t acc = 0;
@@ -78,6 +107,7 @@ using namespace mopoe;
 extern "C" int mopoe_umma_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t variant,
                                    int32_t* err_flag, void* stream) {
   if (mopoe_device_count() == 0) { set_error("no CUDA device"); return MOPOE_ENODEV; }
+  if (variant == 2 && (K % 32 || ((N + 31) & ~31) + K > 512)) { set_error("selftest variant 2 needs K%%32==0 and N+K<=512 TMEM columns"); return MOPOE_EINVAL; }
   if (N % 16 || N < 16 || N > 256 || K % 16 || K < 16) { set_error("selftest needs N%%16==0 (16..256), K%%16==0"); return MOPOE_EINVAL; }
   const int smem = (128 + N) * K * 2 * 2;
   if (smem > 200 * 1024) { set_error("selftest operands too large"); return MOPOE_EINVAL; }
