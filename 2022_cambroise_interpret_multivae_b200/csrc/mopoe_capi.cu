@@ -91,7 +91,7 @@ void build_view(const mopoe_model_desc* d, const mopoe_param_layout* lay, float*
   v->beta = d->beta;
   v->beta_style = d->beta_style;
   v->beta_content = d->beta_content;
-  int off = d->latent_dim;
+  int off = d->latent_dim, poff = (d->latent_dim + 3) & ~3;
   for (int m = 0; m < d->n_mods; ++m) {
     ModView& mv = v->mod[m];
     mv.D = d->dims[m];
@@ -100,6 +100,8 @@ void build_view(const mopoe_model_desc* d, const mopoe_param_layout* lay, float*
     mv.ZD = mv.S + d->latent_dim;
     mv.eps_off = off;
     off += mv.S;
+    mv.peps_off = poff;
+    poff += (mv.S + 3) & ~3;
     mv.w1 = base + lay->enc_w1[m];
     mv.b1 = base + lay->enc_b1[m];
     mv.wh = base + lay->enc_wh[m];
@@ -109,6 +111,7 @@ void build_view(const mopoe_model_desc* d, const mopoe_param_layout* lay, float*
     mv.lv = base + lay->dec_lv[m];
   }
   v->E = off;
+  v->EP = poff;
   build_subsets(d, &v->sub);
 }
 

@@ -39,6 +39,7 @@ struct ModView {
   float* lv;   // (D)
   int D, S, HC, ZD;
   int eps_off;  // column of this modality's style block inside an eps row
+  int peps_off; // the same inside a block-padded noise row (see ModelView::EP)
 };
 
 struct SubsetTable {
@@ -52,6 +53,8 @@ struct ModelView {
   ModView mod[MOPOE_MAX_MODS];
   SubsetTable sub;
   int M, L, E;      // E = eps row width = L + sum S
+  int EP;           // block-padded noise row: content and every style section rounded up to 4 (one
+                    // Philox4x32 block = 4 normals), so a thread that owns a row draws whole blocks
   int method;
   int learn_scale;
   float beta, beta_style, beta_content;

@@ -33,6 +33,7 @@ struct DaaWs {
   double* ybar;                // (n_val, C, N, R)  fixed: mean_j y
   double* syy;                 // (n_val, C, N, R)  fixed: sum_j (y - ybar)^2
   double* xstat;               // (n_val, C, N, 2)  xbar, Sxx
+  double* sacc;                // (n_val*N*C, tiles per series, 64)  pipelined kernel: sum_j (x - xbar) * z[k]
   int* counter;                // work-unit counter of the persistent kernel
   int* err;                    // device error flag (tcgen05 barrier time-out)
   long long* phase;            // [grid][8] per-phase cycle counters of the tcgen05 kernel (profiling runs)
@@ -57,10 +58,11 @@ static int64_t daa_carve(const mopoe_model_desc* d, const mopoe_daa_desc* q, cha
     t.syy = (double*)take(rows * C * R * 8);
   }
   t.xstat = (double*)take(rows * C * 2 * 8);
+  t.sacc = (double*)take(rows * C * ((q->n_samples + 126) / 128 + 1) * 64 * 8);
   t.counter = (int*)take(256);
   t.err = (int*)take(256);
   t.phase = (long long*)take(256 * 8 * 8);
-  t.bsplit = (unsigned char*)take(2 * (448 * 64 * 2) + 2 * (64 * 256 * 2));
+  t.bsplit = (unsigned char*)take(2 * (480 * 64 * 2) + 2 * (64 * 256 * 2));
   t.fwd_ws_bytes = mopoe_workspace_bytes(d, rows);
   t.fwd_ws = take(t.fwd_ws_bytes);
   if (w) *w = t;
@@ -78,20 +80,25 @@ struct DaaCtx {
   int C, R, J, N;
 };
 
-// fill dst[0..E) with the noise elements [base, base+E) using `nthr` cooperating threads (rank tid)
-__device__ __forceinline__ void fill_noise_row(const Noise& nz, int64_t base, int E, float* dst, int tid, int nthr) {
+// Latent noise of the DAA streams is addressed by ROW: injected tensors hold E columns per row; the
+// generator draws row `ridx` as EP/4 whole Philox blocks, block b of the row = counter ridx*(EP/4)+b,
+// laid out [content | style_0 | style_1 ...] with every section padded to a multiple of 4
+// (oracle/philox.py: philox_rows).  fill dst[0..E) with row `ridx` using `nthr` cooperating threads.
+__device__ __forceinline__ void fill_noise_row(const ModelView& mv, const Noise& nz, int64_t ridx, float* dst, int tid, int nthr) {
   if (nz.eps) {
-    for (int e = tid; e < E; e += nthr) dst[e] = nz.eps[base + e];
+    for (int e = tid; e < mv.E; e += nthr) dst[e] = nz.eps[ridx * mv.E + e];
   } else {
-    const int64_t b0 = base >> 2, b1 = (base + E - 1) >> 2;
-    for (int64_t blk = b0 + tid; blk <= b1; blk += nthr) {
+    const int nb = mv.EP >> 2;
+    for (int b = tid; b < nb; b += nthr) {
       float v[4];
-      philox_normal4(nz.seed, nz.stream, (uint64_t)blk, v);
+      philox_normal4(nz.seed, nz.stream, (uint64_t)(ridx * nb + b), v);
+      const int pe = 4 * b;
+      int e0 = pe, lim = mv.L;               // content section
+      for (int m = 0; m < mv.M; ++m)
+        if (pe >= mv.mod[m].peps_off) { e0 = mv.mod[m].eps_off + (pe - mv.mod[m].peps_off); lim = mv.mod[m].eps_off + mv.mod[m].S; }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int64_t e = blk * 4 + i - base;
-        if (e >= 0 && e < E) dst[e] = v[i];
-      }
+      for (int i = 0; i < 4; ++i)
+        if (e0 + i < lim) dst[e0 + i] = v[i];
     }
   }
 }
@@ -114,8 +121,8 @@ __global__ void __launch_bounds__(MOPOE_THREADS) daa_base_kernel(ModelView mv, D
   __syncthreads();
   // mean over the n_base passes of the noise row of this subject
   for (int p = warp; p < cx.q.n_base; p += 8) {
-    const int64_t base = (((int64_t)(cx.v_base_off + v) * cx.q.n_base + p) * cx.N + g) * E;
-    fill_noise_row(cx.nz_base, base, E, s_row + warp * 160, lane, 32);
+    const int64_t ridx = ((int64_t)(cx.v_base_off + v) * cx.q.n_base + p) * cx.N + g;
+    fill_noise_row(mv, cx.nz_base, ridx, s_row + warp * 160, lane, 32);
     __syncwarp();
     for (int e = lane; e < E; e += 32) s_acc[warp * 160 + e] += s_row[warp * 160 + e];
     __syncwarp();
@@ -336,8 +343,8 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_kernel(ModelView 
       if (cx.q.sample_latents) {
         const int jj = t >> 3, sub = t & 7;  // 8 threads per row
         if (jj < nrow) {
-          const int64_t base = ((((int64_t)(cx.v_av_off + v) * J + j0 + jj) * C + c) * N + g) * E;
-          fill_noise_row(cx.nz_av, base, E, s_eps + jj * E, sub, 8);
+          const int64_t ridx = (((int64_t)(cx.v_av_off + v) * J + j0 + jj) * C + c) * N + g;
+          fill_noise_row(mv, cx.nz_av, ridx, s_eps + jj * E, sub, 8);
         }
       }
       if (need_src) {
@@ -499,6 +506,7 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_kernel(ModelView 
 
 }  // namespace mopoe
 #include "mopoe_daa_umma.cuh"
+#include "mopoe_daa_pipe.cuh"
 namespace mopoe {
 
 // poison the result tables when a tcgen05 barrier wait timed out (never silently wrong)
@@ -743,22 +751,44 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   if (av_smem > 227 * 1024) { set_error("DAA avatar kernel needs %d bytes of shared memory (> 227 KB): latent/style dims too large", av_smem); return MOPOE_EINVAL; }
   const int n_units = daa->n_val * N * cx.C;
   const int grid = n_units < num_sms() ? n_units : num_sms();
-  // implementation choice: tensor cores (tcgen05, 3xFP16 split) when the shapes fit its tiling,
-  // else the CUDA-core kernel; MOPOE_DAA_IMPL=ffma|umma forces one (tests cross-check both)
+  // implementation choice (MOPOE_DAA_IMPL=pipe|umma|ffma forces one; the tests cross-check all three):
+  //   pipe  warp-specialised tcgen05 pipeline (hierarchical regression, sampled latents)  -> 2
+  //   umma  phase-serial tcgen05 kernel (also "fixed" regression / mean latents)            -> 1
+  //   ffma  CUDA-core kernel for shapes outside the tcgen05 tilings                          -> 0
   const UmmaDims ud0 = umma_dims(mv, daa->src_mod, daa->dst_mod, CB);
   const int um_smem = umma_plan(mv, daa->src_mod, ud0).total;
-  bool use_umma = cx.J >= UM_ROWS && cx.C <= UM_MAXC && ud0.NH <= 48 && ud0.KZ <= 64 && um_smem <= 227 * 1024;
+  const bool umma_ok = cx.J >= UM_ROWS && cx.C <= UM_MAXC && ud0.NH <= 48 && ud0.KZ <= 64 && um_smem <= 227 * 1024;
+  const int pk_smem = pipe_plan(ud0).total;
+  const bool pipe_ok = umma_ok && daa->reg_method == 0 && daa->sample_latents && ud0.bias_slot >= 0 && ud0.KZ - ud0.KC <= 32 &&
+                       pk_smem <= 227 * 1024 && (int64_t)n_units * cx.J < ((int64_t)1 << 31);
+  int impl = pipe_ok ? 2 : (umma_ok ? 1 : 0);
   const char* force = getenv("MOPOE_DAA_IMPL");
-  if (force && !strcmp(force, "ffma")) use_umma = false;
-  if (force && !strcmp(force, "umma") && !use_umma) { set_error("MOPOE_DAA_IMPL=umma but the shapes do not fit the tcgen05 tiling"); return MOPOE_EINVAL; }
-  g_last_impl = use_umma ? 1 : 0;
+  if (force && !strcmp(force, "ffma")) impl = 0;
+  if (force && !strcmp(force, "umma")) { if (!umma_ok) { set_error("MOPOE_DAA_IMPL=umma but the shapes do not fit the tcgen05 tiling"); return MOPOE_EINVAL; } impl = 1; }
+  if (force && !strcmp(force, "pipe")) { if (!pipe_ok) { set_error("MOPOE_DAA_IMPL=pipe but the configuration does not fit the pipelined kernel"); return MOPOE_EINVAL; } impl = 2; }
+  g_last_impl = impl;
   MOPOE_CUDA(cudaMemsetAsync(ws.err, 0, sizeof(int), stream));
-  if (use_umma) {
+  if (impl == 2) {
+    MOPOE_CUDA(cudaFuncSetAttribute((void*)daa_avatar_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pk_smem));
+    for (int col0 = 0; col0 < cx.R; col0 += PK_CBP) {
+      const UmmaDims ud = umma_dims(mv, daa->src_mod, daa->dst_mod, cx.R - col0 < PK_CBP ? cx.R - col0 : PK_CBP);
+      daa_umma_prep_kernel<<<64, 256, 0, stream>>>(mv, daa->src_mod, daa->dst_mod, col0, ud, PK_CBP, ws.bsplit);
+      MOPOE_CUDA(cudaGetLastError());
+      if (g_profile && col0 == 0) MOPOE_CUDA(cudaEventRecord(g_ev0, stream));
+      daa_avatar_pipe_kernel<<<num_sms(), PK_THREADS, pk_smem, stream>>>(mv, cx, ws, col0);
+      MOPOE_CUDA(cudaGetLastError());
+      if (g_profile && col0 == 0) MOPOE_CUDA(cudaEventRecord(g_ev1, stream));
+    }
+    const int bsm = ud0.KZ * 480 * 4;
+    MOPOE_CUDA(cudaFuncSetAttribute((void*)daa_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bsm));
+    daa_beta_kernel<<<dim3(num_sms(), (cx.R + 479) / 480), 256, bsm, stream>>>(mv, daa->dst_mod, cx.R, n_units, cx.C, N, cx.J, ud0, ws.sacc, ws.xstat, ws.betas);
+    MOPOE_CUDA(cudaGetLastError());
+  } else if (impl == 1) {
     void* ufn = daa->reg_method == 1 ? (void*)daa_avatar_umma_kernel<true> : (void*)daa_avatar_umma_kernel<false>;
     MOPOE_CUDA(cudaFuncSetAttribute(ufn, cudaFuncAttributeMaxDynamicSharedMemorySize, um_smem));
     for (int col0 = 0; col0 < cx.R; col0 += CB) {
       const UmmaDims ud = umma_dims(mv, daa->src_mod, daa->dst_mod, cx.R - col0 < CB ? cx.R - col0 : CB);
-      daa_umma_prep_kernel<<<64, 256, 0, stream>>>(mv, daa->src_mod, daa->dst_mod, col0, ud, ws.bsplit);
+      daa_umma_prep_kernel<<<64, 256, 0, stream>>>(mv, daa->src_mod, daa->dst_mod, col0, ud, CB, ws.bsplit);
       MOPOE_CUDA(cudaGetLastError());
       if (g_profile && col0 == 0) MOPOE_CUDA(cudaEventRecord(g_ev0, stream));
       if (daa->reg_method == 1) daa_avatar_umma_kernel<true><<<grid, MOPOE_THREADS, um_smem, stream>>>(mv, cx, ws, col0);
@@ -776,13 +806,13 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
       MOPOE_CUDA(cudaGetLastError());
     }
   }
-  if (g_profile) MOPOE_CUDA(cudaEventRecord(g_ev1, stream));
+  if (g_profile && impl != 2) MOPOE_CUDA(cudaEventRecord(g_ev1, stream));
   // 4. second level
   const int64_t nstat = (int64_t)daa->n_val * cx.C * cx.R;
   daa_stats_kernel<<<(unsigned)((nstat + 127) / 128), 128, 0, stream>>>(daa->n_val, N, cx.C, cx.J, cx.R, daa->reg_method, ws.betas,
                                                                        ws.ybar, ws.syy, ws.xstat, reconstructions, coefs, pvalues);
   MOPOE_CUDA(cudaGetLastError());
-  if (use_umma) {
+  if (impl != 0) {
     daa_poison_kernel<<<32, 256, 0, stream>>>(ws.err, coefs, pvalues, nstat);
     MOPOE_CUDA(cudaGetLastError());
   }

@@ -1,0 +1,618 @@
+// Pipelined tensor-core DAA avatar kernel (included by mopoe_daa.cu): the production kernel for
+// reg_method = hierarchical, sample_latents = True (workflow.py:406-419 + stat_utils.py:66-68).
+//
+// One persistent CTA per SM walks a contiguous range of 128-row tiles of the avatar tensor (row =
+// (validation, subject, score, sample) in output order, so a tile is one contiguous 128 x R block of
+// rois_digital_avatars.npy).  The tile pipeline is warp specialised and runs through mbarriers only:
+//
+//   producers (8 warps, thread = avatar row, two warps per TMEM lane quarter)
+//       P1  hidden layer of the perturbed src encoder, rank-1 in the score:
+//           h = relu(a0 + W1[:,c] * score), split into fp16 hi/lo and written STRAIGHT INTO TMEM
+//           (tcgen05.st) as the A operand of the class-head GEMM            -> bar h_full
+//       P2  Philox4x32-10 + Box-Muller noise of the row (whole blocks, see fill_noise_row)
+//       P3  class heads read back from TMEM (tcgen05.ld), posterior of the row's mixture owner from
+//           cached per-series partial sums, reparameterisation, z written as the A operand of the
+//           decoder GEMM (shared memory, fp16 hi/lo, double buffered)          -> bar z_full
+//           + the first-level regression sums  sum_rows (x - xbar) * z[k]  in fp64 (warp butterfly):
+//           by linearity  sum_rows (x - xbar) * y[:, roi] = Wd[roi,:] . that vector, so the slope
+//           of every ROI (stat_utils.py:66-68) needs KZ numbers per series, not one FMA per element
+//   heads issuer   (1 thread)  16 x 3 tcgen05.mma kind::f16, A from TMEM, N = 48  -> bar heads_done
+//   decoder issuer (1 thread)  per 96-column chunk 3 x 3 tcgen05.mma, A/B from shared memory,
+//                              accumulators ping-pong between two TMEM buffers      -> bar acc_full
+//   epilogue (4 warps)         tcgen05.ld -> shared-memory transpose -> coalesced streaming float4
+//                              stores of the avatar tile                             -> bar acc_empty
+//   aux (1 warp)               per-series caches one tile ahead (hidden pre-activation without the
+//                              perturbed column, posterior partial sums of the other experts, dst
+//                              style), folds the regression partials, flushes finished series
+//
+// TMEM (512 columns): [0,48) class-head accumulator | [64,192) h hi | [192,320) h lo |
+//                     [320,416) decoder accumulator 0 | [416,512) decoder accumulator 1
+// Shared memory: both weight matrices as fp16 hi/lo UMMA operands for the whole launch (3xFP16
+// split: a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulation in TMEM).
+#pragma once
+
+namespace mopoe {
+
+constexpr int PK_ROWS = 128;
+constexpr int PK_NCH = 96;             // decoder columns per accumulator buffer
+constexpr int PK_MAXCH = 5;            // chunks per launch
+constexpr int PK_CBP = PK_NCH * PK_MAXCH;   // 480 decoder columns per launch
+constexpr int PK_PROD = 8, PK_EPI = 4;
+constexpr int PK_W_EPI = PK_PROD, PK_W_HMMA = PK_PROD + PK_EPI, PK_W_DMMA = PK_W_HMMA + 1, PK_W_AUX = PK_W_HMMA + 2;
+constexpr int PK_THREADS = (PK_PROD + PK_EPI + 3) * 32;   // 480
+constexpr int PK_STAGE_LD = 36;
+constexpr int PK_SLOTS = 4;            // ring of per-series caches (unit & 3)
+constexpr int PK_TM_HEADS = 0, PK_TM_AH_HI = 64, PK_TM_AH_LO = 192, PK_TM_ACC = 320;
+constexpr int PK_CACHE_F = 2 * MOPOE_HIDDEN + 128;   // floats per series cache: a0 | w1c | cs
+
+struct PipeSmem {
+  int bd_hi, bd_lo, bh_hi, bh_lo, az, stage, cache, meta, xbar, biash, part, bars, total;
+};
+
+__host__ __device__ inline PipeSmem pipe_plan(const UmmaDims& d) {
+  PipeSmem p;
+  int off = 0;
+  auto take = [&](int bytes) { int o = off; off += (bytes + 127) & ~127; return o; };
+  p.bd_hi = take(PK_CBP * d.KZ * 2); p.bd_lo = take(PK_CBP * d.KZ * 2);
+  p.bh_hi = take(d.NH * MOPOE_HIDDEN * 2); p.bh_lo = take(d.NH * MOPOE_HIDDEN * 2);
+  p.az = take(2 * 2 * PK_ROWS * d.KZ * 2);             // [buffer][hi|lo]
+  p.stage = take(PK_EPI * 32 * PK_STAGE_LD * 4);
+  p.cache = take(PK_SLOTS * PK_CACHE_F * 4);
+  p.meta = take(PK_SLOTS * 4 * 4);
+  p.xbar = take(PK_SLOTS * 8);
+  p.biash = take(d.NH * 4);
+  p.part = take(2 * PK_PROD * 2 * 32 * 8);             // [tile parity][warp][series 0|1][k] fp64
+  p.bars = take(128);
+  p.total = off;
+  return p;
+}
+
+// upper bound of the 128-row tiles one J-row series can touch
+__host__ __device__ inline int pipe_tiles_per_unit(int J) { return (J + PK_ROWS - 2) / PK_ROWS + 1; }
+
+// bounded mbarrier wait with a CTA-wide sticky abort flag: a protocol bug ends the launch with the
+// error flag set (results are poisoned by the host wrapper) instead of hanging the GPU
+__device__ __forceinline__ bool pk_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
+  const uint32_t addr = umma::smem_u32(bar);
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return true;
+    if ((spin & 255u) == 255u && *abort_flag) return false;
+  }
+  *abort_flag = 1;
+  return false;
+}
+__device__ __forceinline__ void pk_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void pk_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// 32 per-lane fp64 values v[k] -> sum over the 32 lanes of v[k], returned in lane k (transposing butterfly)
+__device__ __forceinline__ double pk_lane_transpose_sum(const float* zq, double xc, int lane) {
+  double a[16];
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const double lo = xc * (double)zq[i], hi = xc * (double)zq[i + 16];
+      const double keep = up ? hi : lo, send = up ? lo : hi;
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+#pragma unroll
+  for (int w = 8; w >= 1; w >>= 1) {
+    const bool up = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const double keep = up ? a[i + w] : a[i], send = up ? a[i] : a[i + w];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return a[0];   // lane holds k = lane (bit b of the lane selected the upper half at width 2^b)
+}
+
+// mixture owner of subject row g and whether its posterior needs the perturbed src expert
+__device__ __forceinline__ int pk_owner_subset(const ModelView& mv, const DaaCtx& cx, int g, bool& need_src) {
+  int owner = 0, kidx = 0, s_own = 0;
+  for (int k = 0; k < cx.b.n_mix; ++k)
+    if (g >= cx.b.joint_bounds[k] && g < cx.b.joint_bounds[k + 1]) owner = k;
+  for (int s = 0; s < mv.sub.n_subsets; ++s) {
+    if (!in_mixture(mv, cx.b, s)) continue;
+    if (kidx == owner) s_own = s;
+    ++kidx;
+  }
+  need_src = ((mv.sub.mask[s_own] >> cx.q.src_mod) & 1) || (mv.method == MOPOE_METHOD_MOE && mv.sub.n_members[s_own] > 1);
+  return s_own;
+}
+
+__global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelView mv, DaaCtx cx, DaaWs ws, int col0) {
+  using namespace umma;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int src = cx.q.src_mod, dst = cx.q.dst_mod;
+  const ModView& ms = mv.mod[src];
+  const ModView& mdst = mv.mod[dst];
+  const int L = mv.L, M = mv.M, E = mv.E, Sd = mdst.S;
+  const int C = cx.C, R = cx.R, J = cx.J, N = cx.N;
+  const UmmaDims dm = umma_dims(mv, src, dst, min(PK_CBP, R - col0));
+  const PipeSmem pl = pipe_plan(dm);
+  const int ncol = dm.ncol, KZ = dm.KZ, KC = dm.KC, NH = dm.NH;
+  const int n_chunks = (ncol + PK_NCH - 1) / PK_NCH;
+  unsigned char* s_bd_hi = smem + pl.bd_hi;
+  unsigned char* s_bd_lo = smem + pl.bd_lo;
+  unsigned char* s_bh_hi = smem + pl.bh_hi;
+  unsigned char* s_bh_lo = smem + pl.bh_lo;
+  unsigned char* s_az = smem + pl.az;
+  const int AZ_PLANE = PK_ROWS * KZ * 2;          // bytes of one fp16 plane of one z buffer
+  float* s_cache = reinterpret_cast<float*>(smem + pl.cache);
+  int* s_meta = reinterpret_cast<int*>(smem + pl.meta);         // [slot][0] need_src
+  double* s_xbar = reinterpret_cast<double*>(smem + pl.xbar);
+  float* s_biash = reinterpret_cast<float*>(smem + pl.biash);
+  double* s_part = reinterpret_cast<double*>(smem + pl.part);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + pl.bars);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + pl.bars + 96);
+  volatile int* s_abort = reinterpret_cast<volatile int*>(smem + pl.bars + 100);
+  uint64_t* bar_h_full = s_bar + 0;       // producers -> heads issuer           (8 arrivals)
+  uint64_t* bar_heads_done = s_bar + 1;   // heads MMAs complete                 (tcgen05.commit)
+  uint64_t* bar_z_full = s_bar + 2;       // [2] producers -> decoder issuer     (8 arrivals)
+  uint64_t* bar_z_free = s_bar + 4;       // [2] decoder MMAs of the tile done   (tcgen05.commit)
+  uint64_t* bar_acc_full = s_bar + 6;     // [2] chunk accumulated               (tcgen05.commit)
+  uint64_t* bar_acc_empty = s_bar + 8;    // [2] epilogue drained the buffer     (4 arrivals)
+
+  // ---- launch-lifetime state ----
+  {
+    const uint4* g = reinterpret_cast<const uint4*>(ws.bsplit);
+    const int nbd = PK_CBP * KZ * 2 / 16, nbh = NH * MOPOE_HIDDEN * 2 / 16;
+    for (int i = t; i < nbd; i += PK_THREADS) {
+      reinterpret_cast<uint4*>(s_bd_hi)[i] = g[i];
+      reinterpret_cast<uint4*>(s_bd_lo)[i] = g[nbd + i];
+    }
+    for (int i = t; i < nbh; i += PK_THREADS) {
+      reinterpret_cast<uint4*>(s_bh_hi)[i] = g[2 * nbd + i];
+      reinterpret_cast<uint4*>(s_bh_lo)[i] = g[2 * nbd + nbh + i];
+    }
+    for (int i = t; i < NH; i += PK_THREADS) s_biash[i] = i < 2 * L ? ms.bh[i] : 0.f;
+  }
+  if (t == 0) {
+    mbar_init(bar_h_full, PK_PROD); mbar_init(bar_heads_done, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_z_full + b, PK_PROD); mbar_init(bar_z_free + b, 1);
+      mbar_init(bar_acc_full + b, 1); mbar_init(bar_acc_empty + b, PK_EPI);
+    }
+    *s_abort = 0;
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(s_tmem, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  // ---- this CTA's contiguous range of 128-row tiles (balanced over the grid) ----
+  const int total_rows = cx.q.n_val * N * C * J;      // < 2^31, checked by the host dispatch
+  const int total_tiles = (total_rows + PK_ROWS - 1) / PK_ROWS;
+  const int tb = total_tiles / gridDim.x, trem = total_tiles % gridDim.x;
+  const int tile0 = (int)blockIdx.x * tb + min((int)blockIdx.x, trem);
+  const int n_tiles = tb + ((int)blockIdx.x < trem ? 1 : 0);
+  const int row_begin = tile0 * PK_ROWS;
+  const int row_end = min(total_rows, (tile0 + n_tiles) * PK_ROWS);
+  const int tpu = pipe_tiles_per_unit(J);
+  auto unit_need = [&](int u) -> bool { bool nd; pk_owner_subset(mv, cx, (u / C) % N, nd); return nd; };
+  auto tile_units = [&](int i, int& uA, int& uB) {
+    const int r0 = row_begin + i * PK_ROWS, r1 = min(r0 + PK_ROWS, row_end) - 1;
+    uA = r0 / J; uB = r1 / J;
+  };
+
+  if (warp < PK_PROD) {
+    // =============================== producers ===============================
+    const int r = t & 127, half = t >> 7;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int nbrow = mv.EP >> 2;
+    const int cnt = half ? Sd : L;                       // latents of this thread's half
+    const int nb = (cnt + 3) >> 2;
+    const int sec_blk = half ? (mdst.peps_off >> 2) : 0, sec_off = half ? mdst.eps_off : 0;
+    uint32_t heads_waits = 0;
+#pragma unroll 1
+    for (int i = 0; i < n_tiles; ++i) {
+      pk_bar_sync(1, (PK_PROD + 1) * 32);                // caches of this tile's series are ready
+      const int tile_row = row_begin + i * PK_ROWS;
+      int uA, uB;
+      tile_units(i, uA, uB);
+      const int rho = tile_row + r;
+      const bool valid = rho < row_end;
+      const int u = valid ? rho / J : uB;
+      const int j = valid ? rho - u * J : 0;
+      const int c = u % C, g = (u / C) % N, v = u / (C * N);
+      const int slot = u & (PK_SLOTS - 1);
+      const float* cache = s_cache + slot * PK_CACHE_F;
+      const float* cs = cache + 2 * MOPOE_HIDDEN;
+      const bool tile_need = s_meta[(uA & (PK_SLOTS - 1)) * 4] || s_meta[(uB & (PK_SLOTS - 1)) * 4];
+      const bool need = valid && s_meta[slot * 4];
+      const float score = valid ? ws.scores[rho] : 0.f;
+      // ---- P1: hidden layer -> TMEM (A operand of the class-head GEMM) ----
+      if (tile_need) {
+        const float4* a0p = reinterpret_cast<const float4*>(cache + half * 128);
+        const float4* wcp = reinterpret_cast<const float4*>(cache + MOPOE_HIDDEN + half * 128);
+#pragma unroll 1
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 a = a0p[kk * 8 + q], w = wcp[kk * 8 + q];
+            const float h0 = fmaxf(fmaf(w.x, score, a.x), 0.f), h1 = fmaxf(fmaf(w.y, score, a.y), 0.f);
+            const float h2 = fmaxf(fmaf(w.z, score, a.z), 0.f), h3 = fmaxf(fmaf(w.w, score, a.w), 0.f);
+            split_pack2(h0, h1, hi[2 * q], lo[2 * q]);
+            split_pack2(h2, h3, hi[2 * q + 1], lo[2 * q + 1]);
+          }
+          const uint32_t colw = (uint32_t)(half * 64 + kk * 16);     // 32-bit column = 2 hidden units
+          tmem_st16(lane_addr + PK_TM_AH_HI + colw, hi);
+          tmem_st16(lane_addr + PK_TM_AH_LO + colw, lo);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) pk_arrive(bar_h_full);
+      }
+      // ---- P2: noise of this row (content half / dst style half) ----
+      float e[32];
+      {
+        const int64_t ridx = (((int64_t)(cx.v_av_off + v) * J + j) * C + c) * N + g;
+        if (cx.nz_av.eps) {
+          const float* ep = cx.nz_av.eps + ridx * E + sec_off;
+#pragma unroll
+          for (int l = 0; l < 32; ++l) e[l] = (valid && l < cnt) ? ep[l] : 0.f;
+        } else {
+          const uint64_t blk0 = (uint64_t)(ridx * nbrow + sec_blk);
+#pragma unroll
+          for (int b = 0; b < 8; ++b) {
+            if (b < nb) philox_normal4(cx.nz_av.seed, cx.nz_av.stream, blk0 + b, e + 4 * b);
+            else { e[4 * b] = e[4 * b + 1] = e[4 * b + 2] = e[4 * b + 3] = 0.f; }
+          }
+        }
+      }
+      // ---- P3: posterior / reparameterisation -> z (A operand of the decoder GEMM) ----
+      float zq[32];      // z exactly as the tensor cores see it (hi + lo), for the regression sums
+      if (half == 0) {
+        if (tile_need) {
+          pk_wait(bar_heads_done, heads_waits & 1, s_abort);
+          ++heads_waits;
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int p16 = 0; p16 < 2; ++p16) {
+          if (p16 * 16 < L) {
+            float hm[16], hl[16];
+            if (tile_need) {
+              tmem_ld16(lane_addr + PK_TM_HEADS + p16 * 16, hm);
+              tmem_ld16(lane_addr + PK_TM_HEADS + L + p16 * 16, hl);
+              tmem_ld_wait();
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int l = p16 * 16 + i;
+              float z = 0.f;
+              if (valid && l < L) {
+                float mu = cs[l], sd = cs[32 + l];
+                if (need) {
+                  const float m_ = hm[i] + s_biash[l], lv = hl[i] + s_biash[L + l];
+                  if (mv.method == MOPOE_METHOD_MOE) { mu = m_; sd = expf(0.5f * lv); }
+                  else {
+                    const float T = 1.f / (expf(lv) + MOPOE_POE_EPS);
+                    const float sT = mu + T;                 // cs[l] = sum of the other precisions
+                    mu = (sd + m_ * T) / sT;                 // cs[32+l] = sum of the other mu*T
+                    sd = expf(0.5f * logf(1.f / sT));
+                  }
+                }
+                z = fmaf(e[l], sd, mu);
+              }
+              zq[l] = z;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) zq[p16 * 16 + i] = 0.f;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int l = 0; l < 32; ++l) zq[l] = (valid && l < Sd) ? fmaf(cs[96 + l], e[l], cs[64 + l]) : 0.f;
+      }
+      // the decoder bias rides in a free pad slot of K: z = 1 there, B holds the bias
+      {
+        const int kb = dm.bias_slot - (half ? KC : 0);
+#pragma unroll
+        for (int l = 0; l < 32; ++l) if (l == kb && valid) zq[l] = 1.0f;
+      }
+      pk_wait(bar_z_free + (i & 1), ((i >> 1) & 1) ^ 1, s_abort);
+      {
+        unsigned char* az_hi = s_az + (i & 1) * 2 * AZ_PLANE;
+        unsigned char* az_lo = az_hi + AZ_PLANE;
+        const int q0 = half ? (KC >> 3) : 0, nq = half ? ((KZ - KC) >> 3) : (KC >> 3);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q < nq) {
+            __half h8[8], l8[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              split_f16(zq[q * 8 + k], h8[k], l8[k]);
+              zq[q * 8 + k] = __half2float(h8[k]) + __half2float(l8[k]);
+            }
+            const uint32_t off = core_off(r, q0 + q, PK_ROWS);
+            *reinterpret_cast<uint4*>(az_hi + off) = *reinterpret_cast<const uint4*>(h8);
+            *reinterpret_cast<uint4*>(az_lo + off) = *reinterpret_cast<const uint4*>(l8);
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) pk_arrive(bar_z_full + (i & 1));
+      // ---- first-level regression sums of this warp's 32 rows (series uA and, past a boundary, uA+1) ----
+      if (col0 == 0) {
+        const double xc = valid ? (double)score - s_xbar[slot] : 0.0;
+        const bool inA = valid && u == uA, inB = valid && u != uA;
+        double* part = s_part + (((i & 1) * PK_PROD + warp) * 2) * 32;
+        const bool anyA = __any_sync(0xffffffffu, inA), anyB = __any_sync(0xffffffffu, inB);
+        double sA = 0.0, sB = 0.0;
+        if (anyA) sA = pk_lane_transpose_sum(zq, inA ? xc : 0.0, lane);
+        if (anyB) sB = pk_lane_transpose_sum(zq, inB ? xc : 0.0, lane);
+        part[lane] = sA;
+        part[32 + lane] = sB;
+      }
+    }
+    pk_bar_sync(1, (PK_PROD + 1) * 32);      // last tile's partial sums are visible to the aux warp
+  } else if (warp < PK_W_HMMA) {
+    // =============================== epilogue ===============================
+    const int q4 = warp & 3;
+    const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
+    float* s_stage = reinterpret_cast<float*>(smem + pl.stage) + q4 * 32 * PK_STAGE_LD;
+    int q = 0;
+#pragma unroll 1
+    for (int i = 0; i < n_tiles; ++i) {
+      const int tile_row = row_begin + i * PK_ROWS;
+      const int rows_left = max(0, min(32, row_end - (tile_row + q4 * 32)));
+#pragma unroll 1
+      for (int ch = 0; ch < n_chunks; ++ch, ++q) {
+        const int b = q & 1;
+        pk_wait(bar_acc_full + b, (q >> 1) & 1, s_abort);
+        tc_fence_after();
+        const int nsub = min(3, (ncol - ch * PK_NCH + 31) >> 5);
+#pragma unroll 1
+        for (int sub = 0; sub < nsub; ++sub) {
+          const int cb0 = ch * PK_NCH + sub * 32;
+          float vv[32];
+          tmem_ld32(lane_base + PK_TM_ACC + b * PK_NCH + sub * 32, vv);
+          tmem_ld_wait();
+          if (sub == nsub - 1) {            // accumulator fully read: hand the buffer back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) pk_arrive(bar_acc_empty + b);
+          }
+          if (cx.avatars) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              *reinterpret_cast<float4*>(s_stage + lane * PK_STAGE_LD + 4 * k) = make_float4(vv[4 * k], vv[4 * k + 1], vv[4 * k + 2], vv[4 * k + 3]);
+            __syncwarp();
+            const int rr0 = lane >> 3, cg = (lane & 7) * 4;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + rr0;
+              if (rr < rows_left) {
+                const float4 o = *reinterpret_cast<const float4*>(s_stage + rr * PK_STAGE_LD + cg);
+                float* dstp = cx.avatars + (int64_t)(tile_row + q4 * 32 + rr) * R + col0 + cb0 + cg;
+                if ((R & 3) == 0 && cb0 + cg + 4 <= ncol) __stcs(reinterpret_cast<float4*>(dstp), o);
+                else {
+                  if (cb0 + cg + 0 < ncol) dstp[0] = o.x;
+                  if (cb0 + cg + 1 < ncol) dstp[1] = o.y;
+                  if (cb0 + cg + 2 < ncol) dstp[2] = o.z;
+                  if (cb0 + cg + 3 < ncol) dstp[3] = o.w;
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp == PK_W_HMMA) {
+    // =============================== class-head MMA issuer ===============================
+    if (lane == 0) {
+      const uint32_t idesc_h = idesc_f16(PK_ROWS, NH);
+      const uint32_t LBO_BH = (NH / 8) * 128;
+      uint32_t hc = 0;
+#pragma unroll 1
+      for (int i = 0; i < n_tiles; ++i) {
+        int uA, uB;
+        tile_units(i, uA, uB);
+        if (!(unit_need(uA) || unit_need(uB))) continue;
+        pk_wait(bar_h_full, hc & 1, s_abort);
+        ++hc;
+        tc_fence_after();
+#pragma unroll 4
+        for (int ks = 0; ks < MOPOE_HIDDEN / 16; ++ks) {
+          const uint32_t ob = ks * 2 * LBO_BH;
+          const uint64_t dbh = smem_desc(smem_u32(s_bh_hi) + ob, LBO_BH, 128), dbl = smem_desc(smem_u32(s_bh_lo) + ob, LBO_BH, 128);
+          const uint32_t ah = tmem + PK_TM_AH_HI + ks * 8, al = tmem + PK_TM_AH_LO + ks * 8;
+          mma_f16_ts(tmem + PK_TM_HEADS, ah, dbh, idesc_h, ks ? 1u : 0u);
+          mma_f16_ts(tmem + PK_TM_HEADS, ah, dbl, idesc_h, 1u);
+          mma_f16_ts(tmem + PK_TM_HEADS, al, dbh, idesc_h, 1u);
+        }
+        mma_commit(bar_heads_done);
+      }
+    }
+  } else if (warp == PK_W_DMMA) {
+    // =============================== decoder MMA issuer ===============================
+    if (lane == 0) {
+      const uint32_t idesc_d = idesc_f16(PK_ROWS, PK_NCH);
+      const uint32_t LBO_A = (PK_ROWS / 8) * 128, LBO_BD = (PK_CBP / 8) * 128;
+      int q = 0;
+#pragma unroll 1
+      for (int i = 0; i < n_tiles; ++i) {
+        pk_wait(bar_z_full + (i & 1), (i >> 1) & 1, s_abort);
+        tc_fence_after();
+        const uint32_t az_hi = smem_u32(s_az + (i & 1) * 2 * AZ_PLANE), az_lo = az_hi + AZ_PLANE;
+#pragma unroll 1
+        for (int ch = 0; ch < n_chunks; ++ch, ++q) {
+          const int b = q & 1;
+          pk_wait(bar_acc_empty + b, ((q >> 1) & 1) ^ 1, s_abort);
+          tc_fence_after();
+          const uint32_t dcol = tmem + PK_TM_ACC + b * PK_NCH;
+          for (int ks = 0; ks < KZ / 16; ++ks) {
+            const uint32_t oa = ks * 2 * LBO_A, ob = ks * 2 * LBO_BD + ch * (PK_NCH / 8) * 128;
+            const uint64_t dah = smem_desc(az_hi + oa, LBO_A, 128), dal = smem_desc(az_lo + oa, LBO_A, 128);
+            const uint64_t dbh = smem_desc(smem_u32(s_bd_hi) + ob, LBO_BD, 128), dbl = smem_desc(smem_u32(s_bd_lo) + ob, LBO_BD, 128);
+            mma_f16(dcol, dah, dbh, idesc_d, ks ? 1u : 0u);
+            mma_f16(dcol, dah, dbl, idesc_d, 1u);
+            mma_f16(dcol, dal, dbh, idesc_d, 1u);
+          }
+          mma_commit(bar_acc_full + b);
+        }
+        mma_commit(bar_z_free + (i & 1));
+      }
+      // every MMA has completed before the CTA tears down TMEM / shared memory
+      if (n_tiles >= 1) pk_wait(bar_z_free + ((n_tiles - 1) & 1), ((n_tiles - 1) >> 1) & 1, s_abort);
+    }
+  } else {
+    // =============================== aux: series caches, regression sums ===============================
+    auto build = [&](int u) {
+      const int slot = u & (PK_SLOTS - 1);
+      const int uc = u % C, ug = (u / C) % N, uv = u / (C * N);
+      const int64_t row = (int64_t)uv * N + ug;
+      float* cache = s_cache + slot * PK_CACHE_F;
+      const float* xs = cx.x[src] + row * C;
+      for (int h = lane; h < MOPOE_HIDDEN; h += 32) {
+        const float* w = ms.w1 + (int64_t)h * C;
+        float a = ms.b1[h];
+        for (int k = 0; k < C; ++k) a = (k == uc) ? a : fmaf(w[k], xs[k], a);
+        cache[h] = a;
+        cache[MOPOE_HIDDEN + h] = w[uc];
+      }
+      bool nd;
+      const int so = pk_owner_subset(mv, cx, ug, nd);
+      float* cs = cache + 2 * MOPOE_HIDDEN;
+      for (int k = lane; k < L + Sd; k += 32) {
+        if (k < L) {
+          float A = 0.f, B = 0.f;
+          if (mv.method == MOPOE_METHOD_MOE) {
+            const int m = mv.sub.members[so][0];
+            A = ws.enc[m][row * mv.mod[m].HC + k];
+            B = expf(0.5f * ws.enc[m][row * mv.mod[m].HC + L + k]);
+          } else {
+            const int nm = mv.sub.n_members[so];
+            for (int q = 0; q < nm; ++q) {
+              const int m = mv.sub.members[so][q];
+              if (m == src) continue;
+              const float T = 1.f / (expf(ws.enc[m][row * mv.mod[m].HC + L + k]) + MOPOE_POE_EPS);
+              A += T; B += ws.enc[m][row * mv.mod[m].HC + k] * T;
+            }
+            if (mv.method == MOPOE_METHOD_POE || nm == M) A += 1.f / (1.f + MOPOE_POE_EPS);
+            if (!((mv.sub.mask[so] >> src) & 1)) {   // owner without src: finished posterior (mu, sd)
+              const float mu = B / A, lv = logf(1.f / A);
+              A = mu; B = expf(0.5f * lv);
+            }
+          }
+          cs[k] = A; cs[32 + k] = B;
+        } else {
+          const int s = k - L;
+          cs[64 + s] = ws.enc[dst][row * mdst.HC + 2 * L + s];
+          cs[96 + s] = expf(0.5f * ws.enc[dst][row * mdst.HC + 2 * L + Sd + s]);
+        }
+      }
+      if (lane == 0) {
+        s_meta[slot * 4] = nd ? 1 : 0;
+        s_xbar[slot] = ws.xstat[(((int64_t)uv * C + uc) * N + ug) * 2];
+      }
+    };
+    // reduce the 4 row quarters of tile i and store the tile's contribution to each of its (<= 2) series:
+    // slot (series, tile index inside the series), summed in fixed order by daa_beta_kernel, so the
+    // tables do not depend on how the tiles were spread over the CTAs
+    auto fold = [&](int i) {
+      int uA, uB;
+      tile_units(i, uA, uB);
+      const int tile_g = tile0 + i;
+      for (int s = 0; s <= uB - uA; ++s) {
+        const int u = uA + s;
+        const int tp = tile_g - (int)(((int64_t)u * J) / PK_ROWS);
+        double* o = ws.sacc + ((int64_t)u * tpu + tp) * 64;
+        for (int k = lane; k < KZ; k += 32) {
+          const int hf = k < KC ? 0 : 1, kk = k - hf * KC;
+          double a = 0.0;
+          for (int w = 0; w < 4; ++w) a += s_part[(((i & 1) * PK_PROD + hf * 4 + w) * 2 + s) * 32 + kk];
+          o[k] = a;
+        }
+      }
+    };
+    if (n_tiles > 0) {
+      int uA, uB;
+      tile_units(0, uA, uB);
+      build(uA);
+      if (uB != uA) build(uB);
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int i = 0; i < n_tiles; ++i) {
+      pk_bar_sync(1, (PK_PROD + 1) * 32);
+      if (i > 0 && col0 == 0) fold(i - 1);
+      if (i + 1 < n_tiles) {
+        int uA, uB, uAn, uBn;
+        tile_units(i, uA, uB);
+        tile_units(i + 1, uAn, uBn);
+        if (uBn != uB) build(uBn);
+      }
+      __syncwarp();
+    }
+    pk_bar_sync(1, (PK_PROD + 1) * 32);
+    if (n_tiles > 0 && col0 == 0) fold(n_tiles - 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (t == 0 && *s_abort) atomicExch(ws.err, 1);
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// per-subject slopes from the regression sums:  beta[v,c,g,roi] = (Wd[roi,:] . sum_tiles sacc[u,tile,:]) / Sxx
+__global__ void __launch_bounds__(256) daa_beta_kernel(ModelView mv, int dst, int R, int n_units, int C, int N, int J, UmmaDims dm,
+                                                        const double* sacc, const double* xstat, double* betas) {
+  extern __shared__ __align__(16) float s_w[];    // [KZ][480] decoder weights in the K order of z (+ bias slot)
+  __shared__ double s_s[64];
+  const ModView& md = mv.mod[dst];
+  const int t = threadIdx.x;
+  const int c0 = blockIdx.y * 480, nc = min(480, R - c0);
+  const int tpu = pipe_tiles_per_unit(J);
+  for (int i = t; i < dm.KZ * nc; i += 256) {
+    const int kz = i / nc, col = c0 + i % nc;
+    float w = 0.f;
+    if (kz < dm.KC) { if (kz < mv.L) w = md.wd[(int64_t)col * md.ZD + md.S + kz]; }
+    else if (kz - dm.KC < md.S) w = md.wd[(int64_t)col * md.ZD + (kz - dm.KC)];
+    if (kz == dm.bias_slot) w = md.bd[col];
+    s_w[kz * 480 + i % nc] = w;
+  }
+  for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+    __syncthreads();
+    if (t < 64) {
+      const int first = (int)(((int64_t)u * J) / PK_ROWS), last = (int)(((int64_t)(u + 1) * J - 1) / PK_ROWS);
+      double a = 0.0;
+      if (t < dm.KZ)
+        for (int tp = 0; tp <= last - first; ++tp) a += sacc[((int64_t)u * tpu + tp) * 64 + t];
+      s_s[t] = a;
+    }
+    __syncthreads();
+    const int uc = u % C, ug = (u / C) % N, uv = u / (C * N);
+    const int64_t obase = ((int64_t)uv * C + uc) * N + ug;
+    const double sxx = xstat[obase * 2 + 1];
+    for (int col = t; col < nc; col += 256) {
+      double sxy = 0.0;
+      for (int k = 0; k < dm.KZ; ++k) sxy = fma(s_s[k], (double)s_w[k * 480 + col], sxy);
+      betas[obase * R + c0 + col] = sxy / sxx;
+    }
+  }
+}
+
+}  // namespace mopoe

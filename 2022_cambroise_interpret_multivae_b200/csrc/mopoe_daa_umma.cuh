@@ -76,19 +76,19 @@ __host__ __device__ inline UmmaSmem umma_plan(const ModelView& mv, int src, cons
 }
 
 // fp32 weights -> fp16 hi/lo planes in UMMA layout (global scratch), once per sweep
-__global__ void daa_umma_prep_kernel(ModelView mv, int src, int dst, int col0, UmmaDims d, unsigned char* out) {
+__global__ void daa_umma_prep_kernel(ModelView mv, int src, int dst, int col0, UmmaDims d, int cb /* decoder rows of the operand */, unsigned char* out) {
   using namespace umma;
   const ModView& ms = mv.mod[src];
   const ModView& md = mv.mod[dst];
   unsigned char* bd_hi = out;
-  unsigned char* bd_lo = bd_hi + CB * d.KZ * 2;
-  unsigned char* bh_hi = bd_lo + CB * d.KZ * 2;
+  unsigned char* bd_lo = bd_hi + cb * d.KZ * 2;
+  unsigned char* bh_hi = bd_lo + cb * d.KZ * 2;
   unsigned char* bh_lo = bh_hi + d.NH * MOPOE_HIDDEN * 2;
-  const int nd = CB * (d.KZ / 8), nh = d.NH * (MOPOE_HIDDEN / 8);
+  const int nd = cb * (d.KZ / 8), nh = d.NH * (MOPOE_HIDDEN / 8);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nd + nh; i += gridDim.x * blockDim.x) {
     float x[8];
     if (i < nd) {
-      const int n = i % CB, k8 = i / CB;       // decoder row (ROI) n, K permuted to [content | style | pad]
+      const int n = i % cb, k8 = i / cb;       // decoder row (ROI) n, K permuted to [content | style | pad]
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int kz = k8 * 8 + q;
@@ -100,7 +100,7 @@ __global__ void daa_umma_prep_kernel(ModelView mv, int src, int dst, int col0, U
         }
         x[q] = w;
       }
-      store_split8(bd_hi, bd_lo, core_off(n, k8, CB), x);
+      store_split8(bd_hi, bd_lo, core_off(n, k8, cb), x);
     } else {
       const int ii = i - nd, n = ii % d.NH, k8 = ii / d.NH;   // class-head output n (mu | logvar), K = hidden
 #pragma unroll
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
     // ================= T2: posterior, reparameterisation, z -> A operand =================
     {
       const float* cs = s_cache + slot * CSLOT;
-      const int64_t ebase = ((((int64_t)(cx.v_av_off + v) * J + j) * C + c) * N + g) * (int64_t)E;
+      const int64_t ridx = (((int64_t)(cx.v_av_off + v) * J + j) * C + c) * N + g;   // noise row (see fill_noise_row)
       const bool my_need = need;
       const int nq = KZ / 8, nqc = dm.KC / 8;
       const int nq0 = nqc < 2 ? nqc : 2;                 // thread half 0: first content chunks, half 1: the rest
@@ -357,9 +357,9 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_umma_kernel(Model
           if (valid && l < (content ? L : Sd)) {
             float e0 = 0.f;
             if (cx.q.sample_latents) {
-              const int64_t idx = ebase + (content ? 0 : mdst.eps_off) + l;
-              if (cx.nz_av.eps) e0 = cx.nz_av.eps[idx];
+              if (cx.nz_av.eps) e0 = cx.nz_av.eps[ridx * E + (content ? 0 : mdst.eps_off) + l];
               else {
+                const int64_t idx = ridx * mv.EP + (content ? 0 : mdst.peps_off) + l;
                 if ((idx >> 2) != blk_have) { blk_have = idx >> 2; nv = philox_normal4_call(cx.nz_av.seed, cx.nz_av.stream, (uint64_t)blk_have); }
                 const int w = (int)(idx & 3);
                 e0 = w == 0 ? nv.x : w == 1 ? nv.y : w == 2 ? nv.z : nv.w;

@@ -61,9 +61,25 @@ def philox_normal(seed, stream, n, start=0):
     return (r * trig).astype(np.float32)
 
 
+def philox_rows(seed, stream, n_rows, latent_dim, style_dims, row_start=0):
+    """(n_rows, E) float32 latent-noise rows of the DAA streams, E = latent_dim + sum(style_dims).
+    Row r is drawn as EP/4 whole Philox blocks (counter = r * EP/4 + b) laid out
+    [content | style_0 | style_1 ...] with every section padded to a multiple of 4 normals; the padding
+    draws are discarded (csrc/mopoe_daa.cu: fill_noise_row)."""
+    pad = lambda n: (n + 3) & ~3
+    widths = [latent_dim] + list(style_dims)
+    ep = sum(pad(w) for w in widths)
+    flat = philox_normal(seed, stream, n_rows * ep, start=row_start * ep).reshape(n_rows, ep)
+    cols, off = [], 0
+    for w in widths:
+        cols.append(flat[:, off:off + w])
+        off += pad(w)
+    return np.ascontiguousarray(np.concatenate(cols, axis=1))
+
+
 # stream ids shared with csrc/mopoe_rng.cuh
-STREAM_DAA_BASE = 1      # eps_base  [n_val, M, N, E]
+STREAM_DAA_BASE = 1      # eps_base  [n_val, M, N, E]                     rows: philox_rows
 STREAM_DAA_SCORE = 2     # eps_score [n_val, n_samples, N, n_scores]
-STREAM_DAA_AVATAR = 3    # eps_av    [n_val, n_samples, n_scores, N, E]
+STREAM_DAA_AVATAR = 3    # eps_av    [n_val, n_samples, n_scores, N, E]   rows: philox_rows
 STREAM_TRAIN = 4         # eps       [n_steps, n_pass, N, E]
 STREAM_FORWARD = 5       # eps       [N, E]

@@ -239,9 +239,10 @@ def test_daa_production_noise_is_shard_invariant_and_matches_oracle():
     part = daa.daa_sweep(spec, flat, src[1:].cuda(), dst[1:].cuda(), J, Mb, seed=seed, val_begin=1, n_val_total=3)
     torch.cuda.synchronize()
     assert torch.equal(full.avatars[1:], part.avatars) and torch.equal(full.pvalues[1:], part.pvalues)
-    eb = torch.from_numpy(philox.philox_normal(seed, philox.STREAM_DAA_BASE, 3 * Mb * N * E)).view(3, Mb, N, E)
+    sd = list(ospec.style_dims)
+    eb = torch.from_numpy(philox.philox_rows(seed, philox.STREAM_DAA_BASE, 3 * Mb * N, ospec.latent_dim, sd)).view(3, Mb, N, E)
     es = torch.from_numpy(philox.philox_normal(seed, philox.STREAM_DAA_SCORE, 3 * J * N * C_)).view(3, J, N, C_)
-    ea = torch.from_numpy(philox.philox_normal(seed, philox.STREAM_DAA_AVATAR, 3 * J * C_ * N * E)).view(3, J, C_, N, E)
+    ea = torch.from_numpy(philox.philox_rows(seed, philox.STREAM_DAA_AVATAR, 3 * J * C_ * N, ospec.latent_dim, sd)).view(3, J, C_, N, E)
     av, sc, rc = daa_oracle.daa_generate(params, ospec, src, dst, eb, es, ea)
     _close(full.avatars, av, "avatars (philox)")
     _close(full.sampled_scores, sc, "scores (philox)")
@@ -261,7 +262,7 @@ def _sweep(spec, flat, src, dst, case, impl, monkeypatch, **kw):
     r = daa.daa_sweep(spec, flat, src.cuda(), dst.cuda(), case["n_samples"], case["n_base"],
                       sample_latents=case["sample_latents"], **kw)
     torch.cuda.synchronize()
-    assert _lib.lib().mopoe_daa_last_impl() == (1 if impl == "umma" else 0)
+    assert _lib.lib().mopoe_daa_last_impl() == {"pipe": 2, "umma": 1, "ffma": 0}[impl]
     return r
 
 
@@ -292,6 +293,37 @@ def test_daa_tensor_core_kernel_vs_oracle_and_cuda_core_kernel(kw, monkeypatch):
     _close(ff.betas, bf, "betas (cuda-core)", rtol=1e-9)
     _close(um.coefs, ff.coefs, "coefs tensor-core vs cuda-core", rtol=1e-3)
     assert np.array_equal(daa_oracle.significant(um.pvalues.cpu().numpy(), 0.7), daa_oracle.significant(pf, 0.7))
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(method="moe", factorized=False), dict(method="poe", n_samples=131),
+                                dict(n_rows=50, n_val=3, n_samples=150), dict(dims=(7, 445), n_rows=9),
+                                dict(dims=(5, 900), n_rows=7, n_val=1, n_samples=140), dict(n_rows=3, n_val=1, n_samples=128)])
+def test_daa_pipelined_kernel_vs_oracle_and_cuda_core_kernel(kw, monkeypatch):
+    """Warp-specialised tcgen05 pipeline (the production kernel) against the oracle on injected noise, and
+    against the CUDA-core kernel; slopes by linearity against the fp64 closed form on its own avatars."""
+    case = _daa_case(**kw)
+    ospec, spec, params, flat = _setup(case)
+    src, dst, eb, es, ea = cases.daa_inputs_of(case, ospec)
+    inj = dict(eps_base=eb.cuda(), eps_score=es.cuda(), eps_av=ea.cuda())
+    pk = _sweep(spec, flat, src, dst, case, "pipe", monkeypatch, **inj)
+    ff = _sweep(spec, flat, src, dst, case, "ffma", monkeypatch, **inj)
+    av, sc, rc = daa_oracle.daa_generate(params, ospec, src, dst, eb, es, ea)
+    _close(pk.avatars, av, "pipelined avatars vs oracle")
+    _close(pk.avatars, ff.avatars, "pipelined vs cuda-core avatars", rtol=2e-5)
+    assert torch.equal(pk.sampled_scores, ff.sampled_scores)
+    p, coef, betas = daa_oracle.hierarchical_regression(pk.avatars.cpu().numpy(), pk.sampled_scores.cpu().numpy())
+    _close(pk.betas, betas, "betas", rtol=1e-5)
+    _close(pk.coefs, coef, "coefs", rtol=1e-5)
+    assert np.all(np.abs(np.log(pk.pvalues.cpu().numpy()) - np.log(p)) <= 1e-4 * np.maximum(1.0, np.abs(np.log(p))))
+    assert np.array_equal(daa_oracle.significant(pk.pvalues.cpu().numpy(), 0.7), daa_oracle.significant(p, 0.7))
+    # production noise: same generator addressing in all three kernels
+    pk2 = _sweep(spec, flat, src, dst, case, "pipe", monkeypatch, seed=11)
+    ff2 = _sweep(spec, flat, src, dst, case, "ffma", monkeypatch, seed=11)
+    _close(pk2.avatars, ff2.avatars, "philox avatars pipelined vs cuda-core", rtol=2e-5)
+    _close(pk2.coefs, ff2.coefs, "philox coefs pipelined vs cuda-core", rtol=1e-3)
+    # no materialisation: same tables
+    nm = _sweep(spec, flat, src, dst, case, "pipe", monkeypatch, seed=11, materialize=False)
+    assert nm.avatars is None and torch.equal(nm.coefs, pk2.coefs) and torch.equal(nm.pvalues, pk2.pvalues)
 
 
 def test_daa_tensor_core_fixed_regression_and_philox(monkeypatch):

@@ -27,3 +27,11 @@ def test_umma_split_gemm(N, K):
     rel, err = _run(N, K)
     assert err == 0, "mbarrier wait timed out"
     assert rel <= 2e-6, rel
+
+
+@pytest.mark.parametrize("N,K", [(48, 256), (96, 64), (16, 32)])
+def test_umma_split_gemm_a_from_tmem(N, K):
+    """A operand written to TMEM with tcgen05.st (thread = row) and consumed by tcgen05.mma [d], [a], b."""
+    rel, err = _run(N, K, variant=2)
+    assert err == 0, "mbarrier wait timed out"
+    assert rel <= 2e-6, rel
