@@ -130,8 +130,9 @@ __device__ __forceinline__ float neg_log_u(float u) {
 __device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t stream, uint64_t blk, float out[4]) {
   uint32_t c0 = (uint32_t)blk, c1 = (uint32_t)(blk >> 32), c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
   philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
-  const float r0 = sqrtf(2.0f * neg_log_u(u01(c0)));
-  const float r1 = sqrtf(2.0f * neg_log_u(u01(c2)));
+  float r0, r1;   // MUFU.SQRT: the argument is a positive normal number, no special cases to patch up
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r0) : "f"(2.0f * neg_log_u(u01(c0))));
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r1) : "f"(2.0f * neg_log_u(u01(c2))));
   float s0, q0, s1, q1;
   __sincosf(6.28318530718f * (u01(c1) - 0.5f), &s0, &q0);
   __sincosf(6.28318530718f * (u01(c3) - 0.5f), &s1, &q1);

@@ -36,7 +36,7 @@ struct DaaWs {
   double* sacc;                // (n_val*N*C, tiles per series, 64)  pipelined kernel: sum_j (x - xbar) * z[k]
   int* counter;                // work-unit counter of the persistent kernel
   int* err;                    // device error flag (tcgen05 barrier time-out)
-  long long* phase;            // [grid][8] per-phase cycle counters of the tcgen05 kernel (profiling runs)
+  long long* phase;            // [grid][32] per-role cycle counters of the tcgen05 kernels (profiling builds)
   unsigned char* bsplit;       // fp16 hi/lo operand planes of the decoder / class-head weights (UMMA layout)
   void* fwd_ws;                // workspace of the encoder forward
   int64_t fwd_ws_bytes;
@@ -61,7 +61,7 @@ static int64_t daa_carve(const mopoe_model_desc* d, const mopoe_daa_desc* q, cha
   t.sacc = (double*)take(rows * C * ((q->n_samples + 126) / 128 + 1) * 64 * 8);
   t.counter = (int*)take(256);
   t.err = (int*)take(256);
-  t.phase = (long long*)take(256 * 8 * 8);
+  t.phase = (long long*)take(256 * 32 * 8);
   t.bsplit = (unsigned char*)take(2 * (480 * 64 * 2) + 2 * (64 * 256 * 2));
   t.fwd_ws_bytes = mopoe_workspace_bytes(d, rows);
   t.fwd_ws = take(t.fwd_ws_bytes);
@@ -821,14 +821,21 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
 
 int mopoe_daa_last_impl(void) { return g_last_impl; }
 
-int mopoe_daa_read_phases(const mopoe_model_desc* desc, const mopoe_daa_desc* daa, void* workspace, int64_t* out8_host) {
+int mopoe_daa_read_phases(const mopoe_model_desc* desc, const mopoe_daa_desc* daa, void* workspace, int64_t* out32_host) {
   if (check_desc(desc)) return MOPOE_EINVAL;
   DaaWs ws;
   daa_carve(desc, daa, (char*)workspace, &ws);
-  long long h[256 * 8];
+  static long long h[256 * 32];
   MOPOE_CUDA(cudaMemcpy(h, ws.phase, sizeof(h), cudaMemcpyDeviceToHost));
   const int grid = num_sms();
-  for (int i = 0; i < 8; ++i) { long long mx = 0; for (int b = 0; b < grid && b < 256; ++b) mx = h[b * 8 + i] > mx ? h[b * 8 + i] : mx; out8_host[i] = mx; }
+  const int stride = g_last_impl == 2 ? 32 : 8, n = g_last_impl == 2 ? 32 : 8;
+  for (int i = 0; i < 32; ++i) out32_host[i] = 0;
+  const char* one = getenv("MOPOE_PHASE_CTA");   // one CTA's counters instead of the max over CTAs
+  for (int i = 0; i < n; ++i) {
+    long long mx = 0;
+    for (int b = 0; b < grid && b < 256; ++b) mx = h[b * stride + i] > mx ? h[b * stride + i] : mx;
+    out32_host[i] = one ? h[(atoi(one) % grid) * stride + i] : mx;
+  }
   return MOPOE_OK;
 }
 

@@ -5,7 +5,8 @@
 // (validation, subject, score, sample) in output order, so a tile is one contiguous 128 x R block of
 // rois_digital_avatars.npy).  The tile pipeline is warp specialised and runs through mbarriers only:
 //
-//   producers (8 warps, thread = avatar row, two warps per TMEM lane quarter)
+//   producers (12 warps, thread = avatar row, three warps per TMEM lane quarter which split the
+//   hidden units of P1 and the 8-latent K chunks of P2/P3 round-robin)
 //       P1  hidden layer of the perturbed src encoder, rank-1 in the score:
 //           h = relu(a0 + W1[:,c] * score), split into fp16 hi/lo and written STRAIGHT INTO TMEM
 //           (tcgen05.st) as the A operand of the class-head GEMM            -> bar h_full
@@ -37,16 +38,18 @@ constexpr int PK_ROWS = 128;
 constexpr int PK_NCH = 96;             // decoder columns per accumulator buffer
 constexpr int PK_MAXCH = 5;            // chunks per launch
 constexpr int PK_CBP = PK_NCH * PK_MAXCH;   // 480 decoder columns per launch
-constexpr int PK_PROD = 8, PK_EPI = 4;
+constexpr int PK_NPW = 3;              // producer warps per TMEM lane quarter
+constexpr int PK_PROD = 4 * PK_NPW, PK_EPI = 4;
 constexpr int PK_W_EPI = PK_PROD, PK_W_HMMA = PK_PROD + PK_EPI, PK_W_DMMA = PK_W_HMMA + 1, PK_W_AUX = PK_W_HMMA + 2;
-constexpr int PK_THREADS = (PK_PROD + PK_EPI + 3) * 32;   // 480
+constexpr int PK_THREADS = (PK_PROD + PK_EPI + 3) * 32;   // 608
 constexpr int PK_STAGE_LD = 36;
 constexpr int PK_SLOTS = 4;            // ring of per-series caches (unit & 3)
 constexpr int PK_TM_HEADS = 0, PK_TM_AH_HI = 64, PK_TM_AH_LO = 192, PK_TM_ACC = 320;
+constexpr int PK_MAXSUBJ = 1024;       // subjects per validation batch (owner table in shared memory)
 constexpr int PK_CACHE_F = 2 * MOPOE_HIDDEN + 128;   // floats per series cache: a0 | w1c | cs
 
 struct PipeSmem {
-  int bd_hi, bd_lo, bh_hi, bh_lo, az, stage, cache, meta, xbar, biash, part, bars, total;
+  int bd_hi, bd_lo, bh_hi, bh_lo, az, stage, cache, meta, xbar, biash, part, gmeta, bars, total;
 };
 
 __host__ __device__ inline PipeSmem pipe_plan(const UmmaDims& d) {
@@ -61,7 +64,8 @@ __host__ __device__ inline PipeSmem pipe_plan(const UmmaDims& d) {
   p.meta = take(PK_SLOTS * 4 * 4);
   p.xbar = take(PK_SLOTS * 8);
   p.biash = take(d.NH * 4);
-  p.part = take(2 * PK_PROD * 2 * 32 * 8);             // [tile parity][warp][series 0|1][k] fp64
+  p.part = take(2 * 4 * 2 * 64 * 8);                    // [tile parity][lane quarter][series 0|1][k] fp64
+  p.gmeta = take(PK_MAXSUBJ);                           // per subject row: bit 7 need_src | owner subset
   p.bars = take(128);
   p.total = off;
   return p;
@@ -74,18 +78,20 @@ __host__ __device__ inline int pipe_tiles_per_unit(int J) { return (J + PK_ROWS 
 // error flag set (results are poisoned by the host wrapper) instead of hanging the GPU
 __device__ __forceinline__ bool pk_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
   const uint32_t addr = umma::smem_u32(bar);
+  // try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or
+  // ~20 us pass), so waiting roles do not burn issue slots of the working ones
 #pragma unroll 1
-  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+  for (uint32_t spin = 0; spin < (1u << 18); ++spin) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(20000u)
         : "memory");
     if (ok) return true;
-    if ((spin & 255u) == 255u && *abort_flag) return false;
+    if ((spin & 63u) == 63u && *abort_flag) return false;
   }
   *abort_flag = 1;
   return false;
@@ -95,20 +101,21 @@ __device__ __forceinline__ void pk_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void pk_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// 32 per-lane fp64 values v[k] -> sum over the 32 lanes of v[k], returned in lane k (transposing butterfly)
-__device__ __forceinline__ double pk_lane_transpose_sum(const float* zq, double xc, int lane) {
-  double a[16];
+// 8 per-lane values xc * zq[k] -> their sum over the 32 lanes, returned in every lane with (lane & 7) == k
+// (transposing butterfly inside each group of 8 lanes, then two exchanges between the groups), fp64
+__device__ __forceinline__ double pk_lane_transpose_sum8(const float* zq, double xc, int lane) {
+  double a[4];
   {
-    const bool up = (lane & 16) != 0;
+    const bool up = (lane & 4) != 0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const double lo = xc * (double)zq[i], hi = xc * (double)zq[i + 16];
+    for (int i = 0; i < 4; ++i) {
+      const double lo = xc * (double)zq[i], hi = xc * (double)zq[i + 4];
       const double keep = up ? hi : lo, send = up ? lo : hi;
-      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
     }
   }
 #pragma unroll
-  for (int w = 8; w >= 1; w >>= 1) {
+  for (int w = 2; w >= 1; w >>= 1) {
     const bool up = (lane & w) != 0;
 #pragma unroll
     for (int i = 0; i < w; ++i) {
@@ -116,8 +123,14 @@ __device__ __forceinline__ double pk_lane_transpose_sum(const float* zq, double 
       a[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
     }
   }
-  return a[0];   // lane holds k = lane (bit b of the lane selected the upper half at width 2^b)
+  double r = a[0];
+  r += __shfl_xor_sync(0xffffffffu, r, 8);
+  r += __shfl_xor_sync(0xffffffffu, r, 16);
+  return r;
 }
+
+__device__ __forceinline__ float pk_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float pk_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // mixture owner of subject row g and whether its posterior needs the perturbed src expert
 __device__ __forceinline__ int pk_owner_subset(const ModelView& mv, const DaaCtx& cx, int g, bool& need_src) {
@@ -132,6 +145,12 @@ __device__ __forceinline__ int pk_owner_subset(const ModelView& mv, const DaaCtx
   need_src = ((mv.sub.mask[s_own] >> cx.q.src_mod) & 1) || (mv.method == MOPOE_METHOD_MOE && mv.sub.n_members[s_own] > 1);
   return s_own;
 }
+
+#ifdef PK_PROF
+#define PK_T(i) do { if (lane == 0) { const long long _n = clock64(); pc[i] += _n - tprev; tprev = _n; } } while (0)
+#else
+#define PK_T(i) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelView mv, DaaCtx cx, DaaWs ws, int col0) {
   using namespace umma;
@@ -157,6 +176,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
   double* s_xbar = reinterpret_cast<double*>(smem + pl.xbar);
   float* s_biash = reinterpret_cast<float*>(smem + pl.biash);
   double* s_part = reinterpret_cast<double*>(smem + pl.part);
+  unsigned char* s_gmeta = smem + pl.gmeta;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + pl.bars);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + pl.bars + 96);
   volatile int* s_abort = reinterpret_cast<volatile int*>(smem + pl.bars + 100);
@@ -180,6 +200,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
       reinterpret_cast<uint4*>(s_bh_lo)[i] = g[2 * nbd + nbh + i];
     }
     for (int i = t; i < NH; i += PK_THREADS) s_biash[i] = i < 2 * L ? ms.bh[i] : 0.f;
+    for (int g = t; g < N; g += PK_THREADS) {
+      bool nd;
+      const int so = pk_owner_subset(mv, cx, g, nd);
+      s_gmeta[g] = (unsigned char)(so | (nd ? 0x80 : 0));
+    }
   }
   if (t == 0) {
     mbar_init(bar_h_full, PK_PROD); mbar_init(bar_heads_done, 1);
@@ -206,24 +231,29 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
   const int row_begin = tile0 * PK_ROWS;
   const int row_end = min(total_rows, (tile0 + n_tiles) * PK_ROWS);
   const int tpu = pipe_tiles_per_unit(J);
-  auto unit_need = [&](int u) -> bool { bool nd; pk_owner_subset(mv, cx, (u / C) % N, nd); return nd; };
+  auto unit_need = [&](int u) -> bool { return (s_gmeta[(u / C) % N] & 0x80) != 0; };
   auto tile_units = [&](int i, int& uA, int& uB) {
     const int r0 = row_begin + i * PK_ROWS, r1 = min(r0 + PK_ROWS, row_end) - 1;
     uA = r0 / J; uB = r1 / J;
   };
 
+#ifdef PK_PROF
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tprev = clock64();
+  const long long tstart = tprev;
+#endif
   if (warp < PK_PROD) {
     // =============================== producers ===============================
-    const int r = t & 127, half = t >> 7;
-    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int q4 = warp & 3, wq = warp >> 2;             // TMEM lane quarter, rank among its producer warps
+    const int r = q4 * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
     const int nbrow = mv.EP >> 2;
-    const int cnt = half ? Sd : L;                       // latents of this thread's half
-    const int nb = (cnt + 3) >> 2;
-    const int sec_blk = half ? (mdst.peps_off >> 2) : 0, sec_off = half ? mdst.eps_off : 0;
+    const int nqc = KC >> 3, nqt = KZ >> 3;              // content chunks, all chunks of 8 latents
     uint32_t heads_waits = 0;
 #pragma unroll 1
     for (int i = 0; i < n_tiles; ++i) {
       pk_bar_sync(1, (PK_PROD + 1) * 32);                // caches of this tile's series are ready
+      PK_T(0);
       const int tile_row = row_begin + i * PK_ROWS;
       int uA, uB;
       tile_units(i, uA, uB);
@@ -238,136 +268,131 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
       const bool tile_need = s_meta[(uA & (PK_SLOTS - 1)) * 4] || s_meta[(uB & (PK_SLOTS - 1)) * 4];
       const bool need = valid && s_meta[slot * 4];
       const float score = valid ? ws.scores[rho] : 0.f;
-      // ---- P1: hidden layer -> TMEM (A operand of the class-head GEMM) ----
+      // ---- P1: hidden layer -> TMEM (A operand of the class-head GEMM), 16 hidden units per step ----
       if (tile_need) {
-        const float4* a0p = reinterpret_cast<const float4*>(cache + half * 128);
-        const float4* wcp = reinterpret_cast<const float4*>(cache + MOPOE_HIDDEN + half * 128);
-#pragma unroll 1
-        for (int kk = 0; kk < 4; ++kk) {
-          uint32_t hi[16], lo[16];
+#pragma unroll 2
+        for (int kc = wq; kc < MOPOE_HIDDEN / 16; kc += PK_NPW) {
+          const float4* a0p = reinterpret_cast<const float4*>(cache + kc * 16);
+          const float4* wcp = reinterpret_cast<const float4*>(cache + MOPOE_HIDDEN + kc * 16);
+          uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 a = a0p[kk * 8 + q], w = wcp[kk * 8 + q];
+          for (int q = 0; q < 4; ++q) {
+            const float4 a = a0p[q], w = wcp[q];
             const float h0 = fmaxf(fmaf(w.x, score, a.x), 0.f), h1 = fmaxf(fmaf(w.y, score, a.y), 0.f);
             const float h2 = fmaxf(fmaf(w.z, score, a.z), 0.f), h3 = fmaxf(fmaf(w.w, score, a.w), 0.f);
             split_pack2(h0, h1, hi[2 * q], lo[2 * q]);
             split_pack2(h2, h3, hi[2 * q + 1], lo[2 * q + 1]);
           }
-          const uint32_t colw = (uint32_t)(half * 64 + kk * 16);     // 32-bit column = 2 hidden units
-          tmem_st16(lane_addr + PK_TM_AH_HI + colw, hi);
-          tmem_st16(lane_addr + PK_TM_AH_LO + colw, lo);
+          tmem_st8(lane_addr + PK_TM_AH_HI + kc * 8, hi);    // 32-bit column = 2 hidden units
+          tmem_st8(lane_addr + PK_TM_AH_LO + kc * 8, lo);
         }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) pk_arrive(bar_h_full);
       }
-      // ---- P2: noise of this row (content half / dst style half) ----
-      float e[32];
+      PK_T(1);
+      pk_wait(bar_z_free + (i & 1), ((i >> 1) & 1) ^ 1, s_abort);
+      PK_T(5);
+      // ---- P2 + P3, one K chunk of 8 latents per pass (content chunks, then dst style chunks): noise,
+      // class heads from TMEM, posterior of the row's mixture owner, reparameterisation, z -> A operand of
+      // the decoder GEMM, first-level regression sums ----
       {
         const int64_t ridx = (((int64_t)(cx.v_av_off + v) * J + j) * C + c) * N + g;
-        if (cx.nz_av.eps) {
-          const float* ep = cx.nz_av.eps + ridx * E + sec_off;
-#pragma unroll
-          for (int l = 0; l < 32; ++l) e[l] = (valid && l < cnt) ? ep[l] : 0.f;
-        } else {
-          const uint64_t blk0 = (uint64_t)(ridx * nbrow + sec_blk);
-#pragma unroll
-          for (int b = 0; b < 8; ++b) {
-            if (b < nb) philox_normal4(cx.nz_av.seed, cx.nz_av.stream, blk0 + b, e + 4 * b);
-            else { e[4 * b] = e[4 * b + 1] = e[4 * b + 2] = e[4 * b + 3] = 0.f; }
-          }
-        }
-      }
-      // ---- P3: posterior / reparameterisation -> z (A operand of the decoder GEMM) ----
-      float zq[32];      // z exactly as the tensor cores see it (hi + lo), for the regression sums
-      if (half == 0) {
-        if (tile_need) {
-          pk_wait(bar_heads_done, heads_waits & 1, s_abort);
-          ++heads_waits;
-          tc_fence_after();
-        }
-#pragma unroll
-        for (int p16 = 0; p16 < 2; ++p16) {
-          if (p16 * 16 < L) {
-            float hm[16], hl[16];
-            if (tile_need) {
-              tmem_ld16(lane_addr + PK_TM_HEADS + p16 * 16, hm);
-              tmem_ld16(lane_addr + PK_TM_HEADS + L + p16 * 16, hl);
-              tmem_ld_wait();
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int l = p16 * 16 + i;
-              float z = 0.f;
-              if (valid && l < L) {
-                float mu = cs[l], sd = cs[32 + l];
-                if (need) {
-                  const float m_ = hm[i] + s_biash[l], lv = hl[i] + s_biash[L + l];
-                  if (mv.method == MOPOE_METHOD_MOE) { mu = m_; sd = expf(0.5f * lv); }
-                  else {
-                    const float T = 1.f / (expf(lv) + MOPOE_POE_EPS);
-                    const float sT = mu + T;                 // cs[l] = sum of the other precisions
-                    mu = (sd + m_ * T) / sT;                 // cs[32+l] = sum of the other mu*T
-                    sd = expf(0.5f * logf(1.f / sT));
-                  }
-                }
-                z = fmaf(e[l], sd, mu);
-              }
-              zq[l] = z;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) zq[p16 * 16 + i] = 0.f;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int l = 0; l < 32; ++l) zq[l] = (valid && l < Sd) ? fmaf(cs[96 + l], e[l], cs[64 + l]) : 0.f;
-      }
-      // the decoder bias rides in a free pad slot of K: z = 1 there, B holds the bias
-      {
-        const int kb = dm.bias_slot - (half ? KC : 0);
-#pragma unroll
-        for (int l = 0; l < 32; ++l) if (l == kb && valid) zq[l] = 1.0f;
-      }
-      pk_wait(bar_z_free + (i & 1), ((i >> 1) & 1) ^ 1, s_abort);
-      {
         unsigned char* az_hi = s_az + (i & 1) * 2 * AZ_PLANE;
         unsigned char* az_lo = az_hi + AZ_PLANE;
-        const int q0 = half ? (KC >> 3) : 0, nq = half ? ((KZ - KC) >> 3) : (KC >> 3);
+        const double xc = valid ? (double)score - s_xbar[slot] : 0.0;
+        const bool inA = valid && u == uA, inB = valid && u != uA;
+        const bool anyA = __any_sync(0xffffffffu, inA), anyB = __any_sync(0xffffffffu, inB);
+        double* part = s_part + (((i & 1) * 4 + q4) * 2) * 64;
+        bool waited = false;
+#pragma unroll 1
+        for (int ci = wq; ci < nqt; ci += PK_NPW) {
+          const bool content = ci < nqc;
+          const int l0 = (content ? ci : ci - nqc) * 8;        // first latent of the chunk inside its section
+          const int cnt = content ? L : Sd;
+          const float* csb = cs + (content ? 0 : 64) + l0;     // [0..32) mean part, [32..64) scale part
+          float e[8];
+          if (cx.nz_av.eps) {
+            const float* ep = cx.nz_av.eps + ridx * E + (content ? 0 : mdst.eps_off) + l0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (q < nq) {
+            for (int k = 0; k < 8; ++k) e[k] = (valid && l0 + k < cnt) ? ep[k] : 0.f;
+          } else {
+            // two independent Philox chains (draws past the end of the section are unused)
+            const uint64_t blk = (uint64_t)(ridx * nbrow + ((content ? 0 : mdst.peps_off) + l0) / 4);
+            philox_normal4(cx.nz_av.seed, cx.nz_av.stream, blk, e);
+            philox_normal4(cx.nz_av.seed, cx.nz_av.stream, blk + 1, e + 4);
+          }
+          const bool heads = content && tile_need;
+          float hm[8], hl[8];
+          if (heads) {
+            if (!waited) {
+              PK_T(2);
+              pk_wait(bar_heads_done, heads_waits & 1, s_abort);
+              ++heads_waits;
+              waited = true;
+              tc_fence_after();
+              PK_T(3);
+            }
+            tmem_ld8(lane_addr + PK_TM_HEADS + l0, hm);
+            tmem_ld8(lane_addr + PK_TM_HEADS + L + l0, hl);
+            tmem_ld_wait();
+          }
+          const bool upd = heads && need;
+          const int kb = dm.bias_slot - ci * 8;          // decoder bias rides in a free pad slot of K
+          float zq[8];      // ends up holding z exactly as the tensor cores see it (hi + lo)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float mu = csb[k], sd = csb[32 + k];
+            if (heads) {        // warp-uniform; rows that do not need the src expert keep the cached posterior
+              const float m_ = hm[k] + s_biash[l0 + k], lv = hl[k] + s_biash[L + l0 + k];
+              float mu2, sd2;
+              if (mv.method == MOPOE_METHOD_MOE) { mu2 = m_; sd2 = pk_ex2(0.5f * 1.4426950408889634f * lv); }
+              else {
+                // poe (mm_div.py:13-20) in MUFU arithmetic: T = 1/(exp(lv)+eps), var = 1/sum T
+                const float T = pk_rcp(pk_ex2(1.4426950408889634f * lv) + MOPOE_POE_EPS);
+                const float sT = mu + T;                 // cs[l] = sum of the other precisions
+                mu2 = (sd + m_ * T) * pk_rcp(sT);        // cs[32+l] = sum of the other mu*T
+                sd2 = rsqrtf(sT);                        // exp(0.5 * log(1 / sT))
+              }
+              mu = upd ? mu2 : mu; sd = upd ? sd2 : sd;
+            }
+            float z = fmaf(e[k], sd, mu);
+            z = (valid && l0 + k < cnt) ? z : 0.f;
+            zq[k] = (k == kb && valid) ? 1.0f : z;
+          }
+          {
             __half h8[8], l8[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              split_f16(zq[q * 8 + k], h8[k], l8[k]);
-              zq[q * 8 + k] = __half2float(h8[k]) + __half2float(l8[k]);
+              split_f16(zq[k], h8[k], l8[k]);
+              zq[k] = __half2float(h8[k]) + __half2float(l8[k]);
             }
-            const uint32_t off = core_off(r, q0 + q, PK_ROWS);
+            const uint32_t off = core_off(r, ci, PK_ROWS);
             *reinterpret_cast<uint4*>(az_hi + off) = *reinterpret_cast<const uint4*>(h8);
             *reinterpret_cast<uint4*>(az_lo + off) = *reinterpret_cast<const uint4*>(l8);
           }
+          // regression sums of this warp's 32 rows (series uA and, past a boundary, uA + 1)
+          if (col0 == 0) {
+#pragma unroll 1
+            for (int sidx = 0; sidx < 2; ++sidx) {
+              double sum = 0.0;
+              if (sidx ? anyB : anyA) sum = pk_lane_transpose_sum8(zq, (sidx ? inB : inA) ? xc : 0.0, lane);
+              if (lane < 8) part[sidx * 64 + ci * 8 + lane] = sum;
+            }
+          }
         }
       }
+      PK_T(4);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) pk_arrive(bar_z_full + (i & 1));
-      // ---- first-level regression sums of this warp's 32 rows (series uA and, past a boundary, uA+1) ----
-      if (col0 == 0) {
-        const double xc = valid ? (double)score - s_xbar[slot] : 0.0;
-        const bool inA = valid && u == uA, inB = valid && u != uA;
-        double* part = s_part + (((i & 1) * PK_PROD + warp) * 2) * 32;
-        const bool anyA = __any_sync(0xffffffffu, inA), anyB = __any_sync(0xffffffffu, inB);
-        double sA = 0.0, sB = 0.0;
-        if (anyA) sA = pk_lane_transpose_sum(zq, inA ? xc : 0.0, lane);
-        if (anyB) sB = pk_lane_transpose_sum(zq, inB ? xc : 0.0, lane);
-        part[lane] = sA;
-        part[32 + lane] = sB;
-      }
+      PK_T(6);
     }
     pk_bar_sync(1, (PK_PROD + 1) * 32);      // last tile's partial sums are visible to the aux warp
+#ifdef PK_PROF
+    if ((warp == 0 || warp == 4) && lane == 0) for (int k = 0; k < 8; ++k) ws.phase[(blockIdx.x * 4 + (warp >> 2)) * 8 + k] = pc[k];
+#endif
   } else if (warp < PK_W_HMMA) {
     // =============================== epilogue ===============================
     const int q4 = warp & 3;
@@ -381,7 +406,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
 #pragma unroll 1
       for (int ch = 0; ch < n_chunks; ++ch, ++q) {
         const int b = q & 1;
+        PK_T(1);
         pk_wait(bar_acc_full + b, (q >> 1) & 1, s_abort);
+        PK_T(0);
         tc_fence_after();
         const int nsub = min(3, (ncol - ch * PK_NCH + 31) >> 5);
 #pragma unroll 1
@@ -401,18 +428,26 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
               *reinterpret_cast<float4*>(s_stage + lane * PK_STAGE_LD + 4 * k) = make_float4(vv[4 * k], vv[4 * k + 1], vv[4 * k + 2], vv[4 * k + 3]);
             __syncwarp();
             const int rr0 = lane >> 3, cg = (lane & 7) * 4;
+            float* gbase = cx.avatars + (int64_t)(tile_row + q4 * 32 + rr0) * R + col0 + cb0 + cg;
+            const float* sbase = s_stage + rr0 * PK_STAGE_LD + cg;
+            if (rows_left == 32 && (R & 3) == 0 && cb0 + 32 <= ncol) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + rr0;
-              if (rr < rows_left) {
-                const float4 o = *reinterpret_cast<const float4*>(s_stage + rr * PK_STAGE_LD + cg);
-                float* dstp = cx.avatars + (int64_t)(tile_row + q4 * 32 + rr) * R + col0 + cb0 + cg;
-                if ((R & 3) == 0 && cb0 + cg + 4 <= ncol) __stcs(reinterpret_cast<float4*>(dstp), o);
-                else {
-                  if (cb0 + cg + 0 < ncol) dstp[0] = o.x;
-                  if (cb0 + cg + 1 < ncol) dstp[1] = o.y;
-                  if (cb0 + cg + 2 < ncol) dstp[2] = o.z;
-                  if (cb0 + cg + 3 < ncol) dstp[3] = o.w;
+              for (int it = 0; it < 8; ++it)
+                __stcs(reinterpret_cast<float4*>(gbase + (int64_t)it * 4 * R), *reinterpret_cast<const float4*>(sbase + it * 4 * PK_STAGE_LD));
+            } else {
+#pragma unroll 1
+              for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + rr0;
+                if (rr < rows_left) {
+                  const float4 o = *reinterpret_cast<const float4*>(sbase + it * 4 * PK_STAGE_LD);
+                  float* dstp = gbase + (int64_t)it * 4 * R;
+                  if ((R & 3) == 0 && cb0 + cg + 4 <= ncol) __stcs(reinterpret_cast<float4*>(dstp), o);
+                  else {
+                    if (cb0 + cg + 0 < ncol) dstp[0] = o.x;
+                    if (cb0 + cg + 1 < ncol) dstp[1] = o.y;
+                    if (cb0 + cg + 2 < ncol) dstp[2] = o.z;
+                    if (cb0 + cg + 3 < ncol) dstp[3] = o.w;
+                  }
                 }
               }
             }
@@ -421,6 +456,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
         }
       }
     }
+#ifdef PK_PROF
+    if (warp == PK_W_EPI && lane == 0) { pc[2] = clock64() - tstart; for (int k = 0; k < 4; ++k) ws.phase[(blockIdx.x * 4 + 2) * 8 + k] = pc[k]; }
+#endif
   } else if (warp == PK_W_HMMA) {
     // =============================== class-head MMA issuer ===============================
     if (lane == 0) {
@@ -455,13 +493,17 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
       int q = 0;
 #pragma unroll 1
       for (int i = 0; i < n_tiles; ++i) {
+        PK_T(2);
         pk_wait(bar_z_full + (i & 1), (i >> 1) & 1, s_abort);
+        PK_T(0);
         tc_fence_after();
         const uint32_t az_hi = smem_u32(s_az + (i & 1) * 2 * AZ_PLANE), az_lo = az_hi + AZ_PLANE;
 #pragma unroll 1
         for (int ch = 0; ch < n_chunks; ++ch, ++q) {
           const int b = q & 1;
+          PK_T(2);
           pk_wait(bar_acc_empty + b, ((q >> 1) & 1) ^ 1, s_abort);
+          PK_T(1);
           tc_fence_after();
           const uint32_t dcol = tmem + PK_TM_ACC + b * PK_NCH;
           for (int ks = 0; ks < KZ / 16; ++ks) {
@@ -478,6 +520,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
       }
       // every MMA has completed before the CTA tears down TMEM / shared memory
       if (n_tiles >= 1) pk_wait(bar_z_free + ((n_tiles - 1) & 1), ((n_tiles - 1) >> 1) & 1, s_abort);
+#ifdef PK_PROF
+      for (int k = 0; k < 4; ++k) ws.phase[(blockIdx.x * 4 + 2) * 8 + 4 + k] = pc[k];
+#endif
     }
   } else {
     // =============================== aux: series caches, regression sums ===============================
@@ -486,16 +531,29 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
       const int uc = u % C, ug = (u / C) % N, uv = u / (C * N);
       const int64_t row = (int64_t)uv * N + ug;
       float* cache = s_cache + slot * PK_CACHE_F;
+      // no L1 to speak of next to 224 KB of shared memory: every load is an L2 round trip, so issue
+      // them in bulk (C <= UM_MAXC = 16 columns, two hidden units per lane in flight)
       const float* xs = cx.x[src] + row * C;
+      float xr[UM_MAXC];
+#pragma unroll
+      for (int k = 0; k < UM_MAXC; ++k) xr[k] = k < C ? xs[k] : 0.f;
+#pragma unroll 2
       for (int h = lane; h < MOPOE_HIDDEN; h += 32) {
         const float* w = ms.w1 + (int64_t)h * C;
-        float a = ms.b1[h];
-        for (int k = 0; k < C; ++k) a = (k == uc) ? a : fmaf(w[k], xs[k], a);
+        float wk[UM_MAXC];
+#pragma unroll
+        for (int k = 0; k < UM_MAXC; ++k) wk[k] = k < C ? w[k] : 0.f;
+        float a = ms.b1[h], wc = 0.f;
+#pragma unroll
+        for (int k = 0; k < UM_MAXC; ++k) {
+          if (k < C) a = (k == uc) ? a : fmaf(wk[k], xr[k], a);
+          wc = (k == uc) ? wk[k] : wc;
+        }
         cache[h] = a;
-        cache[MOPOE_HIDDEN + h] = w[uc];
+        cache[MOPOE_HIDDEN + h] = wc;
       }
-      bool nd;
-      const int so = pk_owner_subset(mv, cx, ug, nd);
+      const bool nd = (s_gmeta[ug] & 0x80) != 0;
+      const int so = s_gmeta[ug] & 0x7f;
       float* cs = cache + 2 * MOPOE_HIDDEN;
       for (int k = lane; k < L + Sd; k += 32) {
         if (k < L) {
@@ -542,34 +600,37 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
         const int tp = tile_g - (int)(((int64_t)u * J) / PK_ROWS);
         double* o = ws.sacc + ((int64_t)u * tpu + tp) * 64;
         for (int k = lane; k < KZ; k += 32) {
-          const int hf = k < KC ? 0 : 1, kk = k - hf * KC;
           double a = 0.0;
-          for (int w = 0; w < 4; ++w) a += s_part[(((i & 1) * PK_PROD + hf * 4 + w) * 2 + s) * 32 + kk];
+          for (int w = 0; w < 4; ++w) a += s_part[(((i & 1) * 4 + w) * 2 + s) * 64 + k];
           o[k] = a;
         }
       }
     };
-    if (n_tiles > 0) {
-      int uA, uB;
-      tile_units(0, uA, uB);
-      build(uA);
-      if (uB != uA) build(uB);
-    }
-    __syncwarp();
+    // iteration i = -1 builds the caches of tile 0; iteration i >= 0 runs behind barrier X(i): it folds
+    // tile i-1 and builds the series that is new in tile i+1, one tile ahead of the producers
+    int built = -1;
 #pragma unroll 1
-    for (int i = 0; i < n_tiles; ++i) {
-      pk_bar_sync(1, (PK_PROD + 1) * 32);
-      if (i > 0 && col0 == 0) fold(i - 1);
+    for (int i = -1; i < n_tiles; ++i) {
+      if (i >= 0) {
+        PK_T(1);
+        pk_bar_sync(1, (PK_PROD + 1) * 32);
+        PK_T(0);
+        if (i > 0 && col0 == 0) fold(i - 1);
+      }
       if (i + 1 < n_tiles) {
-        int uA, uB, uAn, uBn;
-        tile_units(i, uA, uB);
+        int uAn, uBn;
         tile_units(i + 1, uAn, uBn);
-        if (uBn != uB) build(uBn);
+#pragma unroll 1
+        for (int u = max(built + 1, uAn); u <= uBn; ++u) build(u);
+        built = uBn;
       }
       __syncwarp();
     }
     pk_bar_sync(1, (PK_PROD + 1) * 32);
     if (n_tiles > 0 && col0 == 0) fold(n_tiles - 1);
+#ifdef PK_PROF
+    if (lane == 0) for (int k = 0; k < 2; ++k) ws.phase[(blockIdx.x * 4 + 3) * 8 + k] = pc[k];
+#endif
   }
   tc_fence_before();
   __syncthreads();

@@ -83,7 +83,7 @@ def daa_sweep(spec: PathSpec, flat_params, src, dst, n_samples, n_base, *, src_m
 
 def phase_cycles(spec: PathSpec, result):
     """Per-phase cycle counters of the tcgen05 avatar kernel of `result`'s sweep (profiling aid)."""
-    out = (C.c_int64 * 8)()
+    out = (C.c_int64 * 32)()
     torch.cuda.synchronize()
     _lib.check(_lib.lib().mopoe_daa_read_phases(C.byref(spec.desc), C.byref(result._desc), _ptr(result._keep[-1]), out))
     return list(out)

@@ -232,9 +232,9 @@ int mopoe_profile_enable(int on);
 /* which avatar kernel the last mopoe_daa_sweep used: 1 = tcgen05 tensor cores, 0 = CUDA cores
  * (shapes outside the tcgen05 tiling, or MOPOE_DAA_IMPL=ffma in the environment) */
 int mopoe_daa_last_impl(void);
-/* per-phase cycle counters (max over CTAs) of the last tcgen05 avatar kernel run on `workspace`:
- * [0] metadata/caches [1] heads GEMM [2] posterior+z [3] decoder GEMM [4] epilogue [5] series flush */
-int mopoe_daa_read_phases(const mopoe_model_desc* desc, const mopoe_daa_desc* daa, void* workspace, int64_t* out8_host);
+/* per-role cycle counters (max over CTAs, 32 slots) of the last tcgen05 avatar kernel run on
+ * `workspace`; filled by profiling builds of the library only (csrc/Makefile EXTRA=-DPK_PROF) */
+int mopoe_daa_read_phases(const mopoe_model_desc* desc, const mopoe_daa_desc* daa, void* workspace, int64_t* out32_host);
 int mopoe_daa_last_kernel_ms(float* ms_out);
 
 /* Fill `out[0..n)` with philox_normal(seed, stream_id, start + i): the production noise generator,
