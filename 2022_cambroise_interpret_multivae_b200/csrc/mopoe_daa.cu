@@ -113,25 +113,51 @@ __global__ void __launch_bounds__(MOPOE_THREADS) daa_base_kernel(ModelView mv, D
   const int M = mv.M, L = mv.L, E = mv.E;
   const int64_t row = (int64_t)v * cx.N + g;
   float* s_mean = sm;                 // [E] mean eps
-  float* s_acc = s_mean + 160;        // [8][E] per-warp sums
-  float* s_row = s_acc + 8 * 160;     // [8][E] per-warp noise row
-  float* s_zz = s_row + 8 * 160;      // [M][64] decoder inputs
+  float* s_acc = s_mean + 176;        // [threads / nb][EP] per-group sums (block-padded columns)
+  float* s_zz = s_acc + 1024;         // [M][64] decoder inputs
   float* s_loc = s_zz + MOPOE_MAX_MODS * 64;  // [C]
-  for (int i = t; i < 8 * 160; i += MOPOE_THREADS) s_acc[i] = 0.f;
-  __syncthreads();
-  // mean over the n_base passes of the noise row of this subject
-  for (int p = warp; p < cx.q.n_base; p += 8) {
-    const int64_t ridx = ((int64_t)(cx.v_base_off + v) * cx.q.n_base + p) * cx.N + g;
-    fill_noise_row(mv, cx.nz_base, ridx, s_row + warp * 160, lane, 32);
-    __syncwarp();
-    for (int e = lane; e < E; e += 32) s_acc[warp * 160 + e] += s_row[warp * 160 + e];
-    __syncwarp();
-  }
-  __syncthreads();
-  for (int e = t; e < E; e += MOPOE_THREADS) {
-    float a = 0.f;
-    for (int w = 0; w < 8; ++w) a += s_acc[w * 160 + e];
-    s_mean[e] = a / (float)cx.q.n_base;
+  // mean over the n_base passes of the noise row of this subject.  Thread = (Philox block b of the row,
+  // pass group): every lane draws whole blocks, four independent passes in flight per thread.
+  {
+    const int nb = mv.EP >> 2, ngrp = MOPOE_THREADS / nb;
+    const int b = t % nb, grp = t / nb;
+    int e0 = 4 * b, lim = mv.L;           // unpadded column of the block's first element, end of its section
+    for (int m = 0; m < M; ++m)
+      if (4 * b >= mv.mod[m].peps_off) { e0 = mv.mod[m].eps_off + (4 * b - mv.mod[m].peps_off); lim = mv.mod[m].eps_off + mv.mod[m].S; }
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (grp < ngrp) {
+      const int64_t r0 = (int64_t)(cx.v_base_off + v) * cx.q.n_base * cx.N + g;   // noise row of pass 0
+      if (cx.nz_base.eps) {
+        for (int p = grp; p < cx.q.n_base; p += ngrp) {
+          const float* ep = cx.nz_base.eps + (r0 + (int64_t)p * cx.N) * E;
+          if (e0 + 0 < lim) a0 += ep[e0 + 0];
+          if (e0 + 1 < lim) a1 += ep[e0 + 1];
+          if (e0 + 2 < lim) a2 += ep[e0 + 2];
+          if (e0 + 3 < lim) a3 += ep[e0 + 3];
+        }
+      } else {
+#pragma unroll 4
+        for (int p = grp; p < cx.q.n_base; p += ngrp) {
+          float x[4];
+          philox_normal4(cx.nz_base.seed, cx.nz_base.stream, (uint64_t)((r0 + (int64_t)p * cx.N) * nb + b), x);
+          a0 += x[0]; a1 += x[1]; a2 += x[2]; a3 += x[3];
+        }
+      }
+      float* o = s_acc + grp * mv.EP + 4 * b;
+      o[0] = a0; o[1] = a1; o[2] = a2; o[3] = a3;
+    }
+    __syncthreads();
+    if (t < mv.EP) {
+      const int bb = t >> 2, i = t & 3;
+      int ee = 4 * bb, ll = mv.L;
+      for (int m = 0; m < M; ++m)
+        if (4 * bb >= mv.mod[m].peps_off) { ee = mv.mod[m].eps_off + (4 * bb - mv.mod[m].peps_off); ll = mv.mod[m].eps_off + mv.mod[m].S; }
+      if (ee + i < ll) {
+        float a = 0.f;
+        for (int q = 0; q < ngrp; ++q) a += s_acc[q * mv.EP + t];
+        s_mean[ee + i] = a / (float)cx.q.n_base;
+      }
+    }
   }
   __syncthreads();
   // joint posterior of this row (sampling semantics: the row's mixture owner), mean latent
@@ -163,21 +189,23 @@ __global__ void __launch_bounds__(MOPOE_THREADS) daa_base_kernel(ModelView mv, D
     }
   }
   __syncthreads();
-  // decode src -> loc_hat, dst -> reconstruction   (affine decoders: mean over passes == decode of mean z)
+  // decode src -> loc_hat, dst -> reconstruction   (affine decoders: mean over passes == decode of mean z);
+  // warp per output row, lanes over K (coalesced weight rows)
   {
     const ModView& ms = mv.mod[cx.q.src_mod];
-    for (int c = t; c < cx.C; c += MOPOE_THREADS) {
-      float a = ms.bd[c];
-      for (int k = 0; k < ms.ZD; ++k) a = fmaf(s_zz[cx.q.src_mod * 64 + k], ms.wd[(int64_t)c * ms.ZD + k], a);
-      s_loc[c] = a;
-      ws.loc_hat[row * cx.C + c] = a;
+    for (int c = warp; c < cx.C; c += 8) {
+      float a = 0.f;
+      for (int k = lane; k < ms.ZD; k += 32) a = fmaf(s_zz[cx.q.src_mod * 64 + k], ms.wd[(int64_t)c * ms.ZD + k], a);
+      a = warp_sum(a) + ms.bd[c];
+      if (lane == 0) { s_loc[c] = a; ws.loc_hat[row * cx.C + c] = a; }
     }
     const ModView& mdst = mv.mod[cx.q.dst_mod];
     if (cx.recon)
-      for (int r = t; r < cx.R; r += MOPOE_THREADS) {
-        float a = mdst.bd[r];
-        for (int k = 0; k < mdst.ZD; ++k) a = fmaf(s_zz[cx.q.dst_mod * 64 + k], mdst.wd[(int64_t)r * mdst.ZD + k], a);
-        cx.recon[row * cx.R + r] = a;
+      for (int r = warp; r < cx.R; r += 8) {
+        float a = 0.f;
+        for (int k = lane; k < mdst.ZD; k += 32) a = fmaf(s_zz[cx.q.dst_mod * 64 + k], mdst.wd[(int64_t)r * mdst.ZD + k], a);
+        a = warp_sum(a) + mdst.bd[r];
+        if (lane == 0) cx.recon[row * cx.R + r] = a;
       }
   }
   __syncthreads();
@@ -742,7 +770,7 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   cx.avatars = avatars; cx.sampled_scores = sampled_scores; cx.recon = reconstructions; cx.betas = betas;
   cx.C = desc->dims[daa->src_mod]; cx.R = desc->dims[daa->dst_mod]; cx.J = daa->n_samples; cx.N = N;
   // 2. base passes
-  const int base_smem = (160 + 16 * 160 + MOPOE_MAX_MODS * 64 + 64) * 4;
+  const int base_smem = (176 + 1024 + MOPOE_MAX_MODS * 64 + 64) * 4;
   daa_base_kernel<<<daa->n_val * N, MOPOE_THREADS, base_smem, stream>>>(mv, cx, ws);
   MOPOE_CUDA(cudaGetLastError());
   // 3. avatars + first-level regression
@@ -779,9 +807,11 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
       MOPOE_CUDA(cudaGetLastError());
       if (g_profile && col0 == 0) MOPOE_CUDA(cudaEventRecord(g_ev1, stream));
     }
-    const int bsm = ud0.KZ * 480 * 4;
-    MOPOE_CUDA(cudaFuncSetAttribute((void*)daa_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bsm));
-    daa_beta_kernel<<<dim3(num_sms(), (cx.R + 479) / 480), 256, bsm, stream>>>(mv, daa->dst_mod, cx.R, n_units, cx.C, N, cx.J, ud0, ws.sacc, ws.xstat, ws.betas);
+    // slopes + second-level test of the pipelined path (replaces step 4 below)
+    const int bsm = ud0.KZ * BS_COLS * 8;
+    MOPOE_CUDA(cudaFuncSetAttribute((void*)daa_beta_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bsm));
+    daa_beta_stats_kernel<<<dim3(daa->n_val * cx.C, (cx.R + BS_COLS - 1) / BS_COLS), BS_COLS, bsm, stream>>>(
+        mv, daa->dst_mod, cx.R, cx.C, N, cx.J, ud0, ws.sacc, ws.xstat, ws.betas, coefs, pvalues);
     MOPOE_CUDA(cudaGetLastError());
   } else if (impl == 1) {
     void* ufn = daa->reg_method == 1 ? (void*)daa_avatar_umma_kernel<true> : (void*)daa_avatar_umma_kernel<false>;
@@ -809,9 +839,11 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   if (g_profile && impl != 2) MOPOE_CUDA(cudaEventRecord(g_ev1, stream));
   // 4. second level
   const int64_t nstat = (int64_t)daa->n_val * cx.C * cx.R;
-  daa_stats_kernel<<<(unsigned)((nstat + 127) / 128), 128, 0, stream>>>(daa->n_val, N, cx.C, cx.J, cx.R, daa->reg_method, ws.betas,
-                                                                       ws.ybar, ws.syy, ws.xstat, reconstructions, coefs, pvalues);
-  MOPOE_CUDA(cudaGetLastError());
+  if (impl != 2) {
+    daa_stats_kernel<<<(unsigned)((nstat + 127) / 128), 128, 0, stream>>>(daa->n_val, N, cx.C, cx.J, cx.R, daa->reg_method, ws.betas,
+                                                                         ws.ybar, ws.syy, ws.xstat, reconstructions, coefs, pvalues);
+    MOPOE_CUDA(cudaGetLastError());
+  }
   if (impl != 0) {
     daa_poison_kernel<<<32, 256, 0, stream>>>(ws.err, coefs, pvalues, nstat);
     MOPOE_CUDA(cudaGetLastError());

@@ -638,41 +638,86 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-// per-subject slopes from the regression sums:  beta[v,c,g,roi] = (Wd[roi,:] . sum_tiles sacc[u,tile,:]) / Sxx
-__global__ void __launch_bounds__(256) daa_beta_kernel(ModelView mv, int dst, int R, int n_units, int C, int N, int J, UmmaDims dm,
-                                                        const double* sacc, const double* xstat, double* betas) {
-  extern __shared__ __align__(16) float s_w[];    // [KZ][480] decoder weights in the K order of z (+ bias slot)
-  __shared__ double s_s[64];
+// Per-subject slopes and the second-level test of the pipelined path in one pass:
+//   beta[v,c,g,roi] = (Wd[roi,:] . sum_tiles sacc[u,tile,:]) / Sxx[u]            (stat_utils.py:66-68)
+//   coef = mean_g beta, t = coef / (sd_g(beta) / sqrt(N)), p = 2 sf(|t|, N-1)     (stat_utils.py:73-75)
+// CTA = (validation, score) x block of 256 ROIs; the decoder weights of the block sit in shared memory
+// as fp64 in the K order of z (+ bias slot); 10 subjects per batch share every weight load.
+constexpr int BS_COLS = 256, BS_GB = 10;
+
+__device__ double two_sided_t_pvalue(double tval, double nu);
+
+__global__ void __launch_bounds__(BS_COLS) daa_beta_stats_kernel(ModelView mv, int dst, int R, int C, int N, int J, UmmaDims dm,
+                                                                  const double* sacc, const double* xstat, double* betas,
+                                                                  double* coefs, double* pvalues) {
+  extern __shared__ __align__(16) double s_wd[];          // [KZ][BS_COLS]
+  __shared__ __align__(16) double s_s[64][BS_GB];         // regression sums of the batch, k-major
+  __shared__ double s_sxx[BS_GB];
   const ModView& md = mv.mod[dst];
   const int t = threadIdx.x;
-  const int c0 = blockIdx.y * 480, nc = min(480, R - c0);
-  const int tpu = pipe_tiles_per_unit(J);
-  for (int i = t; i < dm.KZ * nc; i += 256) {
-    const int kz = i / nc, col = c0 + i % nc;
-    float w = 0.f;
-    if (kz < dm.KC) { if (kz < mv.L) w = md.wd[(int64_t)col * md.ZD + md.S + kz]; }
-    else if (kz - dm.KC < md.S) w = md.wd[(int64_t)col * md.ZD + (kz - dm.KC)];
-    if (kz == dm.bias_slot) w = md.bd[col];
-    s_w[kz * 480 + i % nc] = w;
+  const int v = blockIdx.x / C, c = blockIdx.x % C;
+  const int c0 = blockIdx.y * BS_COLS, nc = min(BS_COLS, R - c0);
+  const int tpu = pipe_tiles_per_unit(J), KZ = dm.KZ;
+  for (int i = t; i < KZ * BS_COLS; i += BS_COLS) s_wd[i] = 0.0;
+  __syncthreads();
+  for (int i = t; i < nc * md.ZD; i += BS_COLS) {         // coalesced: the block's weight rows are contiguous
+    const int col = i / md.ZD, zd = i % md.ZD;
+    const int kz = zd < md.S ? dm.KC + zd : zd - md.S;   // decoder input = [style | content], z = [content | style]
+    s_wd[kz * BS_COLS + col] = (double)md.wd[(int64_t)c0 * md.ZD + i];
   }
-  for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+  if (dm.bias_slot >= 0 && t < nc) s_wd[dm.bias_slot * BS_COLS + t] = (double)md.bd[c0 + t];
+  const bool active = t < nc;
+  double b0 = 0.0, sd1 = 0.0, sd2 = 0.0;
+  for (int g0 = 0; g0 < N; g0 += BS_GB) {
+    const int ng = min(BS_GB, N - g0);
     __syncthreads();
-    if (t < 64) {
-      const int first = (int)(((int64_t)u * J) / PK_ROWS), last = (int)(((int64_t)(u + 1) * J - 1) / PK_ROWS);
+    for (int i = t; i < BS_GB * 64; i += BS_COLS) {
+      const int gb = i >> 6, k = i & 63;
       double a = 0.0;
-      if (t < dm.KZ)
-        for (int tp = 0; tp <= last - first; ++tp) a += sacc[((int64_t)u * tpu + tp) * 64 + t];
-      s_s[t] = a;
+      if (gb < ng && k < KZ) {
+        const int u = ((v * N) + g0 + gb) * C + c;
+        const int first = (int)(((int64_t)u * J) / PK_ROWS), last = (int)(((int64_t)(u + 1) * J - 1) / PK_ROWS);
+        for (int tp = 0; tp <= last - first; ++tp) a += sacc[((int64_t)u * tpu + tp) * 64 + k];
+      }
+      s_s[k][gb] = a;
     }
+    if (t < BS_GB) s_sxx[t] = t < ng ? xstat[(((int64_t)v * C + c) * N + g0 + t) * 2 + 1] : 1.0;
     __syncthreads();
-    const int uc = u % C, ug = (u / C) % N, uv = u / (C * N);
-    const int64_t obase = ((int64_t)uv * C + uc) * N + ug;
-    const double sxx = xstat[obase * 2 + 1];
-    for (int col = t; col < nc; col += 256) {
-      double sxy = 0.0;
-      for (int k = 0; k < dm.KZ; ++k) sxy = fma(s_s[k], (double)s_w[k * 480 + col], sxy);
-      betas[obase * R + c0 + col] = sxy / sxx;
+    if (active) {
+      double acc[BS_GB];
+#pragma unroll
+      for (int gb = 0; gb < BS_GB; ++gb) acc[gb] = 0.0;
+      for (int k = 0; k < KZ; ++k) {
+        const double w = s_wd[k * BS_COLS + t];
+        const double2* sp = reinterpret_cast<const double2*>(&s_s[k][0]);
+#pragma unroll
+        for (int q = 0; q < BS_GB / 2; ++q) {
+          const double2 sv = sp[q];
+          acc[2 * q] = fma(sv.x, w, acc[2 * q]);
+          acc[2 * q + 1] = fma(sv.y, w, acc[2 * q + 1]);
+        }
+      }
+#pragma unroll
+      for (int gb = 0; gb < BS_GB; ++gb) {
+        if (gb < ng) {
+          const double beta = acc[gb] / s_sxx[gb];
+          betas[(((int64_t)v * C + c) * N + g0 + gb) * R + c0 + t] = beta;
+          if (g0 + gb == 0) b0 = beta;
+          const double d = beta - b0;                     // shifted sums: no cancellation in the variance
+          sd1 += d; sd2 = fma(d, d, sd2);
+        }
+      }
     }
+  }
+  if (active) {
+    const double n = (double)N;
+    const double mean = b0 + sd1 / n;
+    const double ss = sd2 - sd1 * sd1 / n;
+    const double sd = sqrt(ss / (n - 1.0));
+    const double tval = mean / (sd / sqrt(n));
+    const int64_t o = ((int64_t)v * C + c) * R + c0 + t;
+    coefs[o] = mean;
+    pvalues[o] = two_sided_t_pvalue(tval, n - 1.0);
   }
 }
 
