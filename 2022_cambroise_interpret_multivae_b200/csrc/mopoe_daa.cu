@@ -106,7 +106,9 @@ __device__ __forceinline__ void fill_noise_row(const ModelView& mv, const Noise&
 // -------------------------------------------------------------------------------------------
 // 2. base passes + score sampling: one CTA per (validation, subject)
 // -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MOPOE_THREADS) daa_base_kernel(ModelView mv, DaaCtx cx, DaaWs ws) {
+constexpr int BASE_THREADS = 128;   // 8+ CTAs per SM: the (validation, subject) grid fits in one wave
+
+__global__ void __launch_bounds__(BASE_THREADS) daa_base_kernel(ModelView mv, DaaCtx cx, DaaWs ws) {
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int v = blockIdx.x / cx.N, g = blockIdx.x % cx.N;
@@ -114,12 +116,12 @@ __global__ void __launch_bounds__(MOPOE_THREADS) daa_base_kernel(ModelView mv, D
   const int64_t row = (int64_t)v * cx.N + g;
   float* s_mean = sm;                 // [E] mean eps
   float* s_acc = s_mean + 176;        // [threads / nb][EP] per-group sums (block-padded columns)
-  float* s_zz = s_acc + 1024;         // [M][64] decoder inputs
+  float* s_zz = s_acc + 4 * BASE_THREADS;         // [M][64] decoder inputs
   float* s_loc = s_zz + MOPOE_MAX_MODS * 64;  // [C]
   // mean over the n_base passes of the noise row of this subject.  Thread = (Philox block b of the row,
   // pass group): every lane draws whole blocks, four independent passes in flight per thread.
   {
-    const int nb = mv.EP >> 2, ngrp = MOPOE_THREADS / nb;
+    const int nb = mv.EP >> 2, ngrp = BASE_THREADS / nb;
     const int b = t % nb, grp = t / nb;
     int e0 = 4 * b, lim = mv.L;           // unpadded column of the block's first element, end of its section
     for (int m = 0; m < M; ++m)
@@ -190,28 +192,35 @@ __global__ void __launch_bounds__(MOPOE_THREADS) daa_base_kernel(ModelView mv, D
   }
   __syncthreads();
   // decode src -> loc_hat, dst -> reconstruction   (affine decoders: mean over passes == decode of mean z);
-  // warp per output row, lanes over K (coalesced weight rows)
+  // thread per output row, its ZD weights read as float4 (rows are contiguous)
   {
-    const ModView& ms = mv.mod[cx.q.src_mod];
-    for (int c = warp; c < cx.C; c += 8) {
-      float a = 0.f;
-      for (int k = lane; k < ms.ZD; k += 32) a = fmaf(s_zz[cx.q.src_mod * 64 + k], ms.wd[(int64_t)c * ms.ZD + k], a);
-      a = warp_sum(a) + ms.bd[c];
-      if (lane == 0) { s_loc[c] = a; ws.loc_hat[row * cx.C + c] = a; }
-    }
-    const ModView& mdst = mv.mod[cx.q.dst_mod];
-    if (cx.recon)
-      for (int r = warp; r < cx.R; r += 8) {
-        float a = 0.f;
-        for (int k = lane; k < mdst.ZD; k += 32) a = fmaf(s_zz[cx.q.dst_mod * 64 + k], mdst.wd[(int64_t)r * mdst.ZD + k], a);
-        a = warp_sum(a) + mdst.bd[r];
-        if (lane == 0) cx.recon[row * cx.R + r] = a;
+    const ModView ms = mv.mod[cx.q.src_mod];
+    const ModView mdst = mv.mod[cx.q.dst_mod];
+    auto decode = [&](const ModView& md, const float* z, int r) -> float {
+      const float* w = md.wd + (int64_t)r * md.ZD;
+      float a = md.bd[r];
+      if ((md.ZD & 3) == 0) {
+        for (int k = 0; k < md.ZD; k += 4) {
+          const float4 wv = *reinterpret_cast<const float4*>(w + k);
+          a = fmaf(z[k], wv.x, a); a = fmaf(z[k + 1], wv.y, a); a = fmaf(z[k + 2], wv.z, a); a = fmaf(z[k + 3], wv.w, a);
+        }
+      } else {
+        for (int k = 0; k < md.ZD; ++k) a = fmaf(z[k], w[k], a);
       }
+      return a;
+    };
+    for (int c = t; c < cx.C; c += BASE_THREADS) {
+      const float a = decode(ms, s_zz + cx.q.src_mod * 64, c);
+      s_loc[c] = a;
+      ws.loc_hat[row * cx.C + c] = a;
+    }
+    if (cx.recon)
+      for (int r = t; r < cx.R; r += BASE_THREADS) cx.recon[row * cx.R + r] = decode(mdst, s_zz + cx.q.dst_mod * 64, r);
   }
   __syncthreads();
   // scores[j][c] = loc_hat[c] + scale_hat[c] * eps   (Normal(loc_hat, scale_hat).sample, workflow.py:401-405)
   const ModView& ms = mv.mod[cx.q.src_mod];
-  for (int i = t; i < cx.J * cx.C; i += MOPOE_THREADS) {
+  for (int i = t; i < cx.J * cx.C; i += BASE_THREADS) {
     const int j = i / cx.C, c = i % cx.C;
     const int64_t idx = (((int64_t)(cx.v_score_off + v) * cx.J + j) * cx.N + g) * cx.C + c;
     const float s = s_loc[c] + expf(0.5f * ms.lv[c]) * cx.nz_score.at(idx);
@@ -220,7 +229,7 @@ __global__ void __launch_bounds__(MOPOE_THREADS) daa_base_kernel(ModelView mv, D
   }
   __syncthreads();
   // xbar, Sxx of every (subject, score) series in fp64 (centred OLS: slope = Sxy / Sxx)
-  for (int c = warp; c < cx.C; c += 8) {
+  for (int c = warp; c < cx.C; c += BASE_THREADS / 32) {
     const float* sx = ws.scores + (row * cx.C + c) * cx.J;
     double a = 0.0;
     for (int j = lane; j < cx.J; j += 32) a += (double)sx[j];
@@ -770,8 +779,8 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   cx.avatars = avatars; cx.sampled_scores = sampled_scores; cx.recon = reconstructions; cx.betas = betas;
   cx.C = desc->dims[daa->src_mod]; cx.R = desc->dims[daa->dst_mod]; cx.J = daa->n_samples; cx.N = N;
   // 2. base passes
-  const int base_smem = (176 + 1024 + MOPOE_MAX_MODS * 64 + 64) * 4;
-  daa_base_kernel<<<daa->n_val * N, MOPOE_THREADS, base_smem, stream>>>(mv, cx, ws);
+  const int base_smem = (176 + 4 * BASE_THREADS + MOPOE_MAX_MODS * 64 + 64) * 4;
+  daa_base_kernel<<<daa->n_val * N, BASE_THREADS, base_smem, stream>>>(mv, cx, ws);
   MOPOE_CUDA(cudaGetLastError());
   // 3. avatars + first-level regression
   const AvSmem pl = av_plan(mv, daa->src_mod, daa->dst_mod, cx.J);

@@ -49,7 +49,7 @@ constexpr int PK_MAXSUBJ = 1024;       // subjects per validation batch (owner t
 constexpr int PK_CACHE_F = 2 * MOPOE_HIDDEN + 128;   // floats per series cache: a0 | w1c | cs
 
 struct PipeSmem {
-  int bd_hi, bd_lo, bh_hi, bh_lo, az, stage, cache, meta, xbar, biash, part, gmeta, bars, total;
+  int bd_hi, bd_lo, bh_hi, bh_lo, az, stage, cache, meta, xbar, biash, part, gmeta, tinfo, bars, total;
 };
 
 __host__ __device__ inline PipeSmem pipe_plan(const UmmaDims& d) {
@@ -62,7 +62,8 @@ __host__ __device__ inline PipeSmem pipe_plan(const UmmaDims& d) {
   p.stage = take(PK_EPI * 32 * PK_STAGE_LD * 4);
   p.cache = take(PK_SLOTS * PK_CACHE_F * 4);
   p.meta = take(PK_SLOTS * 4 * 4);
-  p.xbar = take(PK_SLOTS * 8);
+  p.xbar = take(PK_SLOTS * 2 * 8);                       // per series: xbar | noise row index of sample 0 (int64)
+  p.tinfo = take(2 * 2 * 4);                             // [tile parity]: first, last series of the tile
   p.biash = take(d.NH * 4);
   p.part = take(2 * 4 * 2 * 64 * 8);                    // [tile parity][lane quarter][series 0|1][k] fp64
   p.gmeta = take(PK_MAXSUBJ);                           // per subject row: bit 7 need_src | owner subset
@@ -78,19 +79,22 @@ __host__ __device__ inline int pipe_tiles_per_unit(int J) { return (J + PK_ROWS 
 // error flag set (results are poisoned by the host wrapper) instead of hanging the GPU
 __device__ __forceinline__ bool pk_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
   const uint32_t addr = umma::smem_u32(bar);
-  // try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or
-  // ~20 us pass), so waiting roles do not burn issue slots of the working ones
+  // waiting roles must not steal issue slots from the working ones: poll with an exponential
+  // __nanosleep backoff (32 .. 256 ns) instead of spinning on try_wait
+  uint32_t ns = 32;
 #pragma unroll 1
-  for (uint32_t spin = 0; spin < (1u << 18); ++spin) {
+  for (uint32_t spin = 0; spin < (1u << 21); ++spin) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity), "r"(20000u)
+        : "r"(addr), "r"(parity)
         : "memory");
     if (ok) return true;
+    __nanosleep(ns);
+    ns = ns < 256 ? ns * 2 : 256;
     if ((spin & 63u) == 63u && *abort_flag) return false;
   }
   *abort_flag = 1;
@@ -174,6 +178,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
   float* s_cache = reinterpret_cast<float*>(smem + pl.cache);
   int* s_meta = reinterpret_cast<int*>(smem + pl.meta);         // [slot][0] need_src
   double* s_xbar = reinterpret_cast<double*>(smem + pl.xbar);
+  const int64_t* s_rbase = reinterpret_cast<const int64_t*>(smem + pl.xbar) + PK_SLOTS;
+  int* s_tinfo = reinterpret_cast<int*>(smem + pl.tinfo);
   float* s_biash = reinterpret_cast<float*>(smem + pl.biash);
   double* s_part = reinterpret_cast<double*>(smem + pl.part);
   unsigned char* s_gmeta = smem + pl.gmeta;
@@ -250,24 +256,24 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
     const int nbrow = mv.EP >> 2;
     const int nqc = KC >> 3, nqt = KZ >> 3;              // content chunks, all chunks of 8 latents
     uint32_t heads_waits = 0;
+    float score_next = (row_begin + r < row_end) ? ws.scores[row_begin + r] : 0.f;
 #pragma unroll 1
     for (int i = 0; i < n_tiles; ++i) {
       pk_bar_sync(1, (PK_PROD + 1) * 32);                // caches of this tile's series are ready
       PK_T(0);
       const int tile_row = row_begin + i * PK_ROWS;
-      int uA, uB;
-      tile_units(i, uA, uB);
+      const int uA = s_tinfo[(i & 1) * 2], uB = s_tinfo[(i & 1) * 2 + 1];   // series of the tile (aux warp)
       const int rho = tile_row + r;
       const bool valid = rho < row_end;
-      const int u = valid ? rho / J : uB;
+      const int u = (rho < (uA + 1) * J) ? uA : uB;
       const int j = valid ? rho - u * J : 0;
-      const int c = u % C, g = (u / C) % N, v = u / (C * N);
       const int slot = u & (PK_SLOTS - 1);
       const float* cache = s_cache + slot * PK_CACHE_F;
       const float* cs = cache + 2 * MOPOE_HIDDEN;
       const bool tile_need = s_meta[(uA & (PK_SLOTS - 1)) * 4] || s_meta[(uB & (PK_SLOTS - 1)) * 4];
       const bool need = valid && s_meta[slot * 4];
-      const float score = valid ? ws.scores[rho] : 0.f;
+      const float score = score_next;
+      if (rho + PK_ROWS < row_end) score_next = ws.scores[rho + PK_ROWS];     // next tile's score: latency hidden
       // ---- P1: hidden layer -> TMEM (A operand of the class-head GEMM), 16 hidden units per step ----
       if (tile_need) {
 #pragma unroll 2
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
       // class heads from TMEM, posterior of the row's mixture owner, reparameterisation, z -> A operand of
       // the decoder GEMM, first-level regression sums ----
       {
-        const int64_t ridx = (((int64_t)(cx.v_av_off + v) * J + j) * C + c) * N + g;
+        const int64_t ridx = s_rbase[slot] + (int64_t)j * (C * N);   // (((v_off + v) J + j) C + c) N + g
         unsigned char* az_hi = s_az + (i & 1) * 2 * AZ_PLANE;
         unsigned char* az_lo = az_hi + AZ_PLANE;
         const double xc = valid ? (double)score - s_xbar[slot] : 0.0;
@@ -586,6 +592,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
       if (lane == 0) {
         s_meta[slot * 4] = nd ? 1 : 0;
         s_xbar[slot] = ws.xstat[(((int64_t)uv * C + uc) * N + ug) * 2];
+        const_cast<int64_t*>(s_rbase)[slot] = ((int64_t)(cx.v_av_off + uv) * J * C + uc) * N + ug;
       }
     };
     // reduce the 4 row quarters of tile i and store the tile's contribution to each of its (<= 2) series:
@@ -620,6 +627,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
       if (i + 1 < n_tiles) {
         int uAn, uBn;
         tile_units(i + 1, uAn, uBn);
+        if (lane == 0) { s_tinfo[((i + 1) & 1) * 2] = uAn; s_tinfo[((i + 1) & 1) * 2 + 1] = uBn; }
 #pragma unroll 1
         for (int u = max(built + 1, uAn); u <= uBn; ++u) build(u);
         built = uBn;
