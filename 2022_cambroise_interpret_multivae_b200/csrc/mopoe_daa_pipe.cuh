@@ -284,10 +284,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 a = a0p[q], w = wcp[q];
-            const float h0 = fmaxf(fmaf(w.x, score, a.x), 0.f), h1 = fmaxf(fmaf(w.y, score, a.y), 0.f);
-            const float h2 = fmaxf(fmaf(w.z, score, a.z), 0.f), h3 = fmaxf(fmaf(w.w, score, a.w), 0.f);
-            split_pack2(h0, h1, hi[2 * q], lo[2 * q]);
-            split_pack2(h2, h3, hi[2 * q + 1], lo[2 * q + 1]);
+            relu_split_pack2(fmaf(w.x, score, a.x), fmaf(w.y, score, a.y), hi[2 * q], lo[2 * q]);
+            relu_split_pack2(fmaf(w.z, score, a.z), fmaf(w.w, score, a.w), hi[2 * q + 1], lo[2 * q + 1]);
           }
           tmem_st8(lane_addr + PK_TM_AH_HI + kc * 8, hi);    // 32-bit column = 2 hidden units
           tmem_st8(lane_addr + PK_TM_AH_LO + kc * 8, lo);

@@ -91,6 +91,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
                : "r"(taddr)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -114,6 +123,15 @@ __device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& hi, ui
   const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// relu(x0), relu(x1) -> packed fp16 hi / lo words of the 3xFP16 split with the ReLU folded into the
+// conversions: hi = cvt.rz.relu (truncation keeps 0 <= hi <= x, so the residual is >= 0 for x >= 0 and
+// equals x < 0 where the ReLU must give 0), lo = cvt.rn.relu(x - hi)
+__device__ __forceinline__ void relu_split_pack2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - hf.y), "f"(x0 - hf.x));
 }
 
 // ---- descriptors ----------------------------------------------------------------------------
