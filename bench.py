@@ -7,7 +7,8 @@ workload BASELINE.json configs[3]: HBN-shaped DAA sweep, n_validation=20 (per GP
          the sharding unit, weak scaling), n_subjects=50, n_samples=150, M=1000 base passes,
          7 scores x 444 ROIs, joint_elbo, factorised default, hierarchical regression.
 step     one full sweep of this rank's 20 validations: encoder pass, M base passes, score
-         sampling, 52 500 avatar forwards per validation, per-subject slopes, t-tests, and (N>1)
+         sampling, 52 500 avatar forwards per validation (warp-specialised tcgen05 pipeline), per-subject
+         slopes, t-tests, and (N>1)
          the NCCL all_gather of the (n_val, 7, 444) fp64 coefs / p-value tables.
 value    inputs resident in HBM, avatar tensor materialised in HBM (1.865 GB per sweep > L2).
 e2e      same sweep through the public API with pinned HOST buffers: H2D of the drawn test batches,
@@ -343,15 +344,17 @@ def run_ours(args, rank, world, local_rank):
                 "e2e_tables_only": {"value": avatars_per_step * args.steps / (ms_tab * 1e-3), "unit": UNIT,
                                     "d2h_bytes_per_step": d2h - host_out["avatars"].numel() * 4,
                                     "note": "avatar tensor left in HBM; scores, reconstructions, betas, coefs, p-values copied"},
-                "gpu_launches": 5 * args.steps,
-                "roofline": {"kernel": "daa_avatar_kernel", "bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9,
+                # per sweep: p1 + p2 (encoder heads), daa_base, operand prep, daa_avatar_pipe, daa_beta_stats, poison check
+                "gpu_launches": 7 * args.steps,
+                "roofline": {"kernel": "daa_avatar_pipe_kernel", "bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9,
                              "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
                              "traffic": traffic, "kernel_ms": k_ms, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                              "algorithmic_bytes_per_launch": alg_bytes,
                              "flops": {"faithful_tflops": 331266.0 * n_val * N * C_ * J / (k_ms * 1e-3) / 1e12,
                                        "executed_tflops": 2 * 29800.0 * n_val * N * C_ * J / (k_ms * 1e-3) / 1e12,
-                                       "note": "fp32 FFMA; faithful = 331 266 FLOP/avatar (reference recomputes both encoders), "
-                                               "executed ~= 59.6 kFLOP/avatar (ROI encoder cached, rank-1 hidden update)"}}}
+                                       "note": "tcgen05 kind::f16 with the 3xFP16 split (fp32-level accuracy, fp32 accumulation in TMEM); "
+                                               "faithful = 331 266 FLOP/avatar (reference recomputes both encoders), executed ~= 59.6 "
+                                               "kFLOP/avatar (ROI encoder cached, rank-1 hidden update; x3 tensor-core passes not counted)"}}}
         if world == 1:
             n, dt, desc = cpu_daa_sample(12.0)
             line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": desc}
