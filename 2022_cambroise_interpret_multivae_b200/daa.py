@@ -124,17 +124,26 @@ def shard_validations(n_validation, rank, world_size):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def gather_tables(local, n_validation, group=None):
+def gather_tables(local, n_validation, group=None, out=None):
     """all_gather the per-validation fp64 tables of every rank into the full (n_validation, ...) table.
-    `local` is this rank's (n_local, ...) block; ranks may own different counts (padded to the max)."""
+    `local` is this rank's (n_local, ...) block.  Equal shards (the usual case) are gathered straight into
+    one tensor (`out` lets the caller reuse it: one NCCL kernel, nothing else); unequal shards are padded
+    to the largest one."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local
     world = dist.get_world_size(group)
     counts = [shard_validations(n_validation, r, world) for r in range(world)]
-    n_max = max(e - b for b, e in counts)
+    sizes = [e - b for b, e in counts]
+    if min(sizes) == max(sizes):
+        shape = (n_validation,) + tuple(local.shape[1:])
+        if out is None or tuple(out.shape) != shape or out.dtype != local.dtype or out.device != local.device:
+            out = torch.empty(shape, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    n_max = max(sizes)
     pad = torch.zeros((n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad, group=group)
-    return torch.cat([bufs[r][: e - b] for r, (b, e) in enumerate(counts)], dim=0)
+    return torch.cat([bufs[r][: n] for r, n in enumerate(sizes)], dim=0)

@@ -245,9 +245,13 @@ def run_ours(args, rank, world, local_rank):
         return daa.daa_sweep(spec, flat, src, dst, J, Mb, seed=DAA["seed"], val_begin=rank * n_val,
                              n_val_total=world * n_val, workspace=ws, out=out)
 
+    full = {}
+
     def gather(r):
-        if world > 1:
-            return (daa.gather_tables(r.coefs, world * n_val), daa.gather_tables(r.pvalues, world * n_val))
+        if world > 1:   # one NCCL all_gather per table, straight into reused full-size tensors
+            full["c"] = daa.gather_tables(r.coefs, world * n_val, out=full.get("c"))
+            full["p"] = daa.gather_tables(r.pvalues, world * n_val, out=full.get("p"))
+            return full["c"], full["p"]
         return r.coefs, r.pvalues
 
     def barrier():

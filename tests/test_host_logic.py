@@ -108,12 +108,16 @@ import mopoe_b200
 from mopoe_b200 import daa
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
-n_val = 5
-b, e = daa.shard_validations(n_val, rank, world)
-local = torch.arange(b, e, dtype=torch.float64).view(-1, 1, 1).expand(-1, 7, 11).contiguous() + 0.5
-full = daa.gather_tables(local, n_val)
-want = torch.arange(n_val, dtype=torch.float64).view(-1, 1, 1).expand(-1, 7, 11) + 0.5
-assert full.shape == (n_val, 7, 11) and torch.equal(full, want), (rank, full[:, 0, 0])
+out = None
+for n_val in (5, 6, 6):          # unequal shards (padded path), equal shards (one collective, reused output)
+    b, e = daa.shard_validations(n_val, rank, world)
+    local = torch.arange(b, e, dtype=torch.float64).view(-1, 1, 1).expand(-1, 7, 11).contiguous() + 0.5
+    full = daa.gather_tables(local, n_val, out=out)
+    want = torch.arange(n_val, dtype=torch.float64).view(-1, 1, 1).expand(-1, 7, 11) + 0.5
+    assert full.shape == (n_val, 7, 11) and torch.equal(full, want), (rank, full[:, 0, 0])
+    if out is not None and tuple(out.shape) == (n_val, 7, 11):
+        assert full.data_ptr() == out.data_ptr()          # reused, no new allocation
+    out = full
 dist.destroy_process_group()
 print("ok", rank)
 '''
