@@ -20,7 +20,12 @@
  *   - noise: `eps` tensors are INJECTED standard-normal draws laid out as documented per call.
  *     A NULL eps pointer selects the built-in counter-based generator
  *     eps[i] = philox_normal(seed, stream_id, i)  (i = flat index into the same layout), so results
- *     do not depend on how a sweep is sharded over GPUs (oracle/philox.py restates it).
+ *     do not depend on how a sweep is sharded over GPUs (oracle/philox.py restates it).  The two
+ *     LATENT noise tensors of the DAA sweep (eps_base, eps_av: E columns per row) are addressed by
+ *     row instead: row r is drawn as whole Philox blocks, counter r * (EP / 4) + b, laid out
+ *     [content | style_0 | style_1 ...] with every section padded to a multiple of 4 normals
+ *     (EP = padded width; oracle/philox.py: philox_rows), so the thread that owns a row draws whole
+ *     blocks and nothing straddles rows.
  *   - no CPU fallback: with no CUDA device every compute entry point returns MOPOE_ENODEV.
  */
 #ifndef MOPOE_B200_H
@@ -204,6 +209,7 @@ int64_t mopoe_daa_workspace_bytes(const mopoe_model_desc* desc, const mopoe_daa_
  *   x[m]        (n_val, n_subjects, D_m) the drawn test batches (every modality)
  *   eps_base    (n_val, n_base, N, E), eps_score (n_val, n_samples, N, C), eps_av
  *               (n_val, n_samples, C, N, E); each NULL => philox(seed, MOPOE_STREAM_DAA_*)
+ *               (eps_base / eps_av by block-padded rows, eps_score by flat index, see "noise" above)
  * outputs (each may be NULL except coefs/pvalues)
  *   avatars         fp32 (n_val, N, C, n_samples, R)  rois_digital_avatars.npy (workflow.py:280-288)
  *   sampled_scores  fp32 (n_val, N, n_samples, C)     sampled_scores.npy       (workflow.py:435)
@@ -229,8 +235,10 @@ int mopoe_daa_regression(int32_t n_val, int32_t n_subjects, int32_t n_scores, in
  * (daa_avatar_kernel) with CUDA events on the caller's stream; mopoe_daa_last_kernel_ms waits for
  * the last bracket and returns its duration. */
 int mopoe_profile_enable(int on);
-/* which avatar kernel the last mopoe_daa_sweep used: 1 = tcgen05 tensor cores, 0 = CUDA cores
- * (shapes outside the tcgen05 tiling, or MOPOE_DAA_IMPL=ffma in the environment) */
+/* which avatar kernel the last mopoe_daa_sweep used: 2 = warp-specialised tcgen05 pipeline (the
+ * production kernel: hierarchical regression, sampled latents), 1 = phase-serial tcgen05 kernel (also
+ * "fixed" regression / mean latents), 0 = CUDA cores (shapes outside the tcgen05 tilings);
+ * MOPOE_DAA_IMPL=pipe|umma|ffma in the environment forces one (the tests cross-check all three) */
 int mopoe_daa_last_impl(void);
 /* per-role cycle counters (max over CTAs, 32 slots) of the last tcgen05 avatar kernel run on
  * `workspace`; filled by profiling builds of the library only (csrc/Makefile EXTRA=-DPK_PROF) */

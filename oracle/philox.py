@@ -6,6 +6,9 @@ workflow.py:401-405); that stream cannot be reproduced across devices, so parity
 INJECTED noise.  Production mode replaces the injected tensor by
     eps[i] = philox_normal(seed, stream, i)         i = flat index into the injected layout
 so "production mode" == "injected mode fed with this tensor", for any sharding of the sweep.
+The two latent-noise tensors of the DAA sweep (eps_base, eps_av) are addressed by ROW instead of by
+flat element (philox_rows below): a row is a whole number of Philox blocks, so the CUDA thread that
+owns an avatar row draws whole blocks.
 
 Algorithm: Philox4x32-10 (Salmon et al., SC'11), key = (seed_lo, seed_hi),
 counter = (i>>2 lo, i>>2 hi, stream lo, stream hi); the four 32-bit outputs become two

@@ -69,3 +69,20 @@ def test_philox_normal_moments_and_slicing():
     assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
     z2 = philox.philox_normal(1037, philox.STREAM_DAA_AVATAR, 1000, start=12345)
     assert np.array_equal(z2, z[12345:13345])       # sharding-invariant: pure function of index
+
+
+def test_philox_rows_layout_and_slicing():
+    """Row-addressed latent noise (DAA streams): sections start on Philox block boundaries, rows are
+    independent of how many rows are drawn and where the slice starts."""
+    L, styles = 20, [3, 20]
+    ep = 20 + 4 + 20
+    rows = philox.philox_rows(1037, philox.STREAM_DAA_AVATAR, 64, L, styles)
+    assert rows.shape == (64, 43) and rows.dtype == np.float32
+    flat = philox.philox_normal(1037, philox.STREAM_DAA_AVATAR, 64 * ep).reshape(64, ep)
+    assert np.array_equal(rows[:, :20], flat[:, :20])            # content: blocks 0..4 of the row
+    assert np.array_equal(rows[:, 20:23], flat[:, 20:23])        # style_0 (3 of its 4 padded draws)
+    assert np.array_equal(rows[:, 23:], flat[:, 24:44])          # style_1 starts on the next block
+    part = philox.philox_rows(1037, philox.STREAM_DAA_AVATAR, 10, L, styles, row_start=37)
+    assert np.array_equal(part, rows[37:47])
+    z = philox.philox_rows(5, philox.STREAM_DAA_BASE, 4096, L, styles)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
