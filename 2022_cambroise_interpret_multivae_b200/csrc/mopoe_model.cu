@@ -70,6 +70,7 @@ struct StepCtx {
   int64_t eps_step_stride;                 // n_pass * max_rows * E   (0 for the forward API)
   int64_t eps_pass_stride;                 // max_rows * E
   int sample_latents, use_expert, with_nll, uni_pass, mode;
+  int heads_only;                          // forward API: only the encoder heads were asked for (DAA sweep)
   mopoe_forward_out out;                   // forward API outputs (NULLs in training)
   float lr, b1, b2, adam_eps;
   float* adam_m; float* adam_v; int32_t* adam_t; float* grads; float* params;
@@ -294,6 +295,7 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
         cx.out.enc_heads[m][(int64_t)(r0 + i / HC) * HC + i % HC] = sh_e[(m * R + i / HC) * HCM + i % HC];
     }
   }
+  if (!BWD && cx.heads_only) return;   // uniform over the CTA; the caller's next tile starts with a barrier
   // ---- latent element-wise forward: thread per (row, latent dim) ----
   const int nsub = mv.sub.n_subsets;
   const float wmix = 1.f / (float)b.n_mix;  // uniform mixture weights (BaseMMVae.py:225, :64-78)
@@ -866,9 +868,11 @@ __global__ void __launch_bounds__(MOPOE_THREADS) train_kernel(ModelView mv, Step
 // -------------------------------------------------------------------------------------------
 // host launchers
 // -------------------------------------------------------------------------------------------
-static int pick_rows(const ModelView& mv, int64_t n_rows, int* smem_bytes) {
-  // small batches: as many row tiles as SMs (a tile's latency is dominated by weight streaming, not by R)
-  int R = n_rows > 2048 ? 16 : (n_rows <= 2 * num_sms() ? 1 : (n_rows <= 4 * num_sms() ? 2 : 4));
+static int pick_rows(const ModelView& mv, int64_t n_rows, int* smem_bytes, int ctas_per_sm = 2) {
+  // small batches: one round of row tiles over the co-resident CTAs (a tile's latency is dominated by
+  // weight streaming, not by R)
+  const int64_t ctas = (int64_t)ctas_per_sm * num_sms();
+  int R = n_rows > 2048 ? 16 : (n_rows <= ctas ? 1 : (n_rows <= 2 * ctas ? 2 : 4));
   int bytes = p2_plan(mv, R).total * 4;
   if (bytes > 220 * 1024) { R = 4; bytes = p2_plan(mv, R).total * 4; }
   const int gemm = 4 * TILE * TLD * 4;
@@ -927,6 +931,11 @@ int mopoe_forward(const mopoe_model_desc* desc, const float* params, const mopoe
   cx.sample_latents = sample_latents; cx.use_expert = use_expert < 0 ? -1 : use_expert;
   cx.with_nll = with_nll; cx.uni_pass = 0; cx.mode = 0;
   cx.out = *out;
+  {
+    bool only = !with_nll && !out->scalars && !out->subset_mu && !out->subset_logvar && !out->joint_mu && !out->joint_logvar && !out->z;
+    for (int m = 0; m < MOPOE_MAX_MODS; ++m) only = only && !out->z_style[m] && !out->rec_loc[m];
+    cx.heads_only = only ? 1 : 0;
+  }
   cx.lay = lay;
   mopoe_batch_desc b = *batch;
   b.row_offset = 0;
@@ -939,7 +948,7 @@ int mopoe_forward(const mopoe_model_desc* desc, const float* params, const mopoe
   p1_kernel<<<nu1 < 8 * sms ? nu1 : 8 * sms, MOPOE_THREADS, 4 * TILE * TLD * 4, stream>>>(mv, cx, b, ws);
   MOPOE_CUDA(cudaGetLastError());
   int smem = 0;
-  const int R = pick_rows(mv, b.n_rows, &smem);
+  const int R = pick_rows(mv, b.n_rows, &smem, 4);
   const int nt = (b.n_rows + R - 1) / R;
   if (R == 1) {
     MOPOE_CUDA(cudaFuncSetAttribute(p2_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
