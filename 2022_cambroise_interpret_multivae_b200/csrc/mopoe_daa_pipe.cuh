@@ -63,7 +63,7 @@ __host__ __device__ inline PipeSmem pipe_plan(const UmmaDims& d) {
   p.cache = take(PK_SLOTS * PK_CACHE_F * 4);
   p.meta = take(PK_SLOTS * 4 * 4);
   p.xbar = take(PK_SLOTS * 2 * 8);                       // per series: xbar | noise row index of sample 0 (int64)
-  p.tinfo = take(2 * 2 * 4);                             // [tile parity]: first, last series of the tile
+  p.tinfo = take(2 * 4 * 4);                             // [tile parity]: first, last series | first, end row of the tile
   p.biash = take(d.NH * 4);
   p.part = take(2 * 4 * 2 * 64 * 8);                    // [tile parity][lane quarter][series 0|1][k] fp64
   p.gmeta = take(PK_MAXSUBJ);                           // per subject row: bit 7 need_src | owner subset
@@ -228,19 +228,27 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  // ---- this CTA's contiguous range of 128-row tiles (balanced over the grid) ----
-  const int total_rows = cx.q.n_val * N * C * J;      // < 2^31, checked by the host dispatch
-  const int total_tiles = (total_rows + PK_ROWS - 1) / PK_ROWS;
+  // ---- this CTA's contiguous range of 128-row tiles (balanced over the grid).  The tile grid restarts at
+  // every validation (the last tile of a validation is partial), so tile boundaries inside a series --
+  // and with them the grouping of the fp64 regression sums -- do not depend on how validations are sharded
+  const int rpv = N * C * J;                          // rows per validation; n_val * rpv < 2^31 (host check)
+  const int tpv = (rpv + PK_ROWS - 1) / PK_ROWS;      // tiles per validation
+  const int total_tiles = cx.q.n_val * tpv;
+  const int total_tiles_rows = cx.q.n_val * rpv;
   const int tb = total_tiles / gridDim.x, trem = total_tiles % gridDim.x;
   const int tile0 = (int)blockIdx.x * tb + min((int)blockIdx.x, trem);
   const int n_tiles = tb + ((int)blockIdx.x < trem ? 1 : 0);
-  const int row_begin = tile0 * PK_ROWS;
-  const int row_end = min(total_rows, (tile0 + n_tiles) * PK_ROWS);
   const int tpu = pipe_tiles_per_unit(J);
   auto unit_need = [&](int u) -> bool { return (s_gmeta[(u / C) % N] & 0x80) != 0; };
+  auto tile_rows = [&](int i, int& r0, int& r1) {     // rows [r0, r1) of this CTA's i-th tile
+    const int gt = tile0 + i, v = gt / tpv;
+    r0 = v * rpv + (gt - v * tpv) * PK_ROWS;
+    r1 = min(r0 + PK_ROWS, (v + 1) * rpv);
+  };
   auto tile_units = [&](int i, int& uA, int& uB) {
-    const int r0 = row_begin + i * PK_ROWS, r1 = min(r0 + PK_ROWS, row_end) - 1;
-    uA = r0 / J; uB = r1 / J;
+    int r0, r1;
+    tile_rows(i, r0, r1);
+    uA = r0 / J; uB = (r1 - 1) / J;
   };
 
 #ifdef PK_PROF
@@ -256,15 +264,20 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
     const int nbrow = mv.EP >> 2;
     const int nqc = KC >> 3, nqt = KZ >> 3;              // content chunks, all chunks of 8 latents
     uint32_t heads_waits = 0;
-    float score_next = (row_begin + r < row_end) ? ws.scores[row_begin + r] : 0.f;
+    float score_next = 0.f;
+    if (n_tiles > 0) {
+      int r0, r1;
+      tile_rows(0, r0, r1);
+      if (r0 + r < r1) score_next = ws.scores[r0 + r];
+    }
 #pragma unroll 1
     for (int i = 0; i < n_tiles; ++i) {
       pk_bar_sync(1, (PK_PROD + 1) * 32);                // caches of this tile's series are ready
       PK_T(0);
-      const int tile_row = row_begin + i * PK_ROWS;
-      const int uA = s_tinfo[(i & 1) * 2], uB = s_tinfo[(i & 1) * 2 + 1];   // series of the tile (aux warp)
+      const int* ti = s_tinfo + (i & 1) * 4;                  // series and rows of the tile (aux warp)
+      const int uA = ti[0], uB = ti[1], tile_row = ti[2], tile_end = ti[3];
       const int rho = tile_row + r;
-      const bool valid = rho < row_end;
+      const bool valid = rho < tile_end;
       const int u = (rho < (uA + 1) * J) ? uA : uB;
       const int j = valid ? rho - u * J : 0;
       const int slot = u & (PK_SLOTS - 1);
@@ -273,7 +286,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
       const bool tile_need = s_meta[(uA & (PK_SLOTS - 1)) * 4] || s_meta[(uB & (PK_SLOTS - 1)) * 4];
       const bool need = valid && s_meta[slot * 4];
       const float score = score_next;
-      if (rho + PK_ROWS < row_end) score_next = ws.scores[rho + PK_ROWS];     // next tile's score: latency hidden
+      // next tile's score (latency hidden): the next tile starts where this one ends, and is never shorter
+      // than this thread's row index unless it is the last tile of a validation (then the load is unused)
+      if (i + 1 < n_tiles && tile_end + r < total_tiles_rows) score_next = ws.scores[tile_end + r];
       // ---- P1: hidden layer -> TMEM (A operand of the class-head GEMM), 16 hidden units per step ----
       if (tile_need) {
 #pragma unroll 2
@@ -405,8 +420,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
     int q = 0;
 #pragma unroll 1
     for (int i = 0; i < n_tiles; ++i) {
-      const int tile_row = row_begin + i * PK_ROWS;
-      const int rows_left = max(0, min(32, row_end - (tile_row + q4 * 32)));
+      int tile_row, tile_end;
+      tile_rows(i, tile_row, tile_end);
+      const int rows_left = max(0, min(32, tile_end - (tile_row + q4 * 32)));
 #pragma unroll 1
       for (int ch = 0; ch < n_chunks; ++ch, ++q) {
         const int b = q & 1;
@@ -601,8 +617,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
       tile_units(i, uA, uB);
       const int tile_g = tile0 + i;
       for (int s = 0; s <= uB - uA; ++s) {
-        const int u = uA + s;
-        const int tp = tile_g - (int)(((int64_t)u * J) / PK_ROWS);
+        const int u = uA + s, uv = u / (N * C);
+        const int tp = tile_g - (uv * tpv + (int)(((int64_t)(u - uv * N * C) * J) / PK_ROWS));   // tile index inside the series
         double* o = ws.sacc + ((int64_t)u * tpu + tp) * 64;
         for (int k = lane; k < KZ; k += 32) {
           double a = 0.0;
@@ -625,7 +641,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
       if (i + 1 < n_tiles) {
         int uAn, uBn;
         tile_units(i + 1, uAn, uBn);
-        if (lane == 0) { s_tinfo[((i + 1) & 1) * 2] = uAn; s_tinfo[((i + 1) & 1) * 2 + 1] = uBn; }
+        if (lane == 0) {
+          int* ti = s_tinfo + ((i + 1) & 1) * 4;
+          ti[0] = uAn; ti[1] = uBn;
+          tile_rows(i + 1, ti[2], ti[3]);
+        }
 #pragma unroll 1
         for (int u = max(built + 1, uAn); u <= uBn; ++u) build(u);
         built = uBn;
@@ -681,8 +701,8 @@ __global__ void __launch_bounds__(BS_COLS) daa_beta_stats_kernel(ModelView mv, i
       const int gb = i >> 6, k = i & 63;
       double a = 0.0;
       if (gb < ng && k < KZ) {
-        const int u = ((v * N) + g0 + gb) * C + c;
-        const int first = (int)(((int64_t)u * J) / PK_ROWS), last = (int)(((int64_t)(u + 1) * J - 1) / PK_ROWS);
+        const int ul = (g0 + gb) * C + c, u = v * N * C + ul;     // series inside its validation (tile grid restarts there)
+        const int first = (int)(((int64_t)ul * J) / PK_ROWS), last = (int)(((int64_t)(ul + 1) * J - 1) / PK_ROWS);
         for (int tp = 0; tp <= last - first; ++tp) a += sacc[((int64_t)u * tpu + tp) * 64 + k];
       }
       s_s[k][gb] = a;

