@@ -385,3 +385,26 @@ def test_daa_full_hbn_sweep_properties():
     # the perturbed scores are draws around loc_hat: their mean over 150 samples is close to the base decode
     sc = full.sampled_scores                                            # (n_val, N, J, C)
     assert float(sc.mean(dim=2).std()) > 0 and bool(torch.isfinite(sc).all())
+
+
+def test_daa_four_modalities_pipelined_vs_cuda_core(monkeypatch):
+    """Stress shape (BASELINE.json configs[4]: 4 modalities, 15 PoE subsets): the perturbed / read-out pair
+    is (clinical, rois) as in daa_exp, the two extra blocks enter every subset posterior.  The reference
+    cannot run this shape through daa_exp (experiment.py:137 hard-codes two modalities), so the check is
+    the agreement of the two independent avatar kernels + the fp64 closed form on the stored avatars."""
+    S = cases.STRESS
+    for method in ("joint_elbo", "poe", "moe"):
+        case = dict(cases._case(S, method, True, (0, 1, 2, 3), 15, 71, 171), n_val=2, n_base=5, n_samples=150,
+                    sample_latents=True)
+        ospec, spec, params, flat = _setup(case)
+        rng = np.random.default_rng(3)
+        f = lambda *s: torch.from_numpy(rng.standard_normal(s).astype(np.float32)).cuda()
+        src, dst = f(2, 15, 7), f(2, 15, 444)
+        others = {2: f(2, 15, 24), 3: f(2, 15, 148)}
+        pk = _sweep(spec, flat, src.cpu(), dst.cpu(), case, "pipe", monkeypatch, seed=5, others=others)
+        ff = _sweep(spec, flat, src.cpu(), dst.cpu(), case, "ffma", monkeypatch, seed=5, others=others)
+        _close(pk.avatars, ff.avatars, method + ": avatars pipelined vs cuda-core (M=4)", rtol=2e-5)
+        assert torch.equal(pk.sampled_scores, ff.sampled_scores)
+        p, coef, betas = daa_oracle.hierarchical_regression(pk.avatars.cpu().numpy(), pk.sampled_scores.cpu().numpy())
+        _close(pk.betas, betas, method + ": betas (M=4)", rtol=1e-5)
+        assert np.array_equal(daa_oracle.significant(pk.pvalues.cpu().numpy(), 0.7), daa_oracle.significant(p, 0.7))
