@@ -228,6 +228,13 @@ __device__ __forceinline__ void block_add(float* red, int slot, float v) {
 // -------------------------------------------------------------------------------------------
 // P2: one tile of R rows, everything between the hidden layer and the per-row gradients.
 // -------------------------------------------------------------------------------------------
+#ifdef TRAIN_PROF
+__device__ float g_p2prof[16];
+#define P2T(i) do { if (BWD && blockIdx.x == 0 && threadIdx.x == 0) { const long long _n = clock64(); g_p2prof[i] += (float)(_n - _tp); _tp = _n; } } while (0)
+#else
+#define P2T(i) do { } while (0)
+#endif
+
 template <int R, bool BWD>
 __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batch_desc& b,
                         const Workspace& ws, int64_t eps_base, int r0, float* sm) {
@@ -249,6 +256,9 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
   const int HCM = pl.hc_max, ZDM = pl.zd_max, SM_ = pl.s_max;
   const bool uni = cx.uni_pass != 0;
 
+#ifdef TRAIN_PROF
+  long long _tp = clock64();
+#endif
   __syncthreads();
   if (t < MOPOE_N_SCALARS) sh_red[t] = 0.f;
   for (int i = t; i < M * 2 * R * ZDM; i += MOPOE_THREADS) sh_dzz[i] = 0.f;
@@ -263,30 +273,45 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
     }
   }
   __syncthreads();
+  P2T(0);
   // ---- heads: e[r][j] = bh[j] + h[r] . wh[j]   (warp per output, lanes split k) ----
   for (int m = 0; m < M; ++m) {
     if (!(present >> m & 1)) continue;
     const ModView& md = mv.mod[m];
-    for (int j = warp; j < md.HC; j += MOPOE_THREADS / 32) {
-      const float4* wrow = reinterpret_cast<const float4*>(md.wh + (int64_t)j * MOPOE_HIDDEN);
-      const float4 wa = wrow[lane], wb = wrow[lane + 32];
-      float acc[R];
+    // every weight read is an L2 round trip (weights change each step, L1 is invalidated by the grid
+    // barrier): keep four outputs per warp (8 x LDG.128 per lane) in flight
+    for (int jb = warp; jb < md.HC; jb += 4 * (MOPOE_THREADS / 32)) {
+      float4 wa[4], wb[4];
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float4* hr = reinterpret_cast<const float4*>(sh_h + (m * R + r) * MOPOE_HIDDEN);
-        const float4 ha = hr[lane], hb = hr[lane + 32];
-        acc[r] = wa.x * ha.x + wa.y * ha.y + wa.z * ha.z + wa.w * ha.w + wb.x * hb.x + wb.y * hb.y +
-                 wb.z * hb.z + wb.w * hb.w;
+      for (int u = 0; u < 4; ++u) {
+        const int j = jb + u * (MOPOE_THREADS / 32);
+        const float4* wrow = reinterpret_cast<const float4*>(md.wh + (int64_t)(j < md.HC ? j : jb) * MOPOE_HIDDEN);
+        wa[u] = wrow[lane]; wb[u] = wrow[lane + 32];
       }
 #pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
-      const float bj = md.bh[j];
+      for (int u = 0; u < 4; ++u) {
+        const int j = jb + u * (MOPOE_THREADS / 32);
+        if (j < md.HC) {
+          float acc[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r)
-        if (lane == r % 32) sh_e[(m * R + r) * HCM + j] = acc[r] + bj;
+          for (int r = 0; r < R; ++r) {
+            const float4* hr = reinterpret_cast<const float4*>(sh_h + (m * R + r) * MOPOE_HIDDEN);
+            const float4 ha = hr[lane], hb = hr[lane + 32];
+            acc[r] = wa[u].x * ha.x + wa[u].y * ha.y + wa[u].z * ha.z + wa[u].w * ha.w + wb[u].x * hb.x + wb[u].y * hb.y +
+                     wb[u].z * hb.z + wb[u].w * hb.w;
+          }
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
+          const float bj = md.bh[j];
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if (lane == r % 32) sh_e[(m * R + r) * HCM + j] = acc[r] + bj;
+        }
+      }
     }
   }
   __syncthreads();
+  P2T(1);
   if (cx.out.enc_heads[0] || cx.out.enc_heads[1] || cx.out.enc_heads[2] || cx.out.enc_heads[3]) {
     for (int m = 0; m < M; ++m) {
       if (!(present >> m & 1) || !cx.out.enc_heads[m]) continue;
@@ -368,6 +393,7 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
       }
     }
   }
+  P2T(2);
   // ---- style element-wise forward ----
   for (int m = 0; m < M; ++m) {
     if (!(present >> m & 1)) continue;
@@ -405,6 +431,7 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
     }
   }
   __syncthreads();
+  P2T(3);
   // ---- decoders (+ NLL, d x_hat, d z) : thread per output feature, 256 features at a time ----
   const int npass = uni ? 2 : 1;
   for (int m = 0; m < M; ++m) {
@@ -428,10 +455,31 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
 #pragma unroll
           for (int r = 0; r < R; ++r) acc[r] = bd;
           const float* w = md.wd + (int64_t)d * ZD;
-          for (int k = 0; k < ZD; ++k) {
-            const float wk = w[k];
+          if ((ZD & 3) == 0) {       // the row is contiguous and 16-byte aligned: 8 x LDG.128 in flight
+            for (int k0 = 0; k0 < ZD; k0 += 32) {
+              float4 wv[8];
 #pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = fmaf(zrow[r * ZDM + k], wk, acc[r]);
+              for (int q = 0; q < 8; ++q) wv[q] = k0 + 4 * q < ZD ? *reinterpret_cast<const float4*>(w + k0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                if (k0 + 4 * q < ZD) {
+                  const int k = k0 + 4 * q;
+#pragma unroll
+                  for (int r = 0; r < R; ++r) {
+                    const float* z = zrow + r * ZDM + k;
+                    acc[r] = fmaf(z[0], wv[q].x, acc[r]); acc[r] = fmaf(z[1], wv[q].y, acc[r]);
+                    acc[r] = fmaf(z[2], wv[q].z, acc[r]); acc[r] = fmaf(z[3], wv[q].w, acc[r]);
+                  }
+                }
+              }
+            }
+          } else {
+#pragma unroll 8
+            for (int k = 0; k < ZD; ++k) {
+              const float wk = w[k];
+#pragma unroll
+              for (int r = 0; r < R; ++r) acc[r] = fmaf(zrow[r * ZDM + k], wk, acc[r]);
+            }
           }
           const float lam = md.lv[d];
           const float iv = expf(-lam);
@@ -467,6 +515,7 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
               const int pr = q % P, sp = q / P;
               const int r = pr / ZD, k = pr % ZD;
               float a = 0.f;
+#pragma unroll 8
               for (int dd = sp; dd < dlen; dd += nsplit)
                 a = fmaf(sh_dx[r * MOPOE_THREADS + dd], md.wd[(int64_t)(d0 + dd) * ZD + k], a);
               if (nsplit == 1) sh_dzz[((m * 2 + p) * R + r) * ZDM + k] += a;
@@ -487,6 +536,7 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
     }
   }
   __syncthreads();
+  P2T(4);
   if (BWD) {
     // ---- latent element-wise backward ----
     const float ckl = mv.beta * mv.beta_content * invN;
@@ -553,6 +603,7 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
           }
       }
     }
+    P2T(5);
     // ---- style element-wise backward ----
     for (int m = 0; m < M; ++m) {
       if (!(present >> m & 1)) continue;
@@ -576,6 +627,7 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
       }
     }
     __syncthreads();
+    P2T(6);
     // ---- d heads -> workspace; d pre-activation = (W_h^T d heads) * relu' ----
     for (int m = 0; m < M; ++m) {
       if (!(present >> m & 1)) continue;
@@ -586,6 +638,7 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
       float acc[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r] = 0.f;
+#pragma unroll 16
       for (int j = 0; j < HC; ++j) {
         const float w = md.wh[(int64_t)j * MOPOE_HIDDEN + t];
 #pragma unroll
@@ -597,6 +650,7 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
     }
   }
   __syncthreads();
+  P2T(7);
   if (t < MOPOE_N_SCALARS && sh_red[t] != 0.f) atomicAdd(ws.acc + t, (double)sh_red[t]);
 }
 
@@ -843,21 +897,47 @@ __global__ void __launch_bounds__(MOPOE_THREADS) train_kernel(ModelView mv, Step
     __syncthreads();
     const mopoe_batch_desc& b = sb;
     if (blockIdx.x == 0 && threadIdx.x < MOPOE_N_SCALARS) ws.acc[threadIdx.x] = 0.0;
+#ifdef TRAIN_PROF
+    const long long tp0 = clock64();
+#endif
     const int nu1 = p1_units(mv, b);
     for (int u = blockIdx.x; u < nu1; u += gridDim.x) p1_unit(mv, cx, b, ws, u, sm);
+#ifdef TRAIN_PROF
+    const long long tp0b = clock64();
+#endif
     grid_barrier(ws.bar, target);
+#ifdef TRAIN_PROF
+    const long long tp1 = clock64();
+#endif
     const int nt = (b.n_rows + R - 1) / R;
     const int64_t eps_base = (int64_t)step * cx.eps_step_stride;
     for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
       if (cx.mode == 0) p2_tile<R, false>(mv, cx, b, ws, eps_base, tile * R, sm);
       else p2_tile<R, true>(mv, cx, b, ws, eps_base, tile * R, sm);
     }
+#ifdef TRAIN_PROF
+    const long long tp1b = clock64();
+#endif
     grid_barrier(ws.bar, target);
+#ifdef TRAIN_PROF
+    const long long tp2 = clock64();
+#endif
     if (blockIdx.x == 0 && threadIdx.x == 0) finalize_scalars(mv, cx, b, ws.acc, scalars + (int64_t)step * MOPOE_N_SCALARS);
     if (cx.mode != 0) {
       const int nu3 = p3_total(mv, b.present_mask);
       for (int u = blockIdx.x; u < nu3; u += gridDim.x) p3_unit(mv, cx, b, ws, u, sm);
+#ifdef TRAIN_PROF
+      const long long tp2b = clock64();
+#endif
       grid_barrier(ws.bar, target);
+#ifdef TRAIN_PROF
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        float* o = scalars + (int64_t)step * MOPOE_N_SCALARS + 56;
+        const long long tp3 = clock64();
+        o[0] = (float)(tp0b - tp0); o[1] = (float)(tp1 - tp0b); o[2] = (float)(tp1b - tp1); o[3] = (float)(tp2 - tp1b);
+        o[4] = (float)(tp2b - tp2); o[5] = (float)(tp3 - tp2b);
+      }
+#endif
       if (cx.mode == 2 && blockIdx.x == 0 && threadIdx.x < mv.M && (b.present_mask >> threadIdx.x & 1))
         cx.adam_t[threadIdx.x] += 1;
       // adam_t is next read in P3 of the following step, two barriers away
@@ -893,6 +973,15 @@ static int validate_batch(const mopoe_model_desc* d, const mopoe_batch_desc* b) 
 using namespace mopoe;
 
 extern "C" {
+
+#ifdef TRAIN_PROF
+int mopoe_debug_p2prof(float* out16_host) {
+  MOPOE_CUDA(cudaMemcpyFromSymbol(out16_host, g_p2prof, 16 * sizeof(float)));
+  float z[16] = {0};
+  MOPOE_CUDA(cudaMemcpyToSymbol(g_p2prof, z, sizeof(z)));
+  return 0;
+}
+#endif
 
 int64_t mopoe_workspace_bytes(const mopoe_model_desc* desc, int64_t max_rows) {
   if (check_desc(desc)) return MOPOE_EINVAL;
