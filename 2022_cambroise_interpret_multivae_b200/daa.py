@@ -147,3 +147,30 @@ def gather_tables(local, n_validation, group=None, out=None):
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad, group=group)
     return torch.cat([bufs[r][: n] for r, n in enumerate(sizes)], dim=0)
+
+
+def gather_tables_many(locals_, n_validation, group=None, outs=None):
+    """gather_tables for several tables of equal shards in ONE coalesced NCCL launch (the sweep itself is
+    under a millisecond, so each extra collective launch shows in the multi-GPU step time).  Falls back to
+    one collective per table when the shards are unequal or coalescing is unavailable."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return list(locals_)
+    world = dist.get_world_size(group)
+    sizes = [e - b for b, e in (shard_validations(n_validation, r, world) for r in range(world))]
+    outs = list(outs) if outs is not None else [None] * len(locals_)
+    # coalescing of all_gather_into_tensor is an NCCL feature (gloo silently mis-gathers under it)
+    if min(sizes) != max(sizes) or not hasattr(dist, "_coalescing_manager") or dist.get_backend(group) != "nccl":
+        return [gather_tables(t, n_validation, group, o) for t, o in zip(locals_, outs)]
+    for i, t in enumerate(locals_):
+        shape = (n_validation,) + tuple(t.shape[1:])
+        if outs[i] is None or tuple(outs[i].shape) != shape or outs[i].dtype != t.dtype or outs[i].device != t.device:
+            outs[i] = torch.empty(shape, dtype=t.dtype, device=t.device)
+    try:
+        with dist._coalescing_manager(group=group, device=locals_[0].device, async_ops=False):
+            for t, o in zip(locals_, outs):
+                dist.all_gather_into_tensor(o, t.contiguous(), group=group)
+    except Exception:
+        for t, o in zip(locals_, outs):
+            dist.all_gather_into_tensor(o, t.contiguous(), group=group)
+    return outs

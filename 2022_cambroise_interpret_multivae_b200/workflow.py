@@ -245,11 +245,8 @@ def daa_exp(dataset, datasetdir, outdir, run, sampling_strategy="likelihood", n_
     r = daa.daa_sweep(model.spec, flat, src, dst, n_samples, M, sample_latents=sample_latents, reg_method=reg_method,
                       seed=0 if seed is None else seed, val_begin=begin, n_val_total=n_validation,
                       materialize=materialize_avatars, workspace=model._ws)
-    coefs = daa.gather_tables(r.coefs, n_validation)
-    pvalues = daa.gather_tables(r.pvalues, n_validation)
-    betas = daa.gather_tables(r.betas, n_validation)
-    scores = daa.gather_tables(r.sampled_scores, n_validation)
-    recons = daa.gather_tables(r.reconstructions, n_validation)
+    coefs, pvalues, betas, scores, recons = daa.gather_tables_many(
+        [r.coefs, r.pvalues, r.betas, r.sampled_scores, r.reconstructions], n_validation)
     torch.cuda.synchronize()
     meta = exp.metadata.iloc[exp.test_idx].reset_index(drop=True)
     meta_cols = list(meta.columns)

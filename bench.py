@@ -248,10 +248,9 @@ def run_ours(args, rank, world, local_rank):
     full = {}
 
     def gather(r):
-        if world > 1:   # one NCCL all_gather per table, straight into reused full-size tensors
-            full["c"] = daa.gather_tables(r.coefs, world * n_val, out=full.get("c"))
-            full["p"] = daa.gather_tables(r.pvalues, world * n_val, out=full.get("p"))
-            return full["c"], full["p"]
+        if world > 1:   # both tables in one coalesced NCCL launch, straight into reused full-size tensors
+            full["t"] = daa.gather_tables_many([r.coefs, r.pvalues], world * n_val, outs=full.get("t"))
+            return full["t"][0], full["t"][1]
         return r.coefs, r.pvalues
 
     def barrier():

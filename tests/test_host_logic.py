@@ -118,6 +118,8 @@ for n_val in (5, 6, 6):          # unequal shards (padded path), equal shards (o
     if out is not None and tuple(out.shape) == (n_val, 7, 11):
         assert full.data_ptr() == out.data_ptr()          # reused, no new allocation
     out = full
+    a, b = daa.gather_tables_many([local, 2 * local], n_val)
+    assert torch.equal(a, want) and torch.equal(b, 2 * want)
 dist.destroy_process_group()
 print("ok", rank)
 '''
