@@ -29,8 +29,19 @@ constexpr float HALF_LOG_2PI = 0.91893853320467274178f;
 // -------------------------------------------------------------------------------------------
 // workspace
 // -------------------------------------------------------------------------------------------
+// Split-K of the encoder's first layer: small batches have too few 32x32 output tiles to fill the GPU
+// and a tile's K loop (up to 444 wide) is their longest serial chain, so wide inputs are cut into
+// partial sums (ws.hp) that the P2 tile adds up (+ bias, ReLU) when it stages its hidden rows.
+constexpr int64_t P1_SPLIT_MAX_ROWS = 4096;
+__host__ __device__ inline int p1_ksplit(int D, int64_t max_rows) {
+  if (max_rows > P1_SPLIT_MAX_ROWS) return 1;
+  return D >= 256 ? 3 : (D >= 128 ? 2 : 1);
+}
+
 struct Workspace {
   float* h[MOPOE_MAX_MODS];    // (N, 256)      post-ReLU hidden
+  float* hp[MOPOE_MAX_MODS];   // (ks, N, 256)  split-K partial pre-activations (ks > 1 only)
+  int ks[MOPOE_MAX_MODS];      // K splits of the first layer of this modality
   float* dA[MOPOE_MAX_MODS];   // (N, 256)      d loss / d pre-activation
   float* de[MOPOE_MAX_MODS];   // (N, HC)       d loss / d heads
   float* zz[MOPOE_MAX_MODS];   // (2, N, ZD)    decoder inputs [style | content], pass 0 / unimodal
@@ -45,11 +56,14 @@ static int64_t carve(const mopoe_model_desc* d, int64_t N, char* base, Workspace
   auto take = [&](int64_t bytes) { int64_t o = off; off += (bytes + 255) & ~(int64_t)255; return base ? base + o : (char*)nullptr; };
   const int L = d->latent_dim;
   Workspace tmp;
+  memset(&tmp, 0, sizeof(tmp));
   tmp.acc = (double*)take(MOPOE_N_SCALARS * sizeof(double));
   tmp.bar = (unsigned int*)take(256);
   for (int m = 0; m < d->n_mods; ++m) {
     const int S = d->style_dims[m], D = d->dims[m];
     tmp.h[m] = (float*)take(N * MOPOE_HIDDEN * 4);
+    tmp.ks[m] = p1_ksplit(D, N);
+    tmp.hp[m] = tmp.ks[m] > 1 ? (float*)take(tmp.ks[m] * N * MOPOE_HIDDEN * 4) : nullptr;
     tmp.dA[m] = (float*)take(N * MOPOE_HIDDEN * 4);
     tmp.de[m] = (float*)take(N * (2 * L + 2 * S) * 4);
     tmp.zz[m] = (float*)take(2 * N * (S + L) * 4);
@@ -142,21 +156,32 @@ __device__ __forceinline__ void tile_gemm(FA fa, FB fb, int K, float acc[2][2], 
 // -------------------------------------------------------------------------------------------
 // P1: encoder first layer.  Work unit = (present modality, 32-row tile, 32-column tile).
 // -------------------------------------------------------------------------------------------
-__device__ __forceinline__ int p1_units(const ModelView& mv, const mopoe_batch_desc& b) {
+__device__ __forceinline__ int p1_units(const ModelView& mv, const mopoe_batch_desc& b, const Workspace& ws) {
   const int tn = (b.n_rows + TILE - 1) / TILE;
-  return __popc(b.present_mask) * tn * (MOPOE_HIDDEN / TILE);
+  int n = 0;
+  for (int m = 0; m < mv.M; ++m)
+    if (b.present_mask >> m & 1) n += tn * (MOPOE_HIDDEN / TILE) * ws.ks[m];
+  return n;
 }
 
 __device__ void p1_unit(const ModelView& mv, const StepCtx& cx, const mopoe_batch_desc& b,
                         const Workspace& ws, int u, float* sm) {
   const int tn = (b.n_rows + TILE - 1) / TILE;
-  const int per_mod = tn * (MOPOE_HIDDEN / TILE);
-  int slot = u / per_mod, rem = u % per_mod, m = 0;
-  for (int mm = 0; mm < mv.M; ++mm)
-    if (b.present_mask >> mm & 1) { if (slot == 0) { m = mm; break; } --slot; }
+  const int per_split = tn * (MOPOE_HIDDEN / TILE);
+  int m = 0, rem = u;
+  for (int mm = 0; mm < mv.M; ++mm) {
+    if (!(b.present_mask >> mm & 1)) continue;
+    const int cnt = per_split * ws.ks[mm];
+    if (rem < cnt) { m = mm; break; }
+    rem -= cnt;
+  }
+  const int ks = ws.ks[m], ksi = rem / per_split;
+  rem -= ksi * per_split;
   const int n0 = (rem / (MOPOE_HIDDEN / TILE)) * TILE, j0 = (rem % (MOPOE_HIDDEN / TILE)) * TILE;
   const ModView& md = mv.mod[m];
   const int D = md.D, N = b.n_rows;
+  const int nch = (D + TILE - 1) / TILE;
+  const int k_lo = (ksi * nch / ks) * TILE, k_hi = min(D, ((ksi + 1) * nch / ks) * TILE);   // this split's K range
   const float* x = cx.x[m];
   const float* w1 = md.w1;
   // this thread always fetches the same rows: resolve the gather once
@@ -169,20 +194,29 @@ __device__ void p1_unit(const ModelView& mv, const StepCtx& cx, const mopoe_batc
   }
   auto fa = [&](int i, int k) -> float {
     const int64_t r = rows[(i - hi) >> 3];
-    return (r >= 0 && k < D) ? x[r * D + k] : 0.f;
+    return (r >= 0 && k_lo + k < k_hi) ? x[r * D + k_lo + k] : 0.f;
   };
-  auto fb = [&](int j, int k) -> float { return k < D ? w1[(int64_t)(j0 + j) * D + k] : 0.f; };
+  auto fb = [&](int j, int k) -> float { return k_lo + k < k_hi ? w1[(int64_t)(j0 + j) * D + k_lo + k] : 0.f; };
   float acc[2][2];
-  tile_gemm<true, true>(fa, fb, D, acc, sm);
+  tile_gemm<true, true>(fa, fb, k_hi - k_lo, acc, sm);
   const int ty = t >> 4, tx = t & 15;
   const int j = j0 + 2 * tx;
-  const float bj0 = md.b1[j], bj1 = md.b1[j + 1];
+  if (ks == 1) {
+    const float bj0 = md.b1[j], bj1 = md.b1[j + 1];
 #pragma unroll
-  for (int a = 0; a < 2; ++a) {
-    const int n = n0 + 2 * ty + a;
-    if (n < N) {
-      float2 o = make_float2(fmaxf(acc[a][0] + bj0, 0.f), fmaxf(acc[a][1] + bj1, 0.f));
-      *reinterpret_cast<float2*>(ws.h[m] + (int64_t)n * MOPOE_HIDDEN + j) = o;
+    for (int a = 0; a < 2; ++a) {
+      const int n = n0 + 2 * ty + a;
+      if (n < N) {
+        float2 o = make_float2(fmaxf(acc[a][0] + bj0, 0.f), fmaxf(acc[a][1] + bj1, 0.f));
+        *reinterpret_cast<float2*>(ws.h[m] + (int64_t)n * MOPOE_HIDDEN + j) = o;
+      }
+    }
+  } else {          // partial sums; bias + ReLU when P2 adds the splits up
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int n = n0 + 2 * ty + a;
+      if (n < N)
+        *reinterpret_cast<float2*>(ws.hp[m] + ((int64_t)ksi * ws.max_rows + n) * MOPOE_HIDDEN + j) = make_float2(acc[a][0], acc[a][1]);
     }
   }
 }
@@ -268,7 +302,18 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
     for (int i = t; i < R * (MOPOE_HIDDEN / 4); i += MOPOE_THREADS) {
       const int r = i / (MOPOE_HIDDEN / 4), c = i % (MOPOE_HIDDEN / 4);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < nr) v = *reinterpret_cast<const float4*>(ws.h[m] + (int64_t)(r0 + r) * MOPOE_HIDDEN + 4 * c);
+      if (r < nr) {
+        if (ws.ks[m] == 1) v = *reinterpret_cast<const float4*>(ws.h[m] + (int64_t)(r0 + r) * MOPOE_HIDDEN + 4 * c);
+        else {      // add the split-K partial sums of P1, bias, ReLU; P3 reads the finished row from ws.h
+          v = *reinterpret_cast<const float4*>(mv.mod[m].b1 + 4 * c);
+          for (int ksi = 0; ksi < ws.ks[m]; ++ksi) {
+            const float4 q = *reinterpret_cast<const float4*>(ws.hp[m] + ((int64_t)ksi * ws.max_rows + r0 + r) * MOPOE_HIDDEN + 4 * c);
+            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+          }
+          v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+          *reinterpret_cast<float4*>(ws.h[m] + (int64_t)(r0 + r) * MOPOE_HIDDEN + 4 * c) = v;
+        }
+      }
       *reinterpret_cast<float4*>(sh_h + (m * R + r) * MOPOE_HIDDEN + 4 * c) = v;
     }
   }
@@ -869,7 +914,7 @@ __device__ void p3_unit(const ModelView& mv, const StepCtx& cx, const mopoe_batc
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MOPOE_THREADS) p1_kernel(ModelView mv, StepCtx cx, mopoe_batch_desc b, Workspace ws) {
   extern __shared__ __align__(16) float sm[];
-  const int nu = p1_units(mv, b);
+  const int nu = p1_units(mv, b, ws);
   for (int u = blockIdx.x; u < nu; u += gridDim.x) p1_unit(mv, cx, b, ws, u, sm);
 }
 
@@ -900,7 +945,7 @@ __global__ void __launch_bounds__(MOPOE_THREADS) train_kernel(ModelView mv, Step
 #ifdef TRAIN_PROF
     const long long tp0 = clock64();
 #endif
-    const int nu1 = p1_units(mv, b);
+    const int nu1 = p1_units(mv, b, ws);
     for (int u = blockIdx.x; u < nu1; u += gridDim.x) p1_unit(mv, cx, b, ws, u, sm);
 #ifdef TRAIN_PROF
     const long long tp0b = clock64();
@@ -1030,9 +1075,9 @@ int mopoe_forward(const mopoe_model_desc* desc, const float* params, const mopoe
   b.row_offset = 0;
   MOPOE_CUDA(cudaMemsetAsync(ws.acc, 0, MOPOE_N_SCALARS * sizeof(double), stream));
   const int tn = (b.n_rows + TILE - 1) / TILE;
-  int present_n = 0;
-  for (int m = 0; m < desc->n_mods; ++m) present_n += b.present_mask >> m & 1;
-  const int nu1 = present_n * tn * (MOPOE_HIDDEN / TILE);
+  int nu1 = 0;
+  for (int m = 0; m < desc->n_mods; ++m)
+    if (b.present_mask >> m & 1) nu1 += tn * (MOPOE_HIDDEN / TILE) * ws.ks[m];
   const int sms = num_sms();
   p1_kernel<<<nu1 < 8 * sms ? nu1 : 8 * sms, MOPOE_THREADS, 4 * TILE * TLD * 4, stream>>>(mv, cx, b, ws);
   MOPOE_CUDA(cudaGetLastError());
