@@ -113,6 +113,23 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c
   }
 }
 
+// The ten round keys of a (seed) are launch constants: the host expands them once (Noise::rk, kernel
+// parameter = constant bank), which removes the 20 per-thread key-schedule adds from every block.
+__host__ __device__ __forceinline__ void philox_round_keys(uint64_t seed, uint32_t* rk /* [20] */) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) { rk[2 * r] = k0; rk[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
+__device__ __forceinline__ void philox4x32_10_rk(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, const uint32_t* rk) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk[2 * r];
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk[2 * r + 1];
+    c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+  }
+}
+
 __device__ __forceinline__ float u01(uint32_t x) {
   return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);
 }
@@ -127,9 +144,7 @@ __device__ __forceinline__ float neg_log_u(float u) {
 
 // the four normals of block `blk` (elements 4*blk .. 4*blk+3) of (seed, stream):
 // Box-Muller with sin/cos evaluated on [-pi, pi) (MUFU range of full accuracy) and negated
-__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t stream, uint64_t blk, float out[4]) {
-  uint32_t c0 = (uint32_t)blk, c1 = (uint32_t)(blk >> 32), c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
-  philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+__device__ __forceinline__ void box_muller4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, float out[4]) {
   float r0, r1;   // MUFU.SQRT: the argument is a positive normal number, no special cases to patch up
   asm("sqrt.approx.f32 %0, %1;" : "=f"(r0) : "f"(2.0f * neg_log_u(u01(c0))));
   asm("sqrt.approx.f32 %0, %1;" : "=f"(r1) : "f"(2.0f * neg_log_u(u01(c2))));
@@ -137,6 +152,11 @@ __device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t stream, u
   __sincosf(6.28318530718f * (u01(c1) - 0.5f), &s0, &q0);
   __sincosf(6.28318530718f * (u01(c3) - 0.5f), &s1, &q1);
   out[0] = -r0 * q0; out[1] = -r0 * s0; out[2] = -r1 * q1; out[3] = -r1 * s1;
+}
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t stream, uint64_t blk, float out[4]) {
+  uint32_t c0 = (uint32_t)blk, c1 = (uint32_t)(blk >> 32), c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
+  philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+  box_muller4(c0, c1, c2, c3, out);
 }
 
 // element `idx` of (seed, stream)
@@ -151,9 +171,26 @@ struct Noise {
   const float* eps;  // NULL => philox
   uint64_t seed;
   uint64_t stream;
-  __device__ __forceinline__ float at(uint64_t idx) const {
-    return eps ? eps[idx] : philox_normal1(seed, stream, idx);
-  }
+  uint32_t rk[20];   // round keys of `seed` (make_noise)
+  __device__ __forceinline__ float at(uint64_t idx) const;
 };
+inline Noise make_noise(const float* eps, uint64_t seed, uint64_t stream) {
+  Noise n;
+  n.eps = eps; n.seed = seed; n.stream = stream;
+  philox_round_keys(seed, n.rk);
+  return n;
+}
+// the four normals of block `blk` of a noise source whose round keys sit in the constant bank
+__device__ __forceinline__ void philox_normal4(const Noise& nz, uint64_t blk, float out[4]) {
+  uint32_t c0 = (uint32_t)blk, c1 = (uint32_t)(blk >> 32), c2 = (uint32_t)nz.stream, c3 = (uint32_t)(nz.stream >> 32);
+  philox4x32_10_rk(c0, c1, c2, c3, nz.rk);
+  box_muller4(c0, c1, c2, c3, out);
+}
+__device__ __forceinline__ float Noise::at(uint64_t idx) const {
+  if (eps) return eps[idx];
+  float v[4];
+  philox_normal4(*this, idx >> 2, v);
+  return v[idx & 3];
+}
 
 }  // namespace mopoe

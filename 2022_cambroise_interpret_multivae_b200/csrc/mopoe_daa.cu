@@ -91,7 +91,7 @@ __device__ __forceinline__ void fill_noise_row(const ModelView& mv, const Noise&
     const int nb = mv.EP >> 2;
     for (int b = tid; b < nb; b += nthr) {
       float v[4];
-      philox_normal4(nz.seed, nz.stream, (uint64_t)(ridx * nb + b), v);
+      philox_normal4(nz, (uint64_t)(ridx * nb + b), v);
       const int pe = 4 * b;
       int e0 = pe, lim = mv.L;               // content section
       for (int m = 0; m < mv.M; ++m)
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(BASE_THREADS) daa_base_kernel(ModelView mv, Da
 #pragma unroll 4
         for (int p = grp; p < cx.q.n_base; p += ngrp) {
           float x[4];
-          philox_normal4(cx.nz_base.seed, cx.nz_base.stream, (uint64_t)((r0 + (int64_t)p * cx.N) * nb + b), x);
+          philox_normal4(cx.nz_base, (uint64_t)((r0 + (int64_t)p * cx.N) * nb + b), x);
           a0 += x[0]; a1 += x[1]; a2 += x[2]; a3 += x[3];
         }
       }
@@ -770,9 +770,9 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   memset(&cx, 0, sizeof(cx));
   cx.q = *daa; cx.b = *batch;
   for (int m = 0; m < M; ++m) cx.x[m] = x[m];
-  cx.nz_base = Noise{eps_base, seed, MOPOE_STREAM_DAA_BASE};
-  cx.nz_score = Noise{eps_score, seed, MOPOE_STREAM_DAA_SCORE};
-  cx.nz_av = Noise{eps_av, seed, MOPOE_STREAM_DAA_AVATAR};
+  cx.nz_base = make_noise(eps_base, seed, MOPOE_STREAM_DAA_BASE);
+  cx.nz_score = make_noise(eps_score, seed, MOPOE_STREAM_DAA_SCORE);
+  cx.nz_av = make_noise(eps_av, seed, MOPOE_STREAM_DAA_AVATAR);
   cx.v_base_off = eps_base ? 0 : daa->val_begin;
   cx.v_score_off = eps_score ? 0 : daa->val_begin;
   cx.v_av_off = eps_av ? 0 : daa->val_begin;

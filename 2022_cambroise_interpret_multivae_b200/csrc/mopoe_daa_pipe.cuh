@@ -339,8 +339,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
           } else {
             // two independent Philox chains (draws past the end of the section are unused)
             const uint64_t blk = (uint64_t)(ridx * nbrow + ((content ? 0 : mdst.peps_off) + l0) / 4);
-            philox_normal4(cx.nz_av.seed, cx.nz_av.stream, blk, e);
-            philox_normal4(cx.nz_av.seed, cx.nz_av.stream, blk + 1, e + 4);
+            philox_normal4(cx.nz_av, blk, e);
+            philox_normal4(cx.nz_av, blk + 1, e + 4);
           }
           const bool heads = content && tile_need;
           float hm[8], hl[8];

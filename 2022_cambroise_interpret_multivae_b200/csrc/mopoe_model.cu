@@ -1060,7 +1060,7 @@ int mopoe_forward(const mopoe_model_desc* desc, const float* params, const mopoe
     cx.x[m] = (batch->present_mask >> m & 1) ? x[m] : nullptr;
     if ((batch->present_mask >> m & 1) && !x[m]) { set_error("x[%d] is NULL but modality is present", m); return MOPOE_EINVAL; }
   }
-  cx.noise.eps = eps; cx.noise.seed = seed; cx.noise.stream = MOPOE_STREAM_FORWARD;
+  cx.noise = make_noise(eps, seed, MOPOE_STREAM_FORWARD);
   cx.eps_pass_stride = (int64_t)batch->n_rows * mv.E;
   cx.sample_latents = sample_latents; cx.use_expert = use_expert < 0 ? -1 : use_expert;
   cx.with_nll = with_nll; cx.uni_pass = 0; cx.mode = 0;
@@ -1135,7 +1135,7 @@ int mopoe_train_steps(const mopoe_model_desc* desc, float* params, float* adam_m
     cx.row_index[m] = row_index ? row_index[m] : nullptr;
   }
   const int n_pass = desc->method == MOPOE_METHOD_POE ? 1 + desc->n_mods : 1;
-  cx.noise.eps = eps; cx.noise.seed = seed; cx.noise.stream = MOPOE_STREAM_TRAIN;
+  cx.noise = make_noise(eps, seed, MOPOE_STREAM_TRAIN);
   cx.eps_pass_stride = max_rows * mv.E;
   cx.eps_step_stride = (int64_t)n_pass * max_rows * mv.E;
   cx.sample_latents = 1; cx.use_expert = -1; cx.with_nll = 1;
