@@ -274,8 +274,8 @@ def run_ours(args, rank, world, local_rank):
         gather(r)
     e1.record()
     barrier()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
+    ms = e0.elapsed_time(e1)   # (the clock sampler keeps running over the e2e regions: K sub-millisecond steps
+                               # are shorter than one nvidia-smi sampling period)
     # dominant kernel alone (same launches, measured by the library's own event bracket)
     for _ in range(min(args.steps, 5)):
         r = sweep(src_d, dst_d, out=r)
@@ -316,6 +316,7 @@ def run_ours(args, rank, world, local_rank):
     g1.record()
     barrier()
     ms_tab = g0.elapsed_time(g1)
+    clocks = sampler.stop()
     times = torch.tensor([ms, ms_e2e, ms_tab], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
