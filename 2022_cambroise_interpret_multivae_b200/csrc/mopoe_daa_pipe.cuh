@@ -14,7 +14,8 @@
 //       P3  class heads read back from TMEM (tcgen05.ld), posterior of the row's mixture owner from
 //           cached per-series partial sums, reparameterisation, z written as the A operand of the
 //           decoder GEMM (shared memory, fp16 hi/lo, double buffered)          -> bar z_full
-//           + the first-level regression sums  sum_rows (x - xbar) * z[k]  in fp64 (warp butterfly):
+//           + the first-level regression sums  sum_rows (x - xbar) * z[k]  (fp32 warp butterfly over 32 rows,
+//           fp64 across warps and tiles):
 //           by linearity  sum_rows (x - xbar) * y[:, roi] = Wd[roi,:] . that vector, so the slope
 //           of every ROI (stat_utils.py:66-68) needs KZ numbers per series, not one FMA per element
 //   heads issuer   (1 thread)  16 x 3 tcgen05.mma kind::f16, A from TMEM, N = 48  -> bar heads_done
@@ -106,15 +107,18 @@ __device__ __forceinline__ void pk_arrive(uint64_t* bar) {
 __device__ __forceinline__ void pk_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // 8 per-lane values xc * zq[k] -> their sum over the 32 lanes, returned in every lane with (lane & 7) == k
-// (transposing butterfly inside each group of 8 lanes, then two exchanges between the groups), fp64
-__device__ __forceinline__ double pk_lane_transpose_sum8(const float* zq, double xc, int lane) {
-  double a[4];
+// (transposing butterfly inside each group of 8 lanes, then two exchanges between the groups).
+// fp32: FP64 arithmetic on the CUDA cores of this part is slow enough that the fp64 version of this
+// reduction was ~45 % of the producers' per-tile time; the 32-row partial sums are exact to ~3e-7 of their
+// absolute sum, everything downstream (accumulation over warps and tiles, slopes, t-test) stays fp64.
+__device__ __forceinline__ float pk_lane_transpose_sum8(const float* zq, float xc, int lane) {
+  float a[4];
   {
     const bool up = (lane & 4) != 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const double lo = xc * (double)zq[i], hi = xc * (double)zq[i + 4];
-      const double keep = up ? hi : lo, send = up ? lo : hi;
+      const float lo = xc * zq[i], hi = xc * zq[i + 4];
+      const float keep = up ? hi : lo, send = up ? lo : hi;
       a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
     }
   }
@@ -123,11 +127,11 @@ __device__ __forceinline__ double pk_lane_transpose_sum8(const float* zq, double
     const bool up = (lane & w) != 0;
 #pragma unroll
     for (int i = 0; i < w; ++i) {
-      const double keep = up ? a[i + w] : a[i], send = up ? a[i] : a[i + w];
+      const float keep = up ? a[i + w] : a[i], send = up ? a[i] : a[i + w];
       a[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
     }
   }
-  double r = a[0];
+  float r = a[0];
   r += __shfl_xor_sync(0xffffffffu, r, 8);
   r += __shfl_xor_sync(0xffffffffu, r, 16);
   return r;
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
         const int64_t ridx = s_rbase[slot] + (int64_t)j * (C * N);   // (((v_off + v) J + j) C + c) N + g
         unsigned char* az_hi = s_az + (i & 1) * 2 * AZ_PLANE;
         unsigned char* az_lo = az_hi + AZ_PLANE;
-        const double xc = valid ? (double)score - s_xbar[slot] : 0.0;
+        const float xc = valid ? (float)((double)score - s_xbar[slot]) : 0.f;
         const bool inA = valid && u == uA, inB = valid && u != uA;
         const bool anyA = __any_sync(0xffffffffu, inA), anyB = __any_sync(0xffffffffu, inB);
         double* part = s_part + (((i & 1) * 4 + q4) * 2) * 64;
@@ -395,9 +399,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
           if (col0 == 0) {
 #pragma unroll 1
             for (int sidx = 0; sidx < 2; ++sidx) {
-              double sum = 0.0;
-              if (sidx ? anyB : anyA) sum = pk_lane_transpose_sum8(zq, (sidx ? inB : inA) ? xc : 0.0, lane);
-              if (lane < 8) part[sidx * 64 + ci * 8 + lane] = sum;
+              float sum = 0.f;
+              if (sidx ? anyB : anyA) sum = pk_lane_transpose_sum8(zq, (sidx ? inB : inA) ? xc : 0.f, lane);
+              if (lane < 8) part[sidx * 64 + ci * 8 + lane] = (double)sum;
             }
           }
         }
