@@ -817,7 +817,7 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
       if (g_profile && col0 == 0) MOPOE_CUDA(cudaEventRecord(g_ev1, stream));
     }
     // slopes + second-level test of the pipelined path (replaces step 4 below)
-    const int bsm = ud0.KZ * BS_COLS * 8;
+    const int bsm = ud0.KZ * BS_COLS * 4;
     MOPOE_CUDA(cudaFuncSetAttribute((void*)daa_beta_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bsm));
     daa_beta_stats_kernel<<<dim3(daa->n_val * cx.C, (cx.R + BS_COLS - 1) / BS_COLS), BS_COLS, bsm, stream>>>(
         mv, daa->dst_mod, cx.R, cx.C, N, cx.J, ud0, ws.sacc, ws.xstat, ws.betas, coefs, pvalues);

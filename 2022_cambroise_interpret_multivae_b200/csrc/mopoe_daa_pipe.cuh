@@ -671,31 +671,37 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
 // Per-subject slopes and the second-level test of the pipelined path in one pass:
 //   beta[v,c,g,roi] = (Wd[roi,:] . sum_tiles sacc[u,tile,:]) / Sxx[u]            (stat_utils.py:66-68)
 //   coef = mean_g beta, t = coef / (sd_g(beta) / sqrt(N)), p = 2 sf(|t|, N-1)     (stat_utils.py:73-75)
-// CTA = (validation, score) x block of 256 ROIs; the decoder weights of the block sit in shared memory
-// as fp64 in the K order of z (+ bias slot); 10 subjects per batch share every weight load.
-constexpr int BS_COLS = 256, BS_GB = 10;
+// CTA = (validation, score) x block of 256 ROIs; the decoder weights of the block sit in shared memory in
+// the K order of z (+ bias slot); 10 subjects per batch share every weight load.
+// Arithmetic: CUDA-core FP64 runs at ~5 TFLOP/s on this part and the regression sums carry fp32-level
+// rounding from their 32-row partial sums anyway, so the 149 M-term contraction is done with fp32 FMAs on
+// the sums split into hi + lo fp32 parts (48 bits of each sum enter the product; accumulation error
+// ~1e-7 of the absolute term sum, the same order as the rounding already in the sums); the sum over tiles,
+// the division by Sxx, the subject statistics (shifted sums) and the t-test are fp64.
+constexpr int BS_COLS = 256, BS_GB = 10, BS_GP = 12;     // BS_GP: padded batch stride (float4 aligned)
 
 __device__ double two_sided_t_pvalue(double tval, double nu);
 
 __global__ void __launch_bounds__(BS_COLS) daa_beta_stats_kernel(ModelView mv, int dst, int R, int C, int N, int J, UmmaDims dm,
                                                                   const double* sacc, const double* xstat, double* betas,
                                                                   double* coefs, double* pvalues) {
-  extern __shared__ __align__(16) double s_wd[];          // [KZ][BS_COLS]
-  __shared__ __align__(16) double s_s[64][BS_GB];         // regression sums of the batch, k-major
+  extern __shared__ __align__(16) float s_wf[];           // [KZ][BS_COLS]
+  __shared__ __align__(16) float s_hi[64][BS_GP];         // regression sums of the batch, k-major: fp32 hi part
+  __shared__ __align__(16) float s_lo[64][BS_GP];         //                                        fp32 lo part
   __shared__ double s_sxx[BS_GB];
   const ModView& md = mv.mod[dst];
   const int t = threadIdx.x;
   const int v = blockIdx.x / C, c = blockIdx.x % C;
   const int c0 = blockIdx.y * BS_COLS, nc = min(BS_COLS, R - c0);
   const int tpu = pipe_tiles_per_unit(J), KZ = dm.KZ;
-  for (int i = t; i < KZ * BS_COLS; i += BS_COLS) s_wd[i] = 0.0;
+  for (int i = t; i < KZ * BS_COLS; i += BS_COLS) s_wf[i] = 0.f;
   __syncthreads();
   for (int i = t; i < nc * md.ZD; i += BS_COLS) {         // coalesced: the block's weight rows are contiguous
     const int col = i / md.ZD, zd = i % md.ZD;
     const int kz = zd < md.S ? dm.KC + zd : zd - md.S;   // decoder input = [style | content], z = [content | style]
-    s_wd[kz * BS_COLS + col] = (double)md.wd[(int64_t)c0 * md.ZD + i];
+    s_wf[kz * BS_COLS + col] = md.wd[(int64_t)c0 * md.ZD + i];
   }
-  if (dm.bias_slot >= 0 && t < nc) s_wd[dm.bias_slot * BS_COLS + t] = (double)md.bd[c0 + t];
+  if (dm.bias_slot >= 0 && t < nc) s_wf[dm.bias_slot * BS_COLS + t] = md.bd[c0 + t];
   const bool active = t < nc;
   double b0 = 0.0, sd1 = 0.0, sd2 = 0.0;
   for (int g0 = 0; g0 < N; g0 += BS_GB) {
@@ -709,28 +715,35 @@ __global__ void __launch_bounds__(BS_COLS) daa_beta_stats_kernel(ModelView mv, i
         const int first = (int)(((int64_t)ul * J) / PK_ROWS), last = (int)(((int64_t)(ul + 1) * J - 1) / PK_ROWS);
         for (int tp = 0; tp <= last - first; ++tp) a += sacc[((int64_t)u * tpu + tp) * 64 + k];
       }
-      s_s[k][gb] = a;
+      const float hi = (float)a;
+      s_hi[k][gb] = hi;
+      s_lo[k][gb] = (float)(a - (double)hi);
     }
-    if (t < BS_GB) s_sxx[t] = t < ng ? xstat[(((int64_t)v * C + c) * N + g0 + t) * 2 + 1] : 1.0;
+    // 1 / Sxx once per subject: an fp64 division per slope would cost as much as the whole contraction
+    if (t < BS_GB) s_sxx[t] = t < ng ? 1.0 / xstat[(((int64_t)v * C + c) * N + g0 + t) * 2 + 1] : 1.0;
     __syncthreads();
     if (active) {
-      double acc[BS_GB];
+      float ah[BS_GB], al[BS_GB];
 #pragma unroll
-      for (int gb = 0; gb < BS_GB; ++gb) acc[gb] = 0.0;
+      for (int gb = 0; gb < BS_GB; ++gb) ah[gb] = al[gb] = 0.f;
+#pragma unroll 4
       for (int k = 0; k < KZ; ++k) {
-        const double w = s_wd[k * BS_COLS + t];
-        const double2* sp = reinterpret_cast<const double2*>(&s_s[k][0]);
-#pragma unroll
-        for (int q = 0; q < BS_GB / 2; ++q) {
-          const double2 sv = sp[q];
-          acc[2 * q] = fma(sv.x, w, acc[2 * q]);
-          acc[2 * q + 1] = fma(sv.y, w, acc[2 * q + 1]);
-        }
+        const float w = s_wf[k * BS_COLS + t];
+        const float4 h0 = *reinterpret_cast<const float4*>(&s_hi[k][0]), h1 = *reinterpret_cast<const float4*>(&s_hi[k][4]);
+        const float2 h2 = *reinterpret_cast<const float2*>(&s_hi[k][8]);
+        const float4 l0 = *reinterpret_cast<const float4*>(&s_lo[k][0]), l1 = *reinterpret_cast<const float4*>(&s_lo[k][4]);
+        const float2 l2 = *reinterpret_cast<const float2*>(&s_lo[k][8]);
+        ah[0] = fmaf(h0.x, w, ah[0]); ah[1] = fmaf(h0.y, w, ah[1]); ah[2] = fmaf(h0.z, w, ah[2]); ah[3] = fmaf(h0.w, w, ah[3]);
+        ah[4] = fmaf(h1.x, w, ah[4]); ah[5] = fmaf(h1.y, w, ah[5]); ah[6] = fmaf(h1.z, w, ah[6]); ah[7] = fmaf(h1.w, w, ah[7]);
+        ah[8] = fmaf(h2.x, w, ah[8]); ah[9] = fmaf(h2.y, w, ah[9]);
+        al[0] = fmaf(l0.x, w, al[0]); al[1] = fmaf(l0.y, w, al[1]); al[2] = fmaf(l0.z, w, al[2]); al[3] = fmaf(l0.w, w, al[3]);
+        al[4] = fmaf(l1.x, w, al[4]); al[5] = fmaf(l1.y, w, al[5]); al[6] = fmaf(l1.z, w, al[6]); al[7] = fmaf(l1.w, w, al[7]);
+        al[8] = fmaf(l2.x, w, al[8]); al[9] = fmaf(l2.y, w, al[9]);
       }
 #pragma unroll
       for (int gb = 0; gb < BS_GB; ++gb) {
         if (gb < ng) {
-          const double beta = acc[gb] / s_sxx[gb];
+          const double beta = ((double)ah[gb] + (double)al[gb]) * s_sxx[gb];
           betas[(((int64_t)v * C + c) * N + g0 + gb) * R + c0 + t] = beta;
           if (g0 + gb == 0) b0 = beta;
           const double d = beta - b0;                     // shifted sums: no cancellation in the variance
