@@ -38,9 +38,12 @@ struct DaaWs {
   int* err;                    // device error flag (tcgen05 barrier time-out)
   long long* phase;            // [grid][32] per-role cycle counters of the tcgen05 kernels (profiling builds)
   unsigned char* bsplit;       // fp16 hi/lo operand planes of the decoder / class-head weights (UMMA layout)
+  float* srec;                 // (n_val*N*C, DAA_SERIES_REC_F)  pipelined kernel: per-series records (daa_series_rec_kernel)
   void* fwd_ws;                // workspace of the encoder forward
   int64_t fwd_ws_bytes;
 };
+
+constexpr int DAA_SERIES_REC_F = 2 * MOPOE_HIDDEN + 128 + 4;   // == PK_REC_F (mopoe_daa_pipe.cuh)
 
 static int64_t daa_carve(const mopoe_model_desc* d, const mopoe_daa_desc* q, char* base, DaaWs* w) {
   int64_t off = 0;
@@ -63,6 +66,7 @@ static int64_t daa_carve(const mopoe_model_desc* d, const mopoe_daa_desc* q, cha
   t.err = (int*)take(256);
   t.phase = (long long*)take(256 * 32 * 8);
   t.bsplit = (unsigned char*)take(2 * (480 * 64 * 2) + 2 * (64 * 256 * 2));
+  t.srec = (float*)take(rows * C * DAA_SERIES_REC_F * 4);
   t.fwd_ws_bytes = mopoe_workspace_bytes(d, rows);
   t.fwd_ws = take(t.fwd_ws_bytes);
   if (w) *w = t;
@@ -811,6 +815,10 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
       const UmmaDims ud = umma_dims(mv, daa->src_mod, daa->dst_mod, cx.R - col0 < PK_CBP ? cx.R - col0 : PK_CBP);
       daa_umma_prep_kernel<<<64, 256, 0, stream>>>(mv, daa->src_mod, daa->dst_mod, col0, ud, PK_CBP, ws.bsplit);
       MOPOE_CUDA(cudaGetLastError());
+      if (col0 == 0) {
+        daa_series_rec_kernel<<<daa->n_val * N, MOPOE_HIDDEN, 0, stream>>>(mv, cx, ws);
+        MOPOE_CUDA(cudaGetLastError());
+      }
       if (g_profile && col0 == 0) MOPOE_CUDA(cudaEventRecord(g_ev0, stream));
       daa_avatar_pipe_kernel<<<num_sms(), PK_THREADS, pk_smem, stream>>>(mv, cx, ws, col0);
       MOPOE_CUDA(cudaGetLastError());

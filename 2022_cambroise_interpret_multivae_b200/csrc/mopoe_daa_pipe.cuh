@@ -48,6 +48,8 @@ constexpr int PK_SLOTS = 4;            // ring of per-series caches (unit & 3)
 constexpr int PK_TM_HEADS = 0, PK_TM_AH_HI = 64, PK_TM_AH_LO = 192, PK_TM_ACC = 320;
 constexpr int PK_MAXSUBJ = 1024;       // subjects per validation batch (owner table in shared memory)
 constexpr int PK_CACHE_F = 2 * MOPOE_HIDDEN + 128;   // floats per series cache: a0 | w1c | cs
+constexpr int PK_REC_F = PK_CACHE_F + 4;             // floats per series record in HBM: cache | xbar (fp64) | need_src | pad
+static_assert(PK_REC_F == DAA_SERIES_REC_F, "workspace carve and record layout disagree");
 
 struct PipeSmem {
   int bd_hi, bd_lo, bh_hi, bh_lo, az, stage, cache, meta, xbar, biash, part, gmeta, tinfo, bars, total;
@@ -154,6 +156,79 @@ __device__ __forceinline__ int pk_owner_subset(const ModelView& mv, const DaaCtx
   return s_own;
 }
 
+// Per-series records of the pipelined kernel, computed once per sweep (CTA = one (validation, subject) row,
+// thread = hidden unit): hidden pre-activation of the src encoder WITHOUT the perturbed column
+// (a0 = b1 + sum_{k != c} W1[:,k] x[k]) and that column of W1 (the rank-1 direction), the posterior partial
+// sums of the row's mixture owner without the src expert (mm_div.py:13-20), the dst style posterior, xbar of
+// the series.  Built inside the persistent kernel by its aux warp this was a chain of L2 round trips per
+// tile on ONE warp -- busy 84 % of the launch, every producer waiting for it at the tile barrier; the aux
+// warp now only copies the 2.5 KB record.
+__global__ void __launch_bounds__(MOPOE_HIDDEN) daa_series_rec_kernel(ModelView mv, DaaCtx cx, DaaWs ws) {
+  const int src = cx.q.src_mod, dst = cx.q.dst_mod;
+  const ModView& ms = mv.mod[src];
+  const ModView& mdst = mv.mod[dst];
+  const int L = mv.L, M = mv.M, Sd = mdst.S, C = cx.C, N = cx.N;
+  const int64_t row = blockIdx.x;                       // (validation, subject)
+  const int ug = (int)(row % N), uv = (int)(row / N);
+  const int h = threadIdx.x;
+  bool nd;
+  const int so = pk_owner_subset(mv, cx, ug, nd);
+  float* rec0 = ws.srec + row * C * PK_REC_F;
+  {
+    const float* xs = cx.x[src] + row * C;
+    const float* w = ms.w1 + (int64_t)h * C;
+    float xr[UM_MAXC], wk[UM_MAXC];
+#pragma unroll
+    for (int k = 0; k < UM_MAXC; ++k) { xr[k] = k < C ? xs[k] : 0.f; wk[k] = k < C ? w[k] : 0.f; }
+    const float b = ms.b1[h];
+    for (int uc = 0; uc < C; ++uc) {
+      float a = b, wc = 0.f;
+#pragma unroll
+      for (int k = 0; k < UM_MAXC; ++k) {
+        if (k < C) a = (k == uc) ? a : fmaf(wk[k], xr[k], a);
+        wc = (k == uc) ? wk[k] : wc;
+      }
+      rec0[uc * PK_REC_F + h] = a;
+      rec0[uc * PK_REC_F + MOPOE_HIDDEN + h] = wc;
+    }
+  }
+  if (h < 128) {
+    float val = 0.f;
+    const int sec = h >> 5, k = h & 31;                 // sections: other precisions | other mu*T | style mu | style sd
+    if (sec < 2 && k < L) {
+      float A = 0.f, B = 0.f;
+      if (mv.method == MOPOE_METHOD_MOE) {
+        const int m = mv.sub.members[so][0];
+        A = ws.enc[m][row * mv.mod[m].HC + k];
+        B = expf(0.5f * ws.enc[m][row * mv.mod[m].HC + L + k]);
+      } else {
+        const int nm = mv.sub.n_members[so];
+        for (int q = 0; q < nm; ++q) {
+          const int m = mv.sub.members[so][q];
+          if (m == src) continue;
+          const float T = 1.f / (expf(ws.enc[m][row * mv.mod[m].HC + L + k]) + MOPOE_POE_EPS);
+          A += T; B += ws.enc[m][row * mv.mod[m].HC + k] * T;
+        }
+        if (mv.method == MOPOE_METHOD_POE || nm == M) A += 1.f / (1.f + MOPOE_POE_EPS);
+        if (!((mv.sub.mask[so] >> src) & 1)) {         // owner without src: finished posterior (mu, sd)
+          const float mu = B / A, lv = logf(1.f / A);
+          A = mu; B = expf(0.5f * lv);
+        }
+      }
+      val = sec == 0 ? A : B;
+    } else if (sec >= 2 && k < Sd) {
+      val = sec == 2 ? ws.enc[dst][row * mdst.HC + 2 * L + k] : expf(0.5f * ws.enc[dst][row * mdst.HC + 2 * L + Sd + k]);
+    }
+    for (int uc = 0; uc < C; ++uc) rec0[uc * PK_REC_F + 2 * MOPOE_HIDDEN + h] = val;
+  }
+  if (h < C) {
+    float* tail = rec0 + h * PK_REC_F + PK_CACHE_F;
+    *reinterpret_cast<double*>(tail) = ws.xstat[(((int64_t)uv * C + h) * N + ug) * 2];
+    reinterpret_cast<int*>(tail)[2] = nd ? 1 : 0;
+    tail[3] = 0.f;
+  }
+}
+
 #ifdef PK_PROF
 #define PK_T(i) do { if (lane == 0) { const long long _n = clock64(); pc[i] += _n - tprev; tprev = _n; } } while (0)
 #else
@@ -167,7 +242,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
   const int src = cx.q.src_mod, dst = cx.q.dst_mod;
   const ModView& ms = mv.mod[src];
   const ModView& mdst = mv.mod[dst];
-  const int L = mv.L, M = mv.M, E = mv.E, Sd = mdst.S;
+  const int L = mv.L, E = mv.E, Sd = mdst.S;
   const int C = cx.C, R = cx.R, J = cx.J, N = cx.N;
   const UmmaDims dm = umma_dims(mv, src, dst, min(PK_CBP, R - col0));
   const PipeSmem pl = pipe_plan(dm);
@@ -553,64 +628,26 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
     auto build = [&](int u) {
       const int slot = u & (PK_SLOTS - 1);
       const int uc = u % C, ug = (u / C) % N, uv = u / (C * N);
-      const int64_t row = (int64_t)uv * N + ug;
-      float* cache = s_cache + slot * PK_CACHE_F;
-      // no L1 to speak of next to 224 KB of shared memory: every load is an L2 round trip, so issue
-      // them in bulk (C <= UM_MAXC = 16 columns, two hidden units per lane in flight)
-      const float* xs = cx.x[src] + row * C;
-      float xr[UM_MAXC];
+      // the record was computed by daa_series_rec_kernel: 161 16-byte loads in flight at once (one L2 round
+      // trip), then the shared-memory stores
+      const float4* rec = reinterpret_cast<const float4*>(ws.srec + (int64_t)u * PK_REC_F);
+      float4* cache4 = reinterpret_cast<float4*>(s_cache + slot * PK_CACHE_F);
+      constexpr int NV = PK_REC_F / 4, NIT = (NV + 31) / 32;
+      float4 vbuf[NIT];
 #pragma unroll
-      for (int k = 0; k < UM_MAXC; ++k) xr[k] = k < C ? xs[k] : 0.f;
-#pragma unroll 2
-      for (int h = lane; h < MOPOE_HIDDEN; h += 32) {
-        const float* w = ms.w1 + (int64_t)h * C;
-        float wk[UM_MAXC];
-#pragma unroll
-        for (int k = 0; k < UM_MAXC; ++k) wk[k] = k < C ? w[k] : 0.f;
-        float a = ms.b1[h], wc = 0.f;
-#pragma unroll
-        for (int k = 0; k < UM_MAXC; ++k) {
-          if (k < C) a = (k == uc) ? a : fmaf(wk[k], xr[k], a);
-          wc = (k == uc) ? wk[k] : wc;
-        }
-        cache[h] = a;
-        cache[MOPOE_HIDDEN + h] = wc;
+      for (int it = 0; it < NIT; ++it) {
+        const int q = it * 32 + lane;
+        vbuf[it] = q < NV ? __ldg(rec + q) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const bool nd = (s_gmeta[ug] & 0x80) != 0;
-      const int so = s_gmeta[ug] & 0x7f;
-      float* cs = cache + 2 * MOPOE_HIDDEN;
-      for (int k = lane; k < L + Sd; k += 32) {
-        if (k < L) {
-          float A = 0.f, B = 0.f;
-          if (mv.method == MOPOE_METHOD_MOE) {
-            const int m = mv.sub.members[so][0];
-            A = ws.enc[m][row * mv.mod[m].HC + k];
-            B = expf(0.5f * ws.enc[m][row * mv.mod[m].HC + L + k]);
-          } else {
-            const int nm = mv.sub.n_members[so];
-            for (int q = 0; q < nm; ++q) {
-              const int m = mv.sub.members[so][q];
-              if (m == src) continue;
-              const float T = 1.f / (expf(ws.enc[m][row * mv.mod[m].HC + L + k]) + MOPOE_POE_EPS);
-              A += T; B += ws.enc[m][row * mv.mod[m].HC + k] * T;
-            }
-            if (mv.method == MOPOE_METHOD_POE || nm == M) A += 1.f / (1.f + MOPOE_POE_EPS);
-            if (!((mv.sub.mask[so] >> src) & 1)) {   // owner without src: finished posterior (mu, sd)
-              const float mu = B / A, lv = logf(1.f / A);
-              A = mu; B = expf(0.5f * lv);
-            }
-          }
-          cs[k] = A; cs[32 + k] = B;
-        } else {
-          const int s = k - L;
-          cs[64 + s] = ws.enc[dst][row * mdst.HC + 2 * L + s];
-          cs[96 + s] = expf(0.5f * ws.enc[dst][row * mdst.HC + 2 * L + Sd + s]);
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int q = it * 32 + lane;
+        if (q < PK_CACHE_F / 4) cache4[q] = vbuf[it];
+        else if (q == PK_CACHE_F / 4) {
+          s_meta[slot * 4] = __float_as_int(vbuf[it].z);
+          s_xbar[slot] = __hiloint2double(__float_as_int(vbuf[it].y), __float_as_int(vbuf[it].x));
+          const_cast<int64_t*>(s_rbase)[slot] = ((int64_t)(cx.v_av_off + uv) * J * C + uc) * N + ug;
         }
-      }
-      if (lane == 0) {
-        s_meta[slot * 4] = nd ? 1 : 0;
-        s_xbar[slot] = ws.xstat[(((int64_t)uv * C + uc) * N + ug) * 2];
-        const_cast<int64_t*>(s_rbase)[slot] = ((int64_t)(cx.v_av_off + uv) * J * C + uc) * N + ug;
       }
     };
     // reduce the 4 row quarters of tile i and store the tile's contribution to each of its (<= 2) series:
