@@ -35,6 +35,9 @@
 
 namespace mopoe {
 
+#ifndef PK_NOBAR
+#define PK_NOBAR 1      // tile hand-over aux -> producers through mbarriers (0: one named barrier of 13 warps per tile)
+#endif
 constexpr int PK_ROWS = 128;
 constexpr int PK_NCH = 96;             // decoder columns per accumulator buffer
 constexpr int PK_MAXCH = 5;            // chunks per launch
@@ -271,6 +274,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
   uint64_t* bar_z_free = s_bar + 4;       // [2] decoder MMAs of the tile done   (tcgen05.commit)
   uint64_t* bar_acc_full = s_bar + 6;     // [2] chunk accumulated               (tcgen05.commit)
   uint64_t* bar_acc_empty = s_bar + 8;    // [2] epilogue drained the buffer     (4 arrivals)
+  uint64_t* bar_cache = s_bar + 10;       // [2] aux -> producers: series caches + tile info of the tile (1 arrival)
 
   // ---- launch-lifetime state ----
   {
@@ -296,6 +300,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_z_full + b, PK_PROD); mbar_init(bar_z_free + b, 1);
       mbar_init(bar_acc_full + b, 1); mbar_init(bar_acc_empty + b, PK_EPI);
+      mbar_init(bar_cache + b, 1);
     }
     *s_abort = 0;
     fence_mbar_init();
@@ -351,7 +356,13 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
     }
 #pragma unroll 1
     for (int i = 0; i < n_tiles; ++i) {
+#if PK_NOBAR
+      pk_wait(bar_cache + (i & 1), (i >> 1) & 1, s_abort);   // caches of this tile's series are ready
+      const int rot = (wq + i) % PK_NPW;                 // the warp with one more P1 step rotates over the tiles
+#else
       pk_bar_sync(1, (PK_PROD + 1) * 32);                // caches of this tile's series are ready
+      const int rot = wq;
+#endif
       PK_T(0);
       const int* ti = s_tinfo + (i & 1) * 4;                  // series and rows of the tile (aux warp)
       const int uA = ti[0], uB = ti[1], tile_row = ti[2], tile_end = ti[3];
@@ -371,7 +382,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
       // ---- P1: hidden layer -> TMEM (A operand of the class-head GEMM), 16 hidden units per step ----
       if (tile_need) {
 #pragma unroll 2
-        for (int kc = wq; kc < MOPOE_HIDDEN / 16; kc += PK_NPW) {
+        for (int kc = rot; kc < MOPOE_HIDDEN / 16; kc += PK_NPW) {
           const float4* a0p = reinterpret_cast<const float4*>(cache + kc * 16);
           const float4* wcp = reinterpret_cast<const float4*>(cache + MOPOE_HIDDEN + kc * 16);
           uint32_t hi[8], lo[8];
@@ -404,8 +415,12 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
         const bool anyA = __any_sync(0xffffffffu, inA), anyB = __any_sync(0xffffffffu, inB);
         double* part = s_part + (((i & 1) * 4 + q4) * 2) * 64;
         bool waited = false;
+        // chunks in DESCENDING order: the style chunks need no class heads, so their whole pass (and the noise
+        // of the content chunk) runs while the class-head MMAs of this tile are still in flight -- in
+        // ascending order every producer warp sat ~2.4 K of its ~15 K cycles per tile in the heads_done wait
+        const int ci_last = rot < nqt ? rot + ((nqt - 1 - rot) / PK_NPW) * PK_NPW : -1;
 #pragma unroll 1
-        for (int ci = wq; ci < nqt; ci += PK_NPW) {
+        for (int ci = ci_last; ci >= 0; ci -= PK_NPW) {
           const bool content = ci < nqc;
           const int l0 = (content ? ci : ci - nqc) * 8;        // first latent of the chunk inside its section
           const int cnt = content ? L : Sd;
@@ -480,6 +495,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
             }
           }
         }
+#if PK_NOBAR
+        // a warp without a content chunk (class_dim <= 16) has not seen the class-head MMAs of this tile
+        // complete: it must, before its P1 of the next tile overwrites their A operand in TMEM
+        if (tile_need && !waited) { pk_wait(bar_heads_done, heads_waits & 1, s_abort); ++heads_waits; }
+#endif
       }
       PK_T(4);
       fence_proxy_async();
@@ -487,7 +507,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
       if (lane == 0) pk_arrive(bar_z_full + (i & 1));
       PK_T(6);
     }
+#if !PK_NOBAR
     pk_bar_sync(1, (PK_PROD + 1) * 32);      // last tile's partial sums are visible to the aux warp
+#endif
 #ifdef PK_PROF
     if ((warp == 0 || warp == 4) && lane == 0) for (int k = 0; k < 8; ++k) ws.phase[(blockIdx.x * 4 + (warp >> 2)) * 8 + k] = pc[k];
 #endif
@@ -675,7 +697,13 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
     for (int i = -1; i < n_tiles; ++i) {
       if (i >= 0) {
         PK_T(1);
+#if PK_NOBAR
+        // every producer has finished tile i-1 (its z_full arrivals): its partial sums are complete, and the
+        // cache slots / tile info that tile i+1 reuses are no longer read
+        if (i > 0) pk_wait(bar_z_full + ((i - 1) & 1), ((i - 1) >> 1) & 1, s_abort);
+#else
         pk_bar_sync(1, (PK_PROD + 1) * 32);
+#endif
         PK_T(0);
         if (i > 0 && col0 == 0) fold(i - 1);
       }
@@ -692,8 +720,15 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
         built = uBn;
       }
       __syncwarp();
+#if PK_NOBAR
+      if (i + 1 < n_tiles && lane == 0) pk_arrive(bar_cache + ((i + 1) & 1));
+#endif
     }
+#if PK_NOBAR
+    if (n_tiles > 0) pk_wait(bar_z_full + ((n_tiles - 1) & 1), ((n_tiles - 1) >> 1) & 1, s_abort);
+#else
     pk_bar_sync(1, (PK_PROD + 1) * 32);
+#endif
     if (n_tiles > 0 && col0 == 0) fold(n_tiles - 1);
 #ifdef PK_PROF
     if (lane == 0) for (int k = 0; k < 2; ++k) ws.phase[(blockIdx.x * 4 + 3) * 8 + k] = pc[k];
