@@ -14,6 +14,7 @@
 //   4. daa_stats_kernel  one thread per (validation, score, roi): second-level t-test
 //      (stat_utils.py:73-75) or the pooled "fixed" regression (stat_utils.py:62-63)
 #include <stdlib.h>
+#include <cuda.h>   // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched through the runtime, no libcuda link)
 
 #include "mopoe_common.cuh"
 #include "mopoe_latent.cuh"
@@ -82,6 +83,7 @@ struct DaaCtx {
   float* avatars; float* sampled_scores; float* recon;
   double* betas;
   int C, R, J, N;
+  int make_rec;        // daa_base_kernel also writes the per-series records of the pipelined kernel
 };
 
 // Latent noise of the DAA streams is addressed by ROW: injected tensors hold E columns per row; the
@@ -112,6 +114,87 @@ __device__ __forceinline__ void fill_noise_row(const ModelView& mv, const Noise&
 // -------------------------------------------------------------------------------------------
 constexpr int BASE_THREADS = 128;   // 8+ CTAs per SM: the (validation, subject) grid fits in one wave
 
+// Per-series records of the pipelined avatar kernel (mopoe_daa_pipe.cuh), computed by the CTA that owns the
+// (validation, subject) row at the end of daa_base_kernel: hidden pre-activation of the src encoder WITHOUT the
+// perturbed column (a0 = b1 + sum_{k != c} W1[:,k] x[k]) and that column of W1 (the rank-1 direction), the
+// posterior partial sums of the row's mixture owner without the src expert (mm_div.py:13-20), the dst style
+// posterior.  (xbar | need_src are appended where xbar is computed.)  Built inside the persistent kernel by
+// its aux warp this was a chain of L2 round trips per tile on ONE warp -- busy 84 % of the launch, every
+// producer waiting for it at the tile barrier; the aux warp now only copies the 2.5 KB record.
+__device__ bool series_owner(const ModelView& mv, const DaaCtx& cx, int g, int& s_own) {
+  int owner = 0, kidx = 0;
+  s_own = 0;
+  for (int k = 0; k < cx.b.n_mix; ++k)
+    if (g >= cx.b.joint_bounds[k] && g < cx.b.joint_bounds[k + 1]) owner = k;
+  for (int s = 0; s < mv.sub.n_subsets; ++s) {
+    if (!in_mixture(mv, cx.b, s)) continue;
+    if (kidx == owner) s_own = s;
+    ++kidx;
+  }
+  return ((mv.sub.mask[s_own] >> cx.q.src_mod) & 1) || (mv.method == MOPOE_METHOD_MOE && mv.sub.n_members[s_own] > 1);
+}
+
+__device__ void series_records(const ModelView& mv, const DaaCtx& cx, const DaaWs& ws, int64_t row, int g, int t, int nthreads) {
+  const int src = cx.q.src_mod, dst = cx.q.dst_mod;
+  const ModView& ms = mv.mod[src];
+  const ModView& mdst = mv.mod[dst];
+  const int L = mv.L, M = mv.M, Sd = mdst.S, C = cx.C;
+  int so;
+  series_owner(mv, cx, g, so);
+  float* rec0 = ws.srec + row * C * DAA_SERIES_REC_F;
+  const float* xs = cx.x[src] + row * C;
+  constexpr int MAXC = 16;                              // the pipelined kernel is selected for C <= UM_MAXC = 16 only
+  float xr[MAXC];
+#pragma unroll
+  for (int k = 0; k < MAXC; ++k) xr[k] = k < C ? xs[k] : 0.f;
+  for (int h = t; h < MOPOE_HIDDEN; h += nthreads) {
+    const float* w = ms.w1 + (int64_t)h * C;
+    float wk[MAXC];
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) wk[k] = k < C ? w[k] : 0.f;
+    const float b = ms.b1[h];
+    for (int uc = 0; uc < C; ++uc) {
+      float a = b, wc = 0.f;
+#pragma unroll
+      for (int k = 0; k < MAXC; ++k) {
+        if (k < C) a = (k == uc) ? a : fmaf(wk[k], xr[k], a);
+        wc = (k == uc) ? wk[k] : wc;
+      }
+      rec0[uc * DAA_SERIES_REC_F + h] = a;
+      rec0[uc * DAA_SERIES_REC_F + MOPOE_HIDDEN + h] = wc;
+    }
+  }
+  for (int i = t; i < 128; i += nthreads) {
+    float val = 0.f;
+    const int sec = i >> 5, k = i & 31;                 // sections: other precisions | other mu*T | style mu | style sd
+    if (sec < 2 && k < L) {
+      float A = 0.f, B = 0.f;
+      if (mv.method == MOPOE_METHOD_MOE) {
+        const int m = mv.sub.members[so][0];
+        A = ws.enc[m][row * mv.mod[m].HC + k];
+        B = expf(0.5f * ws.enc[m][row * mv.mod[m].HC + L + k]);
+      } else {
+        const int nm = mv.sub.n_members[so];
+        for (int q = 0; q < nm; ++q) {
+          const int m = mv.sub.members[so][q];
+          if (m == src) continue;
+          const float T = 1.f / (expf(ws.enc[m][row * mv.mod[m].HC + L + k]) + MOPOE_POE_EPS);
+          A += T; B += ws.enc[m][row * mv.mod[m].HC + k] * T;
+        }
+        if (mv.method == MOPOE_METHOD_POE || nm == M) A += 1.f / (1.f + MOPOE_POE_EPS);
+        if (!((mv.sub.mask[so] >> src) & 1)) {         // owner without src: finished posterior (mu, sd)
+          const float mu = B / A, lv = logf(1.f / A);
+          A = mu; B = expf(0.5f * lv);
+        }
+      }
+      val = sec == 0 ? A : B;
+    } else if (sec >= 2 && k < Sd) {
+      val = sec == 2 ? ws.enc[dst][row * mdst.HC + 2 * L + k] : expf(0.5f * ws.enc[dst][row * mdst.HC + 2 * L + Sd + k]);
+    }
+    for (int uc = 0; uc < C; ++uc) rec0[uc * DAA_SERIES_REC_F + 2 * MOPOE_HIDDEN + i] = val;
+  }
+}
+
 __global__ void __launch_bounds__(BASE_THREADS) daa_base_kernel(ModelView mv, DaaCtx cx, DaaWs ws) {
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -122,6 +205,9 @@ __global__ void __launch_bounds__(BASE_THREADS) daa_base_kernel(ModelView mv, Da
   float* s_acc = s_mean + 176;        // [threads / nb][EP] per-group sums (block-padded columns)
   float* s_zz = s_acc + 4 * BASE_THREADS;         // [M][64] decoder inputs
   float* s_loc = s_zz + MOPOE_MAX_MODS * 64;  // [C]
+  // records of the pipelined avatar kernel first: they depend on the encoder heads and the inputs only, and
+  // their load -> store chains then overlap the Philox loop of the co-resident CTAs
+  if (cx.make_rec) series_records(mv, cx, ws, row, g, t, BASE_THREADS);
   // mean over the n_base passes of the noise row of this subject.  Thread = (Philox block b of the row,
   // pass group): every lane draws whole blocks, four independent passes in flight per thread.
   {
@@ -245,6 +331,13 @@ __global__ void __launch_bounds__(BASE_THREADS) daa_base_kernel(ModelView mv, Da
     if (lane == 0) {
       const int64_t o = (((int64_t)v * cx.C + c) * cx.N + g) * 2;
       ws.xstat[o] = xb; ws.xstat[o + 1] = q;
+      if (cx.make_rec) {
+        int so;
+        float* tail = ws.srec + (row * cx.C + c) * DAA_SERIES_REC_F + 2 * MOPOE_HIDDEN + 128;
+        *reinterpret_cast<double*>(tail) = xb;
+        reinterpret_cast<int*>(tail)[2] = series_owner(mv, cx, g, so) ? 1 : 0;
+        tail[3] = 0.f;
+      }
     }
   }
 }
@@ -692,6 +785,34 @@ __global__ void daa_stats_kernel(int n_val, int N, int C, int J, int R, int reg_
 
 using namespace mopoe;
 
+// 3-D tensor map of the avatar tensor for the TMA epilogue of the pipelined kernel: (column, row inside the
+// validation, validation), fp32, 32 x 32 boxes, 128-byte swizzle.  Returns false when the map cannot be used
+// (driver entry point missing, unaligned buffer, R not a multiple of 4): the kernel then stores through the LSU.
+static bool make_avatar_tmap(float* avatars, int64_t n_val, int64_t rows_per_val, int64_t R, CUtensorMap* out) {
+  memset(out, 0, sizeof(*out));
+  if (!avatars || (R & 3) || (reinterpret_cast<uintptr_t>(avatars) & 15) || !getenv("MOPOE_DAA_TMA")) return false;   // opt-in for now
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (encode_fn)p;
+    else
+      cudaGetLastError();
+  }
+  if (!fn) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)R, (cuuint64_t)rows_per_val, (cuuint64_t)n_val};
+  const cuuint64_t strides[2] = {(cuuint64_t)R * 4, (cuuint64_t)rows_per_val * R * 4};
+  const cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, avatars, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int g_profile = 0;
 static int g_last_impl = 0;
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
@@ -782,10 +903,6 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   cx.v_av_off = eps_av ? 0 : daa->val_begin;
   cx.avatars = avatars; cx.sampled_scores = sampled_scores; cx.recon = reconstructions; cx.betas = betas;
   cx.C = desc->dims[daa->src_mod]; cx.R = desc->dims[daa->dst_mod]; cx.J = daa->n_samples; cx.N = N;
-  // 2. base passes
-  const int base_smem = (176 + 4 * BASE_THREADS + MOPOE_MAX_MODS * 64 + 64) * 4;
-  daa_base_kernel<<<daa->n_val * N, BASE_THREADS, base_smem, stream>>>(mv, cx, ws);
-  MOPOE_CUDA(cudaGetLastError());
   // 3. avatars + first-level regression
   const AvSmem pl = av_plan(mv, daa->src_mod, daa->dst_mod, cx.J);
   const int av_smem = pl.total * 4;
@@ -808,19 +925,22 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   if (force && !strcmp(force, "umma")) { if (!umma_ok) { set_error("MOPOE_DAA_IMPL=umma but the shapes do not fit the tcgen05 tiling"); return MOPOE_EINVAL; } impl = 1; }
   if (force && !strcmp(force, "pipe")) { if (!pipe_ok) { set_error("MOPOE_DAA_IMPL=pipe but the configuration does not fit the pipelined kernel"); return MOPOE_EINVAL; } impl = 2; }
   g_last_impl = impl;
+  cx.make_rec = impl == 2 ? 1 : 0;
+  // 2. base passes
+  const int base_smem = (176 + 4 * BASE_THREADS + MOPOE_MAX_MODS * 64 + 64) * 4;
+  daa_base_kernel<<<daa->n_val * N, BASE_THREADS, base_smem, stream>>>(mv, cx, ws);
+  MOPOE_CUDA(cudaGetLastError());
   MOPOE_CUDA(cudaMemsetAsync(ws.err, 0, sizeof(int), stream));
   if (impl == 2) {
     MOPOE_CUDA(cudaFuncSetAttribute((void*)daa_avatar_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pk_smem));
+    CUtensorMap tmap;
+    const bool tma_ok = make_avatar_tmap(avatars, daa->n_val, (int64_t)N * cx.C * cx.J, cx.R, &tmap);
     for (int col0 = 0; col0 < cx.R; col0 += PK_CBP) {
       const UmmaDims ud = umma_dims(mv, daa->src_mod, daa->dst_mod, cx.R - col0 < PK_CBP ? cx.R - col0 : PK_CBP);
       daa_umma_prep_kernel<<<64, 256, 0, stream>>>(mv, daa->src_mod, daa->dst_mod, col0, ud, PK_CBP, ws.bsplit);
       MOPOE_CUDA(cudaGetLastError());
-      if (col0 == 0) {
-        daa_series_rec_kernel<<<daa->n_val * N, MOPOE_HIDDEN, 0, stream>>>(mv, cx, ws);
-        MOPOE_CUDA(cudaGetLastError());
-      }
       if (g_profile && col0 == 0) MOPOE_CUDA(cudaEventRecord(g_ev0, stream));
-      daa_avatar_pipe_kernel<<<num_sms(), PK_THREADS, pk_smem, stream>>>(mv, cx, ws, col0);
+      daa_avatar_pipe_kernel<<<num_sms(), PK_THREADS, pk_smem, stream>>>(mv, cx, ws, col0, tma_ok ? 1 : 0, tmap);
       MOPOE_CUDA(cudaGetLastError());
       if (g_profile && col0 == 0) MOPOE_CUDA(cudaEventRecord(g_ev1, stream));
     }

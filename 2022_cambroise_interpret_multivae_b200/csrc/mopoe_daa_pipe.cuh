@@ -42,11 +42,15 @@ constexpr int PK_ROWS = 128;
 constexpr int PK_NCH = 96;             // decoder columns per accumulator buffer
 constexpr int PK_MAXCH = 5;            // chunks per launch
 constexpr int PK_CBP = PK_NCH * PK_MAXCH;   // 480 decoder columns per launch
-constexpr int PK_NPW = 3;              // producer warps per TMEM lane quarter
+#ifndef PK_NPW_
+#define PK_NPW_ 3
+#endif
+constexpr int PK_NPW = PK_NPW_;        // producer warps per TMEM lane quarter
 constexpr int PK_PROD = 4 * PK_NPW, PK_EPI = 4;
 constexpr int PK_W_EPI = PK_PROD, PK_W_HMMA = PK_PROD + PK_EPI, PK_W_DMMA = PK_W_HMMA + 1, PK_W_AUX = PK_W_HMMA + 2;
 constexpr int PK_THREADS = (PK_PROD + PK_EPI + 3) * 32;   // 608
 constexpr int PK_STAGE_LD = 36;
+constexpr int PK_STAGE_BYTES = 5 * 1024;   // per epilogue warp: 32 x 36 floats (padded rows) or one 4 KB swizzled TMA box
 constexpr int PK_SLOTS = 4;            // ring of per-series caches (unit & 3)
 constexpr int PK_TM_HEADS = 0, PK_TM_AH_HI = 64, PK_TM_AH_LO = 192, PK_TM_ACC = 320;
 constexpr int PK_MAXSUBJ = 1024;       // subjects per validation batch (owner table in shared memory)
@@ -65,7 +69,8 @@ __host__ __device__ inline PipeSmem pipe_plan(const UmmaDims& d) {
   p.bd_hi = take(PK_CBP * d.KZ * 2); p.bd_lo = take(PK_CBP * d.KZ * 2);
   p.bh_hi = take(d.NH * MOPOE_HIDDEN * 2); p.bh_lo = take(d.NH * MOPOE_HIDDEN * 2);
   p.az = take(2 * 2 * PK_ROWS * d.KZ * 2);             // [buffer][hi|lo]
-  p.stage = take(PK_EPI * 32 * PK_STAGE_LD * 4);
+  off = (off + 1023) & ~1023;                           // TMA 128-byte swizzle: the pattern repeats every 1024 bytes
+  p.stage = take(PK_EPI * PK_STAGE_BYTES);
   p.cache = take(PK_SLOTS * PK_CACHE_F * 4);
   p.meta = take(PK_SLOTS * 4 * 4);
   p.xbar = take(PK_SLOTS * 2 * 8);                       // per series: xbar | noise row index of sample 0 (int64)
@@ -159,86 +164,14 @@ __device__ __forceinline__ int pk_owner_subset(const ModelView& mv, const DaaCtx
   return s_own;
 }
 
-// Per-series records of the pipelined kernel, computed once per sweep (CTA = one (validation, subject) row,
-// thread = hidden unit): hidden pre-activation of the src encoder WITHOUT the perturbed column
-// (a0 = b1 + sum_{k != c} W1[:,k] x[k]) and that column of W1 (the rank-1 direction), the posterior partial
-// sums of the row's mixture owner without the src expert (mm_div.py:13-20), the dst style posterior, xbar of
-// the series.  Built inside the persistent kernel by its aux warp this was a chain of L2 round trips per
-// tile on ONE warp -- busy 84 % of the launch, every producer waiting for it at the tile barrier; the aux
-// warp now only copies the 2.5 KB record.
-__global__ void __launch_bounds__(MOPOE_HIDDEN) daa_series_rec_kernel(ModelView mv, DaaCtx cx, DaaWs ws) {
-  const int src = cx.q.src_mod, dst = cx.q.dst_mod;
-  const ModView& ms = mv.mod[src];
-  const ModView& mdst = mv.mod[dst];
-  const int L = mv.L, M = mv.M, Sd = mdst.S, C = cx.C, N = cx.N;
-  const int64_t row = blockIdx.x;                       // (validation, subject)
-  const int ug = (int)(row % N), uv = (int)(row / N);
-  const int h = threadIdx.x;
-  bool nd;
-  const int so = pk_owner_subset(mv, cx, ug, nd);
-  float* rec0 = ws.srec + row * C * PK_REC_F;
-  {
-    const float* xs = cx.x[src] + row * C;
-    const float* w = ms.w1 + (int64_t)h * C;
-    float xr[UM_MAXC], wk[UM_MAXC];
-#pragma unroll
-    for (int k = 0; k < UM_MAXC; ++k) { xr[k] = k < C ? xs[k] : 0.f; wk[k] = k < C ? w[k] : 0.f; }
-    const float b = ms.b1[h];
-    for (int uc = 0; uc < C; ++uc) {
-      float a = b, wc = 0.f;
-#pragma unroll
-      for (int k = 0; k < UM_MAXC; ++k) {
-        if (k < C) a = (k == uc) ? a : fmaf(wk[k], xr[k], a);
-        wc = (k == uc) ? wk[k] : wc;
-      }
-      rec0[uc * PK_REC_F + h] = a;
-      rec0[uc * PK_REC_F + MOPOE_HIDDEN + h] = wc;
-    }
-  }
-  if (h < 128) {
-    float val = 0.f;
-    const int sec = h >> 5, k = h & 31;                 // sections: other precisions | other mu*T | style mu | style sd
-    if (sec < 2 && k < L) {
-      float A = 0.f, B = 0.f;
-      if (mv.method == MOPOE_METHOD_MOE) {
-        const int m = mv.sub.members[so][0];
-        A = ws.enc[m][row * mv.mod[m].HC + k];
-        B = expf(0.5f * ws.enc[m][row * mv.mod[m].HC + L + k]);
-      } else {
-        const int nm = mv.sub.n_members[so];
-        for (int q = 0; q < nm; ++q) {
-          const int m = mv.sub.members[so][q];
-          if (m == src) continue;
-          const float T = 1.f / (expf(ws.enc[m][row * mv.mod[m].HC + L + k]) + MOPOE_POE_EPS);
-          A += T; B += ws.enc[m][row * mv.mod[m].HC + k] * T;
-        }
-        if (mv.method == MOPOE_METHOD_POE || nm == M) A += 1.f / (1.f + MOPOE_POE_EPS);
-        if (!((mv.sub.mask[so] >> src) & 1)) {         // owner without src: finished posterior (mu, sd)
-          const float mu = B / A, lv = logf(1.f / A);
-          A = mu; B = expf(0.5f * lv);
-        }
-      }
-      val = sec == 0 ? A : B;
-    } else if (sec >= 2 && k < Sd) {
-      val = sec == 2 ? ws.enc[dst][row * mdst.HC + 2 * L + k] : expf(0.5f * ws.enc[dst][row * mdst.HC + 2 * L + Sd + k]);
-    }
-    for (int uc = 0; uc < C; ++uc) rec0[uc * PK_REC_F + 2 * MOPOE_HIDDEN + h] = val;
-  }
-  if (h < C) {
-    float* tail = rec0 + h * PK_REC_F + PK_CACHE_F;
-    *reinterpret_cast<double*>(tail) = ws.xstat[(((int64_t)uv * C + h) * N + ug) * 2];
-    reinterpret_cast<int*>(tail)[2] = nd ? 1 : 0;
-    tail[3] = 0.f;
-  }
-}
-
 #ifdef PK_PROF
 #define PK_T(i) do { if (lane == 0) { const long long _n = clock64(); pc[i] += _n - tprev; tprev = _n; } } while (0)
 #else
 #define PK_T(i) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelView mv, DaaCtx cx, DaaWs ws, int col0) {
+__global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelView mv, DaaCtx cx, DaaWs ws, int col0, int tma_ok,
+                                                                         const __grid_constant__ CUtensorMap tmap) {
   using namespace umma;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -517,13 +450,14 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
     // =============================== epilogue ===============================
     const int q4 = warp & 3;
     const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
-    float* s_stage = reinterpret_cast<float*>(smem + pl.stage) + q4 * 32 * PK_STAGE_LD;
+    float* s_stage = reinterpret_cast<float*>(smem + pl.stage + q4 * PK_STAGE_BYTES);   // 1024-byte aligned (swizzle atom)
     int q = 0;
 #pragma unroll 1
     for (int i = 0; i < n_tiles; ++i) {
       int tile_row, tile_end;
       tile_rows(i, tile_row, tile_end);
       const int rows_left = max(0, min(32, tile_end - (tile_row + q4 * 32)));
+      const int tile_v = tile_row / rpv, row_in_val = tile_row - tile_v * rpv + q4 * 32;
 #pragma unroll 1
       for (int ch = 0; ch < n_chunks; ++ch, ++q) {
         const int b = q & 1;
@@ -543,7 +477,28 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
             __syncwarp();
             if (lane == 0) pk_arrive(bar_acc_empty + b);
           }
-          if (cx.avatars) {
+          if (cx.avatars && tma_ok) {
+            // TMA epilogue: the warp stages its 32 x 32 block in the 128-byte-swizzled box layout (lane = row,
+            // 16-byte chunk k of the row at position k ^ (row & 7): conflict-free) and ONE lane hands the 4 KB box
+            // to the copy engine (3-D map (column, row inside the validation, validation): rows past the end of a
+            // validation and columns past R are clipped by the hardware).  No LDS / STG on the LSU path that the
+            // producers' shared-memory traffic uses.
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous box has left the stage
+            __syncwarp();
+            {
+              unsigned char* rowp = reinterpret_cast<unsigned char*>(s_stage) + lane * 128;
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                *reinterpret_cast<float4*>(rowp + ((k ^ (lane & 7)) << 4)) = make_float4(vv[4 * k], vv[4 * k + 1], vv[4 * k + 2], vv[4 * k + 3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && rows_left > 0) {
+              asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                           ::"l"(reinterpret_cast<uint64_t>(&tmap)), "r"(col0 + cb0), "r"(row_in_val), "r"(tile_v), "r"(smem_u32(s_stage)) : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          } else if (cx.avatars) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
               *reinterpret_cast<float4*>(s_stage + lane * PK_STAGE_LD + 4 * k) = make_float4(vv[4 * k], vv[4 * k + 1], vv[4 * k + 2], vv[4 * k + 3]);
@@ -554,7 +509,13 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
             if (rows_left == 32 && (R & 3) == 0 && cb0 + 32 <= ncol) {
 #pragma unroll
               for (int it = 0; it < 8; ++it)
+#ifdef PK_EXP_NOSTG   // experiment: staging without the global stores (the loaded value is kept alive through a never-true store)
+                { const float4 o_ = *reinterpret_cast<const float4*>(sbase + it * 4 * PK_STAGE_LD); if (o_.x == 1.2345e-30f) __stcs(reinterpret_cast<float4*>(gbase), o_); }
+#elif defined(PK_EXP_WRAP)   // experiment: same stores into a 32 MB (L2-resident) window of the tensor
+                __stcs(reinterpret_cast<float4*>(cx.avatars + (((gbase - cx.avatars) + (int64_t)it * 4 * R) & 0x7FFFFF)), *reinterpret_cast<const float4*>(sbase + it * 4 * PK_STAGE_LD));
+#else
                 __stcs(reinterpret_cast<float4*>(gbase + (int64_t)it * 4 * R), *reinterpret_cast<const float4*>(sbase + it * 4 * PK_STAGE_LD));
+#endif
             } else {
 #pragma unroll 1
               for (int it = 0; it < 8; ++it) {
@@ -577,6 +538,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
         }
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #ifdef PK_PROF
     if (warp == PK_W_EPI && lane == 0) { pc[2] = clock64() - tstart; for (int k = 0; k < 4; ++k) ws.phase[(blockIdx.x * 4 + 2) * 8 + k] = pc[k]; }
 #endif

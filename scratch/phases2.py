@@ -20,3 +20,10 @@ for cta in ("0", "73", "147"):
     print("CTA", cta)
     for n, c in zip(names, ph):
         if n != "-": print("  %-24s %9d cycles  per tile %7.0f" % (n, c, c / 56))
+import ctypes as C
+L = _lib.lib(); L.mopoe_profile_enable(1)
+ts = []
+for i in range(5):
+    r = daa.daa_sweep(spec, flat, src.cuda(), dst.cuda(), 150, 1000, workspace=ws, materialize=os.environ.get("MAT", "1") == "1")
+    ms = C.c_float(); torch.cuda.synchronize(); L.mopoe_daa_last_kernel_ms(C.byref(ms)); ts.append(ms.value)
+print("kernel ms", sorted(ts))
