@@ -207,7 +207,10 @@ __global__ void __launch_bounds__(BASE_THREADS) daa_base_kernel(ModelView mv, Da
   float* s_loc = s_zz + MOPOE_MAX_MODS * 64;  // [C]
   // records of the pipelined avatar kernel first: they depend on the encoder heads and the inputs only, and
   // their load -> store chains then overlap the Philox loop of the co-resident CTAs
-  if (cx.make_rec) series_records(mv, cx, ws, row, g, t, BASE_THREADS);
+  if (cx.make_rec) {
+    if (blockIdx.x == 0 && t == 0) *ws.counter = 0;    // tile counter of the pipelined kernel's dynamic schedule
+    series_records(mv, cx, ws, row, g, t, BASE_THREADS);
+  }
   // mean over the n_base passes of the noise row of this subject.  Thread = (Philox block b of the row,
   // pass group): every lane draws whole blocks, four independent passes in flight per thread.
   {
@@ -790,7 +793,7 @@ using namespace mopoe;
 // (driver entry point missing, unaligned buffer, R not a multiple of 4): the kernel then stores through the LSU.
 static bool make_avatar_tmap(float* avatars, int64_t n_val, int64_t rows_per_val, int64_t R, CUtensorMap* out) {
   memset(out, 0, sizeof(*out));
-  if (!avatars || (R & 3) || (reinterpret_cast<uintptr_t>(avatars) & 15) || !getenv("MOPOE_DAA_TMA")) return false;   // opt-in for now
+  if (!avatars || (R & 3) || (reinterpret_cast<uintptr_t>(avatars) & 15) || getenv("MOPOE_DAA_NO_TMA")) return false;
   typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -939,6 +942,7 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
       const UmmaDims ud = umma_dims(mv, daa->src_mod, daa->dst_mod, cx.R - col0 < PK_CBP ? cx.R - col0 : PK_CBP);
       daa_umma_prep_kernel<<<64, 256, 0, stream>>>(mv, daa->src_mod, daa->dst_mod, col0, ud, PK_CBP, ws.bsplit);
       MOPOE_CUDA(cudaGetLastError());
+      if (col0 > 0) MOPOE_CUDA(cudaMemsetAsync(ws.counter, 0, sizeof(int), stream));   // (the first launch's counter is zeroed by daa_base_kernel)
       if (g_profile && col0 == 0) MOPOE_CUDA(cudaEventRecord(g_ev0, stream));
       daa_avatar_pipe_kernel<<<num_sms(), PK_THREADS, pk_smem, stream>>>(mv, cx, ws, col0, tma_ok ? 1 : 0, tmap);
       MOPOE_CUDA(cudaGetLastError());

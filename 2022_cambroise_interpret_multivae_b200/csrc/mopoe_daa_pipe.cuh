@@ -35,9 +35,6 @@
 
 namespace mopoe {
 
-#ifndef PK_NOBAR
-#define PK_NOBAR 1      // tile hand-over aux -> producers through mbarriers (0: one named barrier of 13 warps per tile)
-#endif
 constexpr int PK_ROWS = 128;
 constexpr int PK_NCH = 96;             // decoder columns per accumulator buffer
 constexpr int PK_MAXCH = 5;            // chunks per launch
@@ -51,7 +48,7 @@ constexpr int PK_W_EPI = PK_PROD, PK_W_HMMA = PK_PROD + PK_EPI, PK_W_DMMA = PK_W
 constexpr int PK_THREADS = (PK_PROD + PK_EPI + 3) * 32;   // 608
 constexpr int PK_STAGE_LD = 36;
 constexpr int PK_STAGE_BYTES = 5 * 1024;   // per epilogue warp: 32 x 36 floats (padded rows) or one 4 KB swizzled TMA box
-constexpr int PK_SLOTS = 4;            // ring of per-series caches (unit & 3)
+constexpr int PK_SLOTS = 4;            // per-series caches: [tile parity][first | second series of the tile]
 constexpr int PK_TM_HEADS = 0, PK_TM_AH_HI = 64, PK_TM_AH_LO = 192, PK_TM_ACC = 320;
 constexpr int PK_MAXSUBJ = 1024;       // subjects per validation batch (owner table in shared memory)
 constexpr int PK_CACHE_F = 2 * MOPOE_HIDDEN + 128;   // floats per series cache: a0 | w1c | cs
@@ -59,7 +56,7 @@ constexpr int PK_REC_F = PK_CACHE_F + 4;             // floats per series record
 static_assert(PK_REC_F == DAA_SERIES_REC_F, "workspace carve and record layout disagree");
 
 struct PipeSmem {
-  int bd_hi, bd_lo, bh_hi, bh_lo, az, stage, cache, meta, xbar, biash, part, gmeta, tinfo, bars, total;
+  int bd_hi, bd_lo, bh_hi, bh_lo, az, stage, cache, meta, xbar, biash, part, gmeta, tinfo, score, bars, total;
 };
 
 __host__ __device__ inline PipeSmem pipe_plan(const UmmaDims& d) {
@@ -78,7 +75,8 @@ __host__ __device__ inline PipeSmem pipe_plan(const UmmaDims& d) {
   p.biash = take(d.NH * 4);
   p.part = take(2 * 4 * 2 * 64 * 8);                    // [tile parity][lane quarter][series 0|1][k] fp64
   p.gmeta = take(PK_MAXSUBJ);                           // per subject row: bit 7 need_src | owner subset
-  p.bars = take(128);
+  p.score = take(2 * PK_ROWS * 4);                      // [tile parity][row] perturbed scores of the tile
+  p.bars = take(256);                                   // mbarriers | tmem base | abort | tile ring | published count
   p.total = off;
   return p;
 }
@@ -201,6 +199,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + pl.bars);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + pl.bars + 96);
   volatile int* s_abort = reinterpret_cast<volatile int*>(smem + pl.bars + 100);
+  volatile int* s_ring = reinterpret_cast<volatile int*>(smem + pl.bars + 128);   // [8] global tile id of iteration i (or -1: no more tiles)
+  volatile int* s_npub = reinterpret_cast<volatile int*>(smem + pl.bars + 160);   // iterations published so far
+  float* s_score = reinterpret_cast<float*>(smem + pl.score);
   uint64_t* bar_h_full = s_bar + 0;       // producers -> heads issuer           (8 arrivals)
   uint64_t* bar_heads_done = s_bar + 1;   // heads MMAs complete                 (tcgen05.commit)
   uint64_t* bar_z_full = s_bar + 2;       // [2] producers -> decoder issuer     (8 arrivals)
@@ -236,6 +237,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
       mbar_init(bar_cache + b, 1);
     }
     *s_abort = 0;
+    *s_npub = 0;
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(s_tmem, 512);
@@ -245,27 +247,39 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  // ---- this CTA's contiguous range of 128-row tiles (balanced over the grid).  The tile grid restarts at
-  // every validation (the last tile of a validation is partial), so tile boundaries inside a series --
-  // and with them the grouping of the fp64 regression sums -- do not depend on how validations are sharded
+  // ---- tiles are handed out DYNAMICALLY: iteration 0 of CTA b is tile b, every further tile comes from a global
+  // counter (the aux warp draws it one tile ahead and publishes it through a small ring in shared memory).
+  // CTAs differ by up to 25 % in speed (the store path of some SMs is slower), a static split waits for the
+  // slowest.  The tile grid restarts at every validation (the last tile of a validation is partial), and every
+  // tile writes its regression sums to its own (series, tile) slot, so neither the grouping of the fp64 sums
+  // nor the tables depend on which CTA ran which tile or on how validations are sharded.
   const int rpv = N * C * J;                          // rows per validation; n_val * rpv < 2^31 (host check)
   const int tpv = (rpv + PK_ROWS - 1) / PK_ROWS;      // tiles per validation
   const int total_tiles = cx.q.n_val * tpv;
-  const int total_tiles_rows = cx.q.n_val * rpv;
-  const int tb = total_tiles / gridDim.x, trem = total_tiles % gridDim.x;
-  const int tile0 = (int)blockIdx.x * tb + min((int)blockIdx.x, trem);
-  const int n_tiles = tb + ((int)blockIdx.x < trem ? 1 : 0);
   const int tpu = pipe_tiles_per_unit(J);
   auto unit_need = [&](int u) -> bool { return (s_gmeta[(u / C) % N] & 0x80) != 0; };
-  auto tile_rows = [&](int i, int& r0, int& r1) {     // rows [r0, r1) of this CTA's i-th tile
-    const int gt = tile0 + i, v = gt / tpv;
+  auto tile_rows = [&](int gt, int& r0, int& r1) {    // rows [r0, r1) of global tile gt
+    const int v = gt / tpv;
     r0 = v * rpv + (gt - v * tpv) * PK_ROWS;
     r1 = min(r0 + PK_ROWS, (v + 1) * rpv);
   };
-  auto tile_units = [&](int i, int& uA, int& uB) {
+  auto tile_units = [&](int gt, int& uA, int& uB) {
     int r0, r1;
-    tile_rows(i, r0, r1);
+    tile_rows(gt, r0, r1);
     uA = r0 / J; uB = (r1 - 1) / J;
+  };
+  // global tile id of this CTA's iteration i, once the aux warp has published it (-1: no more tiles)
+  auto tile_of = [&](int i) -> int {
+    uint32_t ns = 32;
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 21) && *s_npub <= i; ++spin) {
+      __nanosleep(ns);
+      ns = ns < 256 ? ns * 2 : 256;
+      if ((spin & 63u) == 63u && *s_abort) return -1;
+    }
+    if (*s_npub <= i) { *s_abort = 1; return -1; }
+    __threadfence_block();
+    return s_ring[i & 7];
   };
 
 #ifdef PK_PROF
@@ -281,37 +295,24 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
     const int nbrow = mv.EP >> 2;
     const int nqc = KC >> 3, nqt = KZ >> 3;              // content chunks, all chunks of 8 latents
     uint32_t heads_waits = 0;
-    float score_next = 0.f;
-    if (n_tiles > 0) {
-      int r0, r1;
-      tile_rows(0, r0, r1);
-      if (r0 + r < r1) score_next = ws.scores[r0 + r];
-    }
 #pragma unroll 1
-    for (int i = 0; i < n_tiles; ++i) {
-#if PK_NOBAR
-      pk_wait(bar_cache + (i & 1), (i >> 1) & 1, s_abort);   // caches of this tile's series are ready
+    for (int i = 0;; ++i) {
+      if (!pk_wait(bar_cache + (i & 1), (i >> 1) & 1, s_abort)) break;   // tile info, series caches, scores are ready
       const int rot = (wq + i) % PK_NPW;                 // the warp with one more P1 step rotates over the tiles
-#else
-      pk_bar_sync(1, (PK_PROD + 1) * 32);                // caches of this tile's series are ready
-      const int rot = wq;
-#endif
       PK_T(0);
       const int* ti = s_tinfo + (i & 1) * 4;                  // series and rows of the tile (aux warp)
       const int uA = ti[0], uB = ti[1], tile_row = ti[2], tile_end = ti[3];
+      if (tile_row < 0) break;                           // no more tiles
       const int rho = tile_row + r;
       const bool valid = rho < tile_end;
       const int u = (rho < (uA + 1) * J) ? uA : uB;
       const int j = valid ? rho - u * J : 0;
-      const int slot = u & (PK_SLOTS - 1);
+      const int slot = (i & 1) * 2 + (u - uA);           // the tile's (<= 2) series sit in the slots of its parity
       const float* cache = s_cache + slot * PK_CACHE_F;
       const float* cs = cache + 2 * MOPOE_HIDDEN;
-      const bool tile_need = s_meta[(uA & (PK_SLOTS - 1)) * 4] || s_meta[(uB & (PK_SLOTS - 1)) * 4];
+      const bool tile_need = s_meta[(i & 1) * 8] || (uB != uA && s_meta[(i & 1) * 8 + 4]);
       const bool need = valid && s_meta[slot * 4];
-      const float score = score_next;
-      // next tile's score (latency hidden): the next tile starts where this one ends, and is never shorter
-      // than this thread's row index unless it is the last tile of a validation (then the load is unused)
-      if (i + 1 < n_tiles && tile_end + r < total_tiles_rows) score_next = ws.scores[tile_end + r];
+      const float score = s_score[(i & 1) * PK_ROWS + r];
       // ---- P1: hidden layer -> TMEM (A operand of the class-head GEMM), 16 hidden units per step ----
       if (tile_need) {
 #pragma unroll 2
@@ -428,11 +429,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
             }
           }
         }
-#if PK_NOBAR
         // a warp without a content chunk (class_dim <= 16) has not seen the class-head MMAs of this tile
         // complete: it must, before its P1 of the next tile overwrites their A operand in TMEM
         if (tile_need && !waited) { pk_wait(bar_heads_done, heads_waits & 1, s_abort); ++heads_waits; }
-#endif
       }
       PK_T(4);
       fence_proxy_async();
@@ -440,9 +439,6 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
       if (lane == 0) pk_arrive(bar_z_full + (i & 1));
       PK_T(6);
     }
-#if !PK_NOBAR
-    pk_bar_sync(1, (PK_PROD + 1) * 32);      // last tile's partial sums are visible to the aux warp
-#endif
 #ifdef PK_PROF
     if ((warp == 0 || warp == 4) && lane == 0) for (int k = 0; k < 8; ++k) ws.phase[(blockIdx.x * 4 + (warp >> 2)) * 8 + k] = pc[k];
 #endif
@@ -453,9 +449,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
     float* s_stage = reinterpret_cast<float*>(smem + pl.stage + q4 * PK_STAGE_BYTES);   // 1024-byte aligned (swizzle atom)
     int q = 0;
 #pragma unroll 1
-    for (int i = 0; i < n_tiles; ++i) {
+    for (int i = 0;; ++i) {
+      const int gt = tile_of(i);
+      if (gt < 0) break;
       int tile_row, tile_end;
-      tile_rows(i, tile_row, tile_end);
+      tile_rows(gt, tile_row, tile_end);
       const int rows_left = max(0, min(32, tile_end - (tile_row + q4 * 32)));
       const int tile_v = tile_row / rpv, row_in_val = tile_row - tile_v * rpv + q4 * 32;
 #pragma unroll 1
@@ -549,9 +547,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
       const uint32_t LBO_BH = (NH / 8) * 128;
       uint32_t hc = 0;
 #pragma unroll 1
-      for (int i = 0; i < n_tiles; ++i) {
+      for (int i = 0;; ++i) {
+        const int gt = tile_of(i);
+        if (gt < 0) break;
         int uA, uB;
-        tile_units(i, uA, uB);
+        tile_units(gt, uA, uB);
         if (!(unit_need(uA) || unit_need(uB))) continue;
         pk_wait(bar_h_full, hc & 1, s_abort);
         ++hc;
@@ -573,9 +573,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
     if (lane == 0) {
       const uint32_t idesc_d = idesc_f16(PK_ROWS, PK_NCH);
       const uint32_t LBO_A = (PK_ROWS / 8) * 128, LBO_BD = (PK_CBP / 8) * 128;
-      int q = 0;
+      int q = 0, n_tiles = 0;
 #pragma unroll 1
-      for (int i = 0; i < n_tiles; ++i) {
+      for (int i = 0;; ++i) {
+        if (tile_of(i) < 0) break;
+        n_tiles = i + 1;
         PK_T(2);
         pk_wait(bar_z_full + (i & 1), (i >> 1) & 1, s_abort);
         PK_T(0);
@@ -609,11 +611,10 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
     }
   } else {
     // =============================== aux: series caches, regression sums ===============================
-    auto build = [&](int u) {
-      const int slot = u & (PK_SLOTS - 1);
+    auto build = [&](int u, int slot) {
       const int uc = u % C, ug = (u / C) % N, uv = u / (C * N);
-      // the record was computed by daa_series_rec_kernel: 161 16-byte loads in flight at once (one L2 round
-      // trip), then the shared-memory stores
+      // the record was written by daa_base_kernel (series_records): 161 16-byte loads in flight at once (one
+      // L2 round trip), then the shared-memory stores
       const float4* rec = reinterpret_cast<const float4*>(ws.srec + (int64_t)u * PK_REC_F);
       float4* cache4 = reinterpret_cast<float4*>(s_cache + slot * PK_CACHE_F);
       constexpr int NV = PK_REC_F / 4, NIT = (NV + 31) / 32;
@@ -634,64 +635,77 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
         }
       }
     };
-    // reduce the 4 row quarters of tile i and store the tile's contribution to each of its (<= 2) series:
-    // slot (series, tile index inside the series), summed in fixed order by daa_beta_kernel, so the
-    // tables do not depend on how the tiles were spread over the CTAs
-    auto fold = [&](int i) {
+    // reduce the 4 row quarters of a finished tile (global id gt, parity par of its iteration) and store its
+    // contribution to each of its (<= 2) series: slot (series, tile index inside the series), summed in fixed
+    // order by daa_beta_stats_kernel, so the tables do not depend on which CTA ran the tile
+    auto fold = [&](int gt, int par) {
       int uA, uB;
-      tile_units(i, uA, uB);
-      const int tile_g = tile0 + i;
+      tile_units(gt, uA, uB);
       for (int s = 0; s <= uB - uA; ++s) {
         const int u = uA + s, uv = u / (N * C);
-        const int tp = tile_g - (uv * tpv + (int)(((int64_t)(u - uv * N * C) * J) / PK_ROWS));   // tile index inside the series
+        const int tp = gt - (uv * tpv + (int)(((int64_t)(u - uv * N * C) * J) / PK_ROWS));   // tile index inside the series
         double* o = ws.sacc + ((int64_t)u * tpu + tp) * 64;
         for (int k = lane; k < KZ; k += 32) {
           double a = 0.0;
-          for (int w = 0; w < 4; ++w) a += s_part[(((i & 1) * 4 + w) * 2 + s) * 64 + k];
+          for (int w = 0; w < 4; ++w) a += s_part[((par * 4 + w) * 2 + s) * 64 + k];
           o[k] = a;
         }
       }
     };
-    // iteration i = -1 builds the caches of tile 0; iteration i >= 0 runs behind barrier X(i): it folds
-    // tile i-1 and builds the series that is new in tile i+1, one tile ahead of the producers
-    int built = -1;
+    // iteration i of this CTA is global tile gt (or -1: stop): tile info, the records of its (<= 2) series into
+    // the cache slots of its parity, its 128 scores; then the producers (bar_cache) and the lagging roles (ring +
+    // published count) are released
+    auto publish = [&](int i, int gt) {
+      int* ti = s_tinfo + (i & 1) * 4;
+      if (gt >= 0) {
+        int r0, r1;
+        tile_rows(gt, r0, r1);
+        const int uA = r0 / J, uB = (r1 - 1) / J;
+        if (lane == 0) { ti[0] = uA; ti[1] = uB; ti[2] = r0; ti[3] = r1; }
+        float sc[PK_ROWS / 32];
+#pragma unroll
+        for (int k = 0; k < PK_ROWS / 32; ++k) sc[k] = r0 + k * 32 + lane < r1 ? ws.scores[r0 + k * 32 + lane] : 0.f;
 #pragma unroll 1
-    for (int i = -1; i < n_tiles; ++i) {
-      if (i >= 0) {
-        PK_T(1);
-#if PK_NOBAR
-        // every producer has finished tile i-1 (its z_full arrivals): its partial sums are complete, and the
-        // cache slots / tile info that tile i+1 reuses are no longer read
-        if (i > 0) pk_wait(bar_z_full + ((i - 1) & 1), ((i - 1) >> 1) & 1, s_abort);
-#else
-        pk_bar_sync(1, (PK_PROD + 1) * 32);
-#endif
-        PK_T(0);
-        if (i > 0 && col0 == 0) fold(i - 1);
+        for (int u = uA; u <= uB; ++u) build(u, (i & 1) * 2 + (u - uA));
+#pragma unroll
+        for (int k = 0; k < PK_ROWS / 32; ++k) s_score[(i & 1) * PK_ROWS + k * 32 + lane] = sc[k];
+      } else if (lane == 0) {
+        ti[2] = -1;
       }
-      if (i + 1 < n_tiles) {
-        int uAn, uBn;
-        tile_units(i + 1, uAn, uBn);
-        if (lane == 0) {
-          int* ti = s_tinfo + ((i + 1) & 1) * 4;
-          ti[0] = uAn; ti[1] = uBn;
-          tile_rows(i + 1, ti[2], ti[3]);
-        }
-#pragma unroll 1
-        for (int u = max(built + 1, uAn); u <= uBn; ++u) build(u);
-        built = uBn;
-      }
+      if (lane == 0) s_ring[i & 7] = gt;
       __syncwarp();
-#if PK_NOBAR
-      if (i + 1 < n_tiles && lane == 0) pk_arrive(bar_cache + ((i + 1) & 1));
-#endif
+      if (lane == 0) {
+        __threadfence_block();
+        *s_npub = i + 1;
+        pk_arrive(bar_cache + (i & 1));
+      }
+    };
+    int gt_cur = (int)blockIdx.x < total_tiles ? (int)blockIdx.x : -1, gt_prev = -1, n_done = 0;
+    publish(0, gt_cur);
+#pragma unroll 1
+    for (int i = 0; gt_cur >= 0; ++i) {
+      // the next tile of this CTA: the round trip of the atomic overlaps the wait below
+      int gt_next = 0;
+      if (lane == 0) {
+        gt_next = (int)gridDim.x + atomicAdd(ws.counter, 1);
+        if (gt_next >= total_tiles) gt_next = -1;
+      }
+      gt_next = __shfl_sync(0xffffffffu, gt_next, 0);
+      PK_T(1);
+      // every producer has finished tile i-1 (its z_full arrivals): its partial sums are complete, and the
+      // cache slots / tile info / scores of its parity, which iteration i+1 reuses, are no longer read
+      if (i > 0) {
+        pk_wait(bar_z_full + ((i - 1) & 1), ((i - 1) >> 1) & 1, s_abort);
+        if (col0 == 0) fold(gt_prev, (i - 1) & 1);
+      }
+      PK_T(0);
+      publish(i + 1, gt_next);
+      gt_prev = gt_cur; gt_cur = gt_next; n_done = i + 1;
     }
-#if PK_NOBAR
-    if (n_tiles > 0) pk_wait(bar_z_full + ((n_tiles - 1) & 1), ((n_tiles - 1) >> 1) & 1, s_abort);
-#else
-    pk_bar_sync(1, (PK_PROD + 1) * 32);
-#endif
-    if (n_tiles > 0 && col0 == 0) fold(n_tiles - 1);
+    if (n_done > 0) {
+      pk_wait(bar_z_full + ((n_done - 1) & 1), ((n_done - 1) >> 1) & 1, s_abort);
+      if (col0 == 0) fold(gt_prev, (n_done - 1) & 1);
+    }
 #ifdef PK_PROF
     if (lane == 0) for (int k = 0; k < 2; ++k) ws.phase[(blockIdx.x * 4 + 3) * 8 + k] = pc[k];
 #endif
