@@ -646,15 +646,6 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_kernel(ModelView 
 #include "mopoe_daa_pipe.cuh"
 namespace mopoe {
 
-// poison the result tables when a tcgen05 barrier wait timed out (never silently wrong)
-__global__ void daa_poison_kernel(const int* err, double* coefs, double* pvalues, int64_t n) {
-  if (*err == 0) return;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    coefs[i] = __longlong_as_double(0x7ff8000000000000LL);
-    pvalues[i] = __longlong_as_double(0x7ff8000000000000LL);
-  }
-}
-
 // -------------------------------------------------------------------------------------------
 // statistics on a materialised avatar tensor (mopoe_daa_regression): CTA per (v, g, c)
 // -------------------------------------------------------------------------------------------
@@ -729,6 +720,49 @@ __device__ double betai(double a, double b, double x, double xc /* 1 - x, accura
   const double bt = exp(lgamma(a + b) - lgamma(a) - lgamma(b) + a * log(x) + b * log(xc));
   if (x < (a + 1.0) / (a + b + 2.0)) return bt * betacf(a, b, x) / a;
   return 1.0 - bt * betacf(b, a, xc) / b;
+}
+
+// Same continued fraction with ONE fp64 division per half step instead of three (aa = num / den, d = 1 / (1 + aa d)
+// and c = 1 + aa / c share the reciprocal of (den + num d)(c den)); the log-beta prefactor depends on nu only
+// and is passed in (three lgamma evaluations per statistic otherwise).
+__device__ double betacf_fast(double a, double b, double x) {
+  const double EPS = 1e-16;
+  const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+  double c = 1.0, d = 1.0 / (1.0 - qab * x / qap);
+  double h = d;
+  for (int m = 1; m <= 500; ++m) {
+    const double dm = (double)m, m2 = 2.0 * dm;
+    {
+      const double num = dm * (b - dm) * x, den = (qam + m2) * (a + m2);
+      const double e = fma(num, d, den), cd = c * den;
+      const double r = 1.0 / (e * cd);
+      d = den * cd * r;
+      c = (cd + num) * e * r;
+      h *= d * c;
+    }
+    const double num = -(a + dm) * (qab + dm) * x, den = (a + m2) * (qap + m2);
+    const double e = fma(num, d, den), cd = c * den;
+    const double r = 1.0 / (e * cd);
+    d = den * cd * r;
+    c = (cd + num) * e * r;
+    const double del = d * c;
+    h *= del;
+    if (fabs(del - 1.0) < EPS) break;
+  }
+  return h;
+}
+
+__device__ double two_sided_t_pvalue_fast(double tval, double nu, double lg_pref /* lgamma(a+b) - lgamma(a) - lgamma(b), a = nu/2, b = 1/2 */) {
+  if (isnan(tval)) return tval;
+  if (isinf(tval)) return 0.0;
+  const double t2 = tval * tval;
+  const double x = nu / (nu + t2), xc = t2 / (nu + t2);
+  const double a = 0.5 * nu, b = 0.5;
+  if (x <= 0.0) return 0.0;
+  if (xc <= 0.0) return 1.0;
+  const double bt = exp(lg_pref + a * log(x) + b * log(xc));
+  if (x < (a + 1.0) / (a + b + 2.0)) return bt * betacf_fast(a, b, x) / a;
+  return 1.0 - bt * betacf_fast(b, a, xc) / b;
 }
 
 __device__ double two_sided_t_pvalue(double tval, double nu) {
@@ -949,9 +983,11 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
       if (g_profile && col0 == 0) MOPOE_CUDA(cudaEventRecord(g_ev1, stream));
     }
     // slopes + second-level test of the pipelined path (replaces step 4 below)
-    const int bsm = ud0.KZ * BS_COLS * 4;
+    const int bs_nc = cx.R < BS_ROIS ? cx.R : BS_ROIS;
+    const int bs_threads = ((bs_nc + 1) / 2 + 31) / 32 * 32 < 256 ? ((bs_nc + 1) / 2 + 31) / 32 * 32 : 256;
+    const int bsm = (((ud0.KZ * (bs_nc | 1) + 3) & ~3) + 2 * ud0.KZ * BS_GP) * 4 + BS_GB * 8 + 16;
     MOPOE_CUDA(cudaFuncSetAttribute((void*)daa_beta_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bsm));
-    daa_beta_stats_kernel<<<dim3(daa->n_val * cx.C, (cx.R + BS_COLS - 1) / BS_COLS), BS_COLS, bsm, stream>>>(
+    daa_beta_stats_kernel<<<dim3(daa->n_val * cx.C, (cx.R + BS_ROIS - 1) / BS_ROIS), bs_threads, bsm, stream>>>(
         mv, daa->dst_mod, cx.R, cx.C, N, cx.J, ud0, ws.sacc, ws.xstat, ws.betas, coefs, pvalues);
     MOPOE_CUDA(cudaGetLastError());
   } else if (impl == 1) {
@@ -986,7 +1022,9 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
     MOPOE_CUDA(cudaGetLastError());
   }
   if (impl != 0) {
-    daa_poison_kernel<<<32, 256, 0, stream>>>(ws.err, coefs, pvalues, nstat);
+    // p-values of the pipelined path (its slopes kernel leaves the t statistics in `pvalues`) + error poisoning
+    daa_pvalue_kernel<<<(unsigned)((nstat + 127) / 128), 128, 0, stream>>>(ws.err, coefs, pvalues, nstat, (double)(N - 1),
+                                                                            lgamma(0.5 * (N - 1) + 0.5) - lgamma(0.5 * (N - 1)) - lgamma(0.5), impl == 2 ? 1 : 0);
     MOPOE_CUDA(cudaGetLastError());
   }
   return MOPOE_OK;

@@ -172,6 +172,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
                                                                          const __grid_constant__ CUtensorMap tmap) {
   using namespace umma;
   extern __shared__ __align__(1024) unsigned char smem[];
+#ifdef PK_PROF
+  const long long t_entry = clock64();
+  unsigned long long g_entry;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_entry));
+#endif
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int src = cx.q.src_mod, dst = cx.q.dst_mod;
   const ModView& ms = mv.mod[src];
@@ -712,103 +717,188 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
   }
   tc_fence_before();
   __syncthreads();
+#ifdef PK_PROF
+  if (t == 0) {
+    unsigned long long g_exit;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_exit));
+    ws.phase[(blockIdx.x * 4 + 3) * 8 + 2] = tstart - t_entry;          // prologue cycles
+    ws.phase[(blockIdx.x * 4 + 3) * 8 + 3] = clock64() - t_entry;       // whole CTA cycles
+    ws.phase[(blockIdx.x * 4 + 3) * 8 + 4] = (long long)g_entry;        // ns
+    ws.phase[(blockIdx.x * 4 + 3) * 8 + 5] = (long long)g_exit;
+  }
+#endif
   if (t == 0 && *s_abort) atomicExch(ws.err, 1);
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-// Per-subject slopes and the second-level test of the pipelined path in one pass:
+// Per-subject slopes and the second-level t statistic of the pipelined path:
 //   beta[v,c,g,roi] = (Wd[roi,:] . sum_tiles sacc[u,tile,:]) / Sxx[u]            (stat_utils.py:66-68)
-//   coef = mean_g beta, t = coef / (sd_g(beta) / sqrt(N)), p = 2 sf(|t|, N-1)     (stat_utils.py:73-75)
-// CTA = (validation, score) x block of 256 ROIs; the decoder weights of the block sit in shared memory in
-// the K order of z (+ bias slot); 10 subjects per batch share every weight load.
-// Arithmetic: CUDA-core FP64 runs at ~5 TFLOP/s on this part and the regression sums carry fp32-level
-// rounding from their 32-row partial sums anyway, so the 149 M-term contraction is done with fp32 FMAs on
-// the sums split into hi + lo fp32 parts (48 bits of each sum enter the product; accumulation error
-// ~1e-7 of the absolute term sum, the same order as the rounding already in the sums); the sum over tiles,
-// the division by Sxx, the subject statistics (shifted sums) and the t-test are fp64.
-constexpr int BS_COLS = 256, BS_GB = 10, BS_GP = 12;     // BS_GP: padded batch stride (float4 aligned)
+//   coef = mean_g beta, t = coef / (sd_g(beta) / sqrt(N))                         (stat_utils.py:73-75)
+// (the p-value 2 sf(|t|, N-1) is evaluated by daa_pvalue_kernel, one thread per statistic).
+// CTA = (validation, score) x block of <= 512 ROIs.  The decoder weights of the block sit in shared memory as
+// fp32, transposed to the K order of z (+ bias slot), row stride odd (conflict-free transpose and reads);
+// thread = 2 ROIs (t, t + blockDim), subjects in batches of BS_GB = 25: per k step 2 weight loads + 13 broadcast
+// float4 loads feed 100 FMAs.
+// Arithmetic: the regression sums carry fp32-level rounding from their 32-row partial sums anyway, so the
+// 149 M-term contraction is done with fp32 FMAs on the sums split into hi + lo fp32 parts (48 bits of each sum
+// enter the product; accumulation error ~1e-7 of the absolute term sum, the same order as the rounding already
+// in the sums); the sum over tiles, the division by Sxx, the subject statistics (shifted sums) and the t
+// statistic are fp64.
+constexpr int BS_ROIS = 512, BS_GB = 25, BS_GP = 28;     // ROIs per CTA, subjects per batch, padded batch stride
 
 __device__ double two_sided_t_pvalue(double tval, double nu);
 
-__global__ void __launch_bounds__(BS_COLS) daa_beta_stats_kernel(ModelView mv, int dst, int R, int C, int N, int J, UmmaDims dm,
-                                                                  const double* sacc, const double* xstat, double* betas,
-                                                                  double* coefs, double* pvalues) {
-  extern __shared__ __align__(16) float s_wf[];           // [KZ][BS_COLS]
-  __shared__ __align__(16) float s_hi[64][BS_GP];         // regression sums of the batch, k-major: fp32 hi part
-  __shared__ __align__(16) float s_lo[64][BS_GP];         //                                        fp32 lo part
-  __shared__ double s_sxx[BS_GB];
+__global__ void __launch_bounds__(256) daa_beta_stats_kernel(ModelView mv, int dst, int R, int C, int N, int J, UmmaDims dm,
+                                                              const double* sacc, const double* xstat, double* betas,
+                                                              double* coefs, double* tvals) {
+  extern __shared__ __align__(16) float s_dyn[];
   const ModView& md = mv.mod[dst];
-  const int t = threadIdx.x;
+  const int t = threadIdx.x, nt = blockDim.x;
   const int v = blockIdx.x / C, c = blockIdx.x % C;
-  const int c0 = blockIdx.y * BS_COLS, nc = min(BS_COLS, R - c0);
+  const int c0 = blockIdx.y * BS_ROIS, nc = min(BS_ROIS, R - c0);
   const int tpu = pipe_tiles_per_unit(J), KZ = dm.KZ;
-  for (int i = t; i < KZ * BS_COLS; i += BS_COLS) s_wf[i] = 0.f;
+  const int RP = nc | 1;                                   // odd row stride
+  float* s_wf = s_dyn;                                     // [KZ][RP]
+  float* s_hi = s_wf + ((KZ * RP + 3) & ~3);               // [KZ][BS_GP] regression sums of the batch, k-major: fp32 hi part
+  float* s_lo = s_hi + KZ * BS_GP;                         //                                                     fp32 lo part
+  double* s_sxx = reinterpret_cast<double*>(s_lo + KZ * BS_GP);   // [BS_GB] 1 / Sxx
+  for (int i = t; i < KZ * RP; i += nt) s_wf[i] = 0.f;
   __syncthreads();
-  for (int i = t; i < nc * md.ZD; i += BS_COLS) {         // coalesced: the block's weight rows are contiguous
-    const int col = i / md.ZD, zd = i % md.ZD;
-    const int kz = zd < md.S ? dm.KC + zd : zd - md.S;   // decoder input = [style | content], z = [content | style]
-    s_wf[kz * BS_COLS + col] = md.wd[(int64_t)c0 * md.ZD + i];
+  {
+    // coalesced: the block's weight rows are contiguous.  Many independent loads in flight per thread (every
+    // iteration is an L2 round trip otherwise: 80 of them for 444 ROIs)
+    const float* wsrc = md.wd + (int64_t)c0 * md.ZD;
+    const int ntot = nc * md.ZD;
+    auto put = [&](int i, float w) {
+      const int col = i / md.ZD, zd = i % md.ZD;
+      const int kz = zd < md.S ? dm.KC + zd : zd - md.S;   // decoder input = [style | content], z = [content | style]
+      s_wf[kz * RP + col] = w;
+    };
+    if ((ntot & 3) == 0 && (reinterpret_cast<uintptr_t>(wsrc) & 15) == 0) {
+      const float4* w4 = reinterpret_cast<const float4*>(wsrc);
+      const int n4 = ntot >> 2;
+      for (int i0 = 0; i0 < n4; i0 += nt * 8) {
+        float4 buf[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const int i = i0 + q * nt + t; buf[q] = i < n4 ? __ldg(w4 + i) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int i = i0 + q * nt + t;
+          if (i < n4) { put(4 * i, buf[q].x); put(4 * i + 1, buf[q].y); put(4 * i + 2, buf[q].z); put(4 * i + 3, buf[q].w); }
+        }
+      }
+    } else {
+      for (int i = t; i < ntot; i += nt) put(i, wsrc[i]);
+    }
   }
-  if (dm.bias_slot >= 0 && t < nc) s_wf[dm.bias_slot * BS_COLS + t] = md.bd[c0 + t];
-  const bool active = t < nc;
-  double b0 = 0.0, sd1 = 0.0, sd2 = 0.0;
+  if (dm.bias_slot >= 0) for (int i = t; i < nc; i += nt) s_wf[dm.bias_slot * RP + i] = md.bd[c0 + i];
+  const int r0 = t, r1 = t + nt;                           // this thread's ROIs inside the block
+  const bool act0 = r0 < nc, act1 = r1 < nc;
+  const int q0 = act0 ? r0 : 0, q1 = act1 ? r1 : 0;
+  double b0[2] = {0.0, 0.0}, sd1[2] = {0.0, 0.0}, sd2[2] = {0.0, 0.0};
   for (int g0 = 0; g0 < N; g0 += BS_GB) {
     const int ng = min(BS_GB, N - g0);
     __syncthreads();
-    for (int i = t; i < BS_GB * 64; i += BS_COLS) {
-      const int gb = i >> 6, k = i & 63;
-      double a = 0.0;
-      if (gb < ng && k < KZ) {
-        const int ul = (g0 + gb) * C + c, u = v * N * C + ul;     // series inside its validation (tile grid restarts there)
+    // sums over the tiles of each series: 4 items x up to 4 tile slots in flight per thread (independent loads)
+    for (int i0 = 0; i0 < KZ * BS_GB; i0 += nt * 4) {
+      double part[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q * nt + t;
+        const int k = i % KZ, gb = i / KZ;
+        const bool on = i < KZ * BS_GB && gb < ng;
+        const int ul = ((g0 + gb) * C + c), u = v * N * C + ul;   // series index inside the validation / global
         const int first = (int)(((int64_t)ul * J) / PK_ROWS), last = (int)(((int64_t)(ul + 1) * J - 1) / PK_ROWS);
-        for (int tp = 0; tp <= last - first; ++tp) a += sacc[((int64_t)u * tpu + tp) * 64 + k];
+#pragma unroll
+        for (int tp = 0; tp < 4; ++tp) part[q][tp] = (on && tp <= last - first) ? sacc[((int64_t)u * tpu + tp) * 64 + k] : 0.0;
+        if (on && last - first >= 4) for (int tp = 4; tp <= last - first; ++tp) part[q][0] += sacc[((int64_t)u * tpu + tp) * 64 + k];
       }
-      const float hi = (float)a;
-      s_hi[k][gb] = hi;
-      s_lo[k][gb] = (float)(a - (double)hi);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q * nt + t;
+        if (i < KZ * BS_GB) {
+          const int k = i % KZ, gb = i / KZ;
+          const double a = ((part[q][0] + part[q][1]) + part[q][2]) + part[q][3];
+          const float hi = (float)a;
+          s_hi[k * BS_GP + gb] = hi;
+          s_lo[k * BS_GP + gb] = (float)(a - (double)hi);
+        }
+      }
     }
     // 1 / Sxx once per subject: an fp64 division per slope would cost as much as the whole contraction
     if (t < BS_GB) s_sxx[t] = t < ng ? 1.0 / xstat[(((int64_t)v * C + c) * N + g0 + t) * 2 + 1] : 1.0;
     __syncthreads();
-    if (active) {
-      float ah[BS_GB], al[BS_GB];
+    float ah0[BS_GB], al0[BS_GB], ah1[BS_GB], al1[BS_GB];
 #pragma unroll
-      for (int gb = 0; gb < BS_GB; ++gb) ah[gb] = al[gb] = 0.f;
-#pragma unroll 4
-      for (int k = 0; k < KZ; ++k) {
-        const float w = s_wf[k * BS_COLS + t];
-        const float4 h0 = *reinterpret_cast<const float4*>(&s_hi[k][0]), h1 = *reinterpret_cast<const float4*>(&s_hi[k][4]);
-        const float2 h2 = *reinterpret_cast<const float2*>(&s_hi[k][8]);
-        const float4 l0 = *reinterpret_cast<const float4*>(&s_lo[k][0]), l1 = *reinterpret_cast<const float4*>(&s_lo[k][4]);
-        const float2 l2 = *reinterpret_cast<const float2*>(&s_lo[k][8]);
-        ah[0] = fmaf(h0.x, w, ah[0]); ah[1] = fmaf(h0.y, w, ah[1]); ah[2] = fmaf(h0.z, w, ah[2]); ah[3] = fmaf(h0.w, w, ah[3]);
-        ah[4] = fmaf(h1.x, w, ah[4]); ah[5] = fmaf(h1.y, w, ah[5]); ah[6] = fmaf(h1.z, w, ah[6]); ah[7] = fmaf(h1.w, w, ah[7]);
-        ah[8] = fmaf(h2.x, w, ah[8]); ah[9] = fmaf(h2.y, w, ah[9]);
-        al[0] = fmaf(l0.x, w, al[0]); al[1] = fmaf(l0.y, w, al[1]); al[2] = fmaf(l0.z, w, al[2]); al[3] = fmaf(l0.w, w, al[3]);
-        al[4] = fmaf(l1.x, w, al[4]); al[5] = fmaf(l1.y, w, al[5]); al[6] = fmaf(l1.z, w, al[6]); al[7] = fmaf(l1.w, w, al[7]);
-        al[8] = fmaf(l2.x, w, al[8]); al[9] = fmaf(l2.y, w, al[9]);
+    for (int gb = 0; gb < BS_GB; ++gb) ah0[gb] = al0[gb] = ah1[gb] = al1[gb] = 0.f;
+#pragma unroll 2
+    for (int k = 0; k < KZ; ++k) {
+      const float w0 = s_wf[k * RP + q0], w1 = s_wf[k * RP + q1];
+      const float4* hp = reinterpret_cast<const float4*>(s_hi + k * BS_GP);
+      const float4* lp = reinterpret_cast<const float4*>(s_lo + k * BS_GP);
+#pragma unroll
+      for (int q = 0; q < BS_GP / 4; ++q) {
+        const float4 h = hp[q], l = lp[q];
+        const float hv[4] = {h.x, h.y, h.z, h.w}, lv[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int gb = 4 * q + e;
+          if (gb < BS_GB) {
+            ah0[gb] = fmaf(hv[e], w0, ah0[gb]); al0[gb] = fmaf(lv[e], w0, al0[gb]);
+            ah1[gb] = fmaf(hv[e], w1, ah1[gb]); al1[gb] = fmaf(lv[e], w1, al1[gb]);
+          }
+        }
       }
+    }
 #pragma unroll
-      for (int gb = 0; gb < BS_GB; ++gb) {
-        if (gb < ng) {
-          const double beta = ((double)ah[gb] + (double)al[gb]) * s_sxx[gb];
-          betas[(((int64_t)v * C + c) * N + g0 + gb) * R + c0 + t] = beta;
-          if (g0 + gb == 0) b0 = beta;
-          const double d = beta - b0;                     // shifted sums: no cancellation in the variance
-          sd1 += d; sd2 = fma(d, d, sd2);
+    for (int gb = 0; gb < BS_GB; ++gb) {
+      if (gb < ng) {
+        const double isx = s_sxx[gb];
+        double* brow = betas + (((int64_t)v * C + c) * N + g0 + gb) * R + c0;
+        if (act0) {
+          const double beta = ((double)ah0[gb] + (double)al0[gb]) * isx;
+          brow[r0] = beta;
+          if (g0 + gb == 0) b0[0] = beta;
+          const double d = beta - b0[0];                  // shifted sums: no cancellation in the variance
+          sd1[0] += d; sd2[0] = fma(d, d, sd2[0]);
+        }
+        if (act1) {
+          const double beta = ((double)ah1[gb] + (double)al1[gb]) * isx;
+          brow[r1] = beta;
+          if (g0 + gb == 0) b0[1] = beta;
+          const double d = beta - b0[1];
+          sd1[1] += d; sd2[1] = fma(d, d, sd2[1]);
         }
       }
     }
   }
-  if (active) {
-    const double n = (double)N;
-    const double mean = b0 + sd1 / n;
-    const double ss = sd2 - sd1 * sd1 / n;
-    const double sd = sqrt(ss / (n - 1.0));
-    const double tval = mean / (sd / sqrt(n));
-    const int64_t o = ((int64_t)v * C + c) * R + c0 + t;
-    coefs[o] = mean;
-    pvalues[o] = two_sided_t_pvalue(tval, n - 1.0);
+  const double n = (double)N;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    if (e == 0 ? act0 : act1) {
+      const double mean = b0[e] + sd1[e] / n;
+      const double ss = sd2[e] - sd1[e] * sd1[e] / n;
+      const double sd = sqrt(ss / (n - 1.0));
+      const int64_t o = ((int64_t)v * C + c) * R + c0 + (e == 0 ? r0 : r1);
+      coefs[o] = mean;
+      tvals[o] = mean / (sd / sqrt(n));
+    }
+  }
+}
+
+// p = 2 sf(|t|, nu) of every statistic, one thread each (62 160 independent continued fractions: run them
+// all at once instead of one after the other inside the 140 slope CTAs); also poisons the tables when a
+// tcgen05 kernel flagged a protocol error.
+__device__ double two_sided_t_pvalue_fast(double tval, double nu, double lg_pref);
+
+__global__ void __launch_bounds__(128) daa_pvalue_kernel(const int* err, double* coefs, double* pvalues, int64_t n, double nu, double lg_pref, int from_t) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (*err) {
+    coefs[i] = __longlong_as_double(0x7ff8000000000000LL);
+    pvalues[i] = __longlong_as_double(0x7ff8000000000000LL);
+  } else if (from_t) {
+    pvalues[i] = two_sided_t_pvalue_fast(pvalues[i], nu, lg_pref);
   }
 }
 
