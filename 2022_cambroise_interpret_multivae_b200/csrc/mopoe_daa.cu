@@ -39,11 +39,13 @@ struct DaaWs {
   int* err;                    // device error flag (tcgen05 barrier time-out)
   long long* phase;            // [grid][32] per-role cycle counters of the tcgen05 kernels (profiling builds)
   unsigned char* bsplit;       // fp16 hi/lo operand planes of the decoder / class-head weights (UMMA layout)
+  float* mean_eps;             // (n_val*N, 176)  mean noise row of the base passes (two-phase daa_base_kernel)
   float* srec;                 // (n_val*N*C, DAA_SERIES_REC_F)  pipelined kernel: per-series records (daa_series_rec_kernel)
   void* fwd_ws;                // workspace of the encoder forward
   int64_t fwd_ws_bytes;
 };
 
+constexpr int DAA_BASE_SC_MAX = 8192;     // sampled scores of one subject kept in shared memory by daa_base_kernel (floats)
 constexpr int DAA_SERIES_REC_F = 2 * MOPOE_HIDDEN + 128 + 4;   // == PK_REC_F (mopoe_daa_pipe.cuh)
 
 static int64_t daa_carve(const mopoe_model_desc* d, const mopoe_daa_desc* q, char* base, DaaWs* w) {
@@ -68,6 +70,7 @@ static int64_t daa_carve(const mopoe_model_desc* d, const mopoe_daa_desc* q, cha
   t.phase = (long long*)take(256 * 32 * 8);
   t.bsplit = (unsigned char*)take(2 * (480 * 64 * 2) + 2 * (64 * 256 * 2));
   t.srec = (float*)take(rows * C * DAA_SERIES_REC_F * 4);
+  t.mean_eps = (float*)take(rows * 176 * 4);
   t.fwd_ws_bytes = mopoe_workspace_bytes(d, rows);
   t.fwd_ws = take(t.fwd_ws_bytes);
   if (w) *w = t;
@@ -134,7 +137,8 @@ __device__ bool series_owner(const ModelView& mv, const DaaCtx& cx, int g, int& 
   return ((mv.sub.mask[s_own] >> cx.q.src_mod) & 1) || (mv.method == MOPOE_METHOD_MOE && mv.sub.n_members[s_own] > 1);
 }
 
-__device__ void series_records(const ModelView& mv, const DaaCtx& cx, const DaaWs& ws, int64_t row, int g, int t, int nthreads) {
+__device__ void series_records(const ModelView& mv, const DaaCtx& cx, const DaaWs& ws, int64_t row, int g, int t, int nthreads,
+                               int parts /* 1: hidden pre-activations (inputs only) | 2: posterior parts (encoder heads) */) {
   const int src = cx.q.src_mod, dst = cx.q.dst_mod;
   const ModView& ms = mv.mod[src];
   const ModView& mdst = mv.mod[dst];
@@ -142,6 +146,7 @@ __device__ void series_records(const ModelView& mv, const DaaCtx& cx, const DaaW
   int so;
   series_owner(mv, cx, g, so);
   float* rec0 = ws.srec + row * C * DAA_SERIES_REC_F;
+  if (parts & 1) {
   const float* xs = cx.x[src] + row * C;
   constexpr int MAXC = 16;                              // the pipelined kernel is selected for C <= UM_MAXC = 16 only
   float xr[MAXC];
@@ -164,6 +169,8 @@ __device__ void series_records(const ModelView& mv, const DaaCtx& cx, const DaaW
       rec0[uc * DAA_SERIES_REC_F + MOPOE_HIDDEN + h] = wc;
     }
   }
+  }
+  if (!(parts & 2)) return;
   for (int i = t; i < 128; i += nthreads) {
     float val = 0.f;
     const int sec = i >> 5, k = i & 31;                 // sections: other precisions | other mu*T | style mu | style sd
@@ -195,7 +202,9 @@ __device__ void series_records(const ModelView& mv, const DaaCtx& cx, const DaaW
   }
 }
 
-__global__ void __launch_bounds__(BASE_THREADS) daa_base_kernel(ModelView mv, DaaCtx cx, DaaWs ws) {
+// phase 0: whole kernel; phase 1: only the mean noise row of the n_base passes (needs no encoder output: runs
+// concurrently with the encoder kernels on a second stream) -> ws.mean_eps; phase 2: everything after it
+__global__ void __launch_bounds__(BASE_THREADS) daa_base_kernel(ModelView mv, DaaCtx cx, DaaWs ws, int phase) {
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int v = blockIdx.x / cx.N, g = blockIdx.x % cx.N;
@@ -205,13 +214,17 @@ __global__ void __launch_bounds__(BASE_THREADS) daa_base_kernel(ModelView mv, Da
   float* s_acc = s_mean + 176;        // [threads / nb][EP] per-group sums (block-padded columns)
   float* s_zz = s_acc + 4 * BASE_THREADS;         // [M][64] decoder inputs
   float* s_loc = s_zz + MOPOE_MAX_MODS * 64;  // [C]
+  float* s_sc = s_loc + 64;                   // [C][J] sampled scores (when they fit: DAA_BASE_SC_MAX floats)
+  const bool sc_smem = cx.J * cx.C <= DAA_BASE_SC_MAX;
   // records of the pipelined avatar kernel first: they depend on the encoder heads and the inputs only, and
   // their load -> store chains then overlap the Philox loop of the co-resident CTAs
   if (cx.make_rec) {
     if (blockIdx.x == 0 && t == 0) *ws.counter = 0;    // tile counter of the pipelined kernel's dynamic schedule
-    series_records(mv, cx, ws, row, g, t, BASE_THREADS);
+    series_records(mv, cx, ws, row, g, t, BASE_THREADS, phase == 0 ? 3 : phase);
   }
-  // mean over the n_base passes of the noise row of this subject.  Thread = (Philox block b of the row,
+  if (phase == 2) {
+    for (int e = t; e < E; e += BASE_THREADS) s_mean[e] = ws.mean_eps[row * 176 + e];
+  } else  // mean over the n_base passes of the noise row of this subject.  Thread = (Philox block b of the row,
   // pass group): every lane draws whole blocks, four independent passes in flight per thread.
   {
     const int nb = mv.EP >> 2, ngrp = BASE_THREADS / nb;
@@ -251,9 +264,11 @@ __global__ void __launch_bounds__(BASE_THREADS) daa_base_kernel(ModelView mv, Da
         float a = 0.f;
         for (int q = 0; q < ngrp; ++q) a += s_acc[q * mv.EP + t];
         s_mean[ee + i] = a / (float)cx.q.n_base;
+        if (phase == 1) ws.mean_eps[row * 176 + ee + i] = s_mean[ee + i];
       }
     }
   }
+  if (phase == 1) return;
   __syncthreads();
   // joint posterior of this row (sampling semantics: the row's mixture owner), mean latent
   if (t < L) {
@@ -318,12 +333,13 @@ __global__ void __launch_bounds__(BASE_THREADS) daa_base_kernel(ModelView mv, Da
     const int64_t idx = (((int64_t)(cx.v_score_off + v) * cx.J + j) * cx.N + g) * cx.C + c;
     const float s = s_loc[c] + expf(0.5f * ms.lv[c]) * cx.nz_score.at(idx);
     ws.scores[(row * cx.C + c) * cx.J + j] = s;
+    if (sc_smem) s_sc[c * cx.J + j] = s;
     if (cx.sampled_scores) cx.sampled_scores[(row * cx.J + j) * cx.C + c] = s;
   }
   __syncthreads();
   // xbar, Sxx of every (subject, score) series in fp64 (centred OLS: slope = Sxy / Sxx)
   for (int c = warp; c < cx.C; c += BASE_THREADS / 32) {
-    const float* sx = ws.scores + (row * cx.C + c) * cx.J;
+    const float* sx = sc_smem ? s_sc + c * cx.J : ws.scores + (row * cx.C + c) * cx.J;   // (an L2 round trip per load otherwise)
     double a = 0.0;
     for (int j = lane; j < cx.J; j += 32) a += (double)sx[j];
     a = warp_sum(a);
@@ -853,6 +869,9 @@ static bool make_avatar_tmap(float* avatars, int64_t n_val, int64_t rows_per_val
 static int g_profile = 0;
 static int g_last_impl = 0;
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+// fork/join of the sweep: the encoder kernels run on g_side while the caller's stream draws the base-pass noise
+static cudaStream_t g_side = nullptr;
+static cudaEvent_t g_fork = nullptr, g_join = nullptr;
 
 extern "C" {
 
@@ -915,7 +934,18 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   mopoe_param_layout_of(desc, &lay);
   ModelView mv;
   build_view(desc, &lay, const_cast<float*>(params), &mv);
-  // 1. encoder heads of every (validation, subject) row
+  // 1. encoder heads of every (validation, subject) row, on a second stream: the noise phase of the base
+  // passes (most of daa_base_kernel's time) does not depend on them
+  if (!g_side) {
+    MOPOE_CUDA(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
+    MOPOE_CUDA(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
+    MOPOE_CUDA(cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming));
+  }
+  const bool forked = getenv("MOPOE_DAA_NO_FORK") == nullptr;
+  if (forked) {
+    MOPOE_CUDA(cudaEventRecord(g_fork, stream));
+    MOPOE_CUDA(cudaStreamWaitEvent(g_side, g_fork, 0));
+  }
   {
     mopoe_batch_desc fb;
     memset(&fb, 0, sizeof(fb));
@@ -925,8 +955,9 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
     mopoe_forward_out fo;
     memset(&fo, 0, sizeof(fo));
     for (int m = 0; m < M; ++m) fo.enc_heads[m] = ws.enc[m];
-    rc = mopoe_forward(desc, params, &fb, x, nullptr, seed, 0, -1, 0, &fo, ws.fwd_ws, ws.fwd_ws_bytes, stream_);
-    if (rc) return rc;
+    rc = mopoe_forward(desc, params, &fb, x, nullptr, seed, 0, -1, 0, &fo, ws.fwd_ws, ws.fwd_ws_bytes, forked ? (void*)g_side : stream_);
+    if (forked) MOPOE_CUDA(cudaEventRecord(g_join, g_side));   // (recorded even on error: the side stream must rejoin a capture)
+    if (rc) { if (forked) cudaStreamWaitEvent(stream, g_join, 0); return rc; }
   }
   DaaCtx cx;
   memset(&cx, 0, sizeof(cx));
@@ -964,8 +995,15 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   g_last_impl = impl;
   cx.make_rec = impl == 2 ? 1 : 0;
   // 2. base passes
-  const int base_smem = (176 + 4 * BASE_THREADS + MOPOE_MAX_MODS * 64 + 64) * 4;
-  daa_base_kernel<<<daa->n_val * N, BASE_THREADS, base_smem, stream>>>(mv, cx, ws);
+  const int base_smem = (176 + 4 * BASE_THREADS + MOPOE_MAX_MODS * 64 + 64 + (cx.J * cx.C <= DAA_BASE_SC_MAX ? cx.J * cx.C : 0)) * 4;
+  if (forked) {
+    daa_base_kernel<<<daa->n_val * N, BASE_THREADS, base_smem, stream>>>(mv, cx, ws, 1);
+    MOPOE_CUDA(cudaGetLastError());
+    MOPOE_CUDA(cudaStreamWaitEvent(stream, g_join, 0));
+    daa_base_kernel<<<daa->n_val * N, BASE_THREADS, base_smem, stream>>>(mv, cx, ws, 2);
+  } else {
+    daa_base_kernel<<<daa->n_val * N, BASE_THREADS, base_smem, stream>>>(mv, cx, ws, 0);
+  }
   MOPOE_CUDA(cudaGetLastError());
   MOPOE_CUDA(cudaMemsetAsync(ws.err, 0, sizeof(int), stream));
   if (impl == 2) {

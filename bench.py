@@ -348,8 +348,9 @@ def run_ours(args, rank, world, local_rank):
                 "e2e_tables_only": {"value": avatars_per_step * args.steps / (ms_tab * 1e-3), "unit": UNIT,
                                     "d2h_bytes_per_step": d2h - host_out["avatars"].numel() * 4,
                                     "note": "avatar tensor left in HBM; scores, reconstructions, betas, coefs, p-values copied"},
-                # per sweep: p1 + p2 (encoder heads), daa_base, operand prep, daa_avatar_pipe, daa_beta_stats, poison check
-                "gpu_launches": 7 * args.steps,
+                # per sweep: p1 + p2 (encoder heads, second stream), daa_base x 2 (noise | rest), operand prep, daa_avatar_pipe,
+                # daa_beta_stats, daa_pvalue
+                "gpu_launches": 8 * args.steps,
                 "roofline": {"kernel": "daa_avatar_pipe_kernel", "bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9,
                              "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
                              "traffic": traffic, "kernel_ms": k_ms, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
