@@ -17,6 +17,24 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* A, c
   unsigned char* b_hi = a_lo + 128 * K * 2;
   unsigned char* b_lo = b_hi + N * K * 2;
   const int k8n = K / 8;
+  if (variant >= 3) {
+    // MN-major operands (variants 3, 4): element (m, k) of A at (m/8)*(K/8)*128 + (k/8)*128 + (k%8)*16 + (m%8)*2 --
+    // the layout the K-major z tile of the pipelined DAA kernel has when it is read TRANSPOSED (M = latent, K = row)
+    for (int i = t; i < 128 * K; i += 128) {
+      const int m = i % 128, k = i / 128;
+      __half h, l;
+      split_f16(A[m * K + k], h, l);
+      const uint32_t off = (m >> 3) * k8n * 128 + (k >> 3) * 128 + (k & 7) * 16 + (m & 7) * 2;
+      *reinterpret_cast<__half*>(a_hi + off) = h; *reinterpret_cast<__half*>(a_lo + off) = l;
+    }
+    for (int i = t; i < N * K; i += 128) {
+      const int n = i % N, k = i / N;
+      __half h, l;
+      split_f16(B[n * K + k], h, l);
+      const uint32_t off = (n >> 3) * k8n * 128 + (k >> 3) * 128 + (k & 7) * 16 + (n & 7) * 2;
+      *reinterpret_cast<__half*>(b_hi + off) = h; *reinterpret_cast<__half*>(b_lo + off) = l;
+    }
+  } else {
   if (variant != 2)
   for (int i = t; i < 128 * k8n; i += 128) {
     const int row = i % 128, k8 = i / 128;
@@ -29,6 +47,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* A, c
     float x[8];
     for (int q = 0; q < 8; ++q) x[q] = B[row * K + k8 * 8 + q];
     store_split8(b_hi, b_lo, core_off(row, k8, N), x);
+  }
   }
   uint32_t ncols = 32;
   const int a_col = (N + 31) & ~31;   // variant 2: A planes in TMEM behind the accumulator
@@ -67,7 +86,24 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* A, c
     }
     mma_commit(&bar);
   }
-  if (t == 0 && variant != 2) {
+  if (t == 0 && variant >= 3) {
+    // both operands MN-major (instruction descriptor bits 15 / 16); variant 3: LBO = K-group stride (128),
+    // SBO = MN-chunk stride; variant 4: swapped
+    const uint32_t mn_stride = k8n * 128, kg = 128;
+    const uint32_t idesc = idesc_f16(128, N) | (1u << 15) | (1u << 16);
+    uint32_t acc = 0;
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint32_t off = ks * 2 * kg;
+      const uint32_t l_ = variant == 3 ? kg : mn_stride, s_ = variant == 3 ? mn_stride : kg;
+      const uint64_t dah = smem_desc(smem_u32(a_hi) + off, l_, s_), dal = smem_desc(smem_u32(a_lo) + off, l_, s_);
+      const uint64_t dbh = smem_desc(smem_u32(b_hi) + off, l_, s_), dbl = smem_desc(smem_u32(b_lo) + off, l_, s_);
+      mma_f16(tmem, dah, dbh, idesc, acc); acc = 1;
+      mma_f16(tmem, dah, dbl, idesc, 1);
+      mma_f16(tmem, dal, dbh, idesc, 1);
+    }
+    mma_commit(&bar);
+  }
+  if (t == 0 && variant != 2 && variant < 3) {
     const uint32_t lbo_a = (128 / 8) * 128, lbo_b = (N / 8) * 128, sbo = 128;
     const uint32_t idesc = idesc_f16(128, N);
     uint32_t acc = 0;

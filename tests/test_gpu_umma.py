@@ -35,3 +35,12 @@ def test_umma_split_gemm_a_from_tmem(N, K):
     rel, err = _run(N, K, variant=2)
     assert err == 0, "mbarrier wait timed out"
     assert rel <= 2e-6, rel
+
+
+@pytest.mark.parametrize("N,K", [(16, 128), (48, 64), (16, 16)])
+def test_umma_split_gemm_mn_major_operands(N, K):
+    """Both operands MN-major (instruction-descriptor bits 15/16; LBO = stride between 8-element K groups,
+    SBO = stride between 8-element MN chunks): the layout a K-major tile has when it is read transposed."""
+    rel, err = _run(N, K, variant=3)
+    assert err == 0, "mbarrier wait timed out"
+    assert rel <= 2e-6, rel
