@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 HBN = dict(dims=[7, 444], style_dims=[3, 20], latent_dim=20, mod_names=["clinical", "rois"])
 DAA = dict(n_validation=20, n_subjects=50, n_samples=150, n_base=1000, seed=1037)
 METRIC, UNIT = "daa_avatars_per_s", "avatars/s"
+LAUNCH_NOTE = ["direct launches"]
 
 
 def workload_config(n_gpus):
@@ -42,7 +43,7 @@ def workload_config(n_gpus):
                         "style [3,20], n_validation=%d per GPU, n_subjects=50, n_samples=150, M=1000, hierarchical "
                         "regression, 7 scores x 444 ROIs" % DAA["n_validation"],
             "n_validation_total": DAA["n_validation"] * n_gpus, "parallelism": "validations sharded over %d GPU(s)" % n_gpus,
-            "l2": "outputs larger than L2: 1.865 GB avatar tensor written per sweep (126 MB L2)",
+            "l2": "outputs larger than L2: 1.865 GB avatar tensor written per sweep (126 MB L2)", "launch": LAUNCH_NOTE[0],
             "noise": "in-kernel philox (production mode)", "weights": "random init (seed 0)"}
 
 
@@ -262,6 +263,46 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(0, args.warmup - 1)):
         r = sweep(src_d, dst_d, out=r)
         gather(r)
+    # the whole sweep (8 kernels on two streams) captured once into a CUDA graph and replayed: the library only
+    # uses the caller's stream plus a side stream forked / joined with events, so it is capturable.  Falls back to
+    # direct launches if capture is unavailable; the replay is checked bit-for-bit against a direct sweep.
+    graph, graph_note = None, "direct launches"
+    if not os.environ.get("MOPOE_BENCH_NO_GRAPH"):
+        try:
+            want = (r.coefs.clone(), r.pvalues.clone())
+            _lib.check(lib.mopoe_profile_enable(0))
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                r = sweep(src_d, dst_d, out=r)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                r = sweep(src_d, dst_d, out=r)
+            r.coefs.zero_(); r.pvalues.zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            if torch.equal(r.coefs, want[0]) and torch.equal(r.pvalues, want[1]):
+                graph, graph_note = g, "CUDA graph replay of the sweep (verified bit-identical to direct launches)"
+            else:
+                graph_note = "direct launches (graph replay differed)"
+        except Exception as exc:
+            graph_note = "direct launches (graph capture failed: %s)" % type(exc).__name__
+            torch.cuda.synchronize()
+        finally:
+            _lib.check(lib.mopoe_profile_enable(1))
+
+    def step():
+        nonlocal r
+        if graph is not None:
+            graph.replay()
+        else:
+            r = sweep(src_d, dst_d, out=r)
+        gather(r)
+
+    LAUNCH_NOTE[0] = graph_note
+    for _ in range(2):
+        step()
     # ---- value: device-resident inputs ----
     sampler = ClockSampler(local_rank)
     kernel_ms = []
@@ -270,8 +311,7 @@ def run_ours(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        r = sweep(src_d, dst_d, out=r)
-        gather(r)
+        step()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)   # (the clock sampler keeps running over the e2e regions: K sub-millisecond steps
