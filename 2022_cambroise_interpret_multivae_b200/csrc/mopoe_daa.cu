@@ -934,31 +934,6 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   mopoe_param_layout_of(desc, &lay);
   ModelView mv;
   build_view(desc, &lay, const_cast<float*>(params), &mv);
-  // 1. encoder heads of every (validation, subject) row, on a second stream: the noise phase of the base
-  // passes (most of daa_base_kernel's time) does not depend on them
-  if (!g_side) {
-    MOPOE_CUDA(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
-    MOPOE_CUDA(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
-    MOPOE_CUDA(cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming));
-  }
-  const bool forked = getenv("MOPOE_DAA_NO_FORK") == nullptr;
-  if (forked) {
-    MOPOE_CUDA(cudaEventRecord(g_fork, stream));
-    MOPOE_CUDA(cudaStreamWaitEvent(g_side, g_fork, 0));
-  }
-  {
-    mopoe_batch_desc fb;
-    memset(&fb, 0, sizeof(fb));
-    fb.n_rows = daa->n_val * N; fb.present_mask = (1 << M) - 1; fb.n_mix = 1;
-    fb.joint_bounds[0] = 0; fb.joint_bounds[1] = fb.n_rows;
-    for (int k = 1; k <= M; ++k) { fb.moe_bounds[k][0] = 0; for (int i = 1; i <= k; ++i) fb.moe_bounds[k][i] = fb.n_rows; }
-    mopoe_forward_out fo;
-    memset(&fo, 0, sizeof(fo));
-    for (int m = 0; m < M; ++m) fo.enc_heads[m] = ws.enc[m];
-    rc = mopoe_forward(desc, params, &fb, x, nullptr, seed, 0, -1, 0, &fo, ws.fwd_ws, ws.fwd_ws_bytes, forked ? (void*)g_side : stream_);
-    if (forked) MOPOE_CUDA(cudaEventRecord(g_join, g_side));   // (recorded even on error: the side stream must rejoin a capture)
-    if (rc) { if (forked) cudaStreamWaitEvent(stream, g_join, 0); return rc; }
-  }
   DaaCtx cx;
   memset(&cx, 0, sizeof(cx));
   cx.q = *daa; cx.b = *batch;
@@ -994,6 +969,35 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   if (force && !strcmp(force, "pipe")) { if (!pipe_ok) { set_error("MOPOE_DAA_IMPL=pipe but the configuration does not fit the pipelined kernel"); return MOPOE_EINVAL; } impl = 2; }
   g_last_impl = impl;
   cx.make_rec = impl == 2 ? 1 : 0;
+  // 1. encoder heads of every (validation, subject) row, on a second stream: the noise phase of the base
+  // passes (most of daa_base_kernel's time) does not depend on them
+  if (!g_side) {
+    MOPOE_CUDA(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
+    MOPOE_CUDA(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
+    MOPOE_CUDA(cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming));
+  }
+  const bool forked = getenv("MOPOE_DAA_NO_FORK") == nullptr;
+  if (forked) {
+    MOPOE_CUDA(cudaEventRecord(g_fork, stream));
+    MOPOE_CUDA(cudaStreamWaitEvent(g_side, g_fork, 0));
+  }
+  {
+    mopoe_batch_desc fb;
+    memset(&fb, 0, sizeof(fb));
+    fb.n_rows = daa->n_val * N; fb.present_mask = (1 << M) - 1; fb.n_mix = 1;
+    fb.joint_bounds[0] = 0; fb.joint_bounds[1] = fb.n_rows;
+    for (int k = 1; k <= M; ++k) { fb.moe_bounds[k][0] = 0; for (int i = 1; i <= k; ++i) fb.moe_bounds[k][i] = fb.n_rows; }
+    mopoe_forward_out fo;
+    memset(&fo, 0, sizeof(fo));
+    for (int m = 0; m < M; ++m) fo.enc_heads[m] = ws.enc[m];
+    rc = mopoe_forward(desc, params, &fb, x, nullptr, seed, 0, -1, 0, &fo, ws.fwd_ws, ws.fwd_ws_bytes, forked ? (void*)g_side : stream_);
+    if (forked && impl == 2 && rc == 0) {   // operand planes of the first column block: weights only, also off the critical path
+      const UmmaDims ud = umma_dims(mv, daa->src_mod, daa->dst_mod, cx.R < PK_CBP ? cx.R : PK_CBP);
+      daa_umma_prep_kernel<<<64, 256, 0, g_side>>>(mv, daa->src_mod, daa->dst_mod, 0, ud, PK_CBP, ws.bsplit);
+    }
+    if (forked) MOPOE_CUDA(cudaEventRecord(g_join, g_side));   // (recorded even on error: the side stream must rejoin a capture)
+    if (rc) { if (forked) cudaStreamWaitEvent(stream, g_join, 0); return rc; }
+  }
   // 2. base passes
   const int base_smem = (176 + 4 * BASE_THREADS + MOPOE_MAX_MODS * 64 + 64 + (cx.J * cx.C <= DAA_BASE_SC_MAX ? cx.J * cx.C : 0)) * 4;
   if (forked) {
@@ -1012,7 +1016,7 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
     const bool tma_ok = make_avatar_tmap(avatars, daa->n_val, (int64_t)N * cx.C * cx.J, cx.R, &tmap);
     for (int col0 = 0; col0 < cx.R; col0 += PK_CBP) {
       const UmmaDims ud = umma_dims(mv, daa->src_mod, daa->dst_mod, cx.R - col0 < PK_CBP ? cx.R - col0 : PK_CBP);
-      daa_umma_prep_kernel<<<64, 256, 0, stream>>>(mv, daa->src_mod, daa->dst_mod, col0, ud, PK_CBP, ws.bsplit);
+      if (col0 > 0 || !forked) daa_umma_prep_kernel<<<64, 256, 0, stream>>>(mv, daa->src_mod, daa->dst_mod, col0, ud, PK_CBP, ws.bsplit);
       MOPOE_CUDA(cudaGetLastError());
       if (col0 > 0) MOPOE_CUDA(cudaMemsetAsync(ws.counter, 0, sizeof(int), stream));   // (the first launch's counter is zeroed by daa_base_kernel)
       if (g_profile && col0 == 0) MOPOE_CUDA(cudaEventRecord(g_ev0, stream));
