@@ -16,7 +16,7 @@ for cta in ("0", "73", "147"):
     ph = daa.phase_cycles(spec, r)
     names = ["w0 cache wait", "w0 P1", "w0 noise->heads wait", "w0 heads wait", "w0 passes rest", "w0 z_free wait", "w0 arrive", "-",
              "w4 cache wait", "w4 P1", "w4 noise->heads wait", "w4 heads wait", "w4 passes rest", "w4 z_free wait", "w4 arrive", "-",
-             "E work(0)", "E wait acc_full", "E total", "-", "D issue0", "D issue1", "D waits", "-", "AUX work", "AUX wait"]
+             "E wait acc_full (pc0)", "E drain+store work (pc1)", "E total", "-", "D pc0 (after z_full wait)", "D pc1 (issue after acc_empty)", "D pc2 (waits)", "-", "AUX work", "AUX wait"]
     print("CTA", cta)
     for n, c in zip(names, ph):
         if n != "-": print("  %-24s %9d cycles  per tile %7.0f" % (n, c, c / 56))
