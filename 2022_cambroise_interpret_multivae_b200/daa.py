@@ -174,3 +174,28 @@ def gather_tables_many(locals_, n_validation, group=None, outs=None):
         for t, o in zip(locals_, outs):
             dist.all_gather_into_tensor(o, t.contiguous(), group=group)
     return outs
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPU cores local to GPU `device_index` (NVML affinity mask) so that the pinned
+    host buffers it allocates afterwards (the 1.9 GB avatar tensor of a sweep) land on that GPU's NUMA node:
+    with one process per GPU and no binding, several ranks' device-to-host copies cross the socket
+    interconnect and contend there.  Best effort: returns the core list, or None if NVML / the affinity call is
+    unavailable (nothing changes then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+

@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 HBN = dict(dims=[7, 444], style_dims=[3, 20], latent_dim=20, mod_names=["clinical", "rois"])
 DAA = dict(n_validation=20, n_subjects=50, n_samples=150, n_base=1000, seed=1037)
 METRIC, UNIT = "daa_avatars_per_s", "avatars/s"
-LAUNCH_NOTE = ["direct launches"]
+LAUNCH_NOTE = ["direct launches", "none"]
 
 
 def workload_config(n_gpus):
@@ -43,7 +43,7 @@ def workload_config(n_gpus):
                         "style [3,20], n_validation=%d per GPU, n_subjects=50, n_samples=150, M=1000, hierarchical "
                         "regression, 7 scores x 444 ROIs" % DAA["n_validation"],
             "n_validation_total": DAA["n_validation"] * n_gpus, "parallelism": "validations sharded over %d GPU(s)" % n_gpus,
-            "l2": "outputs larger than L2: 1.865 GB avatar tensor written per sweep (126 MB L2)", "launch": LAUNCH_NOTE[0],
+            "l2": "outputs larger than L2: 1.865 GB avatar tensor written per sweep (126 MB L2)", "launch": LAUNCH_NOTE[0], "host_binding": LAUNCH_NOTE[1],
             "noise": "in-kernel philox (production mode)", "weights": "random init (seed 0)"}
 
 
@@ -228,6 +228,12 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback on the product path)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # one process per GPU: keep this rank's pinned host buffers on the GPU's NUMA node (device-to-host copies of
+    # several ranks otherwise contend on the socket interconnect)
+    visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+    phys = int(visible.split(",")[local_rank]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else local_rank
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = None if os.environ.get("MOPOE_BENCH_NO_NUMA") else daa.bind_to_gpu_numa_node(phys)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     spec = mopoe_b200.PathSpec(HBN["dims"], HBN["style_dims"], HBN["latent_dim"], "joint_elbo", HBN["mod_names"])
@@ -301,6 +307,7 @@ def run_ours(args, rank, world, local_rank):
         gather(r)
 
     LAUNCH_NOTE[0] = graph_note
+    LAUNCH_NOTE[1] = ("rank bound to the %d cores local to its GPU" % len(numa_cpus)) if numa_cpus else "none"
     for _ in range(2):
         step()
     # ---- value: device-resident inputs ----
@@ -401,6 +408,7 @@ def run_ours(args, rank, world, local_rank):
                                                "faithful = 331 266 FLOP/avatar (reference recomputes both encoders), executed ~= 59.6 "
                                                "kFLOP/avatar (ROI encoder cached, rank-1 hidden update; x3 tensor-core passes not counted)"}}}
         if world == 1:
+            os.sched_setaffinity(0, all_cpus)            # the CPU baseline uses every host core again
             n, dt, desc = cpu_daa_sample(12.0)
             line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": desc}
             try:

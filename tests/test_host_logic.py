@@ -133,3 +133,19 @@ def test_gather_tables_world_size_2_gloo(tmp_path):
                          capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert res.stdout.count("ok") == 2
+
+
+def test_epoch_plan_equals_the_reference_sampler_golden():
+    """data.epoch_plan reproduces MissingModalitySampler.__iter__ (dataset.py:295-354) batch for batch under the
+    same numpy seed: golden plans from the unmodified reference class (oracle/make_golden_sampler.py)."""
+    import json
+    import os
+    from mopoe_b200 import data
+    from oracle.make_golden_sampler import has_matrix
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_epoch_plans.json")))
+    assert len(gold) >= 4
+    for g in gold:
+        case = g["case"]
+        plan = data.epoch_plan(has_matrix(case), case["batch_size"], np.random.RandomState(case["seed"]))
+        assert [ix.tolist() for _, ix in plan] == g["plan"], case
+
