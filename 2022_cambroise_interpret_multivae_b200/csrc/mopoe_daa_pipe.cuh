@@ -731,6 +731,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+#ifndef BS_ROIS_
+#define BS_ROIS_ 512
+#endif
 // Per-subject slopes and the second-level t statistic of the pipelined path:
 //   beta[v,c,g,roi] = (Wd[roi,:] . sum_tiles sacc[u,tile,:]) / Sxx[u]            (stat_utils.py:66-68)
 //   coef = mean_g beta, t = coef / (sd_g(beta) / sqrt(N))                         (stat_utils.py:73-75)
@@ -744,7 +747,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
 // enter the product; accumulation error ~1e-7 of the absolute term sum, the same order as the rounding already
 // in the sums); the sum over tiles, the division by Sxx, the subject statistics (shifted sums) and the t
 // statistic are fp64.
-constexpr int BS_ROIS = 512, BS_GB = 25, BS_GP = 28;     // ROIs per CTA, subjects per batch, padded batch stride
+constexpr int BS_ROIS = BS_ROIS_, BS_GB = 25, BS_GP = 28;    // ROIs per CTA, subjects per batch, padded batch stride
 
 __device__ double two_sided_t_pvalue(double tval, double nu);
 
