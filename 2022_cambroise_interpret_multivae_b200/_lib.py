@@ -98,6 +98,8 @@ def lib():
     L.mopoe_daa_last_impl.restype = C.c_int
     L.mopoe_daa_read_phases.argtypes = [C.POINTER(ModelDesc), C.POINTER(DaaDesc), vp, C.POINTER(C.c_int64)]
     L.mopoe_daa_read_phases.restype = C.c_int
+    L.mopoe_daa_status.argtypes = [C.POINTER(ModelDesc), C.POINTER(DaaDesc), vp, vp]
+    L.mopoe_daa_status.restype = C.c_int
     L.mopoe_profile_enable.argtypes = [C.c_int]
     L.mopoe_profile_enable.restype = C.c_int
     L.mopoe_daa_last_kernel_ms.argtypes = [C.POINTER(C.c_float)]
@@ -117,4 +119,5 @@ def check(rc):
 EXPORTED = ["mopoe_last_error", "mopoe_version", "mopoe_device_count", "mopoe_param_layout_of",
             "mopoe_workspace_bytes", "mopoe_forward", "mopoe_train_steps", "mopoe_daa_workspace_bytes",
             "mopoe_daa_sweep", "mopoe_daa_regression", "mopoe_philox_normal", "mopoe_profile_enable",
-            "mopoe_daa_last_kernel_ms", "mopoe_umma_selftest", "mopoe_daa_last_impl", "mopoe_daa_read_phases"]
+            "mopoe_daa_last_kernel_ms", "mopoe_umma_selftest", "mopoe_daa_last_impl", "mopoe_daa_read_phases",
+            "mopoe_daa_status"]

@@ -741,6 +741,9 @@ __device__ double betai(double a, double b, double x, double xc /* 1 - x, accura
 // Same continued fraction with ONE fp64 division per half step instead of three (aa = num / den, d = 1 / (1 + aa d)
 // and c = 1 + aa / c share the reciprocal of (den + num d)(c den)); the log-beta prefactor depends on nu only
 // and is passed in (three lgamma evaluations per statistic otherwise).
+// the FPMIN guard of the modified Lentz iteration: a vanishing denominator is replaced by a tiny number
+// (the next step corrects it) instead of producing inf / NaN
+__device__ __forceinline__ double lentz_guard(double v) { return fabs(v) < 1e-150 ? 1e-150 : v; }
 __device__ double betacf_fast(double a, double b, double x) {
   const double EPS = 1e-16;
   const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
@@ -750,17 +753,17 @@ __device__ double betacf_fast(double a, double b, double x) {
     const double dm = (double)m, m2 = 2.0 * dm;
     {
       const double num = dm * (b - dm) * x, den = (qam + m2) * (a + m2);
-      const double e = fma(num, d, den), cd = c * den;
+      const double e = lentz_guard(fma(num, d, den)), cd = c * den;
       const double r = 1.0 / (e * cd);
       d = den * cd * r;
-      c = (cd + num) * e * r;
+      c = lentz_guard(cd + num) * e * r;
       h *= d * c;
     }
     const double num = -(a + dm) * (qab + dm) * x, den = (a + m2) * (qap + m2);
-    const double e = fma(num, d, den), cd = c * den;
+    const double e = lentz_guard(fma(num, d, den)), cd = c * den;
     const double r = 1.0 / (e * cd);
     d = den * cd * r;
-    c = (cd + num) * e * r;
+    c = lentz_guard(cd + num) * e * r;
     const double del = d * c;
     h *= del;
     if (fabs(del - 1.0) < EPS) break;
@@ -1073,6 +1076,21 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
 }
 
 int mopoe_daa_last_impl(void) { return g_last_impl; }
+
+int mopoe_daa_status(const mopoe_model_desc* desc, const mopoe_daa_desc* daa, void* workspace, void* stream_) {
+  if (check_desc(desc)) return MOPOE_EINVAL;
+  if (!daa || !workspace) { set_error("NULL argument"); return MOPOE_EINVAL; }
+  DaaWs ws;
+  daa_carve(desc, daa, (char*)workspace, &ws);
+  int flag = 0;
+  MOPOE_CUDA(cudaMemcpyAsync(&flag, ws.err, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+  MOPOE_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
+  if (flag) {
+    set_error("DAA sweep: a tcgen05 pipeline wait timed out on the device (flag %d); the result tables were poisoned with NaN", flag);
+    return MOPOE_EDEVICE;
+  }
+  return MOPOE_OK;
+}
 
 int mopoe_daa_read_phases(const mopoe_model_desc* desc, const mopoe_daa_desc* daa, void* workspace, int64_t* out32_host) {
   if (check_desc(desc)) return MOPOE_EINVAL;

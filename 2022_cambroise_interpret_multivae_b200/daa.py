@@ -81,6 +81,14 @@ def daa_sweep(spec: PathSpec, flat_params, src, dst, n_samples, n_base, *, src_m
     return r
 
 
+def check_status(spec: PathSpec, result):
+    """Synchronise and raise MopoeError if the sweep that produced `result` flagged a device-side protocol error
+    (a bounded tcgen05 / mbarrier wait timed out; the kernels then poison the tables with NaN rather than hang).
+    Callers that persist results (workflow.daa_exp) call this before writing anything."""
+    _lib.check(_lib.lib().mopoe_daa_status(C.byref(spec.desc), C.byref(result._desc), _ptr(result._keep[-1]), _stream()))
+    return result
+
+
 def phase_cycles(spec: PathSpec, result):
     """Per-phase cycle counters of the tcgen05 avatar kernel of `result`'s sweep (profiling aid)."""
     out = (C.c_int64 * 32)()

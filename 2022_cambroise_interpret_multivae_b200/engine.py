@@ -37,6 +37,25 @@ class Workspace:
         return self.buf
 
 
+def init_params(spec: PathSpec, seed=0):
+    """Random-init weights with torch's nn.Linear default distribution, U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for
+    weights and biases (networks.py:17,23-28,56 construct plain nn.Linear layers), and the decoder logvar filled
+    with initial_out_logvar (networks.py:61-64), drawn from a private CPU generator in state-dict order.
+    -> dict of state-dict tensors (CPU fp32).  Benchmarks and synthetic runs start from this."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    slices = spec.param_slices()
+    params = {}
+    for name, (_, shape) in slices.items():
+        if name.startswith("decoders.") and name.endswith("logvar"):
+            params[name] = torch.full(shape, spec.initial_out_logvar, dtype=torch.float32)
+            continue
+        fan_in = shape[1] if name.endswith(".weight") else slices[name[:-4] + "weight"][1][1]
+        bound = 1.0 / math.sqrt(fan_in)
+        params[name] = ((torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * bound).to(torch.float32)
+    return params
+
+
 def pack_params(spec: PathSpec, params, device):
     """dict of state-dict tensors -> flat fp32 parameter buffer in C-ABI layout."""
     flat = torch.zeros(spec.layout.total, dtype=torch.float32, device=device)

@@ -64,6 +64,7 @@ class VAE(nn.Module):
         self._noise = None
         self._ws = engine.Workspace()
         self.philox_seed = None      # set to an int to use the in-kernel generator instead of torch.randn
+        self._philox_calls = 0       # every forward / ELBO call draws fresh noise: the call count is folded into the seed
 
     # ---- flat parameter storage -------------------------------------------------------------
     def flat_parameters(self):
@@ -89,6 +90,16 @@ class VAE(nn.Module):
     def inject_noise(self, eps):
         """Next forward/step consumes this (N, E) [or (n_pass, N, E)] tensor instead of fresh draws."""
         self._noise = eps
+
+    def _next_seed(self):
+        """Seed of the next in-kernel noise draw.  The generator is counter based (element index = step, pass,
+        row, column), so a constant seed would hand every call the same noise: each call gets its own key,
+        derived from (philox_seed, number of calls so far) -- reproducible for a given philox_seed."""
+        if self.philox_seed is None:
+            return 0
+        seed = (int(self.philox_seed) + 0x9E3779B97F4A7C15 * self._philox_calls) & 0xFFFFFFFFFFFFFFFF
+        self._philox_calls += 1
+        return seed
 
     def _draw(self, n_pass, n_rows, device):
         if self._noise is not None:
@@ -139,7 +150,7 @@ class VAE(nn.Module):
         flat = self.flat_parameters()
         n_rows = len(next(iter(input_batch.values())))
         eps = self._draw(1, n_rows, flat.device) if sample_latents else None
-        seed = self.philox_seed or 0
+        seed = self._next_seed() if (sample_latents and eps is None) else 0
         return engine.forward(self.spec, flat, input_batch, eps=None if eps is None else eps[0], seed=seed,
                               sample_latents=sample_latents, use_expert=use_expert, with_nll=with_nll,
                               workspace=self._ws)
@@ -193,7 +204,8 @@ def elbo_step(model: VAE, input_batch, need_grad=True):
     bdev = engine.make_batches(spec, [(n_rows, mask, 0)], dev)
     grads = torch.zeros_like(flat) if need_grad else None
     sc = engine.train_steps(spec, flat, data, bdev, 1, n_rows, 1 if need_grad else 0,
-                            eps=None if eps is None else eps[None].contiguous(), seed=model.philox_seed or 0,
+                            eps=None if eps is None else eps[None].contiguous(),
+                            seed=model._next_seed() if eps is None else 0,
                             grads=grads, forward_result=res, workspace=model._ws)[0]
     res.scalars = sc
     loss = sc[_lib.S_TOTAL_LOSS]

@@ -245,6 +245,7 @@ def daa_exp(dataset, datasetdir, outdir, run, sampling_strategy="likelihood", n_
     r = daa.daa_sweep(model.spec, flat, src, dst, n_samples, M, sample_latents=sample_latents, reg_method=reg_method,
                       seed=0 if seed is None else seed, val_begin=begin, n_val_total=n_validation,
                       materialize=materialize_avatars, workspace=model._ws)
+    daa.check_status(model.spec, r)           # a device-side protocol error must not end up in result files
     coefs, pvalues, betas, scores, recons = daa.gather_tables_many(
         [r.coefs, r.pvalues, r.betas, r.sampled_scores, r.reconstructions], n_validation)
     torch.cuda.synchronize()

@@ -169,7 +169,6 @@ def bench_train(spec_kw, device, steps=300, warmup=60):
     `steps` consecutive batches of an epoch plan (batch 256, missing blocks allowed)."""
     import mopoe_b200
     from mopoe_b200 import data, engine
-    from oracle import mopoe_oracle as mo
     out = {}
     cohort = data.make_cohort()
     train = np.r_[0:2048, 2560:2560 + 512 + 256]
@@ -177,7 +176,7 @@ def bench_train(spec_kw, device, steps=300, warmup=60):
     host = [torch.from_numpy(cohort["clinical"][train]).pin_memory(), torch.from_numpy(cohort["rois"][train]).pin_memory()]
     for method in ("joint_elbo", "moe", "poe"):
         spec = mopoe_b200.PathSpec(spec_kw["dims"], spec_kw["style_dims"], spec_kw["latent_dim"], method, spec_kw["mod_names"])
-        flat = engine.pack_params(spec, mo.init_params(mo.ModelSpec(**dict(spec_kw, method=method)), seed=0), device)
+        flat = engine.pack_params(spec, engine.init_params(spec, seed=0), device)
         rng = np.random.RandomState(0)
         plan = []
         while len(plan) < steps + warmup:
@@ -221,7 +220,6 @@ def bench_train(spec_kw, device, steps=300, warmup=60):
 def run_ours(args, rank, world, local_rank):
     import mopoe_b200
     from mopoe_b200 import _lib, daa, engine
-    from oracle import mopoe_oracle as mo   # weights init only (same init as the parity cases)
     import ctypes as C
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -237,7 +235,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     spec = mopoe_b200.PathSpec(HBN["dims"], HBN["style_dims"], HBN["latent_dim"], "joint_elbo", HBN["mod_names"])
-    flat = engine.pack_params(spec, mo.init_params(mo.ModelSpec(**HBN), seed=0), device)
+    flat = engine.pack_params(spec, engine.init_params(spec, seed=0), device)
     n_val, N, J, Mb = DAA["n_validation"], DAA["n_subjects"], DAA["n_samples"], DAA["n_base"]
     C_, R = spec.dims[0], spec.dims[1]
     src_h, dst_h = draw_validation_batches(n_val, DAA["seed"], offset=rank)

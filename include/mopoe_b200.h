@@ -49,7 +49,8 @@ enum {
   MOPOE_EINVAL = -1,   /* bad argument / unsupported configuration (message says which) */
   MOPOE_ENODEV = -2,   /* no CUDA device */
   MOPOE_ECUDA = -3,    /* CUDA runtime error (message carries cudaGetErrorString) */
-  MOPOE_ENOSPC = -4    /* workspace too small */
+  MOPOE_ENOSPC = -4,   /* workspace too small */
+  MOPOE_EDEVICE = -5   /* a kernel flagged a device-side protocol error (bounded tcgen05 / mbarrier wait timed out) */
 };
 
 /* Model description: the subset of the reference `flags` namespace (workflow.py:98-149) that the
@@ -240,6 +241,11 @@ int mopoe_profile_enable(int on);
  * "fixed" regression / mean latents), 0 = CUDA cores (shapes outside the tcgen05 tilings);
  * MOPOE_DAA_IMPL=pipe|umma|ffma in the environment forces one (the tests cross-check all three) */
 int mopoe_daa_last_impl(void);
+/* Synchronises `stream` and reports whether the last sweep run on `workspace` hit a device-side protocol error
+ * (a bounded tcgen05 / mbarrier wait that timed out: the kernels then poison coefs / pvalues with NaN instead of
+ * hanging the GPU).  MOPOE_OK, or MOPOE_EDEVICE with mopoe_last_error() set.  Hosts call it before they trust or
+ * write the tables (daa.py: check_status; workflow.daa_exp refuses to write results otherwise). */
+int mopoe_daa_status(const mopoe_model_desc* desc, const mopoe_daa_desc* daa, void* workspace, void* stream);
 /* per-role cycle counters (max over CTAs, 32 slots) of the last tcgen05 avatar kernel run on
  * `workspace`; filled by profiling builds of the library only (csrc/Makefile EXTRA=-DPK_PROF) */
 int mopoe_daa_read_phases(const mopoe_model_desc* desc, const mopoe_daa_desc* daa, void* workspace, int64_t* out32_host);

@@ -69,6 +69,31 @@ def test_forward_results_structure_and_values():
         model(batch)          # CPU tensors: no fallback
 
 
+def test_philox_seed_draws_fresh_noise_per_call():
+    """In-kernel generator through the drop-in interface: every call draws new noise (the reference draws from
+    the advancing global generator, BaseMMVae.py:37-40), reproducibly for a given philox_seed; seed 0 is a seed."""
+    from mopoe_b200 import run_epochs
+    model, ospec, params = _model()
+    g = torch.Generator().manual_seed(3)
+    batch = {"clinical": torch.randn(50, 7, generator=g).cuda(), "rois": torch.randn(50, 444, generator=g).cuda()}
+    for seed in (0, 77):
+        model.philox_seed, model._philox_calls = seed, 0
+        a = model(batch)["class_embeddings"].clone()
+        b = model(batch)["class_embeddings"].clone()
+        assert not torch.equal(a, b)
+        model._philox_calls = 0
+        assert torch.equal(model(batch)["class_embeddings"], a)
+        exp = SimpleNamespace(models=model, flags=model.flags)
+        with torch.no_grad():
+            l0 = float(run_epochs.basic_routine_epoch(exp, 0, (dict(batch), None, None))["total_loss"])
+            l1 = float(run_epochs.basic_routine_epoch(exp, 0, (dict(batch), None, None))["total_loss"])
+        assert l0 != l1
+    model.philox_seed, model._philox_calls = 0, 0
+    z0 = model(batch)["class_embeddings"].clone()
+    model.philox_seed, model._philox_calls = 77, 0
+    assert not torch.equal(model(batch)["class_embeddings"], z0)
+
+
 @pytest.mark.parametrize("method", ["joint_elbo", "poe", "moe"])
 def test_basic_routine_epoch_backward_and_torch_adam(method):
     from mopoe_b200 import run_epochs

@@ -108,8 +108,50 @@ def test_elbo_terms_and_gradients(name):
             assert float(got[k].abs().max()) == 0.0, k
 
 
+# ---- large batches: every row-tile instantiation of the training kernel (R = 2 / 4 / 16 rows per tile, the
+# tensor-core row tiles, the no-split-K first layer) against the CPU oracle.  The reference golden digests
+# stop at 256 rows (the reference's own batch size); beyond that the oracle (pinned to the reference at the
+# golden sizes) is the checker.
+LARGE_CASES = {}
+for _base, _bn in ((cases.HBN, "hbn"), (cases.STRESS, "stress")):
+    for _n in (512, 1024, 4097, 65536):
+        for _method in ("joint_elbo", "poe", "moe"):
+            if _n in (1024, 4097) and _method != "joint_elbo":
+                continue
+            _full = tuple(range(len(_base["dims"])))
+            LARGE_CASES["%s_%s_%d" % (_bn, _method, _n)] = cases._case(_base, _method, True, _full, _n, 300 + _n % 97, 400 + _n % 89)
+LARGE_CASES["stress_joint_elbo_13_4097"] = cases._case(cases.STRESS, "joint_elbo", True, (1, 3), 4097, 310, 410)
+LARGE_CASES["hbn_joint_elbo_nofact_1_1500"] = cases._case(cases.HBN, "joint_elbo", False, (1,), 1500, 311, 411)
+
+
+@pytest.mark.parametrize("name", sorted(LARGE_CASES))
+def test_elbo_large_batches(name):
+    from mopoe_b200 import _lib, engine
+    case = LARGE_CASES[name]
+    ospec, spec, params, flat = _setup(case)
+    batch, eps = cases.inputs_of(case, ospec)
+    grads = torch.zeros_like(flat)
+    sc = _run_step(spec, flat, batch, eps, 1, grads=grads)[0].cpu().numpy()
+    torch.cuda.synchronize()
+    out, g, used = mo.elbo_and_grads(params, ospec, batch, eps)
+    assert abs(sc[_lib.S_TOTAL_LOSS] - float(out["total_loss"])) <= RTOL * abs(float(out["total_loss"]))
+    assert abs(sc[_lib.S_JOINT_DIV] - float(out["joint_divergence"])) <= RTOL * abs(float(out["joint_divergence"]))
+    for k, v in out["log_probs"].items():
+        assert abs(sc[_lib.S_NLL + spec.mod_names.index(k)] - float(v)) <= RTOL * abs(float(v)), k
+    got = engine.unpack_params(spec, grads)
+    for k in g:
+        if used[k]:
+            _close(got[k], g[k], "grad " + k)
+        else:
+            assert float(got[k].abs().max()) == 0.0, k
+    # forward-only mode of the same launch shape: identical loss terms
+    sc0 = _run_step(spec, flat, batch, eps, 0)[0].cpu().numpy()
+    assert np.array_equal(sc0[:_lib.S_MEAN_HEAD], sc[:_lib.S_MEAN_HEAD])
+
+
 @pytest.mark.parametrize("name", ["hbn_joint_elbo_fact_01", "hbn_poe_fact_01", "hbn_moe_nofact_1",
-                                  "stress_joint_elbo_13", "hbn_joint_elbo_fact_01_fixedscale"])
+                                  "stress_joint_elbo_13", "hbn_joint_elbo_fact_01_fixedscale",
+                                  "hbn_joint_elbo_4097", "stress_joint_elbo_1024", "hbn_poe_512"])
 def test_fused_adam_steps(name):
     """3 x (fwd + bwd + Adam) inside ONE launch, with different present-sets across steps to
     exercise the per-modality step counters.
@@ -123,7 +165,7 @@ def test_fused_adam_steps(name):
       (b) the trajectory against the pure-CPU oracle: per-step losses within 2e-4, 99.9 % of the
           parameters within 1e-4 of their tensor's scale and none further than 2*lr*steps."""
     from mopoe_b200 import engine
-    case = cases.ELBO_CASES[name]
+    case = cases.ELBO_CASES[name] if name in cases.ELBO_CASES else LARGE_CASES[name]
     ospec, spec, params, flat = _setup(case)
     dev = flat.device
     lr, steps, batches, eps_l = 0.002, 3, [], []

@@ -27,6 +27,20 @@ def test_library_exports_every_declared_symbol():
     assert set(_lib.EXPORTED) == declared
 
 
+def test_package_init_params_equal_the_oracle_init():
+    """bench.py's product arm initialises weights inside the package (nothing from oracle/ on that path)."""
+    from mopoe_b200 import engine
+    from oracle import cases, mopoe_oracle as mo
+    for base in (cases.HBN, cases.STRESS):
+        spec = mopoe_b200.PathSpec(base["dims"], base["style_dims"], base["latent_dim"], "joint_elbo", base["mod_names"])
+        got, want = engine.init_params(spec, seed=3), mo.init_params(mo.ModelSpec(**base), seed=3)
+        assert list(got) == list(want)
+        assert all(torch.equal(got[k], want[k]) for k in want)
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    ours = src[src.index("def bench_train"):src.index("def main")]
+    assert "from oracle" not in ours and "import oracle" not in ours, "product arm of bench.py imports oracle/"
+
+
 def test_no_device_is_a_loud_error():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
