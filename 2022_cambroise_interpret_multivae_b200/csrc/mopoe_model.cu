@@ -134,6 +134,10 @@ __device__ __forceinline__ void tile_gemm(FA fa, FB fb, int K, float acc[2][2], 
   fetch(0);
   stash(0);
   __syncthreads();
+  // long reductions (weight gradients over tens of thousands of rows) are summed in two levels: a running
+  // fp32 sum of 1 024 products is folded into a second accumulator, which keeps the rounding error of the
+  // sum at the level of the library GEMM the reference calls (a single fp32 chain of 65 536 terms does not)
+  float tot[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
   for (int c = 0; c < nchunk; ++c) {
     const int buf = c & 1;
     if (c + 1 < nchunk) fetch(c + 1);
@@ -148,9 +152,14 @@ __device__ __forceinline__ void tile_gemm(FA fa, FB fb, int K, float acc[2][2], 
       acc[1][0] = fmaf(av.y, bv.x, acc[1][0]);
       acc[1][1] = fmaf(av.y, bv.y, acc[1][1]);
     }
+    if ((c & 31) == 31) {
+      tot[0][0] += acc[0][0]; tot[0][1] += acc[0][1]; tot[1][0] += acc[1][0]; tot[1][1] += acc[1][1];
+      acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = 0.f;
+    }
     if (c + 1 < nchunk) stash(buf ^ 1);
     __syncthreads();
   }
+  acc[0][0] += tot[0][0]; acc[0][1] += tot[0][1]; acc[1][0] += tot[1][0]; acc[1][1] += tot[1][1];
 }
 
 // -------------------------------------------------------------------------------------------
