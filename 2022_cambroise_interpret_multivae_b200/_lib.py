@@ -96,6 +96,7 @@ def lib():
     L.mopoe_umma_selftest.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     L.mopoe_umma_selftest.restype = C.c_int
     L.mopoe_daa_last_impl.restype = C.c_int
+    L.mopoe_train_last_impl.restype = C.c_int
     L.mopoe_daa_read_phases.argtypes = [C.POINTER(ModelDesc), C.POINTER(DaaDesc), vp, C.POINTER(C.c_int64)]
     L.mopoe_daa_read_phases.restype = C.c_int
     L.mopoe_daa_status.argtypes = [C.POINTER(ModelDesc), C.POINTER(DaaDesc), vp, vp]
@@ -120,4 +121,4 @@ EXPORTED = ["mopoe_last_error", "mopoe_version", "mopoe_device_count", "mopoe_pa
             "mopoe_workspace_bytes", "mopoe_forward", "mopoe_train_steps", "mopoe_daa_workspace_bytes",
             "mopoe_daa_sweep", "mopoe_daa_regression", "mopoe_philox_normal", "mopoe_profile_enable",
             "mopoe_daa_last_kernel_ms", "mopoe_umma_selftest", "mopoe_daa_last_impl", "mopoe_daa_read_phases",
-            "mopoe_daa_status"]
+            "mopoe_daa_status", "mopoe_train_last_impl"]

@@ -19,6 +19,7 @@
 
 #include "mopoe_common.cuh"
 #include "mopoe_latent.cuh"
+#include "mopoe_umma.cuh"
 
 namespace mopoe {
 
@@ -269,6 +270,230 @@ __device__ __forceinline__ void block_add(float* red, int slot, float v) {
 }
 
 // -------------------------------------------------------------------------------------------
+// Latent stage of a row tile, shared by the CUDA-core tile (p2_tile) and the tensor-core tile
+// (mopoe_train_tc.cuh): everything between the encoder heads (sh.e, fp32 [modality][row][head column]) and the
+// decoder inputs (sh.zz [modality][pass][row][style | content]), and its backward.  256 threads, thread per
+// (row, latent dim); the caller synchronises before and after.
+// -------------------------------------------------------------------------------------------
+struct LatSh {
+  float *e, *de, *zz, *dzz, *rp, *rps, *red;
+  int R, HCM, ZDM, SM_;
+  int NP;   // decoder passes held per modality in zz / dzz / rps (2 in the CUDA-core tile; 1 or 2 in the tensor-core tile)
+};
+
+__device__ void lat_forward(const ModelView& mv, const StepCtx& cx, const mopoe_batch_desc& b, int64_t eps_base,
+                            int r0, int nr, const LatSh& sh) {
+  const int t = threadIdx.x;
+  const int N = b.n_rows, L = mv.L, M = mv.M, present = b.present_mask;
+  const bool uni = cx.uni_pass != 0;
+  // ---- latent element-wise forward: thread per (row, latent dim) ----
+  const int nsub = mv.sub.n_subsets;
+  const float wmix = 1.f / (float)b.n_mix;  // uniform mixture weights (BaseMMVae.py:225, :64-78)
+  for (int base = 0; base < sh.R * L; base += MOPOE_THREADS) {
+    const int idx = base + t;
+    const int r = idx / L, l = idx % L;
+    const bool valid = idx < sh.R * L && r < nr;
+    const int n = r0 + r;
+    float mu_e[MOPOE_MAX_MODS], lv_e[MOPOE_MAX_MODS];
+#pragma unroll
+    for (int m = 0; m < MOPOE_MAX_MODS; ++m) {
+      const bool on = valid && m < M && (present >> m & 1);
+      mu_e[m] = on ? sh.e[(m * sh.R + r) * sh.HCM + l] : 0.f;
+      lv_e[m] = on ? sh.e[(m * sh.R + r) * sh.HCM + L + l] : 0.f;
+    }
+    for (int m = 0; m < M; ++m) {
+      if (!(present >> m & 1)) continue;
+      block_add(sh.red, MOPOE_S_MEAN_HEAD + 4 * m + 0, valid ? mu_e[m] : 0.f);
+      block_add(sh.red, MOPOE_S_MEAN_HEAD + 4 * m + 1, valid ? lv_e[m] : 0.f);
+    }
+    float jmu = 0.f, jlv = 0.f;
+    float smu[MOPOE_MAX_MODS], slv[MOPOE_MAX_MODS];  // singleton posteriors (poe unimodal passes)
+#pragma unroll
+    for (int m = 0; m < MOPOE_MAX_MODS; ++m) smu[m] = slv[m] = 0.f;
+    int kidx = 0, owner = 0;
+    for (int k = 0; k < b.n_mix; ++k)
+      if (n >= b.joint_bounds[k] && n < b.joint_bounds[k + 1]) owner = k;
+    for (int s = 0; s < nsub; ++s) {
+      if ((mv.sub.mask[s] & present) != mv.sub.mask[s]) continue;
+      const SubsetEval ev = eval_subset(mv, b, s, n, mu_e, lv_e);
+      if (valid) {
+        if (cx.out.subset_mu) cx.out.subset_mu[((int64_t)s * N + n) * L + l] = ev.mu;
+        if (cx.out.subset_logvar) cx.out.subset_logvar[((int64_t)s * N + n) * L + l] = ev.lv;
+      }
+      const float kl = valid ? -0.5f * (1.f - expf(ev.lv) - ev.mu * ev.mu + ev.lv) : 0.f;
+      block_add(sh.red, MOPOE_S_KLD_SUBSET + s, kl);
+      if (mv.sub.n_members[s] == 1) { smu[mv.sub.members[s][0]] = ev.mu; slv[mv.sub.members[s][0]] = ev.lv; }
+      if (in_mixture(mv, b, s)) {
+        if (cx.use_expert < 0) {
+          if (cx.sample_latents) { if (kidx == owner) { jmu = ev.mu; jlv = ev.lv; } }
+          else { jmu += ev.mu; jlv += ev.lv; }
+        }
+        ++kidx;
+      }
+      if (cx.use_expert == s) { jmu = ev.mu; jlv = ev.lv; }
+    }
+    if (cx.use_expert < 0 && !cx.sample_latents) { jmu /= (float)b.n_mix; jlv /= (float)b.n_mix; }
+    if (valid) {
+      float z = jmu, rp = 0.f;
+      if (cx.sample_latents) {
+        const float e0 = cx.noise.at(eps_base + (int64_t)n * mv.E + l);
+        const float sd = expf(0.5f * jlv);
+        z = e0 * sd + jmu;
+        rp = 0.5f * e0 * sd;
+      }
+      sh.rp[r * L + l] = rp;
+      for (int m = 0; m < M; ++m)
+        if (present >> m & 1) sh.zz[((m * sh.NP + 0) * sh.R + r) * sh.ZDM + mv.mod[m].S + l] = z;
+      if (cx.out.joint_mu) cx.out.joint_mu[(int64_t)n * L + l] = jmu;
+      if (cx.out.joint_logvar) cx.out.joint_logvar[(int64_t)n * L + l] = jlv;
+      if (cx.out.z) cx.out.z[(int64_t)n * L + l] = z;
+      if (uni) {
+        for (int m = 0; m < M; ++m) {
+          if (!(present >> m & 1)) continue;
+          const float e1 = cx.noise.at(eps_base + (1 + m) * cx.eps_pass_stride + (int64_t)n * mv.E + l);
+          const float sd = expf(0.5f * slv[m]);
+          sh.zz[((m * sh.NP + 1) * sh.R + r) * sh.ZDM + mv.mod[m].S + l] = e1 * sd + smu[m];
+          sh.rp[((1 + m) * sh.R + r) * L + l] = 0.5f * e1 * sd;
+        }
+      }
+    }
+  }
+  // ---- style element-wise forward ----
+  for (int m = 0; m < M; ++m) {
+    if (!(present >> m & 1)) continue;
+    const ModView& md = mv.mod[m];
+    const int S = md.S;
+    if (S == 0) continue;
+    for (int base = 0; base < sh.R * S; base += MOPOE_THREADS) {
+      const int idx = base + t;
+      const int r = idx / S, s = idx % S;
+      const bool valid = idx < sh.R * S && r < nr;
+      const int n = r0 + r;
+      float klv = 0.f, mu = 0.f, lv = 0.f;
+      if (valid) {
+        mu = sh.e[(m * sh.R + r) * sh.HCM + 2 * L + s];
+        lv = sh.e[(m * sh.R + r) * sh.HCM + 2 * L + S + s];
+        klv = -0.5f * (1.f - expf(lv) - mu * mu + lv);
+        const float sd = expf(0.5f * lv);
+        float zs = mu, rp = 0.f;
+        if (cx.sample_latents) {
+          const float e0 = cx.noise.at(eps_base + (int64_t)n * mv.E + md.eps_off + s);
+          zs = e0 * sd + mu; rp = 0.5f * e0 * sd;
+        }
+        sh.zz[((m * sh.NP + 0) * sh.R + r) * sh.ZDM + s] = zs;
+        sh.rps[((m * sh.NP + 0) * sh.R + r) * sh.SM_ + s] = rp;
+        if (cx.out.z_style[m]) cx.out.z_style[m][(int64_t)n * S + s] = zs;
+        if (uni) {
+          const float e1 = cx.noise.at(eps_base + (1 + m) * cx.eps_pass_stride + (int64_t)n * mv.E + md.eps_off + s);
+          sh.zz[((m * sh.NP + 1) * sh.R + r) * sh.ZDM + s] = e1 * sd + mu;
+          sh.rps[((m * sh.NP + 1) * sh.R + r) * sh.SM_ + s] = 0.5f * e1 * sd;
+        }
+      }
+      block_add(sh.red, MOPOE_S_KLD_STYLE + m, klv);
+      block_add(sh.red, MOPOE_S_MEAN_HEAD + 4 * m + 2, mu);
+      block_add(sh.red, MOPOE_S_MEAN_HEAD + 4 * m + 3, lv);
+    }
+  }
+}
+
+__device__ void lat_backward(const ModelView& mv, const StepCtx& cx, const mopoe_batch_desc& b, int r0, int nr,
+                             const LatSh& sh) {
+  const int t = threadIdx.x;
+  const int N = b.n_rows, L = mv.L, M = mv.M, present = b.present_mask;
+  const bool uni = cx.uni_pass != 0;
+  const float invN = 1.f / (float)N;
+  const int nsub = mv.sub.n_subsets;
+  const float wmix = 1.f / (float)b.n_mix;
+  // ---- latent element-wise backward ----
+  const float ckl = mv.beta * mv.beta_content * invN;
+  for (int base = 0; base < sh.R * L; base += MOPOE_THREADS) {
+    const int idx = base + t;
+    const int r = idx / L, l = idx % L;
+    if (idx < sh.R * L && r < nr) {
+      const int n = r0 + r;
+      float mu_e[MOPOE_MAX_MODS], lv_e[MOPOE_MAX_MODS], dmu[MOPOE_MAX_MODS], dlv[MOPOE_MAX_MODS];
+#pragma unroll
+      for (int m = 0; m < MOPOE_MAX_MODS; ++m) {
+        const bool on = m < M && (present >> m & 1);
+        mu_e[m] = on ? sh.e[(m * sh.R + r) * sh.HCM + l] : 0.f;
+        lv_e[m] = on ? sh.e[(m * sh.R + r) * sh.HCM + L + l] : 0.f;
+        dmu[m] = dlv[m] = 0.f;
+      }
+      float gz = 0.f;
+      for (int m = 0; m < M; ++m)
+        if (present >> m & 1) gz += sh.dzz[((m * sh.NP + 0) * sh.R + r) * sh.ZDM + mv.mod[m].S + l];
+      int kidx = 0, owner = 0;
+      for (int k = 0; k < b.n_mix; ++k)
+        if (n >= b.joint_bounds[k] && n < b.joint_bounds[k + 1]) owner = k;
+      for (int s = 0; s < nsub; ++s) {
+        if ((mv.sub.mask[s] & present) != mv.sub.mask[s]) continue;
+        const SubsetEval ev = eval_subset(mv, b, s, n, mu_e, lv_e);
+        const int nm = mv.sub.n_members[s];
+        float umu = 0.f, ulv = 0.f;
+        const float dkl_lv = 0.5f * (expf(ev.lv) - 1.f);
+        if (in_mixture(mv, b, s)) {
+          umu += ckl * wmix * ev.mu;
+          ulv += ckl * wmix * dkl_lv;
+          if (kidx == owner) { umu += gz; ulv += gz * sh.rp[r * L + l]; }
+          ++kidx;
+        }
+        if (mv.method == MOPOE_METHOD_POE && nm == 1) {  // unimodal ELBO of modality m (run_epochs.py:115-125)
+          const int m = mv.sub.members[s][0];
+          umu += ckl * ev.mu;
+          ulv += ckl * dkl_lv;
+          if (uni) {
+            const float g1 = sh.dzz[((m * sh.NP + 1) * sh.R + r) * sh.ZDM + mv.mod[m].S + l];
+            umu += g1; ulv += g1 * sh.rp[((1 + m) * sh.R + r) * L + l];
+          }
+        }
+        if (umu == 0.f && ulv == 0.f) continue;
+        if (mv.method == MOPOE_METHOD_MOE) {
+          const int m = mv.sub.members[s][ev.sel];
+          dmu[m] += umu; dlv[m] += ulv;
+        } else {
+          const float invP = 1.f / ev.sumT;
+          for (int i = 0; i < nm; ++i) {
+            const int m = mv.sub.members[s][i];
+            const float ex = expf(lv_e[m]);
+            const float T = 1.f / (ex + MOPOE_POE_EPS);
+            dmu[m] += umu * T * invP;
+            const float dT = umu * (mu_e[m] - ev.mu) * invP - ulv * invP;
+            dlv[m] += dT * (-T * T * ex);
+          }
+        }
+      }
+      for (int m = 0; m < M; ++m)
+        if (present >> m & 1) {
+          sh.de[(m * sh.R + r) * sh.HCM + l] = dmu[m];
+          sh.de[(m * sh.R + r) * sh.HCM + L + l] = dlv[m];
+        }
+    }
+  }
+  // ---- style element-wise backward ----
+  for (int m = 0; m < M; ++m) {
+    if (!(present >> m & 1)) continue;
+    const int S = mv.mod[m].S;
+    // style KL enters the joint ELBO and (poe) the unimodal ELBO of m, each with beta*beta_style^2
+    const float cks = mv.beta * mv.beta_style * mv.beta_style * invN * (mv.method == MOPOE_METHOD_POE ? 2.f : 1.f);
+    for (int idx = t; idx < sh.R * S; idx += MOPOE_THREADS) {
+      const int r = idx / S, s = idx % S;
+      if (r >= nr) continue;
+      const float mu = sh.e[(m * sh.R + r) * sh.HCM + 2 * L + s];
+      const float lv = sh.e[(m * sh.R + r) * sh.HCM + 2 * L + S + s];
+      const float g0 = sh.dzz[((m * sh.NP + 0) * sh.R + r) * sh.ZDM + s];
+      float gmu = g0 + cks * mu;
+      float glv = g0 * sh.rps[((m * sh.NP + 0) * sh.R + r) * sh.SM_ + s] + cks * 0.5f * (expf(lv) - 1.f);
+      if (uni) {
+        const float g1 = sh.dzz[((m * sh.NP + 1) * sh.R + r) * sh.ZDM + s];
+        gmu += g1; glv += g1 * sh.rps[((m * sh.NP + 1) * sh.R + r) * sh.SM_ + s];
+      }
+      sh.de[(m * sh.R + r) * sh.HCM + 2 * L + s] = gmu;
+      sh.de[(m * sh.R + r) * sh.HCM + 2 * L + S + s] = glv;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
 // P2: one tile of R rows, everything between the hidden layer and the per-row gradients.
 // -------------------------------------------------------------------------------------------
 #ifdef TRAIN_PROF
@@ -375,115 +600,11 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
     }
   }
   if (!BWD && cx.heads_only) return;   // uniform over the CTA; the caller's next tile starts with a barrier
-  // ---- latent element-wise forward: thread per (row, latent dim) ----
-  const int nsub = mv.sub.n_subsets;
-  const float wmix = 1.f / (float)b.n_mix;  // uniform mixture weights (BaseMMVae.py:225, :64-78)
-  for (int base = 0; base < R * L; base += MOPOE_THREADS) {
-    const int idx = base + t;
-    const int r = idx / L, l = idx % L;
-    const bool valid = idx < R * L && r < nr;
-    const int n = r0 + r;
-    float mu_e[MOPOE_MAX_MODS], lv_e[MOPOE_MAX_MODS];
-#pragma unroll
-    for (int m = 0; m < MOPOE_MAX_MODS; ++m) {
-      const bool on = valid && m < M && (present >> m & 1);
-      mu_e[m] = on ? sh_e[(m * R + r) * HCM + l] : 0.f;
-      lv_e[m] = on ? sh_e[(m * R + r) * HCM + L + l] : 0.f;
-    }
-    for (int m = 0; m < M; ++m) {
-      if (!(present >> m & 1)) continue;
-      block_add(sh_red, MOPOE_S_MEAN_HEAD + 4 * m + 0, valid ? mu_e[m] : 0.f);
-      block_add(sh_red, MOPOE_S_MEAN_HEAD + 4 * m + 1, valid ? lv_e[m] : 0.f);
-    }
-    float jmu = 0.f, jlv = 0.f;
-    float smu[MOPOE_MAX_MODS], slv[MOPOE_MAX_MODS];  // singleton posteriors (poe unimodal passes)
-#pragma unroll
-    for (int m = 0; m < MOPOE_MAX_MODS; ++m) smu[m] = slv[m] = 0.f;
-    int kidx = 0, owner = 0;
-    for (int k = 0; k < b.n_mix; ++k)
-      if (n >= b.joint_bounds[k] && n < b.joint_bounds[k + 1]) owner = k;
-    for (int s = 0; s < nsub; ++s) {
-      if ((mv.sub.mask[s] & present) != mv.sub.mask[s]) continue;
-      const SubsetEval ev = eval_subset(mv, b, s, n, mu_e, lv_e);
-      if (valid) {
-        if (cx.out.subset_mu) cx.out.subset_mu[((int64_t)s * N + n) * L + l] = ev.mu;
-        if (cx.out.subset_logvar) cx.out.subset_logvar[((int64_t)s * N + n) * L + l] = ev.lv;
-      }
-      const float kl = valid ? -0.5f * (1.f - expf(ev.lv) - ev.mu * ev.mu + ev.lv) : 0.f;
-      block_add(sh_red, MOPOE_S_KLD_SUBSET + s, kl);
-      if (mv.sub.n_members[s] == 1) { smu[mv.sub.members[s][0]] = ev.mu; slv[mv.sub.members[s][0]] = ev.lv; }
-      if (in_mixture(mv, b, s)) {
-        if (cx.use_expert < 0) {
-          if (cx.sample_latents) { if (kidx == owner) { jmu = ev.mu; jlv = ev.lv; } }
-          else { jmu += ev.mu; jlv += ev.lv; }
-        }
-        ++kidx;
-      }
-      if (cx.use_expert == s) { jmu = ev.mu; jlv = ev.lv; }
-    }
-    if (cx.use_expert < 0 && !cx.sample_latents) { jmu /= (float)b.n_mix; jlv /= (float)b.n_mix; }
-    if (valid) {
-      float z = jmu, rp = 0.f;
-      if (cx.sample_latents) {
-        const float e0 = cx.noise.at(eps_base + (int64_t)n * mv.E + l);
-        const float sd = expf(0.5f * jlv);
-        z = e0 * sd + jmu;
-        rp = 0.5f * e0 * sd;
-      }
-      sh_rp[r * L + l] = rp;
-      for (int m = 0; m < M; ++m)
-        if (present >> m & 1) sh_zz[((m * 2 + 0) * R + r) * ZDM + mv.mod[m].S + l] = z;
-      if (cx.out.joint_mu) cx.out.joint_mu[(int64_t)n * L + l] = jmu;
-      if (cx.out.joint_logvar) cx.out.joint_logvar[(int64_t)n * L + l] = jlv;
-      if (cx.out.z) cx.out.z[(int64_t)n * L + l] = z;
-      if (uni) {
-        for (int m = 0; m < M; ++m) {
-          if (!(present >> m & 1)) continue;
-          const float e1 = cx.noise.at(eps_base + (1 + m) * cx.eps_pass_stride + (int64_t)n * mv.E + l);
-          const float sd = expf(0.5f * slv[m]);
-          sh_zz[((m * 2 + 1) * R + r) * ZDM + mv.mod[m].S + l] = e1 * sd + smu[m];
-          sh_rp[((1 + m) * R + r) * L + l] = 0.5f * e1 * sd;
-        }
-      }
-    }
-  }
+  LatSh lsh;
+  lsh.e = sh_e; lsh.de = sh_de; lsh.zz = sh_zz; lsh.dzz = sh_dzz; lsh.rp = sh_rp; lsh.rps = sh_rps; lsh.red = sh_red;
+  lsh.R = R; lsh.HCM = HCM; lsh.ZDM = ZDM; lsh.SM_ = SM_; lsh.NP = 2;
+  lat_forward(mv, cx, b, eps_base, r0, nr, lsh);
   P2T(2);
-  // ---- style element-wise forward ----
-  for (int m = 0; m < M; ++m) {
-    if (!(present >> m & 1)) continue;
-    const ModView& md = mv.mod[m];
-    const int S = md.S;
-    if (S == 0) continue;
-    for (int base = 0; base < R * S; base += MOPOE_THREADS) {
-      const int idx = base + t;
-      const int r = idx / S, s = idx % S;
-      const bool valid = idx < R * S && r < nr;
-      const int n = r0 + r;
-      float klv = 0.f, mu = 0.f, lv = 0.f;
-      if (valid) {
-        mu = sh_e[(m * R + r) * HCM + 2 * L + s];
-        lv = sh_e[(m * R + r) * HCM + 2 * L + S + s];
-        klv = -0.5f * (1.f - expf(lv) - mu * mu + lv);
-        const float sd = expf(0.5f * lv);
-        float zs = mu, rp = 0.f;
-        if (cx.sample_latents) {
-          const float e0 = cx.noise.at(eps_base + (int64_t)n * mv.E + md.eps_off + s);
-          zs = e0 * sd + mu; rp = 0.5f * e0 * sd;
-        }
-        sh_zz[((m * 2 + 0) * R + r) * ZDM + s] = zs;
-        sh_rps[((m * 2 + 0) * R + r) * SM_ + s] = rp;
-        if (cx.out.z_style[m]) cx.out.z_style[m][(int64_t)n * S + s] = zs;
-        if (uni) {
-          const float e1 = cx.noise.at(eps_base + (1 + m) * cx.eps_pass_stride + (int64_t)n * mv.E + md.eps_off + s);
-          sh_zz[((m * 2 + 1) * R + r) * ZDM + s] = e1 * sd + mu;
-          sh_rps[((m * 2 + 1) * R + r) * SM_ + s] = 0.5f * e1 * sd;
-        }
-      }
-      block_add(sh_red, MOPOE_S_KLD_STYLE + m, klv);
-      block_add(sh_red, MOPOE_S_MEAN_HEAD + 4 * m + 2, mu);
-      block_add(sh_red, MOPOE_S_MEAN_HEAD + 4 * m + 3, lv);
-    }
-  }
   __syncthreads();
   P2T(3);
   // ---- decoders (+ NLL, d x_hat, d z) : thread per output feature, 256 features at a time ----
@@ -592,94 +713,8 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
   __syncthreads();
   P2T(4);
   if (BWD) {
-    // ---- latent element-wise backward ----
-    const float ckl = mv.beta * mv.beta_content * invN;
-    for (int base = 0; base < R * L; base += MOPOE_THREADS) {
-      const int idx = base + t;
-      const int r = idx / L, l = idx % L;
-      if (idx < R * L && r < nr) {
-        const int n = r0 + r;
-        float mu_e[MOPOE_MAX_MODS], lv_e[MOPOE_MAX_MODS], dmu[MOPOE_MAX_MODS], dlv[MOPOE_MAX_MODS];
-#pragma unroll
-        for (int m = 0; m < MOPOE_MAX_MODS; ++m) {
-          const bool on = m < M && (present >> m & 1);
-          mu_e[m] = on ? sh_e[(m * R + r) * HCM + l] : 0.f;
-          lv_e[m] = on ? sh_e[(m * R + r) * HCM + L + l] : 0.f;
-          dmu[m] = dlv[m] = 0.f;
-        }
-        float gz = 0.f;
-        for (int m = 0; m < M; ++m)
-          if (present >> m & 1) gz += sh_dzz[((m * 2 + 0) * R + r) * ZDM + mv.mod[m].S + l];
-        int kidx = 0, owner = 0;
-        for (int k = 0; k < b.n_mix; ++k)
-          if (n >= b.joint_bounds[k] && n < b.joint_bounds[k + 1]) owner = k;
-        for (int s = 0; s < nsub; ++s) {
-          if ((mv.sub.mask[s] & present) != mv.sub.mask[s]) continue;
-          const SubsetEval ev = eval_subset(mv, b, s, n, mu_e, lv_e);
-          const int nm = mv.sub.n_members[s];
-          float umu = 0.f, ulv = 0.f;
-          const float dkl_lv = 0.5f * (expf(ev.lv) - 1.f);
-          if (in_mixture(mv, b, s)) {
-            umu += ckl * wmix * ev.mu;
-            ulv += ckl * wmix * dkl_lv;
-            if (kidx == owner) { umu += gz; ulv += gz * sh_rp[r * L + l]; }
-            ++kidx;
-          }
-          if (mv.method == MOPOE_METHOD_POE && nm == 1) {  // unimodal ELBO of modality m (run_epochs.py:115-125)
-            const int m = mv.sub.members[s][0];
-            umu += ckl * ev.mu;
-            ulv += ckl * dkl_lv;
-            if (uni) {
-              const float g1 = sh_dzz[((m * 2 + 1) * R + r) * ZDM + mv.mod[m].S + l];
-              umu += g1; ulv += g1 * sh_rp[((1 + m) * R + r) * L + l];
-            }
-          }
-          if (umu == 0.f && ulv == 0.f) continue;
-          if (mv.method == MOPOE_METHOD_MOE) {
-            const int m = mv.sub.members[s][ev.sel];
-            dmu[m] += umu; dlv[m] += ulv;
-          } else {
-            const float invP = 1.f / ev.sumT;
-            for (int i = 0; i < nm; ++i) {
-              const int m = mv.sub.members[s][i];
-              const float ex = expf(lv_e[m]);
-              const float T = 1.f / (ex + MOPOE_POE_EPS);
-              dmu[m] += umu * T * invP;
-              const float dT = umu * (mu_e[m] - ev.mu) * invP - ulv * invP;
-              dlv[m] += dT * (-T * T * ex);
-            }
-          }
-        }
-        for (int m = 0; m < M; ++m)
-          if (present >> m & 1) {
-            sh_de[(m * R + r) * HCM + l] = dmu[m];
-            sh_de[(m * R + r) * HCM + L + l] = dlv[m];
-          }
-      }
-    }
+    lat_backward(mv, cx, b, r0, nr, lsh);
     P2T(5);
-    // ---- style element-wise backward ----
-    for (int m = 0; m < M; ++m) {
-      if (!(present >> m & 1)) continue;
-      const int S = mv.mod[m].S;
-      // style KL enters the joint ELBO and (poe) the unimodal ELBO of m, each with beta*beta_style^2
-      const float cks = mv.beta * mv.beta_style * mv.beta_style * invN * (mv.method == MOPOE_METHOD_POE ? 2.f : 1.f);
-      for (int idx = t; idx < R * S; idx += MOPOE_THREADS) {
-        const int r = idx / S, s = idx % S;
-        if (r >= nr) continue;
-        const float mu = sh_e[(m * R + r) * HCM + 2 * L + s];
-        const float lv = sh_e[(m * R + r) * HCM + 2 * L + S + s];
-        const float g0 = sh_dzz[((m * 2 + 0) * R + r) * ZDM + s];
-        float gmu = g0 + cks * mu;
-        float glv = g0 * sh_rps[((m * 2 + 0) * R + r) * SM_ + s] + cks * 0.5f * (expf(lv) - 1.f);
-        if (uni) {
-          const float g1 = sh_dzz[((m * 2 + 1) * R + r) * ZDM + s];
-          gmu += g1; glv += g1 * sh_rps[((m * 2 + 1) * R + r) * SM_ + s];
-        }
-        sh_de[(m * R + r) * HCM + 2 * L + s] = gmu;
-        sh_de[(m * R + r) * HCM + 2 * L + S + s] = glv;
-      }
-    }
     __syncthreads();
     P2T(6);
     // ---- d heads -> workspace; d pre-activation = (W_h^T d heads) * relu' ----
@@ -1022,6 +1057,22 @@ static int validate_batch(const mopoe_model_desc* d, const mopoe_batch_desc* b) 
   return MOPOE_OK;
 }
 
+#include "mopoe_train_tc.cuh"
+
+// 227 KB of shared memory per CTA minus the kernel's static shared variables (1 KB with alignment)
+constexpr int TC_SMEM_LIMIT = 227 * 1024 - 2048;
+static int g_train_impl = 0;   // implementation of the last mopoe_train_steps call: 0 CUDA cores, 1 tensor cores
+
+// MOPOE_TRAIN_IMPL=tc|ffma forces one implementation (the tests cross-check both); default: tensor cores
+// whenever the configuration fits their tiling
+static int pick_train_impl(const mopoe_model_desc* d, int64_t max_rows, tc::TcPlan* plan) {
+  const char* force = getenv("MOPOE_TRAIN_IMPL");
+  if (force && !strcmp(force, "ffma")) return 0;
+  const bool ok = tc::make_plan(d, max_rows, TC_SMEM_LIMIT, plan);
+  if (force && !strcmp(force, "tc")) return ok ? 1 : -1;
+  return ok ? 1 : 0;
+}
+
 }  // namespace mopoe
 
 using namespace mopoe;
@@ -1040,8 +1091,13 @@ int mopoe_debug_p2prof(float* out16_host) {
 int64_t mopoe_workspace_bytes(const mopoe_model_desc* desc, int64_t max_rows) {
   if (check_desc(desc)) return MOPOE_EINVAL;
   if (max_rows < 1) { set_error("max_rows=%lld", (long long)max_rows); return MOPOE_EINVAL; }
-  return carve(desc, max_rows, nullptr, nullptr);
+  int64_t bytes = (carve(desc, max_rows, nullptr, nullptr) + 1023) & ~(int64_t)1023;
+  tc::TcPlan plan;
+  if (tc::make_plan(desc, max_rows, TC_SMEM_LIMIT, &plan)) bytes += plan.total;   // operand blobs of the tensor-core training step
+  return bytes;
 }
+
+int mopoe_train_last_impl(void) { return g_train_impl; }
 
 int mopoe_forward(const mopoe_model_desc* desc, const float* params, const mopoe_batch_desc* batch,
                   const float* const* x, const float* eps, uint64_t seed, int sample_latents, int use_expert,
@@ -1155,6 +1211,27 @@ int mopoe_train_steps(const mopoe_model_desc* desc, float* params, float* adam_m
   if (out) { cx.out = *out; cx.out.scalars = nullptr; }
   if (mode == 1) MOPOE_CUDA(cudaMemsetAsync(grads, 0, lay.total * sizeof(float), stream));
   MOPOE_CUDA(cudaMemsetAsync(ws.bar, 0, sizeof(unsigned int), stream));
+  tc::TcPlan plan;
+  const int impl = pick_train_impl(desc, max_rows, &plan);
+  if (impl < 0) { set_error("MOPOE_TRAIN_IMPL=tc but the configuration does not fit the tensor-core tiling"); return MOPOE_EINVAL; }
+  g_train_impl = impl;
+  if (impl == 1) {
+    const int64_t base_off = (need + 1023) & ~(int64_t)1023;
+    if (workspace_bytes < base_off + plan.total) { set_error("workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)(base_off + plan.total)); return MOPOE_ENOSPC; }
+    plan.base = (unsigned char*)workspace + base_off;
+    MOPOE_CUDA(cudaMemsetAsync(plan.base + plan.err, 0, 256, stream));
+    MOPOE_CUDA(cudaMemsetAsync(plan.base + plan.p3cnt, 0, (size_t)plan.n_units * 4, stream));
+    void* fn = plan.R == 32 ? (void*)tc::train_tc_kernel<32> : (void*)tc::train_tc_kernel<16>;
+    MOPOE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.s_total));
+    int per_sm = 0;
+    MOPOE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, tc::THREADS, plan.s_total));
+    if (per_sm < 1) { set_error("tensor-core train kernel does not fit on an SM (smem %d)", plan.s_total); return MOPOE_EINVAL; }
+    const mopoe_batch_desc* bptr = batches;
+    float* sptr = scalars;
+    void* args[] = {&mv, &cx, &bptr, &n_steps, &sptr, &ws, &plan};
+    MOPOE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(num_sms()), dim3(tc::THREADS), args, plan.s_total, stream));
+    return MOPOE_OK;
+  }
   int smem = 0;
   const int R = pick_rows(mv, max_rows, &smem);
   void* fn = R == 1 ? (void*)train_kernel<1> : R == 2 ? (void*)train_kernel<2> : R == 4 ? (void*)train_kernel<4> : (void*)train_kernel<16>;

@@ -182,6 +182,10 @@ int mopoe_train_steps(const mopoe_model_desc* desc, float* params, float* adam_m
                       float lr, float b1, float b2, float adam_eps, float* scalars,
                       const mopoe_forward_out* out_host, void* workspace, int64_t workspace_bytes,
                       void* stream);
+/* implementation of the last mopoe_train_steps call: 1 = tensor-core kernel (tcgen05 / TMEM / TMA bulk copies,
+ * csrc/mopoe_train_tc.cuh; the default whenever the configuration fits its tiling), 0 = CUDA-core kernel.
+ * MOPOE_TRAIN_IMPL=tc|ffma in the environment forces one (the tests cross-check both). */
+int mopoe_train_last_impl(void);
 
 /* ---- Digital Avatars Analysis  (workflow.daa_exp, workflow.py:361-537) ----------------------- */
 
