@@ -5,7 +5,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmopoe_b200.so")
+# MOPOE_LIB_PATH: load another build of the library (profiling builds made with `make EXTRA=-D... OUT=...`)
+LIB_PATH = os.environ.get("MOPOE_LIB_PATH") or os.path.join(_HERE, "libmopoe_b200.so")
 
 MAX_MODS = 4
 MAX_SUBSETS = 15

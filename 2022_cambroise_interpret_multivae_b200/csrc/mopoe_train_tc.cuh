@@ -32,6 +32,16 @@ namespace tc {
 
 using namespace umma;
 
+// -DTC_PROF: CTA 0 / thread 0 accumulates cycle counts per stage into the 64 floats behind the error flag
+// (read back with mopoe_debug_tcprof); no effect on results
+#ifdef TC_PROF
+#define TCP_DECL long long _tp = clock64()
+#define TCP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long _n = clock64(); prof[i] += (float)(_n - _tp); _tp = _n; } } while (0)
+#else
+#define TCP_DECL do { } while (0)
+#define TCP(i) do { } while (0)
+#endif
+
 constexpr int THREADS = 320;       // warps 0-7 compute, warp 8 loader, warp 9 MMA issuer
 constexpr int CHUNK = 16384;       // one streamed weight chunk: 128 rows x 32 K x {hi, lo} fp16
 constexpr int MAX_SLOTS = 8;
@@ -105,7 +115,7 @@ static bool make_plan(const mopoe_model_desc* d, int64_t max_rows, int smem_limi
   p.ntiles_max = (int)((max_rows + R - 1) / R);
   int64_t off = 0;
   auto takeg = [&](int64_t n) { int64_t o = off; off += (n + 255) & ~(int64_t)255; return o; };
-  p.err = takeg(256);
+  p.err = takeg(1024);   // [0] error flag, [64..127] profiling counters (floats)
   int col = 0;
   for (int m = 0; m < M; ++m) {
     TcMod& t = p.mod[m];
@@ -344,21 +354,24 @@ __device__ void tile_mma(const TileCtx& c, Ring& rg, Sync& sy, uint32_t tmem) {
   const int present = c.b->present_mask;
   const uint32_t SF = R * 16;                         // bytes between feature groups of 8 in a tile operand
   const uint32_t u = smem_u32(c.sm + pl.s_u);
-  const uint32_t xbuf[2] = {u, u + 128u * R}, hbuf = u + 256u * R, zop = u, dxbuf = u + 256u * R, deop = u;
+  const uint32_t hbuf = u + 256u * R, xbuf[2] = {hbuf, hbuf + 512u * R}, zop = u, dxbuf = u + 256u * R, deop = u;
   const uint32_t id_k = idesc(R, 0, 0), id_mn = idesc(R, 0, 1);
   const uint32_t acc0 = tmem, acc1 = tmem + R, acc2 = tmem + 2 * R;
   for (int m = 0; m < mv.M; ++m) {
     if (!(present >> m & 1)) continue;
     const TcMod& t = pl.mod[m];
-    // P1: h^T = W1 x^T, x chunks double buffered by the compute warps (layout F: K-major B)
+    // P1: h^T = W1 x^T; the compute warps convert x in blocks of 128 features (layout F: K-major B), double
+    // buffered inside the (not yet used) h operand buffer
     uint32_t a0 = 0, a1 = 0;
-    for (int cc = 0; cc < t.NCx; ++cc) {
+    for (int xi = 0; 4 * xi < t.NCx; ++xi) {
       const int xb = sy.nx & 1;
       tc_wait(&bars->xfull[xb], (sy.nx >> 1) & 1, bars, c.gerr);
       tc_fence_after();
-      const int ks = ksteps_of(t.Dk16, cc);
-      mma_chunk(rg, pl, bars, ring, c.gerr, acc0, xbuf[xb], 64u * R, SF, 128, 2 * SF, id_k, ks, a0);
-      mma_chunk(rg, pl, bars, ring, c.gerr, acc1, xbuf[xb], 64u * R, SF, 128, 2 * SF, id_k, ks, a1);
+      for (int c4 = 0; c4 < 4 && 4 * xi + c4 < t.NCx; ++c4) {
+        const int ks = ksteps_of(t.Dk16, 4 * xi + c4);
+        mma_chunk(rg, pl, bars, ring, c.gerr, acc0, xbuf[xb] + c4 * 4 * SF, 256u * R, SF, 128, 2 * SF, id_k, ks, a0);
+        mma_chunk(rg, pl, bars, ring, c.gerr, acc1, xbuf[xb] + c4 * 4 * SF, 256u * R, SF, 128, 2 * SF, id_k, ks, a1);
+      }
       mma_commit(&bars->xempty[xb]);
       ++sy.nx;
     }
@@ -437,8 +450,8 @@ __device__ void tile_compute(const TileCtx& c, Sync& sy, uint32_t tmem) {
   constexpr uint32_t SF = R * 16;
   constexpr int RH = R / 2;                                // rows per column half
   unsigned char* U = c.sm + pl.s_u;
-  unsigned char* xbuf[2] = {U, U + 128 * R};
   unsigned char* hbuf = U + 256 * R;
+  unsigned char* xbuf[2] = {hbuf, hbuf + 512 * R};
   unsigned char* zop = U;
   unsigned char* dxbuf = U + 256 * R;
   unsigned char* deop = U;
@@ -454,6 +467,10 @@ __device__ void tile_compute(const TileCtx& c, Sync& sy, uint32_t tmem) {
   const float invN = 1.f / (float)N, fN = (float)N;
   float* colpart = reinterpret_cast<float*>(pl.base + pl.colpart) + (int64_t)(2 * c.tile) * pl.ccols;
 
+#ifdef TC_PROF
+  float* prof = reinterpret_cast<float*>(pl.base + pl.err) + 64;
+#endif
+  TCP_DECL;
   bar_compute();                                            // previous tile of this CTA is finished with smem
   if (t < MOPOE_N_SCALARS) sh_red[t] = 0.f;
   for (int i = t; i < M * R; i += 256) {
@@ -461,6 +478,7 @@ __device__ void tile_compute(const TileCtx& c, Sync& sy, uint32_t tmem) {
     srow[i] = (n < nr && (present >> m & 1)) ? src_row(cx, b, m, r0 + n) : -1;
   }
   bar_compute();
+  TCP(0);
   // ================= P1 + S1 per modality =================
   for (int m = 0; m < M; ++m) {
     if (!(present >> m & 1)) continue;
@@ -468,23 +486,23 @@ __device__ void tile_compute(const TileCtx& c, Sync& sy, uint32_t tmem) {
     const TcMod& tm = pl.mod[m];
     const int D = md.D;
     unsigned char* g_x = pl.base + tm.xop + (int64_t)c.tile * tm.xop_t;
-    for (int cc = 0; cc < tm.NCx; ++cc) {
+    for (int xi = 0; 4 * xi < tm.NCx; ++xi) {
       const int xb = sy.nx & 1;
       tc_wait(&bars->xempty[xb], ((sy.nx >> 1) & 1) ^ 1, bars, c.gerr);
-      if (t < R * 4) {          // thread = (row, group of 8 features): layout F
-        const int n = t >> 2, g = t & 3;
+      for (int i = t; i < R * 16; i += 256) {          // thread = (row, group of 8 features): layout F
+        const int n = i >> 4, g = i & 15;
         const long long sr = srow[m * R + n];
-        const int d0 = cc * 32 + g * 8;
+        const int d0 = xi * 128 + g * 8;
         float x[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = (sr >= 0 && d0 + i < D) ? cx.x[m][sr * D + d0 + i] : 0.f;
+        for (int k = 0; k < 8; ++k) x[k] = (sr >= 0 && d0 + k < D) ? cx.x[m][sr * D + d0 + k] : 0.f;
         uint4 hi, lo;
         split8(x, hi, lo);
         const uint32_t off = g * SF + (n >> 3) * 128 + (n & 7) * 16;
         *reinterpret_cast<uint4*>(xbuf[xb] + off) = hi;
-        *reinterpret_cast<uint4*>(xbuf[xb] + 64 * R + off) = lo;
-        if (bwd) {
-          const uint32_t goff = (cc * 4 + g) * SF + (n >> 3) * 128 + (n & 7) * 16;
+        *reinterpret_cast<uint4*>(xbuf[xb] + 256 * R + off) = lo;
+        if (bwd && xi * 16 + g < tm.NCx * 4) {
+          const uint32_t goff = (xi * 16 + g) * SF + (n >> 3) * 128 + (n & 7) * 16;
           *reinterpret_cast<uint4*>(g_x + goff) = hi;
           *reinterpret_cast<uint4*>(g_x + tm.xop_t / 2 + goff) = lo;
         }
@@ -494,8 +512,10 @@ __device__ void tile_compute(const TileCtx& c, Sync& sy, uint32_t tmem) {
       if (t == 0) mbar_arrive(&bars->xfull[xb]);
       ++sy.nx;
     }
+    TCP(1);
     // ---- P1 epilogue: h = relu(acc + b1) -> hbuf (layout T), HBM copy for dWheads, relu mask ----
     await_acc(bars, sy, c.gerr);
+    TCP(2);
     {
       const int mt = hf, j = 128 * mt + 32 * q + lane;      // warp = (M tile, lane quarter), all R rows
       float v[R];
@@ -527,8 +547,10 @@ __device__ void tile_compute(const TileCtx& c, Sync& sy, uint32_t tmem) {
       mask[m * 256 + j] = mk;
     }
     publish_b(bars);
+    TCP(3);
     // ---- S1 epilogue: heads -> sh.e[m][row][j] ----
     await_acc(bars, sy, c.gerr);
+    TCP(4);
     {
       const int j = 32 * q + lane;
       float v[RH];
@@ -547,11 +569,13 @@ __device__ void tile_compute(const TileCtx& c, Sync& sy, uint32_t tmem) {
     }
     tc_fence_before();
     bar_compute();
+    TCP(5);
   }
   // ================= latent forward =================
   for (int i = t; i < M * pl.np * R * pl.zdm; i += 256) sh.dzz[i] = 0.f;
   lat_forward(mv, cx, b, c.eps_base, r0, nr, sh);
   bar_compute();
+  TCP(6);
   // ================= decoders (+ NLL, d x_hat, d z) =================
   for (int m = 0; m < M; ++m) {
     if (!(present >> m & 1)) continue;
@@ -580,10 +604,12 @@ __device__ void tile_compute(const TileCtx& c, Sync& sy, uint32_t tmem) {
         }
       }
       publish_b(bars);
+      TCP(7);
       unsigned char* g_dx = pl.base + tm.dxop + ((int64_t)c.tile * pl.np + p) * tm.dxop_t;
       float nll = 0.f;
       for (int mt = 0; mt < tm.MtD; ++mt) {
         await_acc(bars, sy, c.gerr);
+        TCP(8);
         const int f = 32 * q + lane, d = 128 * mt + f;
         float v[RH];
         tmem_ld_cols<RH>(lane_base + (mt & 1) * R + hf * RH, v);
@@ -634,10 +660,12 @@ __device__ void tile_compute(const TileCtx& c, Sync& sy, uint32_t tmem) {
         }
         if (bwd || mt + 1 < tm.MtD) publish_b(bars);
         else { tc_fence_before(); bar_compute(); }
+        TCP(9);
       }
       if (cx.with_nll) block_add(sh_red, (p == 0 ? MOPOE_S_NLL : MOPOE_S_NLL_UNI) + m, nll);
       if (bwd) {        // d z of this (modality, pass): 1/N applied here, fp32 from now on
         await_acc(bars, sy, c.gerr);
+        TCP(10);
         const int z = 32 * q + lane;
         if (q < 2) {
           float v[RH];
@@ -650,6 +678,7 @@ __device__ void tile_compute(const TileCtx& c, Sync& sy, uint32_t tmem) {
         }
         tc_fence_before();
         bar_compute();
+        TCP(11);
       }
     }
   }
@@ -657,6 +686,7 @@ __device__ void tile_compute(const TileCtx& c, Sync& sy, uint32_t tmem) {
     // ================= latent backward (d heads overwrite the heads in place) =================
     lat_backward(mv, cx, b, r0, nr, sh);
     bar_compute();
+    TCP(12);
     for (int m = 0; m < M; ++m) {
       if (!(present >> m & 1)) continue;
       const ModView& md = mv.mod[m];
@@ -688,8 +718,10 @@ __device__ void tile_compute(const TileCtx& c, Sync& sy, uint32_t tmem) {
         colpart[pl.ccols + tm.col0 + 256 + t] = 0.f;
       }
       publish_b(bars);
+      TCP(13);
       // ---- S4 epilogue: d pre-activation x N = (Wh^T d heads) * relu' -> HBM operand of dW1, column sums (d b1) ----
       await_acc(bars, sy, c.gerr);
+      TCP(14);
       {
         const int mt = hf, j = 128 * mt + 32 * q + lane;
         float v[R];
@@ -718,6 +750,7 @@ __device__ void tile_compute(const TileCtx& c, Sync& sy, uint32_t tmem) {
       }
       tc_fence_before();
       bar_compute();
+      TCP(15);
     }
   }
   bar_compute();
@@ -954,9 +987,15 @@ __global__ void __launch_bounds__(THREADS, 1) train_tc_kernel(ModelView mv, Step
     __syncthreads();
     const mopoe_batch_desc& b = sb;
     if (blockIdx.x == 0 && t < MOPOE_N_SCALARS) ws.acc[t] = 0.0;
+#ifdef TC_PROF
+    float* prof = reinterpret_cast<float*>(pl.base + pl.err) + 64;
+#endif
+    TCP_DECL;
     tc_prep(mv, pl);
+    TCP(20);
     grid_barrier(ws.bar, target);
     fence_async_all();
+    TCP(21);
     const int nt = (b.n_rows + R - 1) / R;
     const bool bwd = cx.mode != 0;
     // ---- P1 + P2 ----
@@ -970,8 +1009,10 @@ __global__ void __launch_bounds__(THREADS, 1) train_tc_kernel(ModelView mv, Step
       else tile_compute<R>(c, sy, tmem);
     }
     fence_async_all();
+    TCP(22);
     grid_barrier(ws.bar, target);
     fence_async_all();
+    TCP(23);
     if (blockIdx.x == 0 && t == 0) finalize_scalars(mv, cx, b, ws.acc, scalars + (int64_t)step * MOPOE_N_SCALARS);
     if (bwd) {
       // ---- P3 ----
@@ -991,7 +1032,9 @@ __global__ void __launch_bounds__(THREADS, 1) train_tc_kernel(ModelView mv, Step
           p3_columns(mv, cx, b, pl, nt, item - n_items);
         }
       }
+      TCP(24);
       grid_barrier(ws.bar, target);
+      TCP(25);
       if (cx.mode == 2 && blockIdx.x == 0 && t < mv.M && (b.present_mask >> t & 1)) cx.adam_t[t] += 1;
     }
   }
