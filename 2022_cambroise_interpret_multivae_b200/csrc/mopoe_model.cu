@@ -281,30 +281,116 @@ struct LatSh {
   int NP;   // decoder passes held per modality in zz / dzz / rps (2 in the CUDA-core tile; 1 or 2 in the tensor-core tile)
 };
 
+// posterior of subset s at one (row, latent) element, from per-modality precisions T_m = 1 / (exp(lv_m) + eps)
+// and mu_m T_m held in registers (every index is a compile-time constant after unrolling: no local memory).
+// poe_fusion + poe: mm_div.py:13-20, BaseMMVae.py:109-122; moe_fusion: BaseMMVae.py:96-106, utils.py:63-85.
+struct SubPost { float mu, lv, var, inv; int sel_m; };   // var = exp(lv); inv = 1 / sum T (PoE); sel_m: chosen member (MoE)
+
+template <int S_>
+__device__ __forceinline__ SubPost sub_post(const ModelView& mv, const mopoe_batch_desc& b, int n, const float* mu_e,
+                                            const float* lv_e, const float* ex, const float* T, const float* muT) {
+  SubPost r;
+  const int mask = mv.sub.mask[S_], nm = mv.sub.n_members[S_];
+  r.sel_m = 0;
+  if (mv.method == MOPOE_METHOD_MOE) {
+    int sel = 0;
+    for (int i = 0; i < nm; ++i)
+      if (n >= b.moe_bounds[nm][i] && n < b.moe_bounds[nm][i + 1]) sel = i;
+    int mem = 0;
+#pragma unroll
+    for (int i = 0; i < MOPOE_MAX_MODS; ++i)
+      if (i == sel) mem = mv.sub.members[S_][i];
+    r.mu = 0.f; r.lv = 0.f; r.var = 1.f;
+#pragma unroll
+    for (int m = 0; m < MOPOE_MAX_MODS; ++m)
+      if (m == mem) { r.mu = mu_e[m]; r.lv = lv_e[m]; r.var = ex[m]; }
+    r.sel_m = mem; r.inv = 1.f;
+  } else {
+    float sT = 0.f, sMT = 0.f;
+#pragma unroll
+    for (int m = 0; m < MOPOE_MAX_MODS; ++m)
+      if (mask >> m & 1) { sT += T[m]; sMT += muT[m]; }
+    if (mv.method == MOPOE_METHOD_POE || nm == mv.M) sT += 1.f / (1.f + MOPOE_POE_EPS);   // prior expert N(0, I)
+    r.inv = 1.f / sT;
+    r.mu = sMT * r.inv;
+    r.var = r.inv;
+    r.lv = logf(r.inv);
+  }
+  return r;
+}
+
+// forward of one subset (S_ compile-time): KL sum, outputs, singleton / joint selection
+template <int S_>
+__device__ __forceinline__ void lat_fwd_subset(const ModelView& mv, const StepCtx& cx, const mopoe_batch_desc& b, int n, int N,
+                                               int l, bool valid, int present, int owner, int& kidx, const float* mu_e,
+                                               const float* lv_e, const float* ex, const float* T, const float* muT, float* kl_acc,
+                                               float* smu, float* slv, float& jmu, float& jlv) {
+  if (S_ >= mv.sub.n_subsets) return;
+  const int mask = mv.sub.mask[S_];
+  if ((mask & present) != mask) return;
+  const SubPost ev = sub_post<S_>(mv, b, n, mu_e, lv_e, ex, T, muT);
+  if (valid) {
+    if (cx.out.subset_mu) cx.out.subset_mu[((int64_t)S_ * N + n) * mv.L + l] = ev.mu;
+    if (cx.out.subset_logvar) cx.out.subset_logvar[((int64_t)S_ * N + n) * mv.L + l] = ev.lv;
+    kl_acc[S_] += -0.5f * (1.f - ev.var - ev.mu * ev.mu + ev.lv);
+  }
+  if (mv.sub.n_members[S_] == 1) {
+#pragma unroll
+    for (int m = 0; m < MOPOE_MAX_MODS; ++m)
+      if (mask == (1 << m)) { smu[m] = ev.mu; slv[m] = ev.lv; }
+  }
+  if (in_mixture(mv, b, S_)) {
+    if (cx.use_expert < 0) {
+      if (cx.sample_latents) { if (kidx == owner) { jmu = ev.mu; jlv = ev.lv; } }
+      else { jmu += ev.mu; jlv += ev.lv; }
+    }
+    ++kidx;
+  }
+  if (cx.use_expert == S_) { jmu = ev.mu; jlv = ev.lv; }
+}
+
+template <int S_>
+struct LatFwdLoop {
+  template <class... A>
+  static __device__ __forceinline__ void run(A&&... a) {
+    LatFwdLoop<S_ - 1>::run(a...);
+    lat_fwd_subset<S_>(a...);
+  }
+};
+template <>
+struct LatFwdLoop<-1> {
+  template <class... A>
+  static __device__ __forceinline__ void run(A&&...) {}
+};
+
 __device__ void lat_forward(const ModelView& mv, const StepCtx& cx, const mopoe_batch_desc& b, int64_t eps_base,
                             int r0, int nr, const LatSh& sh) {
   const int t = threadIdx.x;
   const int N = b.n_rows, L = mv.L, M = mv.M, present = b.present_mask;
   const bool uni = cx.uni_pass != 0;
-  // ---- latent element-wise forward: thread per (row, latent dim) ----
-  const int nsub = mv.sub.n_subsets;
-  const float wmix = 1.f / (float)b.n_mix;  // uniform mixture weights (BaseMMVae.py:225, :64-78)
+  // ---- latent element-wise forward: thread per (row, latent dim); the scalar sums are kept in registers over the
+  // thread's items and reduced once (one shuffle tree + one shared atomic per scalar) ----
+  float kl_acc[MOPOE_MAX_SUBSETS], mh_acc[2 * MOPOE_MAX_MODS];
+#pragma unroll
+  for (int s = 0; s < MOPOE_MAX_SUBSETS; ++s) kl_acc[s] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2 * MOPOE_MAX_MODS; ++i) mh_acc[i] = 0.f;
   for (int base = 0; base < sh.R * L; base += MOPOE_THREADS) {
     const int idx = base + t;
     const int r = idx / L, l = idx % L;
     const bool valid = idx < sh.R * L && r < nr;
     const int n = r0 + r;
-    float mu_e[MOPOE_MAX_MODS], lv_e[MOPOE_MAX_MODS];
+    float mu_e[MOPOE_MAX_MODS], lv_e[MOPOE_MAX_MODS], ex[MOPOE_MAX_MODS], T[MOPOE_MAX_MODS], muT[MOPOE_MAX_MODS];
 #pragma unroll
     for (int m = 0; m < MOPOE_MAX_MODS; ++m) {
       const bool on = valid && m < M && (present >> m & 1);
       mu_e[m] = on ? sh.e[(m * sh.R + r) * sh.HCM + l] : 0.f;
       lv_e[m] = on ? sh.e[(m * sh.R + r) * sh.HCM + L + l] : 0.f;
-    }
-    for (int m = 0; m < M; ++m) {
-      if (!(present >> m & 1)) continue;
-      block_add(sh.red, MOPOE_S_MEAN_HEAD + 4 * m + 0, valid ? mu_e[m] : 0.f);
-      block_add(sh.red, MOPOE_S_MEAN_HEAD + 4 * m + 1, valid ? lv_e[m] : 0.f);
+      ex[m] = expf(lv_e[m]);
+      T[m] = 1.f / (ex[m] + MOPOE_POE_EPS);
+      muT[m] = mu_e[m] * T[m];
+      mh_acc[2 * m] += mu_e[m];
+      mh_acc[2 * m + 1] += lv_e[m];
     }
     float jmu = 0.f, jlv = 0.f;
     float smu[MOPOE_MAX_MODS], slv[MOPOE_MAX_MODS];  // singleton posteriors (poe unimodal passes)
@@ -313,25 +399,7 @@ __device__ void lat_forward(const ModelView& mv, const StepCtx& cx, const mopoe_
     int kidx = 0, owner = 0;
     for (int k = 0; k < b.n_mix; ++k)
       if (n >= b.joint_bounds[k] && n < b.joint_bounds[k + 1]) owner = k;
-    for (int s = 0; s < nsub; ++s) {
-      if ((mv.sub.mask[s] & present) != mv.sub.mask[s]) continue;
-      const SubsetEval ev = eval_subset(mv, b, s, n, mu_e, lv_e);
-      if (valid) {
-        if (cx.out.subset_mu) cx.out.subset_mu[((int64_t)s * N + n) * L + l] = ev.mu;
-        if (cx.out.subset_logvar) cx.out.subset_logvar[((int64_t)s * N + n) * L + l] = ev.lv;
-      }
-      const float kl = valid ? -0.5f * (1.f - expf(ev.lv) - ev.mu * ev.mu + ev.lv) : 0.f;
-      block_add(sh.red, MOPOE_S_KLD_SUBSET + s, kl);
-      if (mv.sub.n_members[s] == 1) { smu[mv.sub.members[s][0]] = ev.mu; slv[mv.sub.members[s][0]] = ev.lv; }
-      if (in_mixture(mv, b, s)) {
-        if (cx.use_expert < 0) {
-          if (cx.sample_latents) { if (kidx == owner) { jmu = ev.mu; jlv = ev.lv; } }
-          else { jmu += ev.mu; jlv += ev.lv; }
-        }
-        ++kidx;
-      }
-      if (cx.use_expert == s) { jmu = ev.mu; jlv = ev.lv; }
-    }
+    LatFwdLoop<MOPOE_MAX_SUBSETS - 1>::run(mv, cx, b, n, N, l, valid, present, owner, kidx, mu_e, lv_e, ex, T, muT, kl_acc, smu, slv, jmu, jlv);
     if (cx.use_expert < 0 && !cx.sample_latents) { jmu /= (float)b.n_mix; jlv /= (float)b.n_mix; }
     if (valid) {
       float z = jmu, rp = 0.f;
@@ -348,8 +416,9 @@ __device__ void lat_forward(const ModelView& mv, const StepCtx& cx, const mopoe_
       if (cx.out.joint_logvar) cx.out.joint_logvar[(int64_t)n * L + l] = jlv;
       if (cx.out.z) cx.out.z[(int64_t)n * L + l] = z;
       if (uni) {
-        for (int m = 0; m < M; ++m) {
-          if (!(present >> m & 1)) continue;
+#pragma unroll
+        for (int m = 0; m < MOPOE_MAX_MODS; ++m) {
+          if (m >= M || !(present >> m & 1)) continue;
           const float e1 = cx.noise.at(eps_base + (1 + m) * cx.eps_pass_stride + (int64_t)n * mv.E + l);
           const float sd = expf(0.5f * slv[m]);
           sh.zz[((m * sh.NP + 1) * sh.R + r) * sh.ZDM + mv.mod[m].S + l] = e1 * sd + smu[m];
@@ -358,22 +427,32 @@ __device__ void lat_forward(const ModelView& mv, const StepCtx& cx, const mopoe_
       }
     }
   }
+#pragma unroll
+  for (int m = 0; m < MOPOE_MAX_MODS; ++m)
+    if (m < M && (present >> m & 1)) {
+      block_add(sh.red, MOPOE_S_MEAN_HEAD + 4 * m + 0, mh_acc[2 * m]);
+      block_add(sh.red, MOPOE_S_MEAN_HEAD + 4 * m + 1, mh_acc[2 * m + 1]);
+    }
+#pragma unroll
+  for (int s = 0; s < MOPOE_MAX_SUBSETS; ++s)
+    if (s < mv.sub.n_subsets && (mv.sub.mask[s] & present) == mv.sub.mask[s]) block_add(sh.red, MOPOE_S_KLD_SUBSET + s, kl_acc[s]);
   // ---- style element-wise forward ----
   for (int m = 0; m < M; ++m) {
     if (!(present >> m & 1)) continue;
     const ModView& md = mv.mod[m];
     const int S = md.S;
     if (S == 0) continue;
+    float a_kl = 0.f, a_mu = 0.f, a_lv = 0.f;
     for (int base = 0; base < sh.R * S; base += MOPOE_THREADS) {
       const int idx = base + t;
       const int r = idx / S, s = idx % S;
       const bool valid = idx < sh.R * S && r < nr;
       const int n = r0 + r;
-      float klv = 0.f, mu = 0.f, lv = 0.f;
       if (valid) {
-        mu = sh.e[(m * sh.R + r) * sh.HCM + 2 * L + s];
-        lv = sh.e[(m * sh.R + r) * sh.HCM + 2 * L + S + s];
-        klv = -0.5f * (1.f - expf(lv) - mu * mu + lv);
+        const float mu = sh.e[(m * sh.R + r) * sh.HCM + 2 * L + s];
+        const float lv = sh.e[(m * sh.R + r) * sh.HCM + 2 * L + S + s];
+        a_kl += -0.5f * (1.f - expf(lv) - mu * mu + lv);
+        a_mu += mu; a_lv += lv;
         const float sd = expf(0.5f * lv);
         float zs = mu, rp = 0.f;
         if (cx.sample_latents) {
@@ -389,12 +468,75 @@ __device__ void lat_forward(const ModelView& mv, const StepCtx& cx, const mopoe_
           sh.rps[((m * sh.NP + 1) * sh.R + r) * sh.SM_ + s] = 0.5f * e1 * sd;
         }
       }
-      block_add(sh.red, MOPOE_S_KLD_STYLE + m, klv);
-      block_add(sh.red, MOPOE_S_MEAN_HEAD + 4 * m + 2, mu);
-      block_add(sh.red, MOPOE_S_MEAN_HEAD + 4 * m + 3, lv);
     }
+    block_add(sh.red, MOPOE_S_KLD_STYLE + m, a_kl);
+    block_add(sh.red, MOPOE_S_MEAN_HEAD + 4 * m + 2, a_mu);
+    block_add(sh.red, MOPOE_S_MEAN_HEAD + 4 * m + 3, a_lv);
   }
 }
+
+// backward of one subset: upstream gradients of its posterior (mixture KL share, reparameterised z of the owner
+// rows, unimodal ELBO in poe mode) distributed to the experts (hand-derived)
+template <int S_>
+__device__ __forceinline__ void lat_bwd_subset(const ModelView& mv, const mopoe_batch_desc& b, const LatSh& sh, int n, int r, int l,
+                                               int present, bool uni, int owner, int& kidx, float gz, float ckl, float wmix,
+                                               const float* mu_e, const float* lv_e, const float* ex, const float* T, const float* muT,
+                                               float* dmu, float* dlv) {
+  if (S_ >= mv.sub.n_subsets) return;
+  const int mask = mv.sub.mask[S_];
+  if ((mask & present) != mask) return;
+  const SubPost ev = sub_post<S_>(mv, b, n, mu_e, lv_e, ex, T, muT);
+  const int nm = mv.sub.n_members[S_], L = mv.L;
+  float umu = 0.f, ulv = 0.f;
+  const float dkl_lv = 0.5f * (ev.var - 1.f);
+  if (in_mixture(mv, b, S_)) {
+    umu += ckl * wmix * ev.mu;
+    ulv += ckl * wmix * dkl_lv;
+    if (kidx == owner) { umu += gz; ulv += gz * sh.rp[r * L + l]; }
+    ++kidx;
+  }
+  if (mv.method == MOPOE_METHOD_POE && nm == 1) {  // unimodal ELBO of modality m (run_epochs.py:115-125)
+    umu += ckl * ev.mu;
+    ulv += ckl * dkl_lv;
+    if (uni) {
+#pragma unroll
+      for (int m = 0; m < MOPOE_MAX_MODS; ++m)
+        if (mask == (1 << m)) {
+          const float g1 = sh.dzz[((m * sh.NP + 1) * sh.R + r) * sh.ZDM + mv.mod[m].S + l];
+          umu += g1; ulv += g1 * sh.rp[((1 + m) * sh.R + r) * L + l];
+        }
+    }
+  }
+  if (umu == 0.f && ulv == 0.f) return;
+  if (mv.method == MOPOE_METHOD_MOE) {
+#pragma unroll
+    for (int m = 0; m < MOPOE_MAX_MODS; ++m)
+      if (m == ev.sel_m) { dmu[m] += umu; dlv[m] += ulv; }
+  } else {
+    const float invP = ev.inv;
+#pragma unroll
+    for (int m = 0; m < MOPOE_MAX_MODS; ++m)
+      if (mask >> m & 1) {
+        dmu[m] += umu * T[m] * invP;
+        const float dT = umu * (mu_e[m] - ev.mu) * invP - ulv * invP;
+        dlv[m] += dT * (-T[m] * T[m] * ex[m]);
+      }
+  }
+}
+
+template <int S_>
+struct LatBwdLoop {
+  template <class... A>
+  static __device__ __forceinline__ void run(A&&... a) {
+    LatBwdLoop<S_ - 1>::run(a...);
+    lat_bwd_subset<S_>(a...);
+  }
+};
+template <>
+struct LatBwdLoop<-1> {
+  template <class... A>
+  static __device__ __forceinline__ void run(A&&...) {}
+};
 
 __device__ void lat_backward(const ModelView& mv, const StepCtx& cx, const mopoe_batch_desc& b, int r0, int nr,
                              const LatSh& sh) {
@@ -402,7 +544,6 @@ __device__ void lat_backward(const ModelView& mv, const StepCtx& cx, const mopoe
   const int N = b.n_rows, L = mv.L, M = mv.M, present = b.present_mask;
   const bool uni = cx.uni_pass != 0;
   const float invN = 1.f / (float)N;
-  const int nsub = mv.sub.n_subsets;
   const float wmix = 1.f / (float)b.n_mix;
   // ---- latent element-wise backward ----
   const float ckl = mv.beta * mv.beta_content * invN;
@@ -411,59 +552,27 @@ __device__ void lat_backward(const ModelView& mv, const StepCtx& cx, const mopoe
     const int r = idx / L, l = idx % L;
     if (idx < sh.R * L && r < nr) {
       const int n = r0 + r;
-      float mu_e[MOPOE_MAX_MODS], lv_e[MOPOE_MAX_MODS], dmu[MOPOE_MAX_MODS], dlv[MOPOE_MAX_MODS];
+      float mu_e[MOPOE_MAX_MODS], lv_e[MOPOE_MAX_MODS], ex[MOPOE_MAX_MODS], T[MOPOE_MAX_MODS], muT[MOPOE_MAX_MODS];
+      float dmu[MOPOE_MAX_MODS], dlv[MOPOE_MAX_MODS];
+      float gz = 0.f;
 #pragma unroll
       for (int m = 0; m < MOPOE_MAX_MODS; ++m) {
         const bool on = m < M && (present >> m & 1);
         mu_e[m] = on ? sh.e[(m * sh.R + r) * sh.HCM + l] : 0.f;
         lv_e[m] = on ? sh.e[(m * sh.R + r) * sh.HCM + L + l] : 0.f;
+        ex[m] = expf(lv_e[m]);
+        T[m] = 1.f / (ex[m] + MOPOE_POE_EPS);
+        muT[m] = mu_e[m] * T[m];
         dmu[m] = dlv[m] = 0.f;
+        if (on) gz += sh.dzz[((m * sh.NP + 0) * sh.R + r) * sh.ZDM + mv.mod[m].S + l];
       }
-      float gz = 0.f;
-      for (int m = 0; m < M; ++m)
-        if (present >> m & 1) gz += sh.dzz[((m * sh.NP + 0) * sh.R + r) * sh.ZDM + mv.mod[m].S + l];
       int kidx = 0, owner = 0;
       for (int k = 0; k < b.n_mix; ++k)
         if (n >= b.joint_bounds[k] && n < b.joint_bounds[k + 1]) owner = k;
-      for (int s = 0; s < nsub; ++s) {
-        if ((mv.sub.mask[s] & present) != mv.sub.mask[s]) continue;
-        const SubsetEval ev = eval_subset(mv, b, s, n, mu_e, lv_e);
-        const int nm = mv.sub.n_members[s];
-        float umu = 0.f, ulv = 0.f;
-        const float dkl_lv = 0.5f * (expf(ev.lv) - 1.f);
-        if (in_mixture(mv, b, s)) {
-          umu += ckl * wmix * ev.mu;
-          ulv += ckl * wmix * dkl_lv;
-          if (kidx == owner) { umu += gz; ulv += gz * sh.rp[r * L + l]; }
-          ++kidx;
-        }
-        if (mv.method == MOPOE_METHOD_POE && nm == 1) {  // unimodal ELBO of modality m (run_epochs.py:115-125)
-          const int m = mv.sub.members[s][0];
-          umu += ckl * ev.mu;
-          ulv += ckl * dkl_lv;
-          if (uni) {
-            const float g1 = sh.dzz[((m * sh.NP + 1) * sh.R + r) * sh.ZDM + mv.mod[m].S + l];
-            umu += g1; ulv += g1 * sh.rp[((1 + m) * sh.R + r) * L + l];
-          }
-        }
-        if (umu == 0.f && ulv == 0.f) continue;
-        if (mv.method == MOPOE_METHOD_MOE) {
-          const int m = mv.sub.members[s][ev.sel];
-          dmu[m] += umu; dlv[m] += ulv;
-        } else {
-          const float invP = 1.f / ev.sumT;
-          for (int i = 0; i < nm; ++i) {
-            const int m = mv.sub.members[s][i];
-            const float ex = expf(lv_e[m]);
-            const float T = 1.f / (ex + MOPOE_POE_EPS);
-            dmu[m] += umu * T * invP;
-            const float dT = umu * (mu_e[m] - ev.mu) * invP - ulv * invP;
-            dlv[m] += dT * (-T * T * ex);
-          }
-        }
-      }
-      for (int m = 0; m < M; ++m)
-        if (present >> m & 1) {
+      LatBwdLoop<MOPOE_MAX_SUBSETS - 1>::run(mv, b, sh, n, r, l, present, uni, owner, kidx, gz, ckl, wmix, mu_e, lv_e, ex, T, muT, dmu, dlv);
+#pragma unroll
+      for (int m = 0; m < MOPOE_MAX_MODS; ++m)
+        if (m < M && (present >> m & 1)) {
           sh.de[(m * sh.R + r) * sh.HCM + l] = dmu[m];
           sh.de[(m * sh.R + r) * sh.HCM + L + l] = dlv[m];
         }
