@@ -282,24 +282,22 @@ struct LatSh {
 };
 
 // posterior of subset s at one (row, latent) element, from per-modality precisions T_m = 1 / (exp(lv_m) + eps)
-// and mu_m T_m held in registers (every index is a compile-time constant after unrolling: no local memory).
+// and mu_m T_m held in registers.  The subset loop is a RUNTIME loop (compact code: an unrolled 15-subset
+// version was 7 500 instructions and ran out of the instruction cache); only the modality loops are unrolled, so
+// every register array is indexed by compile-time constants and predicated on the subset's member mask.
 // poe_fusion + poe: mm_div.py:13-20, BaseMMVae.py:109-122; moe_fusion: BaseMMVae.py:96-106, utils.py:63-85.
 struct SubPost { float mu, lv, var, inv; int sel_m; };   // var = exp(lv); inv = 1 / sum T (PoE); sel_m: chosen member (MoE)
 
-template <int S_>
-__device__ __forceinline__ SubPost sub_post(const ModelView& mv, const mopoe_batch_desc& b, int n, const float* mu_e,
+__device__ __forceinline__ SubPost sub_post(const ModelView& mv, const mopoe_batch_desc& b, int s, int n, const float* mu_e,
                                             const float* lv_e, const float* ex, const float* T, const float* muT) {
   SubPost r;
-  const int mask = mv.sub.mask[S_], nm = mv.sub.n_members[S_];
+  const int mask = mv.sub.mask[s], nm = mv.sub.n_members[s];
   r.sel_m = 0;
   if (mv.method == MOPOE_METHOD_MOE) {
     int sel = 0;
     for (int i = 0; i < nm; ++i)
       if (n >= b.moe_bounds[nm][i] && n < b.moe_bounds[nm][i + 1]) sel = i;
-    int mem = 0;
-#pragma unroll
-    for (int i = 0; i < MOPOE_MAX_MODS; ++i)
-      if (i == sel) mem = mv.sub.members[S_][i];
+    const int mem = mv.sub.members[s][sel];
     r.mu = 0.f; r.lv = 0.f; r.var = 1.f;
 #pragma unroll
     for (int m = 0; m < MOPOE_MAX_MODS; ++m)
@@ -319,60 +317,24 @@ __device__ __forceinline__ SubPost sub_post(const ModelView& mv, const mopoe_bat
   return r;
 }
 
-// forward of one subset (S_ compile-time): KL sum, outputs, singleton / joint selection
-template <int S_>
-__device__ __forceinline__ void lat_fwd_subset(const ModelView& mv, const StepCtx& cx, const mopoe_batch_desc& b, int n, int N,
-                                               int l, bool valid, int present, int owner, int& kidx, const float* mu_e,
-                                               const float* lv_e, const float* ex, const float* T, const float* muT, float* kl_acc,
-                                               float* smu, float* slv, float& jmu, float& jlv) {
-  if (S_ >= mv.sub.n_subsets) return;
-  const int mask = mv.sub.mask[S_];
-  if ((mask & present) != mask) return;
-  const SubPost ev = sub_post<S_>(mv, b, n, mu_e, lv_e, ex, T, muT);
-  if (valid) {
-    if (cx.out.subset_mu) cx.out.subset_mu[((int64_t)S_ * N + n) * mv.L + l] = ev.mu;
-    if (cx.out.subset_logvar) cx.out.subset_logvar[((int64_t)S_ * N + n) * mv.L + l] = ev.lv;
-    kl_acc[S_] += -0.5f * (1.f - ev.var - ev.mu * ev.mu + ev.lv);
-  }
-  if (mv.sub.n_members[S_] == 1) {
-#pragma unroll
-    for (int m = 0; m < MOPOE_MAX_MODS; ++m)
-      if (mask == (1 << m)) { smu[m] = ev.mu; slv[m] = ev.lv; }
-  }
-  if (in_mixture(mv, b, S_)) {
-    if (cx.use_expert < 0) {
-      if (cx.sample_latents) { if (kidx == owner) { jmu = ev.mu; jlv = ev.lv; } }
-      else { jmu += ev.mu; jlv += ev.lv; }
-    }
-    ++kidx;
-  }
-  if (cx.use_expert == S_) { jmu = ev.mu; jlv = ev.lv; }
-}
-
-template <int S_>
-struct LatFwdLoop {
-  template <class... A>
-  static __device__ __forceinline__ void run(A&&... a) {
-    LatFwdLoop<S_ - 1>::run(a...);
-    lat_fwd_subset<S_>(a...);
-  }
-};
-template <>
-struct LatFwdLoop<-1> {
-  template <class... A>
-  static __device__ __forceinline__ void run(A&&...) {}
-};
+#ifdef TC_PROF
+__device__ float g_latprof[16];
+#define LTP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long _n = clock64(); g_latprof[i] += (float)(_n - _lt); _lt = _n; } } while (0)
+#else
+#define LTP(i) do { } while (0)
+#endif
 
 __device__ void lat_forward(const ModelView& mv, const StepCtx& cx, const mopoe_batch_desc& b, int64_t eps_base,
                             int r0, int nr, const LatSh& sh) {
   const int t = threadIdx.x;
+#ifdef TC_PROF
+  long long _lt = clock64();
+#endif
   const int N = b.n_rows, L = mv.L, M = mv.M, present = b.present_mask;
   const bool uni = cx.uni_pass != 0;
   // ---- latent element-wise forward: thread per (row, latent dim); the scalar sums are kept in registers over the
   // thread's items and reduced once (one shuffle tree + one shared atomic per scalar) ----
-  float kl_acc[MOPOE_MAX_SUBSETS], mh_acc[2 * MOPOE_MAX_MODS];
-#pragma unroll
-  for (int s = 0; s < MOPOE_MAX_SUBSETS; ++s) kl_acc[s] = 0.f;
+  float mh_acc[2 * MOPOE_MAX_MODS];
 #pragma unroll
   for (int i = 0; i < 2 * MOPOE_MAX_MODS; ++i) mh_acc[i] = 0.f;
   for (int base = 0; base < sh.R * L; base += MOPOE_THREADS) {
@@ -392,6 +354,7 @@ __device__ void lat_forward(const ModelView& mv, const StepCtx& cx, const mopoe_
       mh_acc[2 * m] += mu_e[m];
       mh_acc[2 * m + 1] += lv_e[m];
     }
+    LTP(0);
     float jmu = 0.f, jlv = 0.f;
     float smu[MOPOE_MAX_MODS], slv[MOPOE_MAX_MODS];  // singleton posteriors (poe unimodal passes)
 #pragma unroll
@@ -399,7 +362,33 @@ __device__ void lat_forward(const ModelView& mv, const StepCtx& cx, const mopoe_
     int kidx = 0, owner = 0;
     for (int k = 0; k < b.n_mix; ++k)
       if (n >= b.joint_bounds[k] && n < b.joint_bounds[k + 1]) owner = k;
-    LatFwdLoop<MOPOE_MAX_SUBSETS - 1>::run(mv, cx, b, n, N, l, valid, present, owner, kidx, mu_e, lv_e, ex, T, muT, kl_acc, smu, slv, jmu, jlv);
+    LTP(1);
+#pragma unroll 1
+    for (int s = 0; s < mv.sub.n_subsets; ++s) {
+      const int mask = mv.sub.mask[s];
+      if ((mask & present) != mask) continue;
+      const SubPost ev = sub_post(mv, b, s, n, mu_e, lv_e, ex, T, muT);
+      if (valid) {
+        if (cx.out.subset_mu) cx.out.subset_mu[((int64_t)s * N + n) * L + l] = ev.mu;
+        if (cx.out.subset_logvar) cx.out.subset_logvar[((int64_t)s * N + n) * L + l] = ev.lv;
+      }
+      // KL of the subset posterior, summed over the CTA's items: one shuffle tree + one shared atomic per warp
+      block_add(sh.red, MOPOE_S_KLD_SUBSET + s, valid ? -0.5f * (1.f - ev.var - ev.mu * ev.mu + ev.lv) : 0.f);
+      if (mv.sub.n_members[s] == 1) {
+#pragma unroll
+        for (int m = 0; m < MOPOE_MAX_MODS; ++m)
+          if (mask == (1 << m)) { smu[m] = ev.mu; slv[m] = ev.lv; }
+      }
+      if (in_mixture(mv, b, s)) {
+        if (cx.use_expert < 0) {
+          if (cx.sample_latents) { if (kidx == owner) { jmu = ev.mu; jlv = ev.lv; } }
+          else { jmu += ev.mu; jlv += ev.lv; }
+        }
+        ++kidx;
+      }
+      if (cx.use_expert == s) { jmu = ev.mu; jlv = ev.lv; }
+    }
+    LTP(2);
     if (cx.use_expert < 0 && !cx.sample_latents) { jmu /= (float)b.n_mix; jlv /= (float)b.n_mix; }
     if (valid) {
       float z = jmu, rp = 0.f;
@@ -426,6 +415,7 @@ __device__ void lat_forward(const ModelView& mv, const StepCtx& cx, const mopoe_
         }
       }
     }
+    LTP(3);
   }
 #pragma unroll
   for (int m = 0; m < MOPOE_MAX_MODS; ++m)
@@ -433,9 +423,7 @@ __device__ void lat_forward(const ModelView& mv, const StepCtx& cx, const mopoe_
       block_add(sh.red, MOPOE_S_MEAN_HEAD + 4 * m + 0, mh_acc[2 * m]);
       block_add(sh.red, MOPOE_S_MEAN_HEAD + 4 * m + 1, mh_acc[2 * m + 1]);
     }
-#pragma unroll
-  for (int s = 0; s < MOPOE_MAX_SUBSETS; ++s)
-    if (s < mv.sub.n_subsets && (mv.sub.mask[s] & present) == mv.sub.mask[s]) block_add(sh.red, MOPOE_S_KLD_SUBSET + s, kl_acc[s]);
+  LTP(4);
   // ---- style element-wise forward ----
   for (int m = 0; m < M; ++m) {
     if (!(present >> m & 1)) continue;
@@ -469,74 +457,13 @@ __device__ void lat_forward(const ModelView& mv, const StepCtx& cx, const mopoe_
         }
       }
     }
+    LTP(5);
     block_add(sh.red, MOPOE_S_KLD_STYLE + m, a_kl);
     block_add(sh.red, MOPOE_S_MEAN_HEAD + 4 * m + 2, a_mu);
     block_add(sh.red, MOPOE_S_MEAN_HEAD + 4 * m + 3, a_lv);
+    LTP(6);
   }
 }
-
-// backward of one subset: upstream gradients of its posterior (mixture KL share, reparameterised z of the owner
-// rows, unimodal ELBO in poe mode) distributed to the experts (hand-derived)
-template <int S_>
-__device__ __forceinline__ void lat_bwd_subset(const ModelView& mv, const mopoe_batch_desc& b, const LatSh& sh, int n, int r, int l,
-                                               int present, bool uni, int owner, int& kidx, float gz, float ckl, float wmix,
-                                               const float* mu_e, const float* lv_e, const float* ex, const float* T, const float* muT,
-                                               float* dmu, float* dlv) {
-  if (S_ >= mv.sub.n_subsets) return;
-  const int mask = mv.sub.mask[S_];
-  if ((mask & present) != mask) return;
-  const SubPost ev = sub_post<S_>(mv, b, n, mu_e, lv_e, ex, T, muT);
-  const int nm = mv.sub.n_members[S_], L = mv.L;
-  float umu = 0.f, ulv = 0.f;
-  const float dkl_lv = 0.5f * (ev.var - 1.f);
-  if (in_mixture(mv, b, S_)) {
-    umu += ckl * wmix * ev.mu;
-    ulv += ckl * wmix * dkl_lv;
-    if (kidx == owner) { umu += gz; ulv += gz * sh.rp[r * L + l]; }
-    ++kidx;
-  }
-  if (mv.method == MOPOE_METHOD_POE && nm == 1) {  // unimodal ELBO of modality m (run_epochs.py:115-125)
-    umu += ckl * ev.mu;
-    ulv += ckl * dkl_lv;
-    if (uni) {
-#pragma unroll
-      for (int m = 0; m < MOPOE_MAX_MODS; ++m)
-        if (mask == (1 << m)) {
-          const float g1 = sh.dzz[((m * sh.NP + 1) * sh.R + r) * sh.ZDM + mv.mod[m].S + l];
-          umu += g1; ulv += g1 * sh.rp[((1 + m) * sh.R + r) * L + l];
-        }
-    }
-  }
-  if (umu == 0.f && ulv == 0.f) return;
-  if (mv.method == MOPOE_METHOD_MOE) {
-#pragma unroll
-    for (int m = 0; m < MOPOE_MAX_MODS; ++m)
-      if (m == ev.sel_m) { dmu[m] += umu; dlv[m] += ulv; }
-  } else {
-    const float invP = ev.inv;
-#pragma unroll
-    for (int m = 0; m < MOPOE_MAX_MODS; ++m)
-      if (mask >> m & 1) {
-        dmu[m] += umu * T[m] * invP;
-        const float dT = umu * (mu_e[m] - ev.mu) * invP - ulv * invP;
-        dlv[m] += dT * (-T[m] * T[m] * ex[m]);
-      }
-  }
-}
-
-template <int S_>
-struct LatBwdLoop {
-  template <class... A>
-  static __device__ __forceinline__ void run(A&&... a) {
-    LatBwdLoop<S_ - 1>::run(a...);
-    lat_bwd_subset<S_>(a...);
-  }
-};
-template <>
-struct LatBwdLoop<-1> {
-  template <class... A>
-  static __device__ __forceinline__ void run(A&&...) {}
-};
 
 __device__ void lat_backward(const ModelView& mv, const StepCtx& cx, const mopoe_batch_desc& b, int r0, int nr,
                              const LatSh& sh) {
@@ -569,7 +496,47 @@ __device__ void lat_backward(const ModelView& mv, const StepCtx& cx, const mopoe
       int kidx = 0, owner = 0;
       for (int k = 0; k < b.n_mix; ++k)
         if (n >= b.joint_bounds[k] && n < b.joint_bounds[k + 1]) owner = k;
-      LatBwdLoop<MOPOE_MAX_SUBSETS - 1>::run(mv, b, sh, n, r, l, present, uni, owner, kidx, gz, ckl, wmix, mu_e, lv_e, ex, T, muT, dmu, dlv);
+      // upstream gradients of each subset posterior (mixture KL share, reparameterised z of the owner rows,
+      // unimodal ELBO in poe mode) distributed to the experts (hand-derived)
+#pragma unroll 1
+      for (int s = 0; s < mv.sub.n_subsets; ++s) {
+        const int mask = mv.sub.mask[s];
+        if ((mask & present) != mask) continue;
+        const SubPost ev = sub_post(mv, b, s, n, mu_e, lv_e, ex, T, muT);
+        const int nm = mv.sub.n_members[s];
+        float umu = 0.f, ulv = 0.f;
+        const float dkl_lv = 0.5f * (ev.var - 1.f);
+        if (in_mixture(mv, b, s)) {
+          umu += ckl * wmix * ev.mu;
+          ulv += ckl * wmix * dkl_lv;
+          if (kidx == owner) { umu += gz; ulv += gz * sh.rp[r * L + l]; }
+          ++kidx;
+        }
+        if (mv.method == MOPOE_METHOD_POE && nm == 1) {  // unimodal ELBO of modality m (run_epochs.py:115-125)
+          umu += ckl * ev.mu;
+          ulv += ckl * dkl_lv;
+          if (uni) {
+            const int m = mv.sub.members[s][0];
+            const float g1 = sh.dzz[((m * sh.NP + 1) * sh.R + r) * sh.ZDM + mv.mod[m].S + l];
+            umu += g1; ulv += g1 * sh.rp[((1 + m) * sh.R + r) * L + l];
+          }
+        }
+        if (umu == 0.f && ulv == 0.f) continue;
+        if (mv.method == MOPOE_METHOD_MOE) {
+#pragma unroll
+          for (int m = 0; m < MOPOE_MAX_MODS; ++m)
+            if (m == ev.sel_m) { dmu[m] += umu; dlv[m] += ulv; }
+        } else {
+          const float invP = ev.inv;
+#pragma unroll
+          for (int m = 0; m < MOPOE_MAX_MODS; ++m)
+            if (mask >> m & 1) {
+              dmu[m] += umu * T[m] * invP;
+              const float dT = umu * (mu_e[m] - ev.mu) * invP - ulv * invP;
+              dlv[m] += dT * (-T[m] * T[m] * ex[m]);
+            }
+        }
+      }
 #pragma unroll
       for (int m = 0; m < MOPOE_MAX_MODS; ++m)
         if (m < M && (present >> m & 1)) {
@@ -1220,6 +1187,9 @@ int mopoe_debug_tcprof(float* out64_host) {
   if (!g_tc_prof) { set_error("no tensor-core launch yet"); return MOPOE_EINVAL; }
   MOPOE_CUDA(cudaMemcpy(out64_host, g_tc_prof, 64 * sizeof(float), cudaMemcpyDeviceToHost));
   MOPOE_CUDA(cudaMemset(g_tc_prof, 0, 64 * sizeof(float)));
+  MOPOE_CUDA(cudaMemcpyFromSymbol(out64_host + 40, g_latprof, 16 * sizeof(float)));
+  float z16[16] = {0};
+  MOPOE_CUDA(cudaMemcpyToSymbol(g_latprof, z16, sizeof(z16)));
   return MOPOE_OK;
 }
 #endif

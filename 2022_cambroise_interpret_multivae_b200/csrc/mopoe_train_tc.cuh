@@ -35,16 +35,18 @@ using namespace umma;
 // -DTC_PROF: CTA 0 / thread 0 accumulates cycle counts per stage into the 64 floats behind the error flag
 // (read back with mopoe_debug_tcprof); no effect on results
 #ifdef TC_PROF
+#define TCW(i, stmt) do { const long long _w0 = clock64(); stmt; if (blockIdx.x == 0) (reinterpret_cast<float*>(pl.base + pl.err) + 64)[i] += (float)(clock64() - _w0); } while (0)
 #define TCP_DECL long long _tp = clock64()
 #define TCP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long _n = clock64(); prof[i] += (float)(_n - _tp); _tp = _n; } } while (0)
 #else
+#define TCW(i, stmt) stmt
 #define TCP_DECL do { } while (0)
 #define TCP(i) do { } while (0)
 #endif
 
 constexpr int THREADS = 320;       // warps 0-7 compute, warp 8 loader, warp 9 MMA issuer
 constexpr int CHUNK = 16384;       // one streamed weight chunk: 128 rows x 32 K x {hi, lo} fp16
-constexpr int MAX_SLOTS = 8;
+constexpr int MAX_SLOTS = 10;
 constexpr int MAX_UNITS = 96;
 
 struct TcMod {
@@ -95,7 +97,7 @@ static bool make_plan(const mopoe_model_desc* d, int64_t max_rows, int smem_limi
     if (cand == 32 && max_rows <= 2048) continue;   // small batches: more, smaller tiles (each tile re-streams the weights at the per-SM rate)
     int off = 0;
     auto take = [&](int n) { int o = off; off += (n + 127) & ~127; return o; };
-    p.s_bar = take(512);
+    p.s_bar = take(640);
     p.s_red = take(MOPOE_N_SCALARS * 4);
     p.s_srow = take(M * cand * 8);
     p.s_mask = take(M * 256 * 4);
@@ -251,16 +253,49 @@ __device__ void prep_blob(unsigned char* blob, const float* src, int mrows, int 
   }
 }
 
-__device__ void tc_prep(const ModelView& mv, const TcPlan& pl) {
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gth = gridDim.x * blockDim.x;
-  for (int m = 0; m < mv.M; ++m) {
-    const ModView& md = mv.mod[m];
-    const TcMod& t = pl.mod[m];
-    prep_blob(pl.base + t.w1, md.w1, MOPOE_HIDDEN, md.D, md.D, 1, 2, t.NCx, gtid, gth);
-    prep_blob(pl.base + t.wh, md.wh, md.HC, MOPOE_HIDDEN, MOPOE_HIDDEN, 1, 1, 8, gtid, gth);
-    prep_blob(pl.base + t.wht, md.wh, MOPOE_HIDDEN, md.HC, 1, MOPOE_HIDDEN, 2, t.NCh, gtid, gth);
-    prep_blob(pl.base + t.wd, md.wd, md.D, md.ZD, md.ZD, 1, t.MtD, t.NCz, gtid, gth);
-    prep_blob(pl.base + t.wdt, md.wd, md.ZD, md.D, 1, md.ZD, 1, t.NCx, gtid, gth);
+// all weight blobs of the model as ONE index space of 16-byte groups (a thread converts one or two groups per step,
+// all its loads independent); the blob table is built in shared memory by the first threads of the CTA
+struct PrepBlob { unsigned char* blob; const float* src; int mrows, kcols, ld_r, ld_c, NC, first; };
+
+__device__ void tc_prep(const ModelView& mv, const TcPlan& pl, PrepBlob* tab) {
+  const int t = threadIdx.x;
+  if (t == 0) {
+    int first = 0, nb = 0;
+    for (int m = 0; m < mv.M; ++m) {
+      const ModView& md = mv.mod[m];
+      const TcMod& tm = pl.mod[m];
+      auto add = [&](int64_t off, const float* src, int mrows, int kcols, int ld_r, int ld_c, int Mt, int NC) {
+        tab[nb].blob = pl.base + off; tab[nb].src = src; tab[nb].mrows = mrows; tab[nb].kcols = kcols;
+        tab[nb].ld_r = ld_r; tab[nb].ld_c = ld_c; tab[nb].NC = NC; tab[nb].first = first;
+        first += Mt * NC * 512; ++nb;
+      };
+      add(tm.w1, md.w1, MOPOE_HIDDEN, md.D, md.D, 1, 2, tm.NCx);
+      add(tm.wh, md.wh, md.HC, MOPOE_HIDDEN, MOPOE_HIDDEN, 1, 1, 8);
+      add(tm.wht, md.wh, MOPOE_HIDDEN, md.HC, 1, MOPOE_HIDDEN, 2, tm.NCh);
+      add(tm.wd, md.wd, md.D, md.ZD, md.ZD, 1, tm.MtD, tm.NCz);
+      add(tm.wdt, md.wd, md.ZD, md.D, 1, md.ZD, 1, tm.NCx);
+    }
+    tab[nb].first = first;   // sentinel: total number of groups
+    tab[nb].blob = nullptr;
+  }
+  __syncthreads();
+  const int nb = 5 * mv.M, total = tab[nb].first;
+  for (int g0 = blockIdx.x * blockDim.x + t; g0 < total; g0 += gridDim.x * blockDim.x) {
+    int bi = 0;
+    for (int k = 1; k < nb; ++k) if (g0 >= tab[k].first) bi = k;
+    const PrepBlob& pb = tab[bi];
+    const int g = g0 - pb.first;
+    const int rr = g & 127, plane = (g >> 7) & 3, ch = g >> 9;
+    const int tt = ch / pb.NC, cc = ch - tt * pb.NC;
+    const int r = tt * 128 + rr, c0 = cc * 32 + plane * 8;
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = (r < pb.mrows && c0 + i < pb.kcols) ? pb.src[(int64_t)r * pb.ld_r + (int64_t)(c0 + i) * pb.ld_c] : 0.f;
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    unsigned char* dst = pb.blob + (int64_t)ch * CHUNK + plane * 2048 + (rr >> 3) * 128 + (rr & 7) * 16;
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + 8192) = lo;
   }
   fence_async_all();
 }
@@ -273,7 +308,7 @@ struct Ring {
 
 // loader: one 16 KB weight chunk into the next ring slot
 __device__ __forceinline__ void load_chunk(Ring& rg, const TcPlan& pl, Bars* bars, unsigned char* ring, const unsigned char* src, int* gerr) {
-  tc_wait(&bars->ring_empty[rg.slot], rg.phase ^ 1, bars, gerr);
+  TCW(30, tc_wait(&bars->ring_empty[rg.slot], rg.phase ^ 1, bars, gerr));
   mbar_expect_tx(&bars->ring_full[rg.slot], CHUNK);
   bulk_g2s(ring + rg.slot * CHUNK, src, CHUNK, &bars->ring_full[rg.slot]);
   rg.next(pl.nslot);
@@ -284,7 +319,7 @@ __device__ __forceinline__ void load_chunk(Ring& rg, const TcPlan& pl, Bars* bar
 __device__ __forceinline__ void mma_chunk(Ring& rg, const TcPlan& pl, Bars* bars, unsigned char* ring, int* gerr, uint32_t tmem_d,
                                           uint32_t b_addr, uint32_t b_lo, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep,
                                           uint32_t id, int ksteps, uint32_t& accum) {
-  tc_wait(&bars->ring_full[rg.slot], rg.phase, bars, gerr);
+  TCW(31, tc_wait(&bars->ring_full[rg.slot], rg.phase, bars, gerr));
   tc_fence_after();
   const uint32_t a = smem_u32(ring + rg.slot * CHUNK);
   for (int ks = 0; ks < ksteps; ++ks) {
@@ -365,7 +400,7 @@ __device__ void tile_mma(const TileCtx& c, Ring& rg, Sync& sy, uint32_t tmem) {
     uint32_t a0 = 0, a1 = 0;
     for (int xi = 0; 4 * xi < t.NCx; ++xi) {
       const int xb = sy.nx & 1;
-      tc_wait(&bars->xfull[xb], (sy.nx >> 1) & 1, bars, c.gerr);
+      TCW(32, tc_wait(&bars->xfull[xb], (sy.nx >> 1) & 1, bars, c.gerr));
       tc_fence_after();
       for (int c4 = 0; c4 < 4 && 4 * xi + c4 < t.NCx; ++c4) {
         const int ks = ksteps_of(t.Dk16, 4 * xi + c4);
@@ -377,7 +412,7 @@ __device__ void tile_mma(const TileCtx& c, Ring& rg, Sync& sy, uint32_t tmem) {
     }
     mma_commit(&bars->acc_done); ++sy.na;
     // S1: heads^T = Wh h^T (B = hbuf, layout T: MN-major, K groups SF apart)
-    tc_wait(&bars->b_ready, sy.nb & 1, bars, c.gerr); ++sy.nb;
+    TCW(33, tc_wait(&bars->b_ready, sy.nb & 1, bars, c.gerr)); ++sy.nb;
     tc_fence_after();
     uint32_t a2 = 0;
     for (int cc = 0; cc < 8; ++cc)
@@ -388,7 +423,7 @@ __device__ void tile_mma(const TileCtx& c, Ring& rg, Sync& sy, uint32_t tmem) {
     if (!(present >> m & 1)) continue;
     const TcMod& t = pl.mod[m];
     for (int p = 0; p < pl.np; ++p) {
-      tc_wait(&bars->b_ready, sy.nb & 1, bars, c.gerr); ++sy.nb;     // zop ready
+      TCW(33, tc_wait(&bars->b_ready, sy.nb & 1, bars, c.gerr)); ++sy.nb;     // zop ready
       tc_fence_after();
       {
         uint32_t a = 0;
@@ -399,7 +434,7 @@ __device__ void tile_mma(const TileCtx& c, Ring& rg, Sync& sy, uint32_t tmem) {
       uint32_t adz = 0;
       for (int mt = 0; mt < t.MtD; ++mt) {
         if (!c.bwd && mt + 1 >= t.MtD) break;
-        tc_wait(&bars->b_ready, sy.nb & 1, bars, c.gerr); ++sy.nb;   // epilogue of decoder tile mt done (dxbuf ready)
+        TCW(33, tc_wait(&bars->b_ready, sy.nb & 1, bars, c.gerr)); ++sy.nb;   // epilogue of decoder tile mt done (dxbuf ready)
         tc_fence_after();
         if (c.bwd)
           for (int c4 = 0; c4 < 4 && 4 * mt + c4 < t.NCx; ++c4)
@@ -417,7 +452,7 @@ __device__ void tile_mma(const TileCtx& c, Ring& rg, Sync& sy, uint32_t tmem) {
     for (int m = 0; m < mv.M; ++m) {
       if (!(present >> m & 1)) continue;
       const TcMod& t = pl.mod[m];
-      tc_wait(&bars->b_ready, sy.nb & 1, bars, c.gerr); ++sy.nb;     // deop ready
+      TCW(33, tc_wait(&bars->b_ready, sy.nb & 1, bars, c.gerr)); ++sy.nb;     // deop ready
       tc_fence_after();
       for (int mt = 0; mt < 2; ++mt) {
         uint32_t a = 0;
@@ -486,25 +521,38 @@ __device__ void tile_compute(const TileCtx& c, Sync& sy, uint32_t tmem) {
     const TcMod& tm = pl.mod[m];
     const int D = md.D;
     unsigned char* g_x = pl.base + tm.xop + (int64_t)c.tile * tm.xop_t;
-    for (int xi = 0; 4 * xi < tm.NCx; ++xi) {
-      const int xb = sy.nx & 1;
-      tc_wait(&bars->xempty[xb], ((sy.nx >> 1) & 1) ^ 1, bars, c.gerr);
-      for (int i = t; i < R * 16; i += 256) {          // thread = (row, group of 8 features): layout F
-        const int n = i >> 4, g = i & 15;
+    // x rows -> fp16 hi/lo operand blocks of 128 features (layout F).  Software pipelined: the global loads of
+    // block xi + 1 are in flight while block xi is converted, handed over and multiplied.
+    constexpr int NI = (R * 16) / 256;                      // (row, 8-feature group) items per thread and block
+    float xr[NI][8];
+    auto x_load = [&](int xi) {
+#pragma unroll
+      for (int it = 0; it < NI; ++it) {
+        const int i = t + 256 * it, n = i >> 4, g = i & 15;
         const long long sr = srow[m * R + n];
         const int d0 = xi * 128 + g * 8;
-        float x[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = (sr >= 0 && d0 + k < D) ? cx.x[m][sr * D + d0 + k] : 0.f;
-        uint4 hi, lo;
-        split8(x, hi, lo);
+        for (int k = 0; k < 8; ++k) xr[it][k] = (sr >= 0 && d0 + k < D) ? __ldg(cx.x[m] + sr * D + d0 + k) : 0.f;
+      }
+    };
+    x_load(0);
+    for (int xi = 0; 4 * xi < tm.NCx; ++xi) {
+      const int xb = sy.nx & 1;
+      uint4 hi[NI], lo[NI];
+#pragma unroll
+      for (int it = 0; it < NI; ++it) split8(xr[it], hi[it], lo[it]);
+      if (4 * (xi + 1) < tm.NCx) x_load(xi + 1);
+      tc_wait(&bars->xempty[xb], ((sy.nx >> 1) & 1) ^ 1, bars, c.gerr);
+#pragma unroll
+      for (int it = 0; it < NI; ++it) {
+        const int i = t + 256 * it, n = i >> 4, g = i & 15;
         const uint32_t off = g * SF + (n >> 3) * 128 + (n & 7) * 16;
-        *reinterpret_cast<uint4*>(xbuf[xb] + off) = hi;
-        *reinterpret_cast<uint4*>(xbuf[xb] + 256 * R + off) = lo;
+        *reinterpret_cast<uint4*>(xbuf[xb] + off) = hi[it];
+        *reinterpret_cast<uint4*>(xbuf[xb] + 256 * R + off) = lo[it];
         if (bwd && xi * 16 + g < tm.NCx * 4) {
           const uint32_t goff = (xi * 16 + g) * SF + (n >> 3) * 128 + (n & 7) * 16;
-          *reinterpret_cast<uint4*>(g_x + goff) = hi;
-          *reinterpret_cast<uint4*>(g_x + tm.xop_t / 2 + goff) = lo;
+          *reinterpret_cast<uint4*>(g_x + goff) = hi[it];
+          *reinterpret_cast<uint4*>(g_x + tm.xop_t / 2 + goff) = lo[it];
         }
       }
       fence_proxy_async();
@@ -859,31 +907,17 @@ __device__ void p3_item(const ModelView& mv, const StepCtx& cx, const mopoe_batc
       bc1 = 1.f - powf(cx.b1, tt);
       bc2s = sqrtf(1.f - powf(cx.b2, tt));
     }
-    const int i = 128 * g.mt + 32 * q + lane;               // output row (out feature)
-    const int cw = g.nw / 2;                                // columns of this warp
-    const int c0 = hf * cw;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     if (nchunk > 0) await_acc(bars, sy, gerr);
     float* part = reinterpret_cast<float*>(pl.base + pl.p3part) + ((int64_t)ui * pl.ksplit) * (128 * 256);
     int* cnt = reinterpret_cast<int*>(pl.base + pl.p3cnt) + ui;
+    float* stile = reinterpret_cast<float*>(sm + pl.s_e);          // [128][CW + 1] staging tile (the P2 buffers are idle)
     __shared__ int s_last;
-    if (pl.ksplit == 1) {
-      for (int cb = 0; cb < cw; cb += 8) {
-        float v[8];
-        if (nchunk > 0) { tmem_ld8(lane_base + c0 + cb, v); tmem_ld_wait(); }
-        else { for (int k = 0; k < 8; ++k) v[k] = 0.f; }
-        if (i < g.rows_valid)
-          for (int k = 0; k < 8; ++k) {
-            const int j = g.n0 + c0 + cb + k;
-            if (j < g.cols_valid) apply_grad(cx, g.pbase + (int64_t)i * g.ld + j, v[k] * invN, bc1, bc2s);
-          }
-      }
-      tc_fence_before();
-      bar_compute();
-      if (t == 0) mbar_arrive(&bars->acc_free);
-    } else {
+    bool reduce = false;
+    if (pl.ksplit > 1) {
       // partial tile, column major ([col][lane row]: coalesced), then the last CTA to arrive sums in split order
       float* mine = part + (int64_t)split * (128 * 256);
+      const int cw = g.nw / 2, c0 = hf * cw;
       for (int cb = 0; cb < cw; cb += 8) {
         float v[8];
         if (nchunk > 0) { tmem_ld8(lane_base + c0 + cb, v); tmem_ld_wait(); }
@@ -900,18 +934,63 @@ __device__ void p3_item(const ModelView& mv, const StepCtx& cx, const mopoe_batc
         if (s_last) *cnt = 0;
       }
       bar_compute();
-      if (s_last) {
-        __threadfence();
-        if (i < g.rows_valid)
-          for (int cc = 0; cc < cw; ++cc) {
-            const int j = g.n0 + c0 + cc;
-            if (j >= g.cols_valid) continue;
-            float s = 0.f;
-            for (int sp = 0; sp < pl.ksplit; ++sp) s += __ldcg(part + (int64_t)sp * (128 * 256) + (c0 + cc) * 128 + 32 * q + lane);
-            apply_grad(cx, g.pbase + (int64_t)i * g.ld + j, s * invN, bc1, bc2s);
+      reduce = s_last != 0;
+      if (reduce) __threadfence();
+    }
+    if (pl.ksplit == 1 || reduce) {
+      // 32 (or 16) output columns at a time: accumulator (or the sum of the partials) -> staging tile, then the
+      // parameter update with consecutive threads on consecutive columns of a row and all loads in flight
+      const int CW = (g.nw & 31) ? 16 : 32;
+      for (int cbase = 0; cbase < g.nw; cbase += CW) {
+        const int hw = CW / 2, cc0 = cbase + hf * hw;
+        if (!reduce) {
+          float v[16];
+          if (CW == 32) tmem_ld16(lane_base + cc0, v); else tmem_ld8(lane_base + cc0, v);
+          tmem_ld_wait();
+          for (int k = 0; k < hw; ++k) stile[(32 * q + lane) * (CW + 1) + hf * hw + k] = v[k];
+        } else {
+          for (int k = 0; k < hw; ++k) {
+            float sum = 0.f;
+            for (int sp = 0; sp < pl.ksplit; ++sp) sum += __ldcg(part + (int64_t)sp * (128 * 256) + (cc0 + k) * 128 + 32 * q + lane);
+            stile[(32 * q + lane) * (CW + 1) + hf * hw + k] = sum;
           }
+        }
+        bar_compute();
+        constexpr int EPT = 16;
+        float gv[EPT], pm[EPT], pv[EPT], pp[EPT];
+        int64_t ix[EPT];
+        const int per = (128 * CW) / 256;                     // 16 or 8 elements per thread
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+          ix[k] = -1;
+          if (k < per) {
+            const int e = t + 256 * k, il = e / CW, jj = e - il * CW;
+            const int i = 128 * g.mt + il, j = g.n0 + cbase + jj;
+            if (i < g.rows_valid && j < g.cols_valid) { ix[k] = g.pbase + (int64_t)i * g.ld + j; gv[k] = stile[il * (CW + 1) + jj] * invN; }
+          }
+        }
+        if (cx.mode == 1) {
+#pragma unroll
+          for (int k = 0; k < EPT; ++k) if (ix[k] >= 0) cx.grads[ix[k]] = gv[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < EPT; ++k) if (ix[k] >= 0) { pm[k] = cx.adam_m[ix[k]]; pv[k] = cx.adam_v[ix[k]]; pp[k] = cx.params[ix[k]]; }
+#pragma unroll
+          for (int k = 0; k < EPT; ++k) if (ix[k] >= 0) {
+            const float m_ = cx.b1 * pm[k] + (1.f - cx.b1) * gv[k];
+            const float v_ = cx.b2 * pv[k] + (1.f - cx.b2) * gv[k] * gv[k];
+            cx.adam_m[ix[k]] = m_;
+            cx.adam_v[ix[k]] = v_;
+            cx.params[ix[k]] = pp[k] - (cx.lr / bc1) * (m_ / (sqrtf(v_) / bc2s + cx.adam_eps));
+          }
+        }
+        bar_compute();
       }
+    }
+    if (pl.ksplit == 1) {
+      tc_fence_before();
       bar_compute();
+      if (t == 0) mbar_arrive(&bars->acc_free);
     }
   }
 }
@@ -991,7 +1070,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_tc_kernel(ModelView mv, Step
     float* prof = reinterpret_cast<float*>(pl.base + pl.err) + 64;
 #endif
     TCP_DECL;
-    tc_prep(mv, pl);
+    tc_prep(mv, pl, reinterpret_cast<PrepBlob*>(sm + pl.s_e));
     TCP(20);
     grid_barrier(ws.bar, target);
     fence_async_all();
