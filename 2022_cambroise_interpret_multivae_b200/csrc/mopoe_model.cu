@@ -16,6 +16,7 @@
 //   modality.py:42-45 (calc_log_prob), run_epochs.py:73-135 (basic_routine_epoch),
 //   utils.py:88-112 (calc_elbo), experiment.py:268-271 (Adam).
 #include <cooperative_groups.h>
+#include <algorithm>
 
 #include "mopoe_common.cuh"
 #include "mopoe_latent.cuh"
@@ -1316,7 +1317,7 @@ int mopoe_train_steps(const mopoe_model_desc* desc, float* params, float* adam_m
     plan.base = (unsigned char*)workspace + base_off;
     MOPOE_CUDA(cudaMemsetAsync(plan.base + plan.err, 0, 256, stream));
     g_tc_prof = reinterpret_cast<float*>(plan.base + plan.err) + 64;
-    MOPOE_CUDA(cudaMemsetAsync(plan.base + plan.p3cnt, 0, (size_t)plan.n_units * 4, stream));
+    MOPOE_CUDA(cudaMemsetAsync(plan.base + plan.p3cnt, 0, (size_t)(tc::MAX_UNITS + 64) * 4, stream));
     void* fn = plan.R == 32 ? (void*)tc::train_tc_kernel<32> : (void*)tc::train_tc_kernel<16>;
     MOPOE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.s_total));
     int per_sm = 0;

@@ -159,12 +159,21 @@ static bool make_plan(const mopoe_model_desc* d, int64_t max_rows, int smem_limi
     for (int mt = 0; mt < t.MtD; ++mt) { if (nu >= MAX_UNITS) return false; p.unit[nu++] = {(unsigned char)m, 2, (unsigned char)mt, 0}; }
   }
   p.n_units = nu;
+  {   // heaviest units first (cost ~ operand bytes per row): longest-processing-time order for the dynamic queue
+    auto cost = [&](const TcUnit& u) {
+      const TcMod& t = p.mod[u.m];
+      if (u.g == 0) { const int nb0 = cdiv(t.Dk16, nwmax); return 128 + cdiv(cdiv(t.Dk16, nb0), 16) * 16; }
+      if (u.g == 1) return 128 + nw1;
+      return (128 + t.ZDk16) * p.np;
+    };
+    std::stable_sort(p.unit, p.unit + nu, [&](const TcUnit& a, const TcUnit& b) { return cost(a) > cost(b); });
+  }
   p.nw[0] = nwmax; p.nw[1] = nw1;   // nw[0] is the CAP of the per-modality width of GEMM 0 (recomputed on the device)
   p.slot3 = (128 + max(max(nw0max, nw1), 64)) * R * 4;
   const int sms = num_sms();
   p.ksplit = max_rows <= 512 ? 1 : max(1, min(p.ntiles_max, (2 * sms) / max(1, nu)));
   p.p3part = takeg((int64_t)nu * p.ksplit * 128 * 256 * 4);
-  p.p3cnt = takeg((int64_t)nu * 4);
+  p.p3cnt = takeg((int64_t)(MAX_UNITS + 64) * 4);   // per-unit arrival counters, then the P3 work-queue counter
   p.total = off;
   *out = p;
   return true;
@@ -302,7 +311,7 @@ __device__ void tc_prep(const ModelView& mv, const TcPlan& pl, PrepBlob* tab) {
 
 // ---- streaming state of the loader / MMA roles -----------------------------------------------
 struct Ring {
-  int slot; uint32_t phase;
+  int slot; uint32_t phase;     // P2: one phase bit for the whole ring; P3: bit s = parity of the uses of slot s
   __device__ __forceinline__ void next(int nslot) { if (++slot == nslot) { slot = 0; phase ^= 1; } }
 };
 
@@ -853,25 +862,30 @@ __device__ void p3_item(const ModelView& mv, const StepCtx& cx, const mopoe_batc
   const P3Geom g = p3_geom<R>(mv, cx, pl, pl.unit[ui]);
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   unsigned char* ring = sm + pl.s_ring;
-  const int nslot3 = min(MAX_SLOTS, (pl.nslot * CHUNK) / pl.slot3);
+  // ring of this item: as many slots as fit (the slot holds one row tile of both operands); every item starts at
+  // slot 0, the parity of each slot's uses is carried in the bits of rg.phase across items of different slot size
+  const uint32_t a_bytes = 128 * R * 2, b_bytes = g.nw * R * 2;
+  const int slot_bytes = 2 * (a_bytes + b_bytes);
+  const int nslot3 = min(MAX_SLOTS, (pl.nslot * CHUNK) / slot_bytes);
+  rg.slot = 0;
   const int t_lo = (int)((int64_t)split * nt / pl.ksplit), t_hi = (int)((int64_t)(split + 1) * nt / pl.ksplit);
   const int nchunk = (t_hi - t_lo) * g.np;
-  const uint32_t a_bytes = 128 * R * 2, b_bytes = g.nw * R * 2;
   constexpr uint32_t SF = R * 16;
   if (warp == 8) {
     if (lane == 0)
       for (int ci = 0; ci < nchunk; ++ci) {
         const int64_t tp = (int64_t)t_lo * g.np + ci;            // (tile, pass) index
-        tc_wait(&bars->ring3_empty[rg.slot], rg.phase ^ 1, bars, gerr);
+        TCW(34, tc_wait(&bars->ring3_empty[rg.slot], ((rg.phase >> rg.slot) & 1) ^ 1, bars, gerr));
         mbar_expect_tx(&bars->ring3_full[rg.slot], 2 * a_bytes + 2 * b_bytes);
-        unsigned char* dst = ring + rg.slot * pl.slot3;
+        unsigned char* dst = ring + rg.slot * slot_bytes;
         const unsigned char* as = g.a + tp * g.a_t + g.a_off;
         const unsigned char* bs = g.bq + tp * g.b_t + g.b_off;
         bulk_g2s(dst, as, a_bytes, &bars->ring3_full[rg.slot]);
         bulk_g2s(dst + a_bytes, as + g.a_half, a_bytes, &bars->ring3_full[rg.slot]);
         bulk_g2s(dst + 2 * a_bytes, bs, b_bytes, &bars->ring3_full[rg.slot]);
         bulk_g2s(dst + 2 * a_bytes + b_bytes, bs + g.b_half, b_bytes, &bars->ring3_full[rg.slot]);
-        if (++rg.slot == nslot3) { rg.slot = 0; rg.phase ^= 1; }
+        rg.phase ^= 1u << rg.slot;
+        if (++rg.slot == nslot3) rg.slot = 0;
       }
   } else if (warp == 9) {
     if (lane == 0) {
@@ -881,9 +895,9 @@ __device__ void p3_item(const ModelView& mv, const StepCtx& cx, const mopoe_batc
       if (sy.nf > 0) { tc_wait(&bars->acc_free, (sy.nf - 1) & 1, bars, gerr); tc_fence_after(); }
       ++sy.nf;
       for (int ci = 0; ci < nchunk; ++ci) {
-        tc_wait(&bars->ring3_full[rg.slot], rg.phase, bars, gerr);
+        TCW(35, tc_wait(&bars->ring3_full[rg.slot], (rg.phase >> rg.slot) & 1, bars, gerr));
         tc_fence_after();
-        const uint32_t a = smem_u32(ring + rg.slot * pl.slot3);
+        const uint32_t a = smem_u32(ring + rg.slot * slot_bytes);
         const uint32_t bb = a + 2 * a_bytes;
         for (int ks = 0; ks < R / 16; ++ks) {
           // K = rows: K groups of 8 rows are 128 bytes apart, MN groups of 8 features SF apart (both layouts)
@@ -894,7 +908,8 @@ __device__ void p3_item(const ModelView& mv, const StepCtx& cx, const mopoe_batc
           mma_f16(tmem, al, bh, id, 1);
         }
         mma_commit(&bars->ring3_empty[rg.slot]);
-        if (++rg.slot == nslot3) { rg.slot = 0; rg.phase ^= 1; }
+        rg.phase ^= 1u << rg.slot;
+        if (++rg.slot == nslot3) rg.slot = 0;
       }
       if (nchunk > 0) { mma_commit(&bars->acc_done); ++sy.na; }
     }
@@ -908,7 +923,12 @@ __device__ void p3_item(const ModelView& mv, const StepCtx& cx, const mopoe_batc
       bc2s = sqrtf(1.f - powf(cx.b2, tt));
     }
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+#ifdef TC_PROF
+    float* prof = reinterpret_cast<float*>(pl.base + pl.err) + 64;
+#endif
+    TCP_DECL;
     if (nchunk > 0) await_acc(bars, sy, gerr);
+    TCP(36);
     float* part = reinterpret_cast<float*>(pl.base + pl.p3part) + ((int64_t)ui * pl.ksplit) * (128 * 256);
     int* cnt = reinterpret_cast<int*>(pl.base + pl.p3cnt) + ui;
     float* stile = reinterpret_cast<float*>(sm + pl.s_e);          // [128][CW + 1] staging tile (the P2 buffers are idle)
@@ -956,32 +976,34 @@ __device__ void p3_item(const ModelView& mv, const StepCtx& cx, const mopoe_batc
           }
         }
         bar_compute();
-        constexpr int EPT = 16;
-        float gv[EPT], pm[EPT], pv[EPT], pp[EPT];
-        int64_t ix[EPT];
+        // 4 elements per thread and pass (all their loads in flight), a compact loop instead of one long
+        // unrolled sequence: the update code runs once per column block and would otherwise be fetched cold
         const int per = (128 * CW) / 256;                     // 16 or 8 elements per thread
+#pragma unroll 1
+        for (int k0 = 0; k0 < per; k0 += 4) {
+          float gv[4], pm[4], pv[4], pp[4];
+          int64_t ix[4];
 #pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-          ix[k] = -1;
-          if (k < per) {
-            const int e = t + 256 * k, il = e / CW, jj = e - il * CW;
+          for (int k = 0; k < 4; ++k) {
+            const int e = t + 256 * (k0 + k), il = e / CW, jj = e - il * CW;
             const int i = 128 * g.mt + il, j = g.n0 + cbase + jj;
-            if (i < g.rows_valid && j < g.cols_valid) { ix[k] = g.pbase + (int64_t)i * g.ld + j; gv[k] = stile[il * (CW + 1) + jj] * invN; }
+            ix[k] = (i < g.rows_valid && j < g.cols_valid) ? g.pbase + (int64_t)i * g.ld + j : -1;
+            gv[k] = stile[il * (CW + 1) + jj] * invN;
           }
-        }
-        if (cx.mode == 1) {
+          if (cx.mode == 1) {
 #pragma unroll
-          for (int k = 0; k < EPT; ++k) if (ix[k] >= 0) cx.grads[ix[k]] = gv[k];
-        } else {
+            for (int k = 0; k < 4; ++k) if (ix[k] >= 0) cx.grads[ix[k]] = gv[k];
+          } else {
 #pragma unroll
-          for (int k = 0; k < EPT; ++k) if (ix[k] >= 0) { pm[k] = cx.adam_m[ix[k]]; pv[k] = cx.adam_v[ix[k]]; pp[k] = cx.params[ix[k]]; }
+            for (int k = 0; k < 4; ++k) if (ix[k] >= 0) { pm[k] = cx.adam_m[ix[k]]; pv[k] = cx.adam_v[ix[k]]; pp[k] = cx.params[ix[k]]; }
 #pragma unroll
-          for (int k = 0; k < EPT; ++k) if (ix[k] >= 0) {
-            const float m_ = cx.b1 * pm[k] + (1.f - cx.b1) * gv[k];
-            const float v_ = cx.b2 * pv[k] + (1.f - cx.b2) * gv[k] * gv[k];
-            cx.adam_m[ix[k]] = m_;
-            cx.adam_v[ix[k]] = v_;
-            cx.params[ix[k]] = pp[k] - (cx.lr / bc1) * (m_ / (sqrtf(v_) / bc2s + cx.adam_eps));
+            for (int k = 0; k < 4; ++k) if (ix[k] >= 0) {
+              const float m_ = cx.b1 * pm[k] + (1.f - cx.b1) * gv[k];
+              const float v_ = cx.b2 * pv[k] + (1.f - cx.b2) * gv[k] * gv[k];
+              cx.adam_m[ix[k]] = m_;
+              cx.adam_v[ix[k]] = v_;
+              cx.params[ix[k]] = pp[k] - (cx.lr / bc1) * (m_ / (sqrtf(v_) / bc2s + cx.adam_eps));
+            }
           }
         }
         bar_compute();
@@ -992,6 +1014,7 @@ __device__ void p3_item(const ModelView& mv, const StepCtx& cx, const mopoe_batc
       bar_compute();
       if (t == 0) mbar_arrive(&bars->acc_free);
     }
+    TCP(37);
   }
 }
 
@@ -1099,7 +1122,12 @@ __global__ void __launch_bounds__(THREADS, 1) train_tc_kernel(ModelView mv, Step
       for (int ui = 0; ui < pl.n_units; ++ui) n_active += (b.present_mask >> pl.unit[ui].m) & 1;
       const int n_items = n_active * pl.ksplit;
       const int n_col_items = (pl.ccols + 255) / 256;
-      for (int item = blockIdx.x; item < n_items + n_col_items; item += gridDim.x) {
+      // dynamic queue (units are sorted by cost on the host, heaviest first): the CTA takes its first item by
+      // index, every further one from a global counter; all three roles of the CTA follow the same item
+      int* queue = reinterpret_cast<int*>(pl.base + pl.p3cnt) + MAX_UNITS;
+      __shared__ int s_item;
+      int item = blockIdx.x;
+      while (item < n_items + n_col_items) {
         if (item < n_items) {
           const int au = item / pl.ksplit, split = item - au * pl.ksplit;
           int ui = 0, seen = 0;
@@ -1110,10 +1138,15 @@ __global__ void __launch_bounds__(THREADS, 1) train_tc_kernel(ModelView mv, Step
         } else {
           p3_columns(mv, cx, b, pl, nt, item - n_items);
         }
+        __syncthreads();
+        if (t == 0) s_item = gridDim.x + atomicAdd(queue, 1);
+        __syncthreads();
+        item = s_item;
       }
       TCP(24);
       grid_barrier(ws.bar, target);
       TCP(25);
+      if (blockIdx.x == 0 && t == 0) *(reinterpret_cast<int*>(pl.base + pl.p3cnt) + MAX_UNITS) = 0;   // next read two barriers away
       if (cx.mode == 2 && blockIdx.x == 0 && t < mv.M && (b.present_mask >> t & 1)) cx.adam_t[t] += 1;
     }
   }

@@ -8,7 +8,7 @@ from mopoe_b200 import engine, _lib
 from oracle import cases
 NAMES = {0: "setup", 1: "x convert (+wait xempty)", 2: "wait P1 acc", 3: "P1 epilogue", 4: "wait S1 acc", 5: "S1 epilogue", 6: "latent fwd",
          7: "zop convert", 8: "wait S2 acc", 9: "S2 epilogue", 10: "wait dz acc", 11: "dz epilogue", 12: "latent bwd", 13: "deop convert",
-         14: "wait S4 acc", 15: "S4 epilogue", 30: "loader: ring full (wait empty)", 31: "mma: wait chunk (ring_full)", 32: "mma: wait x block", 33: "mma: wait B operand", 40: "lat: loads+exp", 41: "lat: owner", 42: "lat: subsets", 43: "lat: noise+z", 44: "lat: class reductions", 45: "lat: style loop", 46: "lat: style reductions", 20: "prep", 21: "barrier 1", 22: "P2 (CTA 0)", 23: "barrier 2", 24: "P3 (CTA 0)", 25: "barrier 3"}
+         14: "wait S4 acc", 15: "S4 epilogue", 30: "loader: ring full (wait empty)", 31: "mma: wait chunk (ring_full)", 32: "mma: wait x block", 33: "mma: wait B operand", 40: "lat: loads+exp", 41: "lat: owner", 42: "lat: subsets", 43: "lat: noise+z", 44: "lat: class reductions", 45: "lat: style loop", 46: "lat: style reductions", 34: "P3 loader: ring full", 35: "P3 mma: wait chunk", 36: "P3 compute: wait acc", 37: "P3 epilogue", 20: "prep", 21: "barrier 1", 22: "P2 (CTA 0)", 23: "barrier 2", 24: "P3 (CTA 0)", 25: "barrier 3"}
 def prof(base, method, n, steps, inject=False):
     spec = mopoe_b200.PathSpec(base["dims"], base["style_dims"], base["latent_dim"], method, base["mod_names"])
     dev = torch.device("cuda")
