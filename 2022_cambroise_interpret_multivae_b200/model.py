@@ -64,6 +64,7 @@ class VAE(nn.Module):
         self._noise = None
         self._ws = engine.Workspace()
         self.philox_seed = None      # set to an int to use the in-kernel generator instead of torch.randn
+        self.rng_mode = "reference"   # "reference": torch.randn in the reference's call order; "block": one (n_pass, N, E) draw
         self._philox_calls = 0       # every forward / ELBO call draws fresh noise: the call count is folded into the seed
 
     # ---- flat parameter storage -------------------------------------------------------------
@@ -101,13 +102,39 @@ class VAE(nn.Module):
         self._philox_calls += 1
         return seed
 
-    def _draw(self, n_pass, n_rows, device):
+    def _draw(self, n_pass, n_rows, device, batch_keys=None):
+        """Noise of one forward / ELBO call as an (n_pass, N, E) tensor (E = content | style_0 | style_1 ...).
+        Default (`rng_mode == "reference"`): torch.randn calls in the shapes and ORDER in which the reference consumes
+        the global generator, so a same-seed run on the same device reproduces a reference run without injection:
+        BaseMMVae.forward draws the joint content noise (N, L) first (BaseMMVae.py:143-144), then one (N, S_m) tensor
+        per present modality with a style block, in `modalities` order (:155-159); in poe mode basic_routine_epoch
+        then runs one unimodal forward per key of the batch dict (run_epochs.py:108-118), each drawing (N, L), (N, S_m)."""
         if self._noise is not None:
             eps, self._noise = self._noise, None
             return eps.to(device=device, dtype=torch.float32).reshape(n_pass, n_rows, self.spec.eps_width).contiguous()
         if self.philox_seed is not None:
             return None
-        return torch.randn(n_pass, n_rows, self.spec.eps_width, device=device)   # global torch generator
+        spec = self.spec
+        if self.rng_mode != "reference" or batch_keys is None:
+            return torch.randn(n_pass, n_rows, spec.eps_width, device=device)   # one draw from the global torch generator
+        L = spec.latent_dim
+        eps = torch.zeros(n_pass, n_rows, spec.eps_width, device=device)
+        present = [m for m, n in enumerate(spec.mod_names) if n in batch_keys]
+
+        def one(p, mods):
+            eps[p, :, :L] = torch.randn(n_rows, L, device=device)
+            for m in mods:
+                S = spec.style_dims[m]
+                if S > 0:
+                    o = spec.style_offset(m)
+                    eps[p, :, o:o + S] = torch.randn(n_rows, S, device=device)
+        one(0, present)
+        if n_pass > 1:                                   # poe: unimodal forwards in the order of the batch dict's keys
+            for name in batch_keys:
+                if name in spec.mod_names:
+                    m = spec.mod_names.index(name)
+                    one(1 + m, [m])
+        return eps
 
     # ---- reference API ----------------------------------------------------------------------
     def reparameterize(self, mu, logvar):
@@ -149,7 +176,7 @@ class VAE(nn.Module):
     def _forward_raw(self, input_batch, sample_latents=True, use_expert=None, with_nll=False):
         flat = self.flat_parameters()
         n_rows = len(next(iter(input_batch.values())))
-        eps = self._draw(1, n_rows, flat.device) if sample_latents else None
+        eps = self._draw(1, n_rows, flat.device, list(input_batch.keys())) if sample_latents else None
         seed = self._next_seed() if (sample_latents and eps is None) else 0
         return engine.forward(self.spec, flat, input_batch, eps=None if eps is None else eps[0], seed=seed,
                               sample_latents=sample_latents, use_expert=use_expert, with_nll=with_nll,
@@ -199,7 +226,7 @@ def elbo_step(model: VAE, input_batch, need_grad=True):
         if x is not None:
             engine._require_cuda(x, "input batch")
     n_rows = next(x for x in data if x is not None).shape[0]
-    eps = model._draw(spec.n_pass, n_rows, dev)
+    eps = model._draw(spec.n_pass, n_rows, dev, list(input_batch.keys()))
     res = engine.ForwardResult(spec, n_rows, mask, dev)
     bdev = engine.make_batches(spec, [(n_rows, mask, 0)], dev)
     grads = torch.zeros_like(flat) if need_grad else None

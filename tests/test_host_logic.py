@@ -163,3 +163,30 @@ def test_epoch_plan_equals_the_reference_sampler_golden():
         plan = data.epoch_plan(has_matrix(case), case["batch_size"], np.random.RandomState(case["seed"]))
         assert [ix.tolist() for _, ix in plan] == g["plan"], case
 
+
+
+def test_reference_rng_order_matches_the_reference_consumption():
+    """model._draw issues torch.randn in the shapes / order the reference consumes the generator
+    (BaseMMVae.py:143-159, run_epochs.py:108-118): the same seed gives the tensors the oracle's
+    reference_eps_list expects, for joint_elbo and poe, with a missing block."""
+    from types import SimpleNamespace
+    from mopoe_b200.model import VAE
+    from oracle import mopoe_oracle as mo
+    for method, keys in (("joint_elbo", ["clinical", "rois"]), ("poe", ["clinical", "rois"]), ("poe", ["rois"])):
+        flags = SimpleNamespace(input_dim=[7, 444], style_dim=[3, 20], class_dim=20, factorized_representation=True,
+                                modality_poe=method == "poe", modality_moe=False, modality_jsd=False, joint_elbo=method == "joint_elbo",
+                                learn_output_scale=True, learn_output_sample_scale=False, beta=1.0, beta_style=1.0, beta_content=1.0,
+                                num_hidden_layer_encoder=1, num_hidden_layer_decoder=0, likelihood="normal", initial_out_logvar=-3.0,
+                                dropout_rate=0.0, num_models=1, dir_checkpoints="")
+        model = VAE(flags, {"clinical": None, "rois": None})
+        spec = model.spec
+        N = 9
+        torch.manual_seed(123)
+        eps = model._draw(spec.n_pass, N, torch.device("cpu"), keys)
+        ospec = mo.ModelSpec(method=method)
+        present = [spec.mod_names.index(k) for k in keys]
+        want_list = mo.reference_eps_list(ospec, present, eps)
+        torch.manual_seed(123)
+        for want in want_list:                       # the reference: one randn_like per reparameterize call
+            got = torch.randn(want.shape)
+            assert torch.equal(got, want)
