@@ -50,6 +50,14 @@ class DaaDesc(C.Structure):
                                          "src_mod", "dst_mod", "sample_latents", "reg_method")]
 
 
+MAX_PEERS = 8
+
+
+class TableExchangeDesc(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("elems_local", C.c_int64), ("elem_offset", C.c_int64),
+                ("elems_total", C.c_int64), ("peer_base", C.c_void_p * MAX_PEERS)]
+
+
 class MopoeError(RuntimeError):
     pass
 
@@ -97,6 +105,10 @@ def lib():
     L.mopoe_umma_selftest.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     L.mopoe_umma_selftest.restype = C.c_int
     L.mopoe_daa_last_impl.restype = C.c_int
+    L.mopoe_table_exchange_bytes.argtypes = [i64]
+    L.mopoe_table_exchange_bytes.restype = i64
+    L.mopoe_daa_exchange_tables.argtypes = [C.POINTER(TableExchangeDesc), vp, vp, vp]
+    L.mopoe_daa_exchange_tables.restype = C.c_int
     L.mopoe_train_last_impl.restype = C.c_int
     L.mopoe_daa_read_phases.argtypes = [C.POINTER(ModelDesc), C.POINTER(DaaDesc), vp, C.POINTER(C.c_int64)]
     L.mopoe_daa_read_phases.restype = C.c_int
@@ -122,4 +134,4 @@ EXPORTED = ["mopoe_last_error", "mopoe_version", "mopoe_device_count", "mopoe_pa
             "mopoe_workspace_bytes", "mopoe_forward", "mopoe_train_steps", "mopoe_daa_workspace_bytes",
             "mopoe_daa_sweep", "mopoe_daa_regression", "mopoe_philox_normal", "mopoe_profile_enable",
             "mopoe_daa_last_kernel_ms", "mopoe_umma_selftest", "mopoe_daa_last_impl", "mopoe_daa_read_phases",
-            "mopoe_daa_status", "mopoe_train_last_impl"]
+            "mopoe_daa_status", "mopoe_train_last_impl", "mopoe_table_exchange_bytes", "mopoe_daa_exchange_tables"]

@@ -1075,7 +1075,89 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   return MOPOE_OK;
 }
 
+// ---- multi-GPU: push-style exchange of the association tables over peer memory ---------------------
+// Every rank owns a slice (its validations) of the (n_val_total, C, R) fp64 coefs / p-value tables.  Instead of
+// an NCCL all_gather launched behind the sweep, the slice is stored straight into EVERY rank's full table through
+// peer-mapped pointers (NVLink P2P stores into symmetric memory), followed by a system-scope release of a
+// per-source sequence flag; a one-warp kernel on each rank acquires the flags of all sources.  Both kernels are
+// ordinary launches on the caller's stream (capturable: the sequence number lives in device memory).
+// Exchange buffer layout (bytes): [0] uint64 seq, [8] uint32 block counter, [64 + 8 r] uint64 flag of source rank r,
+// [256 ...) two slots (seq parity) x {coefs, pvalues} x elems_total doubles.
+constexpr int64_t EX_HDR = 256;
+struct ExPeers { unsigned char* base[MOPOE_MAX_PEERS]; };
+
+__global__ void __launch_bounds__(256) daa_table_push_kernel(ExPeers peers, int world, int rank, int64_t elems_local, int64_t elem_offset,
+                                                             int64_t elems_total, const double* coefs, const double* pvalues) {
+  unsigned char* own = peers.base[rank];
+  const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(own) + 1ull;
+  const int64_t slot_off = EX_HDR + (int64_t)(seq & 1ull) * 2 * elems_total * 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < elems_local; i += (int64_t)gridDim.x * blockDim.x) {
+    const double c = coefs[i], p = pvalues[i];
+    for (int r = 0; r < world; ++r) {
+      double* dst = reinterpret_cast<double*>(peers.base[r] + slot_off);
+      dst[elem_offset + i] = c;
+      dst[elems_total + elem_offset + i] = p;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* counter = reinterpret_cast<unsigned int*>(own + 8);
+    if (atomicAdd(counter, 1u) == gridDim.x - 1) {      // last block: every block's stores are fenced
+      *counter = 0;
+      *reinterpret_cast<volatile unsigned long long*>(own) = seq;
+      __threadfence_system();
+      for (int r = 0; r < world; ++r) {
+        unsigned long long* flag = reinterpret_cast<unsigned long long*>(peers.base[r] + 64 + 8 * rank);
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
+      }
+    }
+  }
+}
+
+__global__ void daa_table_wait_kernel(unsigned char* own, int world, int64_t elems_total) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(own);
+  const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(own + 64 + 8 * r);
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= seq) break;
+    if (clock64() - t0 > 8000000000LL) {   // a peer never arrived: poison this rank's view instead of hanging
+      double* dst = reinterpret_cast<double*>(own + EX_HDR + (int64_t)(seq & 1ull) * 2 * elems_total * 8);
+      dst[0] = __longlong_as_double(0x7ff8000000000000LL);
+      break;
+    }
+    __nanosleep(64);
+  }
+}
+
 int mopoe_daa_last_impl(void) { return g_last_impl; }
+
+int64_t mopoe_table_exchange_bytes(int64_t elems_total) {
+  if (elems_total < 1) { set_error("elems_total=%lld", (long long)elems_total); return MOPOE_EINVAL; }
+  return EX_HDR + 2 * 2 * elems_total * 8;
+}
+
+int mopoe_daa_exchange_tables(const mopoe_table_exchange* ex, const double* coefs_local, const double* pvalues_local, void* stream_) {
+  if (mopoe_device_count() == 0) { set_error("no CUDA device"); return MOPOE_ENODEV; }
+  if (!ex || !coefs_local || !pvalues_local) { set_error("NULL argument"); return MOPOE_EINVAL; }
+  if (ex->world < 1 || ex->world > MOPOE_MAX_PEERS || ex->rank < 0 || ex->rank >= ex->world) { set_error("world=%d rank=%d invalid", ex->world, ex->rank); return MOPOE_EINVAL; }
+  if (ex->elems_local < 0 || ex->elem_offset < 0 || ex->elem_offset + ex->elems_local > ex->elems_total) { set_error("table slice out of range"); return MOPOE_EINVAL; }
+  ExPeers peers;
+  for (int r = 0; r < MOPOE_MAX_PEERS; ++r) peers.base[r] = r < ex->world ? (unsigned char*)ex->peer_base[r] : nullptr;
+  for (int r = 0; r < ex->world; ++r) if (!peers.base[r]) { set_error("peer_base[%d] is NULL", r); return MOPOE_EINVAL; }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int64_t n = ex->elems_local;
+  const int grid = (int)((n + 255) / 256 < 1 ? 1 : ((n + 255) / 256 > 4 * num_sms() ? 4 * num_sms() : (n + 255) / 256));
+  daa_table_push_kernel<<<grid, 256, 0, stream>>>(peers, ex->world, ex->rank, n, ex->elem_offset, ex->elems_total, coefs_local, pvalues_local);
+  MOPOE_CUDA(cudaGetLastError());
+  daa_table_wait_kernel<<<1, 32, 0, stream>>>(peers.base[ex->rank], ex->world, ex->elems_total);
+  MOPOE_CUDA(cudaGetLastError());
+  return MOPOE_OK;
+}
 
 int mopoe_daa_status(const mopoe_model_desc* desc, const mopoe_daa_desc* daa, void* workspace, void* stream_) {
   if (check_desc(desc)) return MOPOE_EINVAL;

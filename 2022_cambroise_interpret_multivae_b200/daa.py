@@ -184,6 +184,61 @@ def gather_tables_many(locals_, n_validation, group=None, outs=None):
     return outs
 
 
+class TableExchange:
+    """The coefs / p-value tables of every rank's validations in EVERY rank's memory without a collective launch:
+    each rank stores its (n_local, C, R) slices straight into all ranks' full tables through NVLink peer pointers
+    (symmetric memory) and releases a sequence flag; a one-warp kernel acquires the flags of all sources
+    (C-ABI mopoe_daa_exchange_tables; two small launches on the current stream, capturable in a CUDA graph).
+    Replaces the NCCL all_gather of `gather_tables` on the sweep's critical path."""
+
+    def __init__(self, n_val_total, n_scores, n_rois, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        lib = _lib.lib()
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > _lib.MAX_PEERS:
+            raise _lib.MopoeError("table exchange supports up to %d ranks" % _lib.MAX_PEERS)
+        self.shape = (int(n_val_total), int(n_scores), int(n_rois))
+        self.elems_total = self.shape[0] * self.shape[1] * self.shape[2]
+        nbytes = int(lib.mopoe_table_exchange_bytes(self.elems_total))
+        try:
+            symm.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:
+            pass
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize()
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.peer_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        dist.barrier(self.group)                      # every buffer is zeroed and mapped before anyone pushes
+        torch.cuda.synchronize()
+        self.calls = 0                                # launches so far == the device-side sequence number
+
+    def exchange(self, coefs_local, pvalues_local, val_begin):
+        """Push this rank's slices (n_local, C, R) that start at validation `val_begin`; returns the number of
+        exchanges issued so far (its parity selects the slot that holds the result, see `tables`)."""
+        c, p = coefs_local.contiguous(), pvalues_local.contiguous()
+        assert c.dtype == torch.float64 and p.dtype == torch.float64 and tuple(c.shape[1:]) == self.shape[1:]
+        per_val = self.shape[1] * self.shape[2]
+        d = _lib.TableExchangeDesc(world=self.world, rank=self.rank, elems_local=c.shape[0] * per_val,
+                                   elem_offset=int(val_begin) * per_val, elems_total=self.elems_total)
+        for r, ptr in enumerate(self.peer_ptrs):
+            d.peer_base[r] = ptr
+        _lib.check(_lib.lib().mopoe_daa_exchange_tables(C.byref(d), _ptr(c), _ptr(p), _stream()))
+        self._keep = (c, p)
+        self.calls += 1
+        return self.calls
+
+    def tables(self, calls=None):
+        """(coefs, pvalues) views, each (n_val_total, C, R) fp64, of the slot written by exchange number `calls`
+        (default: the last one issued from Python; pass the replay count when the exchange runs inside a CUDA graph)."""
+        calls = self.calls if calls is None else calls
+        off = 256 + (calls & 1) * 2 * self.elems_total * 8
+        flat = self.buf[off:off + 2 * self.elems_total * 8].view(torch.float64)
+        return flat[:self.elems_total].view(self.shape), flat[self.elems_total:].view(self.shape)
+
+
 def bind_to_gpu_numa_node(device_index):
     """Pin this process to the CPU cores local to GPU `device_index` (NVML affinity mask) so that the pinned
     host buffers it allocates afterwards (the 1.9 GB avatar tensor of a sweep) land on that GPU's NUMA node:

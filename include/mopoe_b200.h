@@ -236,6 +236,27 @@ int mopoe_daa_regression(int32_t n_val, int32_t n_subjects, int32_t n_scores, in
                          const float* sampled_scores, const float* reconstructions, double* betas,
                          double* coefs, double* pvalues, void* stream);
 
+/* ---- multi-GPU: the association tables over NVLink peer memory (the only exchange step) ------
+ * Each rank computes the (n_val_local, C, R) slice of coefs / pvalues of ITS validations.  Instead of an NCCL
+ * all_gather behind the sweep, mopoe_daa_exchange_tables stores the slice into every rank's FULL table through
+ * peer-mapped pointers and releases a per-source sequence flag (system scope); a one-warp kernel then acquires
+ * the flags of all sources.  Two small launches on `stream`, capturable in a CUDA graph (the sequence number lives
+ * in the buffer).  The buffers are symmetric memory the host allocates and maps on every rank (Python:
+ * torch.distributed._symmetric_memory, see daa.TableExchange); they must be zero-filled before the first call.
+ * After the call, slot (number of calls so far) & 1 of the local buffer holds the full tables:
+ *   local_base + 256 + slot * 2 * elems_total * 8 : coefs (elems_total doubles), then pvalues. */
+#define MOPOE_MAX_PEERS 8
+typedef struct mopoe_table_exchange {
+  int32_t world, rank;
+  int64_t elems_local;   /* n_val_local * C * R */
+  int64_t elem_offset;   /* val_begin * C * R */
+  int64_t elems_total;   /* n_val_total * C * R */
+  void* peer_base[MOPOE_MAX_PEERS];   /* exchange buffer of every rank as mapped in THIS process; [rank] = own */
+} mopoe_table_exchange;
+int64_t mopoe_table_exchange_bytes(int64_t elems_total);
+int mopoe_daa_exchange_tables(const mopoe_table_exchange* ex, const double* coefs_local, const double* pvalues_local,
+                              void* stream);
+
 /* Measurement hook (bench.py): when enabled, mopoe_daa_sweep brackets its dominant kernel
  * (daa_avatar_kernel) with CUDA events on the caller's stream; mopoe_daa_last_kernel_ms waits for
  * the last bracket and returns its duration. */

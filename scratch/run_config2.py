@@ -78,4 +78,4 @@ out["run_550_epochs"] = {"wall_s": wall, "train_steps": int(len(tr)), "steps_per
                          "all_finite": bool(np.isfinite(tr).all() and np.isfinite(te).all()),
                          "checkpoint_keys_match_reference": list(sd.keys()) == list(mo.param_shapes(ospec).keys()),
                          "reference_cpu_estimate_s": "9.5 ms per step on 8 host cores (oracle port) x %d steps = %.0f s" % (len(tr), 9.5e-3 * len(tr))}
-print(json.dumps(out))
+print(json.dumps(out, default=float))
