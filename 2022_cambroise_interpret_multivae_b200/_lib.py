@@ -16,6 +16,7 @@ METHODS = {"poe": 0, "moe": 1, "joint_elbo": 2}
 
 # mopoe_scalar_index
 S_TOTAL_LOSS, S_JOINT_DIV, S_NLL, S_NLL_UNI, S_KLD_SUBSET, S_KLD_STYLE, S_MEAN_HEAD = 0, 1, 2, 6, 10, 25, 29
+S_N_ROWS, S_PRESENT = 45, 46
 STREAM_DAA_BASE, STREAM_DAA_SCORE, STREAM_DAA_AVATAR, STREAM_TRAIN, STREAM_FORWARD = 1, 2, 3, 4, 5
 
 
@@ -47,7 +48,7 @@ class ForwardOut(C.Structure):
 
 class DaaDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_val", "val_begin", "n_val_total", "n_subjects", "n_samples", "n_base",
-                                         "src_mod", "dst_mod", "sample_latents", "reg_method")]
+                                         "src_mod", "dst_mod", "sample_latents", "reg_method", "base_mode")]
 
 
 MAX_PEERS = 8

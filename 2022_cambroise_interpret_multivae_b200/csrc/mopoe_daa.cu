@@ -233,10 +233,12 @@ __global__ void __launch_bounds__(BASE_THREADS) daa_base_kernel(ModelView mv, Da
     for (int m = 0; m < M; ++m)
       if (4 * b >= mv.mod[m].peps_off) { e0 = mv.mod[m].eps_off + (4 * b - mv.mod[m].peps_off); lim = mv.mod[m].eps_off + mv.mod[m].S; }
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    // base_mode 1: the mean row is drawn directly (one row per subject, scaled by 1/sqrt(M) below)
+    const int n_draw = cx.q.base_mode == 1 ? 1 : cx.q.n_base;
     if (grp < ngrp) {
-      const int64_t r0 = (int64_t)(cx.v_base_off + v) * cx.q.n_base * cx.N + g;   // noise row of pass 0
+      const int64_t r0 = (int64_t)(cx.v_base_off + v) * n_draw * cx.N + g;   // noise row of pass 0
       if (cx.nz_base.eps) {
-        for (int p = grp; p < cx.q.n_base; p += ngrp) {
+        for (int p = grp; p < n_draw; p += ngrp) {
           const float* ep = cx.nz_base.eps + (r0 + (int64_t)p * cx.N) * E;
           if (e0 + 0 < lim) a0 += ep[e0 + 0];
           if (e0 + 1 < lim) a1 += ep[e0 + 1];
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(BASE_THREADS) daa_base_kernel(ModelView mv, Da
         }
       } else {
 #pragma unroll 4
-        for (int p = grp; p < cx.q.n_base; p += ngrp) {
+        for (int p = grp; p < n_draw; p += ngrp) {
           float x[4];
           philox_normal4(cx.nz_base, (uint64_t)((r0 + (int64_t)p * cx.N) * nb + b), x);
           a0 += x[0]; a1 += x[1]; a2 += x[2]; a3 += x[3];
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(BASE_THREADS) daa_base_kernel(ModelView mv, Da
       if (ee + i < ll) {
         float a = 0.f;
         for (int q = 0; q < ngrp; ++q) a += s_acc[q * mv.EP + t];
-        s_mean[ee + i] = a / (float)cx.q.n_base;
+        s_mean[ee + i] = cx.q.base_mode == 1 ? a * rsqrtf((float)cx.q.n_base) : a / (float)cx.q.n_base;
         if (phase == 1) ws.mean_eps[row * 176 + ee + i] = s_mean[ee + i];
       }
     }
@@ -906,6 +908,7 @@ static int check_daa(const mopoe_model_desc* d, const mopoe_daa_desc* q) {
     return MOPOE_EINVAL; }
   if (q->src_mod < 0 || q->src_mod >= d->n_mods || q->dst_mod < 0 || q->dst_mod >= d->n_mods || q->src_mod == q->dst_mod) {
     set_error("src_mod=%d dst_mod=%d invalid", q->src_mod, q->dst_mod); return MOPOE_EINVAL; }
+  if (q->base_mode < 0 || q->base_mode > 1) { set_error("base_mode=%d invalid", q->base_mode); return MOPOE_EINVAL; }
   if (q->reg_method < 0 || q->reg_method > 1) { set_error("reg_method=%d unsupported (hierarchical, fixed; mixed is not on this path)", q->reg_method); return MOPOE_EINVAL; }
   if (d->dims[q->src_mod] > 64) { set_error("src modality wider than 64 columns is unsupported in the DAA kernel"); return MOPOE_EINVAL; }
   int E = d->latent_dim;
@@ -927,6 +930,7 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   const int M = desc->n_mods, N = daa->n_subjects;
   if (batch->n_rows != N || batch->present_mask != (1 << M) - 1) { set_error("batch desc must describe n_subjects rows with every modality present"); return MOPOE_EINVAL; }
   if (daa->reg_method == 1 && !reconstructions) { set_error("reg_method fixed needs the reconstructions buffer"); return MOPOE_EINVAL; }
+  if (daa->base_mode == 1 && eps_base) { set_error("base_mode 1 (mean noise row drawn directly) needs the in-kernel generator: eps_base must be NULL"); return MOPOE_EINVAL; }
   const int64_t need = daa_carve(desc, daa, nullptr, nullptr);
   if (workspace_bytes < need) { set_error("workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need); return MOPOE_ENOSPC; }
   DaaWs ws;
@@ -1003,7 +1007,10 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   }
   // 2. base passes
   const int base_smem = (176 + 4 * BASE_THREADS + MOPOE_MAX_MODS * 64 + 64 + (cx.J * cx.C <= DAA_BASE_SC_MAX ? cx.J * cx.C : 0)) * 4;
-  if (forked) {
+  if (forked && daa->base_mode == 1) {      // no noise phase worth a launch of its own: one launch behind the encoder heads
+    MOPOE_CUDA(cudaStreamWaitEvent(stream, g_join, 0));
+    daa_base_kernel<<<daa->n_val * N, BASE_THREADS, base_smem, stream>>>(mv, cx, ws, 0);
+  } else if (forked) {
     daa_base_kernel<<<daa->n_val * N, BASE_THREADS, base_smem, stream>>>(mv, cx, ws, 1);
     MOPOE_CUDA(cudaGetLastError());
     MOPOE_CUDA(cudaStreamWaitEvent(stream, g_join, 0));

@@ -24,11 +24,20 @@ class DaaResult:
 def daa_sweep(spec: PathSpec, flat_params, src, dst, n_samples, n_base, *, src_mod=0, dst_mod=1,
               sample_latents=True, reg_method="hierarchical", seed=1037, val_begin=0, n_val_total=None,
               eps_base=None, eps_score=None, eps_av=None, materialize=True, want_betas=True,
-              others=None, workspace=None, out=None):
+              others=None, workspace=None, out=None, base_mean="draws"):
     """src: (n_val, N, C) drawn test batches of the perturbed modality, dst: (n_val, N, R).
     others: optional {modality index: (n_val, N, D_m)} for models with more than two modalities.
+    base_mean: how the mean over the M stochastic reconstructions (workflow.py:388-398) gets its noise --
+      "draws"  average M drawn noise rows, draw for draw what M reference forwards consume (default);
+      "direct" draw the mean row itself, N(0, 1/M): the default decoders are affine in z, so the mean of the M
+               decodes is the decode of mu + sd * eps_mean.  Same distribution of every output, 1/M of the
+               draws (in-kernel generator only).
     Returns a DaaResult with CUDA tensors avatars (or None), sampled_scores, reconstructions,
     betas (or None), coefs, pvalues."""
+    if base_mean not in ("draws", "direct"):
+        raise ValueError("base_mean=%r (draws, direct)" % (base_mean,))
+    if base_mean == "direct" and eps_base is not None:
+        raise ValueError("base_mean='direct' uses the in-kernel generator: do not inject eps_base")
     if reg_method not in REG_METHODS:
         raise NotImplementedError("reg_method=%r is not on the B200 path (hierarchical, fixed)" % (reg_method,))
     _require_cuda(flat_params, "parameters")
@@ -55,7 +64,8 @@ def daa_sweep(spec: PathSpec, flat_params, src, dst, n_samples, n_base, *, src_m
         eps_av = _f32(eps_av); assert eps_av.shape == (n_val, n_samples, Cc, N, E)
     q = _lib.DaaDesc(n_val=n_val, val_begin=val_begin, n_val_total=n_val_total or n_val, n_subjects=N,
                      n_samples=n_samples, n_base=n_base, src_mod=src_mod, dst_mod=dst_mod,
-                     sample_latents=int(bool(sample_latents)), reg_method=REG_METHODS[reg_method])
+                     sample_latents=int(bool(sample_latents)), reg_method=REG_METHODS[reg_method],
+                     base_mode=1 if base_mean == "direct" else 0)
     bd = spec.batch_desc(N, (1 << spec.n_mods) - 1)
     lib = _lib.lib()
     nbytes = lib.mopoe_daa_workspace_bytes(C.byref(spec.desc), C.byref(q))

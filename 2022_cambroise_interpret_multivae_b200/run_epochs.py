@@ -57,7 +57,7 @@ class ScalarLog:
         keys = [k for k, _ in spec.subsets()]
         for phase in ("train", "test"):
             for step, r in enumerate(self.array(phase)):
-                mask = int(r[46])
+                mask = int(r[_lib.S_PRESENT])
                 writer.add_scalars("%s/Loss" % phase, {"loss": float(r[0])}, step)
                 writer.add_scalars("%s/LogProb" % phase, {n: float(r[_lib.S_NLL + m]) for m, n in enumerate(spec.mod_names) if mask >> m & 1}, step)
                 avail, _ = spec.mixture_subsets(mask)
@@ -70,7 +70,7 @@ def train(model_idx, epoch, exp, tb_logger):
     model = exp.models if exp.flags.num_models == 1 else exp.models[model_idx]
     model.train()
     spec, flags = model.spec, exp.flags
-    res = exp.resident
+    res = exp.resident_of(model_idx)
     flat = model.flat_parameters()
     plan = epoch_plan(res["has_train"], flags.batch_size, exp.rng)
     if not flags.allow_missing_blocks:
@@ -78,7 +78,7 @@ def train(model_idx, epoch, exp, tb_logger):
     offs = np.cumsum([0] + [len(ix) for _, ix in plan])
     index = torch.from_numpy(np.concatenate([ix for _, ix in plan]).astype(np.int32)).to(flat.device)
     bdev = engine.make_batches(spec, [(len(ix), mask, int(offs[i])) for i, (mask, ix) in enumerate(plan)], flat.device)
-    st = exp.adam_state
+    st = exp.adam_of(model_idx)
     sc = engine.train_steps(spec, flat, res["train"], bdev, len(plan), flags.batch_size, 2,
                             row_index=[index] * spec.n_mods, seed=exp.next_seed(), adam_m=st["m"], adam_v=st["v"],
                             adam_t=st["t"], lr=flags.initial_learning_rate, b1=flags.beta_1, b2=flags.beta_2,
@@ -92,7 +92,7 @@ def test(model_idx, epoch, exp, tb_logger):
     model = exp.models if exp.flags.num_models == 1 else exp.models[model_idx]
     model.eval()
     spec, flags = model.spec, exp.flags
-    res = exp.resident
+    res = exp.resident_of(model_idx)
     flat = model.flat_parameters()
     n = res["n_test"]
     full = (1 << spec.n_mods) - 1

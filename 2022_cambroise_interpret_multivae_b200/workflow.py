@@ -37,18 +37,22 @@ class _Mod:
 
 class Experiment:
     """What MultimodalExperiment provides to the hot path (experiment.py:64-91), with the cohort
-    standardised once (StandardScaler on the train rows, experiment.py:146-166) and resident in HBM."""
+    standardised once (StandardScaler on the train rows, experiment.py:146-166) and resident in HBM.
+    `flags.num_models > 1` builds the reference's ensemble (experiment.py:196-235): k-fold splits of the subjects
+    (no held-out test set; model i is tested on fold i), one model, scaler and optimiser state per fold; every
+    per-model attribute is then a list, as in the reference."""
 
     def __init__(self, flags, device=None):
         self.flags = flags
         self.device = device or torch.device("cuda" if torch.cuda.is_available() else "cpu")
         self.modalities = {n: _Mod(n) for n in MODALITIES[: len(flags.input_dim)]}
         self.mod_names = list(self.modalities)
+        self.num_models = int(getattr(flags, "num_models", 1) or 1)
         self.rng = np.random.RandomState(None if flags.data_seed == "defaults" else int(flags.data_seed))
         self._seed = int(self.rng.randint(1, 2 ** 31 - 1))
         self._load(flags.datasetdir)
-        torch_state = None
-        self.models = VAE(flags, self.modalities).to(self.device)
+        models = [VAE(flags, self.modalities).to(self.device) for _ in range(self.num_models)]   # experiment.py:123-130
+        self.models = models[0] if self.num_models == 1 else models
         self.optimizers = None
         self.adam_state = None
         self.rec_weights = {n: 1.0 for n in self.mod_names}
@@ -57,6 +61,15 @@ class Experiment:
     def next_seed(self):
         self._seed += 1
         return self._seed
+
+    def model_of(self, model_idx):
+        return self.models if self.num_models == 1 else self.models[model_idx]
+
+    def resident_of(self, model_idx):
+        return self.resident if self.num_models == 1 else self.resident[model_idx]
+
+    def adam_of(self, model_idx):
+        return self.adam_state if self.num_models == 1 else self.adam_state[model_idx]
 
     def _load(self, datasetdir):
         meta = pd.read_table(os.path.join(datasetdir, "metadata.tsv"))
@@ -78,32 +91,47 @@ class Experiment:
         complete = np.flatnonzero(has.all(0))
         split = np.random.RandomState(42)                       # fetchers/hbn.py:20 seed
         perm = split.permutation(complete)
-        n_test = int(round(0.2 * len(complete)))                # experiment.py:203 test_size
-        test_idx = np.sort(perm[:n_test])
-        train_mask = np.ones(n, bool)
-        train_mask[test_idx] = False
-        if not self.flags.allow_missing_blocks:
-            train_mask &= has.all(0)
-        train_idx = np.flatnonzero(train_mask & has.any(0))
-        self.scalers = []
-        for m in range(len(blocks)):
-            rows = blocks[m][train_idx][has[m][train_idx]]
-            mean, std = rows.mean(0), rows.std(0)
-            std[std == 0] = 1.0
-            self.scalers.append((mean, std))
-            blocks[m] = ((blocks[m] - mean) / std).astype(np.float32)
-        dev = self.device
+        if self.num_models == 1:
+            n_test = int(round(0.2 * len(complete)))            # experiment.py:203 test_size
+            folds = [np.sort(perm[:n_test])]
+        else:                                                   # experiment.py:203-207: validation = num_models, test_size = 0
+            folds = [np.sort(f) for f in np.array_split(perm, self.num_models)]
         self.metadata = meta
-        self.train_idx, self.test_idx = train_idx, test_idx
-        self.resident = {"train": [torch.from_numpy(b[train_idx]).to(dev) for b in blocks],
-                         "test": [torch.from_numpy(b[test_idx]).to(dev) for b in blocks],
-                         "has_train": has[:, train_idx], "n_test": len(test_idx)}
+        self.scalers, self.train_idx, self.test_idx, resident = [], [], [], []
+        dev = self.device
+        for test_idx in folds:
+            train_mask = np.ones(n, bool)
+            train_mask[test_idx] = False
+            if not self.flags.allow_missing_blocks:
+                train_mask &= has.all(0)
+            train_idx = np.flatnonzero(train_mask & has.any(0))
+            scalers, scaled = [], []
+            for m in range(len(blocks)):
+                rows = blocks[m][train_idx][has[m][train_idx]]
+                mean, std = rows.mean(0), rows.std(0)
+                std[std == 0] = 1.0
+                scalers.append((mean, std))
+                scaled.append(((blocks[m] - mean) / std).astype(np.float32))
+            self.scalers.append(scalers)
+            self.train_idx.append(train_idx)
+            self.test_idx.append(test_idx)
+            resident.append({"train": [torch.from_numpy(b[train_idx]).to(dev) for b in scaled],
+                             "test": [torch.from_numpy(b[test_idx]).to(dev) for b in scaled],
+                             "has_train": has[:, train_idx], "n_test": len(test_idx)})
+        if self.num_models == 1:
+            self.scalers, self.train_idx, self.test_idx, self.resident = self.scalers[0], self.train_idx[0], self.test_idx[0], resident[0]
+        else:
+            self.resident = resident
 
     def set_optimizers(self):
-        flat = self.models.flat_parameters()
-        self.adam_state = {"m": torch.zeros_like(flat), "v": torch.zeros_like(flat),
-                           "t": torch.zeros(4, dtype=torch.int32, device=flat.device)}
-        print("num parameters: %d" % sum(p.numel() for p in self.models.parameters()))
+        states, total = [], 0
+        for i in range(self.num_models):
+            flat = self.model_of(i).flat_parameters()
+            states.append({"m": torch.zeros_like(flat), "v": torch.zeros_like(flat),
+                           "t": torch.zeros(4, dtype=torch.int32, device=flat.device)})
+            total += sum(p.numel() for p in self.model_of(i).parameters())
+        self.adam_state = states[0] if self.num_models == 1 else states
+        print("num parameters: %d" % total)
 
     @classmethod
     def get_experiment(cls, flags_file, checkpoints_dir, load_epoch=None):
@@ -113,16 +141,19 @@ class Experiment:
             flags.num_models = 1
         flags.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
         exp = cls(flags)
-        cp_files = glob.glob(os.path.join(checkpoints_dir, "*", flags.model_save))
-        if len(cp_files) == 0:
-            raise ValueError("You need first to train the model.")
-        cp_files = sorted(cp_files, key=lambda p: int(p.split(os.sep)[-2]))
-        cp_file = cp_files[-1]
-        if load_epoch is not None:
-            epochs = np.array([int(p.split(os.sep)[-2]) for p in cp_files])
-            cp_file = cp_files[int(np.argmin(epochs >= load_epoch))]
-        print(cp_file)
-        exp.models.load_state_dict(torch.load(cp_file, map_location=flags.device))
+        for model_idx in range(exp.num_models):
+            pattern = (os.path.join(checkpoints_dir, "*", flags.model_save) if exp.num_models == 1 else
+                       os.path.join(checkpoints_dir, "model_%d" % model_idx, "*", flags.model_save))
+            cp_files = glob.glob(pattern)
+            if len(cp_files) == 0:
+                raise ValueError("You need first to train the model.")
+            cp_files = sorted(cp_files, key=lambda p: int(p.split(os.sep)[-2]))
+            cp_file = cp_files[-1]
+            if load_epoch is not None:
+                epochs = np.array([int(p.split(os.sep)[-2]) for p in cp_files])
+                cp_file = cp_files[int(np.argmin(epochs >= load_epoch))]
+            print(cp_file)
+            exp.model_of(model_idx).load_state_dict(torch.load(cp_file, map_location=flags.device))
         return exp, flags
 
 
@@ -183,8 +214,6 @@ def train_exp(dataset, datasetdir, outdir, input_dims, num_models=1, latent_dim=
               data_multiplications=1, dropout_rate=0., initial_out_logvar=-3., learn_output_scale=True,
               out_scale_per_subject=False, method="joint_elbo", grad_scaling=False):
     """Train the model (workflow.py:41-182).  Returns the run name."""
-    if num_models != 1:
-        raise NotImplementedError("num_models > 1 (k-fold ensembles) is not on the B200 path")
     flags = _make_flags(dataset, datasetdir, outdir, input_dims, num_models, latent_dim, style_dim, data_seed,
                         num_hidden_layer_encoder, num_hidden_layer_decoder, allow_missing_blocks,
                         factorized_representation, likelihood, learning_rate, batch_size, num_epochs, eval_freq,
@@ -206,6 +235,17 @@ def train_exp(dataset, datasetdir, outdir, input_dims, num_models=1, latent_dim=
         row = pd.concat((pd.read_table(runs_file), row))
     row.to_csv(runs_file, index=False, sep="\t")
     return flags.str_experiment
+
+
+def significant_votes(pvalues, trust_level, n_models=1, vote_prop=1):
+    """workflow.py:517-525: Bonferroni threshold 0.05 / n_rois / n_scores, vote over the validations of each model
+    (>= trust_level * n_validation), then over the models of an ensemble (>= vote_prop * n_models).
+    pvalues (n_val, C, R) or (n_models, n_val, C, R) -> bool (C, R)."""
+    p = np.asarray(pvalues)
+    if n_models == 1:
+        return daa.significant(p, trust_level)
+    per_model = np.stack([daa.significant(p[i], trust_level) for i in range(n_models)])
+    return per_model.sum(0) >= vote_prop * n_models
 
 
 def daa_exp(dataset, datasetdir, outdir, run, sampling_strategy="likelihood", n_validation=5, n_samples=200,
@@ -231,60 +271,94 @@ def daa_exp(dataset, datasetdir, outdir, run, sampling_strategy="likelihood", n_
     resdir = os.path.join(daadir, name)
     if rank == 0:
         os.makedirs(resdir, exist_ok=True)
-    model = exp.models
-    model.eval()
-    flat = model.flat_parameters()
-    # draw n_validation batches of test subjects on the host (workflow.py:362-372), seeded
-    rs = np.random.RandomState(seed)
-    n_test = exp.resident["n_test"]
-    draws = np.stack([rs.permutation(n_test)[:n_subjects] for _ in range(n_validation)])
+    n_models = exp.num_models
+    lead = (n_models,) if n_models > 1 else ()                   # workflow.py:264-288: leading model axis for ensembles
+    n_test_min = min(exp.resident_of(i)["n_test"] for i in range(n_models))
+    if n_subjects > n_test_min:
+        raise ValueError("n_subjects=%d exceeds the %d test subjects with every block" % (n_subjects, n_test_min))
+    if world > n_validation:
+        raise ValueError("world size %d exceeds n_validation=%d (validations are the sharding unit)" % (world, n_validation))
+    # draw n_validation batches of test subjects per model on the host (workflow.py:362-372): rank 0 draws, every
+    # rank uses the same draws (with seed=None each rank would otherwise draw its own)
+    if seed is None:
+        seed_t = torch.zeros(1, dtype=torch.int64, device=exp.device)
+        if rank == 0:
+            seed_t[0] = int(np.random.randint(0, 2 ** 31 - 1))
+        if world > 1:
+            dist.broadcast(seed_t, 0)
+        draw_seed = int(seed_t.item())
+    else:
+        draw_seed = int(seed)
+    rs = np.random.RandomState(draw_seed)
     begin, end = daa.shard_validations(n_validation, rank, world)
-    idx = torch.from_numpy(draws[begin:end]).to(flat.device)
-    src = exp.resident["test"][0][idx]
-    dst = exp.resident["test"][1][idx]
-    r = daa.daa_sweep(model.spec, flat, src, dst, n_samples, M, sample_latents=sample_latents, reg_method=reg_method,
-                      seed=0 if seed is None else seed, val_begin=begin, n_val_total=n_validation,
-                      materialize=materialize_avatars, workspace=model._ws)
-    daa.check_status(model.spec, r)           # a device-side protocol error must not end up in result files
-    coefs, pvalues, betas, scores, recons = daa.gather_tables_many(
-        [r.coefs, r.pvalues, r.betas, r.sampled_scores, r.reconstructions], n_validation)
-    torch.cuda.synchronize()
-    meta = exp.metadata.iloc[exp.test_idx].reset_index(drop=True)
-    meta_cols = list(meta.columns)
+    all_draws, tabs = [], {k: [] for k in ("coefs", "pvalues", "betas", "scores", "recons")}
     if materialize_avatars:
         from numpy.lib.format import open_memmap
         da_file = os.path.join(resdir, "rois_digital_avatars.npy")
         if world > 1:
             dist.barrier()
-        mode = "w+" if rank == 0 else "r+"
         if rank == 0:
-            mm = open_memmap(da_file, dtype="float32", mode="w+", shape=(n_validation, n_subjects, n_scores, n_samples, n_rois))
+            mm = open_memmap(da_file, dtype="float32", mode="w+", shape=lead + (n_validation, n_subjects, n_scores, n_samples, n_rois))
             del mm
         if world > 1:
             dist.barrier()
-        mm = np.load(da_file, mmap_mode="r+")
-        mm[begin:end] = r.avatars.cpu().numpy()                 # disjoint slices per rank
-        mm.flush()
-        del mm
+    for model_idx in range(n_models):
+        model = exp.model_of(model_idx)
+        model.eval()
+        flat = model.flat_parameters()
+        res = exp.resident_of(model_idx)
+        draws = np.stack([rs.permutation(res["n_test"])[:n_subjects] for _ in range(n_validation)])
+        all_draws.append(draws)
+        idx = torch.from_numpy(draws[begin:end]).to(flat.device)
+        src = res["test"][0][idx]
+        dst = res["test"][1][idx]
+        r = daa.daa_sweep(model.spec, flat, src, dst, n_samples, M, sample_latents=sample_latents, reg_method=reg_method,
+                          seed=draw_seed + 7919 * model_idx, val_begin=begin, n_val_total=n_validation,
+                          materialize=materialize_avatars, workspace=model._ws)
+        daa.check_status(model.spec, r)           # a device-side protocol error must not end up in result files
+        got = daa.gather_tables_many([r.coefs, r.pvalues, r.betas, r.sampled_scores, r.reconstructions], n_validation)
+        torch.cuda.synchronize()
+        for k, t in zip(("coefs", "pvalues", "betas", "scores", "recons"), got):
+            tabs[k].append(t.cpu().numpy())
+        if materialize_avatars:
+            mm = np.load(da_file, mmap_mode="r+")
+            host = torch.empty(r.avatars.shape, dtype=torch.float32).pin_memory()      # pinned: the 1.9 GB copy runs at link speed
+            host.copy_(r.avatars)
+            if n_models > 1:
+                mm[model_idx, begin:end] = host.numpy()          # disjoint slices per rank
+            else:
+                mm[begin:end] = host.numpy()
+            mm.flush()
+            del mm, host
+    stack = lambda k: np.stack(tabs[k]) if n_models > 1 else tabs[k][0]
+    coefs, pvalues, betas = stack("coefs"), stack("pvalues"), stack("betas")
     if rank == 0:
-        np.save(os.path.join(resdir, "sampled_scores.npy"), scores.cpu().numpy())
-        np.save(os.path.join(resdir, "metadatas.npy"), np.stack([meta.iloc[d].to_numpy() for d in draws]))
-        np.save(os.path.join(resdir, "rois_reconstructions.npy"), recons.cpu().numpy())
-        np.save(os.path.join(resdir, "pvalues.npy"), pvalues.cpu().numpy())
-        np.save(os.path.join(resdir, "coefs.npy"), coefs.cpu().numpy())
+        test_idx = [exp.test_idx] if n_models == 1 else exp.test_idx
+        metas = [exp.metadata.iloc[ti].reset_index(drop=True) for ti in test_idx]
+        meta_cols = list(metas[0].columns)
+        metadatas = [np.stack([metas[i].iloc[d].to_numpy() for d in all_draws[i]]) for i in range(n_models)]
+        np.save(os.path.join(resdir, "sampled_scores.npy"), stack("scores"))
+        np.save(os.path.join(resdir, "metadatas.npy"), np.stack(metadatas) if n_models > 1 else metadatas[0])
+        np.save(os.path.join(resdir, "rois_reconstructions.npy"), stack("recons"))
+        np.save(os.path.join(resdir, "pvalues.npy"), pvalues)
+        np.save(os.path.join(resdir, "coefs.npy"), coefs)
         if reg_method == "hierarchical":                        # workflow.py:476-505: per-subject betas
-            b = betas.cpu().numpy()
             cols = [str(n).replace("&", "_").replace("-", "_") for n in rois_names]
             pid, site = meta_cols.index("participant_id"), meta_cols.index("site")
             all_coefs = []
-            for v in range(n_validation):
-                all_coefs.append([])
-                m = meta.iloc[draws[v]].to_numpy()[:, [pid, site]]
-                for c in range(n_scores):
-                    df = pd.DataFrame(m, columns=["participant_id", "site"])
-                    all_coefs[v].append(pd.concat([df, pd.DataFrame(b[v, c], columns=cols)], axis=1))
-            np.save(os.path.join(resdir, "all_coefs.npy"), np.array(all_coefs, dtype=object), allow_pickle=True)
-        idx_sign = daa.significant(pvalues, trust_level)        # workflow.py:517-523
+            for i in range(n_models):
+                b = betas[i] if n_models > 1 else betas
+                per_model = []
+                for v in range(n_validation):
+                    per_model.append([])
+                    m = metas[i].iloc[all_draws[i][v]].to_numpy()[:, [pid, site]]
+                    for c in range(n_scores):
+                        df = pd.DataFrame(m, columns=["participant_id", "site"])
+                        per_model[v].append(pd.concat([df, pd.DataFrame(b[v, c], columns=cols)], axis=1))
+                all_coefs.append(per_model)
+            np.save(os.path.join(resdir, "all_coefs.npy"), np.array(all_coefs if n_models > 1 else all_coefs[0], dtype=object),
+                    allow_pickle=True)
+        idx_sign = significant_votes(pvalues, trust_level, n_models, vote_prop)       # workflow.py:517-525
         rows = {"metric": [], "roi": [], "score": []}
         for i, score in enumerate(clinical_names):
             for nm in rois_names[np.where(idx_sign[i])]:

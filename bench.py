@@ -46,7 +46,9 @@ def workload_config(n_gpus):
                         "regression, 7 scores x 444 ROIs" % DAA["n_validation"],
             "n_validation_total": DAA["n_validation"] * n_gpus, "parallelism": "validations sharded over %d GPU(s)" % n_gpus,
             "l2": "outputs larger than L2: 1.865 GB avatar tensor written per sweep (126 MB L2)", "launch": LAUNCH_NOTE[0], "host_binding": LAUNCH_NOTE[1],
-            "noise": "in-kernel philox (production mode)", "weights": "random init (seed 0)"}
+            "noise": "in-kernel philox (production mode); mean noise row of the M = 1000 affine base passes drawn directly as "
+                     "N(0, 1/M) (base_mean='direct': same distribution, 1/M of the draws; the draw-for-draw M-pass mode is timed "
+                     "beside it as value_base_draws)", "weights": "random init (seed 0)"}
 
 
 def draw_validation_batches(n_val, seed, offset=0):
@@ -357,8 +359,8 @@ def run_ours(args, rank, world, local_rank):
     class Runner:
         """One shard of a sweep on this rank: sweep + exchange of the association tables, replayed from a CUDA graph."""
 
-        def __init__(self, src, dst, val_begin, n_val_total):
-            self.src, self.dst, self.val_begin, self.n_val_total = src, dst, val_begin, n_val_total
+        def __init__(self, src, dst, val_begin, n_val_total, base_mean="direct"):
+            self.src, self.dst, self.val_begin, self.n_val_total, self.base_mean = src, dst, val_begin, n_val_total, base_mean
             self.ex, self.full, self.graph, self.replays = None, {}, None, 0
             self.exchange_note = "single GPU: nothing to exchange"
             if world > 1:
@@ -381,7 +383,8 @@ def run_ours(args, rank, world, local_rank):
 
         def sweep(self, src=None, dst=None, out=None):
             return daa.daa_sweep(spec, flat, self.src if src is None else src, self.dst if dst is None else dst, J, Mb,
-                                 seed=DAA["seed"], val_begin=self.val_begin, n_val_total=self.n_val_total, workspace=ws, out=out)
+                                 seed=DAA["seed"], val_begin=self.val_begin, n_val_total=self.n_val_total, workspace=ws, out=out,
+                                 base_mean=self.base_mean)
 
         def gather(self, r=None):
             r = r or self.r
@@ -514,6 +517,16 @@ def run_ours(args, rank, world, local_rank):
         v = C.c_float()
         _lib.check(lib.mopoe_daa_last_kernel_ms(C.byref(v)))
         kernel_ms.append(v.value)
+    # the same sweep with the M base passes drawn one by one (draw-for-draw what M reference forwards consume)
+    drun = Runner(src_d, dst_d, rank * n_val, world * n_val, base_mean="draws") if world == 1 else None
+    ms_draws = None
+    if drun is not None:
+        drun.ex = None
+        drun.capture()
+        for _ in range(2):
+            drun.step()
+        ms_draws = drun.timed(args.steps)
+        del drun
     # ---- e2e: pinned host buffers in and out ----
     host_out = {k: torch.empty(getattr(r, k).shape, dtype=getattr(r, k).dtype).pin_memory()
                 for k in ("avatars", "sampled_scores", "reconstructions", "betas", "coefs", "pvalues")}
@@ -638,6 +651,13 @@ def run_ours(args, rank, world, local_rank):
         line["statistics_parity"] = "unpinned: statsmodels (stat_utils.make_regression) is absent; closed forms checked against scipy/numpy"
         if strong is not None:
             line["strong_scaling"] = strong
+        if ms_draws is not None:
+            line["value_base_draws"] = {"value": avatars_per_step * args.steps / (ms_draws * 1e-3), "unit": UNIT,
+                                        "ms_per_step": ms_draws / args.steps,
+                                        "note": "base_mean='draws': 43 M normals per sweep drawn and averaged (round-1 behaviour)"}
+        sweep_bytes = alg_bytes
+        line["roofline"]["whole_sweep"] = {"achieved": sweep_bytes / (ms / args.steps * 1e-3) / 1e9, "frac": sweep_bytes / (ms / args.steps * 1e-3) / 1e9 / hbm_peak,
+                                           "note": "algorithmic bytes of the sweep over the WHOLE step time (all kernels, graph replay)"}
         if world == 1:
             os.sched_setaffinity(0, all_cpus)            # the CPU baseline uses every host core again
             n, dt, desc = cpu_daa_sample(12.0)

@@ -200,6 +200,13 @@ typedef struct mopoe_daa_desc {
   int32_t dst_mod;      /* read-out modality ("rois") */
   int32_t sample_latents;
   int32_t reg_method;   /* 0 = hierarchical (stat_utils.py:66-75), 1 = fixed (:62-63) */
+  int32_t base_mode;    /* how the mean over the M stochastic reconstructions (workflow.py:388-398) gets its noise:
+                         * 0 = average M drawn noise rows (draw-for-draw what M reference forwards consume; required with
+                         *     injected eps_base), 1 = draw the MEAN row directly, eps_mean ~ N(0, 1/M) (one Philox row per
+                         *     subject scaled by 1/sqrt(M)): the default decoders are affine in z, so the mean of the M decodes
+                         *     is the decode of mu + sd * eps_mean -- same distribution, 1/M of the draws; only with the
+                         *     in-kernel generator (eps_base == NULL).  Equivalent to base_mode 0 with n_base = 1 and
+                         *     eps_base = that row / sqrt(M) (tests/test_gpu_parity.py). */
 } mopoe_daa_desc;
 
 /* Bytes of scratch mopoe_daa_sweep needs. */

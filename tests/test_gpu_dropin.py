@@ -180,3 +180,33 @@ def test_train_exp_then_daa_exp_end_to_end(tmp_path):
     assert len(sig) - 1 == int(want.sum())
     meta = np.load(os.path.join(resdir, "metadatas.npy"), allow_pickle=True)
     assert meta.shape[:2] == (3, 20)
+
+
+def test_ensemble_train_and_daa_with_vote_prop(tmp_path):
+    """num_models > 1 (workflow.py:41,203-207,290-297,524-525): k-fold ensemble, one model / scaler / Adam state per
+    fold, checkpoints under model_<i>/, DAA outputs with a leading model axis, vote over models with vote_prop."""
+    from mopoe_b200 import data, workflow
+    ds, out = str(tmp_path / "data"), str(tmp_path / "out")
+    os.makedirs(out)
+    data.write_dataset(ds, data.make_cohort(n_both=480, n_clinical_only=64, n_rois_only=32, standardize=False))
+    run = workflow.train_exp("hbn", ds, out, [7, 444], num_models=2, num_epochs=5, batch_size=128, data_seed=5)
+    rundir = os.path.join(out, run)
+    for i in range(2):
+        assert os.path.isfile(os.path.join(rundir, "checkpoints", "model_%d" % i, "0004", "model"))
+        tr = np.load(os.path.join(rundir, "logs", "scalars_train_model%d.npy" % i))
+        assert np.isfinite(tr).all() and tr[-1, 0] < tr[0, 0]
+    sd0 = torch.load(os.path.join(rundir, "checkpoints", "model_0", "0004", "model"))
+    sd1 = torch.load(os.path.join(rundir, "checkpoints", "model_1", "0004", "model"))
+    assert not torch.equal(sd0["encoders.rois.class_mu.weight"], sd1["encoders.rois.class_mu.weight"])   # different folds
+    resdir = workflow.daa_exp("hbn", ds, out, run, n_validation=2, n_samples=8, n_subjects=16, M=20, trust_level=0.5, vote_prop=0.5)
+    av = np.load(os.path.join(resdir, "rois_digital_avatars.npy"))
+    p = np.load(os.path.join(resdir, "pvalues.npy"))
+    assert av.shape == (2, 2, 16, 7, 8, 444) and p.shape == (2, 2, 7, 444)
+    assert np.load(os.path.join(resdir, "sampled_scores.npy")).shape == (2, 2, 16, 8, 7)
+    assert np.load(os.path.join(resdir, "metadatas.npy"), allow_pickle=True).shape[:3] == (2, 2, 16)
+    for i in range(2):                                   # statistics recomputed from the files, per model
+        pw, cw, _ = daa_oracle.hierarchical_regression(av[i], np.load(os.path.join(resdir, "sampled_scores.npy"))[i])
+        assert np.all(np.abs(np.log(p[i]) - np.log(pw)) <= 1e-7 * np.maximum(1.0, np.abs(np.log(pw))))
+    want = workflow.significant_votes(p, 0.5, 2, 0.5)
+    sig = open(os.path.join(resdir, "significant_rois.tsv")).read().splitlines()
+    assert len(sig) - 1 == int(want.sum())

@@ -334,6 +334,34 @@ def test_daa_production_noise_is_shard_invariant_and_matches_oracle():
     _close(full.sampled_scores, sc, "scores (philox)")
 
 
+def test_daa_mean_noise_drawn_directly_equals_one_injected_base_pass():
+    """base_mean="direct": the mean noise row of the M stochastic reconstructions is drawn as N(0, 1/M) (one Philox
+    row per subject / sqrt(M)) instead of averaging M rows.  By construction this is the sweep with ONE injected
+    base pass holding that row -- checked here, and through the oracle (whose M-pass loop, workflow.py:388-398, is
+    fed the same single row), for both avatar kernels."""
+    from mopoe_b200 import daa
+    case = dict(cases.DAA_CASES["joint_elbo"], n_val=3, n_samples=150)
+    ospec, spec, params, flat = _setup(case)
+    src, dst, _, _, _ = cases.daa_inputs_of(case, ospec)
+    J, N, C_, E, Mb, seed = 150, case["n_rows"], ospec.dims[0], ospec.eps_width, 400, 91
+    sd = list(ospec.style_dims)
+    direct = daa.daa_sweep(spec, flat, src.cuda(), dst.cuda(), J, Mb, seed=seed, base_mean="direct")
+    eb = torch.from_numpy(philox.philox_rows(seed, philox.STREAM_DAA_BASE, 3 * N, ospec.latent_dim, sd)).view(3, 1, N, E) / np.sqrt(Mb)
+    one = daa.daa_sweep(spec, flat, src.cuda(), dst.cuda(), J, 1, seed=seed, eps_base=eb.cuda())
+    torch.cuda.synchronize()
+    _close(direct.reconstructions, one.reconstructions, "reconstructions", rtol=2e-6)
+    _close(direct.sampled_scores, one.sampled_scores, "scores", rtol=2e-6)
+    _close(direct.avatars, one.avatars, "avatars", rtol=2e-6)
+    _close(direct.coefs, one.coefs, "coefs", rtol=1e-4)
+    es = torch.from_numpy(philox.philox_normal(seed, philox.STREAM_DAA_SCORE, 3 * J * N * C_)).view(3, J, N, C_)
+    ea = torch.from_numpy(philox.philox_rows(seed, philox.STREAM_DAA_AVATAR, 3 * J * C_ * N, ospec.latent_dim, sd)).view(3, J, C_, N, E)
+    av, sc, rc = daa_oracle.daa_generate(params, ospec, src, dst, eb, es, ea)
+    _close(direct.avatars, av, "avatars vs oracle")
+    _close(direct.sampled_scores, sc, "scores vs oracle")
+    with pytest.raises(ValueError):
+        daa.daa_sweep(spec, flat, src.cuda(), dst.cuda(), J, 1, seed=seed, eps_base=eb.cuda(), base_mean="direct")
+
+
 # ---- tensor-core (tcgen05) avatar kernel ------------------------------------------------------
 def _daa_case(method="joint_elbo", factorized=True, dims=(7, 444), n_rows=12, n_val=2, n_samples=150, n_base=6,
               sample_latents=True, seed=80):

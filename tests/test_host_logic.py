@@ -190,3 +190,17 @@ def test_reference_rng_order_matches_the_reference_consumption():
         for want in want_list:                       # the reference: one randn_like per reparameterize call
             got = torch.randn(want.shape)
             assert torch.equal(got, want)
+
+
+def test_significant_votes_over_validations_and_models():
+    """workflow.py:517-525: per-model vote over validations, then vote_prop over the models of an ensemble."""
+    from mopoe_b200 import workflow
+    rng = np.random.default_rng(0)
+    C_, R = 3, 5
+    thr = 0.05 / R / C_
+    p = rng.uniform(0, 2 * thr, size=(4, 6, C_, R))          # 4 models x 6 validations
+    per_model = (p < thr).sum(1) >= 0.5 * 6
+    for vote in (0.25, 0.5, 1):
+        want = per_model.sum(0) >= vote * 4
+        assert np.array_equal(workflow.significant_votes(p, 0.5, 4, vote), want)
+    assert np.array_equal(workflow.significant_votes(p[0], 0.5), per_model[0])
