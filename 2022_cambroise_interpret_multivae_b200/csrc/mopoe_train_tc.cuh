@@ -171,7 +171,7 @@ static bool make_plan(const mopoe_model_desc* d, int64_t max_rows, int smem_limi
   p.nw[0] = nwmax; p.nw[1] = nw1;   // nw[0] is the CAP of the per-modality width of GEMM 0 (recomputed on the device)
   p.slot3 = (128 + max(max(nw0max, nw1), 64)) * R * 4;
   const int sms = num_sms();
-  p.ksplit = max_rows <= 512 ? 1 : max(1, min(p.ntiles_max, (4 * sms) / max(1, nu)));   // ~4 items per CTA for the dynamic queue
+  p.ksplit = max_rows <= 512 ? 1 : max(1, min(p.ntiles_max, (2 * sms) / max(1, nu)));   // ~2 items per CTA (4 measured slower: more partial tiles to reduce)
   p.p3part = takeg((int64_t)nu * p.ksplit * 128 * 256 * 4);
   p.p3cnt = takeg((int64_t)(MAX_UNITS + 64) * 4);   // per-unit arrival counters, then the P3 work-queue counter
   p.total = off;

@@ -41,6 +41,10 @@ def daa_sweep(spec: PathSpec, flat_params, src, dst, n_samples, n_base, *, src_m
     if reg_method not in REG_METHODS:
         raise NotImplementedError("reg_method=%r is not on the B200 path (hierarchical, fixed)" % (reg_method,))
     _require_cuda(flat_params, "parameters")
+    if n_samples < 128:
+        import warnings
+        warnings.warn("n_samples=%d < 128: the tcgen05 avatar kernels tile 128 samples per series, this sweep runs on the "
+                      "CUDA-core avatar kernel (about 7x slower per avatar)" % n_samples, stacklevel=2)
     device = flat_params.device
     src, dst = _f32(src), _f32(dst)
     _require_cuda(src, "src")
