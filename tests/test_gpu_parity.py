@@ -261,6 +261,58 @@ def test_fused_adam_steps(name, train_impl):
         assert np.abs(a - w).max() <= 2 * lr * steps, k
 
 
+@pytest.mark.parametrize("base,method", [(cases.HBN, "joint_elbo"), (cases.STRESS, "poe")])
+def test_tensor_core_trainer_mixed_batch_sizes_in_one_launch(base, method, monkeypatch):
+    """One launch of the tensor-core kernel over steps of very different sizes and present-sets (an epoch plan with
+    its tail batches): row-range splits of the weight-gradient tiles that receive no rows, partial row tiles, absent
+    modalities.  Checked step by step against the oracle trajectory and against the CUDA-core kernel."""
+    from mopoe_b200 import engine, _lib
+    case = cases._case(base, method, True, tuple(range(len(base["dims"]))), 3000, 77, 177)
+    ospec, spec, params, flat0 = _setup(case)
+    dev = flat0.device
+    sizes, masks = [3000, 100, 1700, 33], None
+    full = (1 << spec.n_mods) - 1
+    masks = [full, full, full & ~1 if spec.n_mods > 2 else 2, full]
+    rng = np.random.default_rng(5)
+    max_rows, E = max(sizes), ospec.eps_width
+    data = [torch.from_numpy(rng.standard_normal((sum(sizes), d)).astype(np.float32)) for d in ospec.dims]
+    eps = torch.from_numpy(rng.standard_normal((len(sizes), spec.n_pass, max_rows, E)).astype(np.float32))
+    offs = np.cumsum([0] + sizes)
+    bl = [(n, m, int(offs[i])) for i, (n, m) in enumerate(zip(sizes, masks))]
+    idx = torch.arange(sum(sizes), dtype=torch.int32, device=dev)
+    out = {}
+    for impl in ("tc", "ffma"):
+        monkeypatch.setenv("MOPOE_TRAIN_IMPL", impl)
+        flat = flat0.clone()
+        m_, v_ = torch.zeros_like(flat), torch.zeros_like(flat)
+        t_ = torch.zeros(4, dtype=torch.int32, device=dev)
+        sc = engine.train_steps(spec, flat, [d.to(dev) for d in data], engine.make_batches(spec, bl, dev), len(sizes), max_rows, 2,
+                                row_index=[idx] * spec.n_mods, eps=eps.to(dev), adam_m=m_, adam_v=v_, adam_t=t_, lr=0.002)
+        torch.cuda.synchronize()
+        assert _lib.lib().mopoe_train_last_impl() == (1 if impl == "tc" else 0)
+        out[impl] = (sc.cpu().numpy(), flat.cpu(), t_.cpu().tolist())
+    # oracle trajectory
+    batches, eps_l = [], []
+    for i, (n, m) in enumerate(zip(sizes, masks)):
+        batches.append({name: data[k][offs[i]:offs[i] + n] for k, name in enumerate(spec.mod_names) if m >> k & 1})
+        eps_l.append(eps[i][:, :n])
+    new, opt, losses = mo.train_steps(params, ospec, batches, eps_l, lr=0.002)
+    for impl in ("tc", "ffma"):
+        sc, flat, tt = out[impl]
+        for i in range(len(sizes)):
+            assert abs(sc[i, 0] - float(losses[i]["total_loss"])) <= 2 * RTOL * abs(float(losses[i]["total_loss"])), (impl, i)
+        assert tt[:spec.n_mods] == [sum(m >> k & 1 for m in masks) for k in range(spec.n_mods)]
+        got = engine.unpack_params(spec, flat)
+        for k in new:
+            a, w = got[k].double().numpy(), new[k].double().numpy()
+            err = np.abs(a - w) / max(np.abs(w).max(), 1e-30)
+            # a ReLU-kink disagreement (see _relu_kink_units) moves one whole row of W1 (1/256 of the tensor), and Adam
+            # turns it into an O(lr) difference that the following steps carry into that unit's column of the heads
+            assert np.mean(err <= RTOL) >= 0.99, (impl, k, float(np.mean(err <= RTOL)))
+    a, b = out["tc"][1], out["ffma"][1]
+    assert float((a - b).abs().max()) <= 2 * 0.002 * len(sizes)
+
+
 @pytest.mark.parametrize("name", sorted(cases.DAA_CASES))
 def test_daa_sweep_injected(name):
     from mopoe_b200 import daa
