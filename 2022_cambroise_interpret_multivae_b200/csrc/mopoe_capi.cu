@@ -23,14 +23,16 @@ int cuda_fail(cudaError_t e, const char* what) {
   return MOPOE_ECUDA;
 }
 
-int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+int num_sms() {   // of the CURRENT device (cached per device ordinal)
+  static int sms[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (sms[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms[dev] = n;
   }
-  return sms;
+  return sms[dev];
 }
 
 int check_desc(const mopoe_model_desc* d) {

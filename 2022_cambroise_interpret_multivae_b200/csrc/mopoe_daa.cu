@@ -17,6 +17,8 @@
 #include <cuda.h>   // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched through the runtime, no libcuda link)
 
 #include "mopoe_common.cuh"
+#include <mutex>
+
 #include "mopoe_latent.cuh"
 #include "mopoe_umma.cuh"
 
@@ -875,8 +877,25 @@ static int g_profile = 0;
 static int g_last_impl = 0;
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 // fork/join of the sweep: the encoder kernels run on g_side while the caller's stream draws the base-pass noise
-static cudaStream_t g_side = nullptr;
-static cudaEvent_t g_fork = nullptr, g_join = nullptr;
+// (one set per device, created under a lock: a process may drive several GPUs, from several host threads)
+constexpr int MAX_DEVICES = 64;
+struct SideStream { cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static SideStream g_sides[MAX_DEVICES];
+static std::mutex g_side_mutex;
+static int side_stream_of_current_device(SideStream** out) {
+  int dev = 0;
+  MOPOE_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= MAX_DEVICES) { set_error("device ordinal %d out of range", dev); return MOPOE_EINVAL; }
+  std::lock_guard<std::mutex> lock(g_side_mutex);
+  SideStream& s = g_sides[dev];
+  if (!s.side) {
+    MOPOE_CUDA(cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking));
+    MOPOE_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    MOPOE_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+  }
+  *out = &s;
+  return MOPOE_OK;
+}
 
 extern "C" {
 
@@ -978,11 +997,10 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   cx.make_rec = impl == 2 ? 1 : 0;
   // 1. encoder heads of every (validation, subject) row, on a second stream: the noise phase of the base
   // passes (most of daa_base_kernel's time) does not depend on them
-  if (!g_side) {
-    MOPOE_CUDA(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
-    MOPOE_CUDA(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
-    MOPOE_CUDA(cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming));
-  }
+  SideStream* ss = nullptr;
+  if ((rc = side_stream_of_current_device(&ss))) return rc;
+  cudaStream_t g_side = ss->side;
+  cudaEvent_t g_fork = ss->fork, g_join = ss->join;
   const bool forked = getenv("MOPOE_DAA_NO_FORK") == nullptr;
   if (forked) {
     MOPOE_CUDA(cudaEventRecord(g_fork, stream));
@@ -1001,6 +1019,7 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
     if (forked && impl == 2 && rc == 0) {   // operand planes of the first column block: weights only, also off the critical path
       const UmmaDims ud = umma_dims(mv, daa->src_mod, daa->dst_mod, cx.R < PK_CBP ? cx.R : PK_CBP);
       daa_umma_prep_kernel<<<64, 256, 0, g_side>>>(mv, daa->src_mod, daa->dst_mod, 0, ud, PK_CBP, ws.bsplit);
+      if (cudaGetLastError() != cudaSuccess) rc = MOPOE_ECUDA;
     }
     if (forked) MOPOE_CUDA(cudaEventRecord(g_join, g_side));   // (recorded even on error: the side stream must rejoin a capture)
     if (rc) { if (forked) cudaStreamWaitEvent(stream, g_join, 0); return rc; }
