@@ -236,7 +236,7 @@ __device__ void p1_unit(const ModelView& mv, const StepCtx& cx, const mopoe_batc
 // P2 shared-memory plan
 // -------------------------------------------------------------------------------------------
 struct P2Smem {
-  int h, e, de, zz, dzz, rp, rps, dx, part, red, total;  // offsets in floats
+  int h, e, de, zz, dzz, rp, rps, dx, part, red, srow, total;  // offsets in floats
   int hc_max, zd_max, s_max;
 };
 
@@ -261,6 +261,7 @@ __host__ __device__ inline P2Smem p2_plan(const ModelView& mv, int R) {
   p.dx = take(R * MOPOE_THREADS);
   p.part = take(R * zd > MOPOE_THREADS ? R * zd : MOPOE_THREADS);
   p.red = take(MOPOE_N_SCALARS);
+  p.srow = take(2 * mv.M * R);     // int64 source row of every (modality, tile row)
   p.total = off;
   return p;
 }
@@ -580,9 +581,13 @@ __device__ float g_p2prof[16];
 #define P2T(i) do { } while (0)
 #endif
 
+// head / decoder weights of every modality resident in shared memory (small models, small batches: the tile's
+// phases are chains of weight reads, a round trip to L2 each; from shared memory they cost a tenth)
+struct SmemWeights { const float* wh[MOPOE_MAX_MODS]; const float* wd[MOPOE_MAX_MODS]; };
+
 template <int R, bool BWD>
 __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batch_desc& b,
-                        const Workspace& ws, int64_t eps_base, int r0, float* sm) {
+                        const Workspace& ws, int64_t eps_base, int r0, float* sm, const SmemWeights* sw = nullptr) {
   const P2Smem pl = p2_plan(mv, R);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int N = b.n_rows, L = mv.L, M = mv.M, present = b.present_mask;
@@ -598,6 +603,7 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
   float* sh_dx = sm + pl.dx;
   float* sh_part = sm + pl.part;
   float* sh_red = sm + pl.red;
+  long long* sh_srow = reinterpret_cast<long long*>(sm + pl.srow);
   const int HCM = pl.hc_max, ZDM = pl.zd_max, SM_ = pl.s_max;
   const bool uni = cx.uni_pass != 0;
 
@@ -607,6 +613,10 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
   __syncthreads();
   if (t < MOPOE_N_SCALARS) sh_red[t] = 0.f;
   for (int i = t; i < M * 2 * R * ZDM; i += MOPOE_THREADS) sh_dzz[i] = 0.f;
+  for (int i = t; i < M * R; i += MOPOE_THREADS) {      // gather indices of the tile's rows, resolved once
+    const int m = i / R, r = i - m * R;
+    sh_srow[i] = ((present >> m & 1) && r < nr && cx.with_nll) ? src_row(cx, b, m, r0 + r) : 0;
+  }
   // ---- hidden rows -> smem ----
   for (int m = 0; m < M; ++m) {
     if (!(present >> m & 1)) continue;
@@ -638,11 +648,13 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
     // barrier): keep four outputs per warp (8 x LDG.128 per lane) in flight
     for (int jb = warp; jb < md.HC; jb += 4 * (MOPOE_THREADS / 32)) {
       float4 wa[4], wb[4];
+      float bjs[4];          // (the bias travels with the weights: loaded after the dot product it is one more L2 round trip per output)
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int j = jb + u * (MOPOE_THREADS / 32);
-        const float4* wrow = reinterpret_cast<const float4*>(md.wh + (int64_t)(j < md.HC ? j : jb) * MOPOE_HIDDEN);
+        const float4* wrow = reinterpret_cast<const float4*>((sw ? sw->wh[m] : md.wh) + (int64_t)(j < md.HC ? j : jb) * MOPOE_HIDDEN);
         wa[u] = wrow[lane]; wb[u] = wrow[lane + 32];
+        bjs[u] = md.bh[j < md.HC ? j : jb];
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -658,7 +670,7 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
           }
 #pragma unroll
           for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
-          const float bj = md.bh[j];
+          const float bj = bjs[u];
 #pragma unroll
           for (int r = 0; r < R; ++r)
             if (lane == r % 32) sh_e[(m * R + r) * HCM + j] = acc[r] + bj;
@@ -690,6 +702,7 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
     if (!(present >> m & 1)) continue;
     const ModView& md = mv.mod[m];
     const int D = md.D, ZD = md.ZD;
+    const float* wd_m = sw ? sw->wd[m] : md.wd;
     if (BWD) {  // decoder inputs -> workspace for the weight-gradient phase
       for (int p = 0; p < npass; ++p)
         for (int i = t; i < nr * ZD; i += MOPOE_THREADS)
@@ -702,11 +715,15 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
         const int dlen = min(MOPOE_THREADS, D - d0);
         float nll = 0.f;
         if (d < D) {
-          float acc[R];
+          float acc[R], xv[R];
           const float bd = md.bd[d];
+          const float lam = md.lv[d];        // log-variance and targets: in flight with the weight rows (not behind them)
 #pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] = bd;
-          const float* w = md.wd + (int64_t)d * ZD;
+          for (int r = 0; r < R; ++r) {
+            acc[r] = bd;
+            xv[r] = (cx.with_nll && r < nr) ? cx.x[m][sh_srow[m * R + r] * D + d] : 0.f;
+          }
+          const float* w = (sw ? sw->wd[m] : md.wd) + (int64_t)d * ZD;
           if ((ZD & 3) == 0) {       // the row is contiguous and 16-byte aligned: 8 x LDG.128 in flight
             for (int k0 = 0; k0 < ZD; k0 += 32) {
               float4 wv[8];
@@ -733,7 +750,6 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
               for (int r = 0; r < R; ++r) acc[r] = fmaf(zrow[r * ZDM + k], wk, acc[r]);
             }
           }
-          const float lam = md.lv[d];
           const float iv = expf(-lam);
 #pragma unroll
           for (int r = 0; r < R; ++r) {
@@ -741,8 +757,7 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
               const int n = r0 + r;
               if (p == 0 && cx.out.rec_loc[m]) cx.out.rec_loc[m][(int64_t)n * D + d] = acc[r];
               if (cx.with_nll) {
-                const float xv = cx.x[m][src_row(cx, b, m, n) * D + d];
-                const float diff = xv - acc[r];
+                const float diff = xv[r] - acc[r];
                 nll += 0.5f * diff * diff * iv + 0.5f * lam + HALF_LOG_2PI;
                 if (BWD) {
                   const float g = -diff * iv * invN;
@@ -769,7 +784,7 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
               float a = 0.f;
 #pragma unroll 8
               for (int dd = sp; dd < dlen; dd += nsplit)
-                a = fmaf(sh_dx[r * MOPOE_THREADS + dd], md.wd[(int64_t)(d0 + dd) * ZD + k], a);
+                a = fmaf(sh_dx[r * MOPOE_THREADS + dd], wd_m[(int64_t)(d0 + dd) * ZD + k], a);
               if (nsplit == 1) sh_dzz[((m * 2 + p) * R + r) * ZDM + k] += a;
               else sh_part[sp * P + pr] = a;
             }
@@ -799,6 +814,7 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
       if (!(present >> m & 1)) continue;
       const ModView& md = mv.mod[m];
       const int HC = md.HC;
+      const float* wh_m = sw ? sw->wh[m] : md.wh;
       for (int i = t; i < nr * HC; i += MOPOE_THREADS)
         ws.de[m][(int64_t)(r0 + i / HC) * HC + i % HC] = sh_de[(m * R + i / HC) * HCM + i % HC];
       float acc[R];
@@ -806,7 +822,7 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
       for (int r = 0; r < R; ++r) acc[r] = 0.f;
 #pragma unroll 16
       for (int j = 0; j < HC; ++j) {
-        const float w = md.wh[(int64_t)j * MOPOE_HIDDEN + t];
+        const float w = wh_m[(int64_t)j * MOPOE_HIDDEN + t];
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = fmaf(sh_de[(m * R + r) * HCM + j], w, acc[r]);
       }
@@ -1051,11 +1067,31 @@ __global__ void finalize_kernel(ModelView mv, StepCtx cx, mopoe_batch_desc b, Wo
 }
 
 // the fused persistent training kernel: n_steps x (P1 | barrier | P2 | barrier | P3 | barrier)
-template <int R>
+// WS: the head and decoder weights of every modality are copied into shared memory at the start of each step (one
+// cp.async.bulk per matrix, in flight while P1 runs) and the row tiles of P2 read them from there (one CTA per SM).
+template <int R, bool WS>
 __global__ void __launch_bounds__(MOPOE_THREADS) train_kernel(ModelView mv, StepCtx cx, const mopoe_batch_desc* batches,
-                                                              int n_steps, float* scalars, Workspace ws) {
+                                                              int n_steps, float* scalars, Workspace ws, int ws_smem_off) {
   extern __shared__ __align__(16) float sm[];
   __shared__ mopoe_batch_desc sb;
+  __shared__ __align__(8) uint64_t wbar;
+  SmemWeights sw;
+  uint32_t wbytes = 0;
+  if (WS) {
+    float* wbase = sm + ws_smem_off;
+    int off = 0;
+    for (int m = 0; m < MOPOE_MAX_MODS; ++m) {
+      sw.wh[m] = sw.wd[m] = nullptr;
+      if (m >= mv.M) continue;
+      const int nh = (mv.mod[m].HC * MOPOE_HIDDEN + 3) & ~3, nd = (mv.mod[m].D * mv.mod[m].ZD + 3) & ~3;
+      sw.wh[m] = wbase + off; off += nh;
+      sw.wd[m] = wbase + off; off += nd;
+      wbytes += (uint32_t)(nh + nd) * 4;
+    }
+    if (threadIdx.x == 0) { umma::mbar_init(&wbar, 1); umma::fence_mbar_init(); }
+    __syncthreads();
+  }
+  uint32_t wphase = 0;
   unsigned int target = 0;
   for (int step = 0; step < n_steps; ++step) {
     __syncthreads();
@@ -1063,6 +1099,18 @@ __global__ void __launch_bounds__(MOPOE_THREADS) train_kernel(ModelView mv, Step
     __syncthreads();
     const mopoe_batch_desc& b = sb;
     if (blockIdx.x == 0 && threadIdx.x < MOPOE_N_SCALARS) ws.acc[threadIdx.x] = 0.0;
+    if (WS && threadIdx.x == 0) {
+      // the weights were updated by other CTAs (generic-proxy stores, ordered by the grid barrier): make them
+      // visible to the async proxy, then one bulk copy per matrix (sizes rounded up to 16 bytes: every block of the
+      // parameter buffer is 128-byte aligned, the tail is padding)
+      umma::fence_async_all();
+      umma::mbar_expect_tx(&wbar, wbytes);
+      for (int m = 0; m < mv.M; ++m) {
+        const int nh = (mv.mod[m].HC * MOPOE_HIDDEN + 3) & ~3, nd = (mv.mod[m].D * mv.mod[m].ZD + 3) & ~3;
+        umma::bulk_g2s(const_cast<float*>(sw.wh[m]), mv.mod[m].wh, nh * 4, &wbar);
+        umma::bulk_g2s(const_cast<float*>(sw.wd[m]), mv.mod[m].wd, nd * 4, &wbar);
+      }
+    }
 #ifdef TRAIN_PROF
     const long long tp0 = clock64();
 #endif
@@ -1075,11 +1123,12 @@ __global__ void __launch_bounds__(MOPOE_THREADS) train_kernel(ModelView mv, Step
 #ifdef TRAIN_PROF
     const long long tp1 = clock64();
 #endif
+    if (WS) { umma::mbar_wait(&wbar, wphase); wphase ^= 1; }
     const int nt = (b.n_rows + R - 1) / R;
     const int64_t eps_base = (int64_t)step * cx.eps_step_stride;
     for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
-      if (cx.mode == 0) p2_tile<R, false>(mv, cx, b, ws, eps_base, tile * R, sm);
-      else p2_tile<R, true>(mv, cx, b, ws, eps_base, tile * R, sm);
+      if (cx.mode == 0) p2_tile<R, false>(mv, cx, b, ws, eps_base, tile * R, sm, WS ? &sw : nullptr);
+      else p2_tile<R, true>(mv, cx, b, ws, eps_base, tile * R, sm, WS ? &sw : nullptr);
     }
 #ifdef TRAIN_PROF
     const long long tp1b = clock64();
@@ -1333,8 +1382,28 @@ int mopoe_train_steps(const mopoe_model_desc* desc, float* params, float* adam_m
     return MOPOE_OK;
   }
   int smem = 0;
-  const int R = pick_rows(mv, max_rows, &smem);
-  void* fn = R == 1 ? (void*)train_kernel<1> : R == 2 ? (void*)train_kernel<2> : R == 4 ? (void*)train_kernel<4> : (void*)train_kernel<16>;
+  int R = pick_rows(mv, max_rows, &smem);
+  // small model + small batch: head / decoder weights resident in shared memory, one CTA per SM.  OPT-IN
+  // (MOPOE_TRAIN_SMEM_WEIGHTS=1): measured on B200 at 256 rows it is SLOWER (82 vs 65 us per step) -- the tile's phases
+  // are bound by their other round trips and by cold code, not by the weight reads, and with one CTA per SM the
+  // first-layer and weight-gradient phases need two rounds of work units (P3 18 -> 35 us)
+  int wfloats = 0;
+  for (int m = 0; m < desc->n_mods; ++m)
+    wfloats += ((mv.mod[m].HC * MOPOE_HIDDEN + 3) & ~3) + ((mv.mod[m].D * mv.mod[m].ZD + 3) & ~3);
+  bool use_ws = false;
+  int ws_smem_off = 0;
+  {
+    const char* e = getenv("MOPOE_TRAIN_SMEM_WEIGHTS");
+    int smem1 = 0;
+    const int R1 = pick_rows(mv, max_rows, &smem1, 1);
+    const int total = ((smem1 + 15) & ~15) + wfloats * 4;
+    if (e && e[0] == '1' && R1 <= 2 && total <= 227 * 1024 - 1024) {
+      use_ws = true; R = R1; ws_smem_off = ((smem1 + 15) & ~15) / 4; smem = total;
+    }
+  }
+  void* fn = use_ws ? (R == 1 ? (void*)train_kernel<1, true> : (void*)train_kernel<2, true>)
+                    : (R == 1 ? (void*)train_kernel<1, false> : R == 2 ? (void*)train_kernel<2, false>
+                       : R == 4 ? (void*)train_kernel<4, false> : (void*)train_kernel<16, false>);
   MOPOE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int per_sm = 0;
   MOPOE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, MOPOE_THREADS, smem));
@@ -1342,10 +1411,10 @@ int mopoe_train_steps(const mopoe_model_desc* desc, float* params, float* adam_m
   // small batches are latency bound (serial weight-streaming chains per tile): two co-resident CTAs per SM
   // hide each other's latency and give every phase one round of work units; large batches keep one CTA
   // per SM (the phases are tile loops, extra CTAs only lengthen the barriers)
-  const int grid = (R <= 2 && per_sm >= 2) ? 2 * num_sms() : num_sms();   // measured: 130 / 86 / 90 / 99 us per step at 1 / 2 / 3 / 4 CTAs per SM
+  const int grid = (!use_ws && R <= 2 && per_sm >= 2) ? 2 * num_sms() : num_sms();   // measured: 130 / 86 / 90 / 99 us per step at 1 / 2 / 3 / 4 CTAs per SM
   const mopoe_batch_desc* bptr = batches;
   float* sptr = scalars;
-  void* args[] = {&mv, &cx, &bptr, &n_steps, &sptr, &ws};
+  void* args[] = {&mv, &cx, &bptr, &n_steps, &sptr, &ws, &ws_smem_off};
   MOPOE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(MOPOE_THREADS), args, smem, stream));
   return MOPOE_OK;
 }

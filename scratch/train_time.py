@@ -2,7 +2,7 @@ import sys, numpy as np, torch
 sys.path.insert(0, "/root/repo")
 import mopoe_b200, bench
 from mopoe_b200 import data, engine
-from oracle import mopoe_oracle as mo
+
 device = torch.device("cuda")
 spec_kw = bench.HBN
 cohort = data.make_cohort()
@@ -11,7 +11,7 @@ dev_data = [torch.from_numpy(cohort["clinical"][train]).to(device), torch.from_n
 steps = 300
 for method in ("joint_elbo",):
     spec = mopoe_b200.PathSpec(spec_kw["dims"], spec_kw["style_dims"], spec_kw["latent_dim"], method, spec_kw["mod_names"])
-    flat = engine.pack_params(spec, mo.init_params(mo.ModelSpec(**dict(spec_kw, method=method)), seed=0), device)
+    flat = engine.pack_params(spec, engine.init_params(spec, seed=0), device)
     for N in (256,):
         nb = 2048 // N
         plan = [(N, 3, (i % nb) * N) for i in range(steps)]

@@ -14,12 +14,14 @@ pytestmark = pytest.mark.gpu
 GOLD = load_golden()
 
 
-@pytest.fixture(params=["tc", "ffma"])
+@pytest.fixture(params=["tc", "ffma", "ffma_smem"])
 def train_impl(request, monkeypatch):
-    """Both implementations of mopoe_train_steps behind the same C-ABI call: the tensor-core kernel
-    (csrc/mopoe_train_tc.cuh, the default) and the CUDA-core kernel."""
-    monkeypatch.setenv("MOPOE_TRAIN_IMPL", request.param)
-    return {"tc": 1, "ffma": 0}[request.param]
+    """The implementations of mopoe_train_steps behind the same C-ABI call: the tensor-core kernel
+    (csrc/mopoe_train_tc.cuh), the CUDA-core kernel, and its opt-in variant with the head / decoder weights
+    resident in shared memory (small models and batches only; elsewhere the variable is ignored)."""
+    monkeypatch.setenv("MOPOE_TRAIN_IMPL", "tc" if request.param == "tc" else "ffma")
+    monkeypatch.setenv("MOPOE_TRAIN_SMEM_WEIGHTS", "1" if request.param == "ffma_smem" else "0")
+    return {"tc": 1, "ffma": 0, "ffma_smem": 0}[request.param]
 
 
 def _ran(impl):
