@@ -55,7 +55,8 @@ MAX_PEERS = 8
 
 
 class TableExchangeDesc(C.Structure):
-    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("elems_local", C.c_int64), ("elem_offset", C.c_int64),
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("root", C.c_int32), ("reserved", C.c_int32),
+                ("elems_local", C.c_int64), ("elem_offset", C.c_int64),
                 ("elems_total", C.c_int64), ("peer_base", C.c_void_p * MAX_PEERS)]
 
 

@@ -1112,14 +1112,31 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
 constexpr int64_t EX_HDR = 256;
 struct ExPeers { unsigned char* base[MOPOE_MAX_PEERS]; };
 
-__global__ void __launch_bounds__(256) daa_table_push_kernel(ExPeers peers, int world, int rank, int64_t elems_local, int64_t elem_offset,
-                                                             int64_t elems_total, const double* coefs, const double* pvalues) {
+// root < 0: every rank receives every slice (all-gather); root >= 0: only `root` receives (gather: what daa_exp needs,
+// 1/world of the bytes, and no rank but the root ever waits).  In gather mode the senders are kept at most two
+// sequence numbers ahead of the root by an acknowledgement flag ([64 + 8 * MOPOE_MAX_PEERS]) the root releases to every
+// rank once a step's tables are complete, so a slot is never overwritten before the root has finished with it.
+__global__ void __launch_bounds__(256) daa_table_push_kernel(ExPeers peers, int world, int rank, int root, int64_t elems_local,
+                                                             int64_t elem_offset, int64_t elems_total, const double* coefs,
+                                                             const double* pvalues) {
   unsigned char* own = peers.base[rank];
   const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(own) + 1ull;
+  if (root >= 0 && rank != root && seq > 2 && threadIdx.x == 0) {
+    const unsigned long long* ack = reinterpret_cast<const unsigned long long*>(own + 64 + 8 * MOPOE_MAX_PEERS);
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(ack) : "memory");
+      if (v + 2 >= seq || clock64() - t0 > 8000000000LL) break;
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
   const int64_t slot_off = EX_HDR + (int64_t)(seq & 1ull) * 2 * elems_total * 8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < elems_local; i += (int64_t)gridDim.x * blockDim.x) {
     const double c = coefs[i], p = pvalues[i];
     for (int r = 0; r < world; ++r) {
+      if (root >= 0 && r != root) continue;
       double* dst = reinterpret_cast<double*>(peers.base[r] + slot_off);
       dst[elem_offset + i] = c;
       dst[elems_total + elem_offset + i] = p;
@@ -1134,6 +1151,7 @@ __global__ void __launch_bounds__(256) daa_table_push_kernel(ExPeers peers, int 
       *reinterpret_cast<volatile unsigned long long*>(own) = seq;
       __threadfence_system();
       for (int r = 0; r < world; ++r) {
+        if (root >= 0 && r != root) continue;
         unsigned long long* flag = reinterpret_cast<unsigned long long*>(peers.base[r] + 64 + 8 * rank);
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
       }
@@ -1141,22 +1159,29 @@ __global__ void __launch_bounds__(256) daa_table_push_kernel(ExPeers peers, int 
   }
 }
 
-__global__ void daa_table_wait_kernel(unsigned char* own, int world, int64_t elems_total) {
+__global__ void daa_table_wait_kernel(ExPeers peers, int world, int rank, int root, int64_t elems_total) {
+  unsigned char* own = peers.base[rank];
   const int r = threadIdx.x;
-  if (r >= world) return;
   const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(own);
-  const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(own + 64 + 8 * r);
-  const long long t0 = clock64();
-  for (;;) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-    if (v >= seq) break;
-    if (clock64() - t0 > 8000000000LL) {   // a peer never arrived: poison this rank's view instead of hanging
-      double* dst = reinterpret_cast<double*>(own + EX_HDR + (int64_t)(seq & 1ull) * 2 * elems_total * 8);
-      dst[0] = __longlong_as_double(0x7ff8000000000000LL);
-      break;
+  if (r < world) {
+    const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(own + 64 + 8 * r);
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+      if (v >= seq) break;
+      if (clock64() - t0 > 8000000000LL) {   // a peer never arrived: poison this rank's view instead of hanging
+        double* dst = reinterpret_cast<double*>(own + EX_HDR + (int64_t)(seq & 1ull) * 2 * elems_total * 8);
+        dst[0] = __longlong_as_double(0x7ff8000000000000LL);
+        break;
+      }
+      __nanosleep(64);
     }
-    __nanosleep(64);
+  }
+  __syncwarp();
+  if (root >= 0 && r < world && r != rank) {     // gather mode: tell the senders that this step's tables are complete
+    unsigned long long* ack = reinterpret_cast<unsigned long long*>(peers.base[r] + 64 + 8 * MOPOE_MAX_PEERS);
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(ack), "l"(seq) : "memory");
   }
 }
 
@@ -1178,10 +1203,14 @@ int mopoe_daa_exchange_tables(const mopoe_table_exchange* ex, const double* coef
   cudaStream_t stream = (cudaStream_t)stream_;
   const int64_t n = ex->elems_local;
   const int grid = (int)((n + 255) / 256 < 1 ? 1 : ((n + 255) / 256 > 4 * num_sms() ? 4 * num_sms() : (n + 255) / 256));
-  daa_table_push_kernel<<<grid, 256, 0, stream>>>(peers, ex->world, ex->rank, n, ex->elem_offset, ex->elems_total, coefs_local, pvalues_local);
+  if (ex->root >= ex->world) { set_error("root=%d invalid", ex->root); return MOPOE_EINVAL; }
+  const int root = ex->root < 0 ? -1 : ex->root;
+  daa_table_push_kernel<<<grid, 256, 0, stream>>>(peers, ex->world, ex->rank, root, n, ex->elem_offset, ex->elems_total, coefs_local, pvalues_local);
   MOPOE_CUDA(cudaGetLastError());
-  daa_table_wait_kernel<<<1, 32, 0, stream>>>(peers.base[ex->rank], ex->world, ex->elems_total);
-  MOPOE_CUDA(cudaGetLastError());
+  if (root < 0 || root == ex->rank) {       // receivers only: in gather mode no other rank ever waits
+    daa_table_wait_kernel<<<1, 32, 0, stream>>>(peers, ex->world, ex->rank, root, ex->elems_total);
+    MOPOE_CUDA(cudaGetLastError());
+  }
   return MOPOE_OK;
 }
 

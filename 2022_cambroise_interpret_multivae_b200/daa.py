@@ -205,8 +205,11 @@ class TableExchange:
     (C-ABI mopoe_daa_exchange_tables; two small launches on the current stream, capturable in a CUDA graph).
     Replaces the NCCL all_gather of `gather_tables` on the sweep's critical path."""
 
-    def __init__(self, n_val_total, n_scores, n_rois, device, group=None):
+    def __init__(self, n_val_total, n_scores, n_rois, device, group=None, root=None):
+        """root=None: every rank ends up with the full tables (all-gather); root=r: only rank r does (gather, what
+        daa_exp needs: 1/world of the bytes, and no rank but r ever waits for another)."""
         import torch.distributed as dist
+        self.root = -1 if root is None else int(root)
         import torch.distributed._symmetric_memory as symm
         lib = _lib.lib()
         self.group = group if group is not None else dist.group.WORLD
@@ -235,7 +238,7 @@ class TableExchange:
         c, p = coefs_local.contiguous(), pvalues_local.contiguous()
         assert c.dtype == torch.float64 and p.dtype == torch.float64 and tuple(c.shape[1:]) == self.shape[1:]
         per_val = self.shape[1] * self.shape[2]
-        d = _lib.TableExchangeDesc(world=self.world, rank=self.rank, elems_local=c.shape[0] * per_val,
+        d = _lib.TableExchangeDesc(world=self.world, rank=self.rank, root=self.root, reserved=0, elems_local=c.shape[0] * per_val,
                                    elem_offset=int(val_begin) * per_val, elems_total=self.elems_total)
         for r, ptr in enumerate(self.peer_ptrs):
             d.peer_base[r] = ptr

@@ -367,7 +367,7 @@ def run_ours(args, rank, world, local_rank):
                 ok = torch.zeros(1, device=device)
                 if not os.environ.get("MOPOE_BENCH_NO_EXCHANGE"):
                     try:
-                        self.ex = daa.TableExchange(n_val_total, C_, R, device)
+                        self.ex = daa.TableExchange(n_val_total, C_, R, device, root=0)
                         ok += 1
                     except Exception as exc:
                         self.exchange_note = "NCCL all_gather (peer-memory exchange unavailable: %s)" % type(exc).__name__
@@ -377,7 +377,9 @@ def run_ours(args, rank, world, local_rank):
                     if self.exchange_note.startswith("single"):
                         self.exchange_note = "NCCL all_gather (peer-memory exchange disabled)"
                 else:
-                    self.exchange_note = "peer-memory table exchange: NVLink P2P stores into every rank's table + system-scope flags, no NCCL launch"
+                    self.exchange_note = ("peer-memory gather of the association tables to rank 0 (what daa_exp needs): NVLink P2P stores into "
+                                          "rank 0's table + system-scope flags and acknowledgements, no NCCL launch; senders run at most "
+                                          "two sweeps ahead of rank 0")
             self.r = self.sweep()
             self.gather()
 
@@ -407,7 +409,11 @@ def run_ours(args, rank, world, local_rank):
             cf, pv = self.tables()
             ref = [daa.gather_tables(t, self.n_val_total) for t in (self.r.coefs, self.r.pvalues)]
             torch.cuda.synchronize()
-            return bool(torch.equal(cf, ref[0]) and torch.equal(pv, ref[1]))
+            ok = torch.ones(1, device=device)
+            if rank == 0 and not (torch.equal(cf, ref[0]) and torch.equal(pv, ref[1])):     # the root holds the gathered tables
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            return bool(ok.item() > 0)
 
         def capture(self):
             """the whole step (8 kernels of the sweep on two streams + the table exchange) captured once and replayed;

@@ -255,6 +255,10 @@ int mopoe_daa_regression(int32_t n_val, int32_t n_subjects, int32_t n_scores, in
 #define MOPOE_MAX_PEERS 8
 typedef struct mopoe_table_exchange {
   int32_t world, rank;
+  int32_t root;          /* -1: every rank receives every slice (all-gather); >= 0: only `root` receives (gather -- what
+                          * daa_exp needs: 1/world of the bytes and no rank but the root ever waits; senders stay at most two
+                          * calls ahead of the root, which acknowledges every completed step) */
+  int32_t reserved;
   int64_t elems_local;   /* n_val_local * C * R */
   int64_t elem_offset;   /* val_begin * C * R */
   int64_t elems_total;   /* n_val_total * C * R */
