@@ -930,6 +930,10 @@ static int check_daa(const mopoe_model_desc* d, const mopoe_daa_desc* q) {
   if (q->base_mode < 0 || q->base_mode > 1) { set_error("base_mode=%d invalid", q->base_mode); return MOPOE_EINVAL; }
   if (q->reg_method < 0 || q->reg_method > 1) { set_error("reg_method=%d unsupported (hierarchical, fixed; mixed is not on this path)", q->reg_method); return MOPOE_EINVAL; }
   if (d->dims[q->src_mod] > 64) { set_error("src modality wider than 64 columns is unsupported in the DAA kernel"); return MOPOE_EINVAL; }
+  if ((q->unit_begin || q->unit_end) &&
+      (q->unit_begin < 0 || q->unit_begin >= q->unit_end || (int64_t)q->unit_end > (int64_t)q->n_val * d->dims[q->src_mod])) {
+    set_error("unit range [%d, %d) outside the %d x %d (validation, score) units of this call", q->unit_begin, q->unit_end, q->n_val, d->dims[q->src_mod]);
+    return MOPOE_EINVAL; }
   int E = d->latent_dim;
   for (int m = 0; m < d->n_mods; ++m) E += d->style_dims[m];
   if (E > 160) { set_error("noise row wider than 160"); return MOPOE_EINVAL; }
@@ -976,6 +980,8 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   const AvSmem pl = av_plan(mv, daa->src_mod, daa->dst_mod, cx.J);
   const int av_smem = pl.total * 4;
   if (av_smem > 227 * 1024) { set_error("DAA avatar kernel needs %d bytes of shared memory (> 227 KB): latent/style dims too large", av_smem); return MOPOE_EINVAL; }
+  const int unit_begin = daa->unit_end ? daa->unit_begin : 0, unit_end = daa->unit_end ? daa->unit_end : daa->n_val * cx.C;
+  cx.q.unit_begin = unit_begin; cx.q.unit_end = unit_end;
   const int n_units = daa->n_val * N * cx.C;
   const int grid = n_units < num_sms() ? n_units : num_sms();
   // implementation choice (MOPOE_DAA_IMPL=pipe|umma|ffma forces one; the tests cross-check all three):
@@ -1058,8 +1064,8 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
     const int bs_threads = ((bs_nc + 1) / 2 + 31) / 32 * 32 < 256 ? ((bs_nc + 1) / 2 + 31) / 32 * 32 : 256;
     const int bsm = (((ud0.KZ * (bs_nc | 1) + 3) & ~3) + 2 * ud0.KZ * BS_GP) * 4 + BS_GB * 8 + 16;
     MOPOE_CUDA(cudaFuncSetAttribute((void*)daa_beta_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bsm));
-    daa_beta_stats_kernel<<<dim3(daa->n_val * cx.C, (cx.R + BS_ROIS - 1) / BS_ROIS), bs_threads, bsm, stream>>>(
-        mv, daa->dst_mod, cx.R, cx.C, N, cx.J, ud0, ws.sacc, ws.xstat, ws.betas, coefs, pvalues);
+    daa_beta_stats_kernel<<<dim3(unit_end - unit_begin, (cx.R + BS_ROIS - 1) / BS_ROIS), bs_threads, bsm, stream>>>(
+        mv, daa->dst_mod, cx.R, cx.C, N, cx.J, ud0, unit_begin, ws.sacc, ws.xstat, ws.betas, coefs, pvalues);
     MOPOE_CUDA(cudaGetLastError());
   } else if (impl == 1) {
     void* ufn = daa->reg_method == 1 ? (void*)daa_avatar_umma_kernel<true> : (void*)daa_avatar_umma_kernel<false>;
@@ -1086,7 +1092,9 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   }
   if (g_profile && impl != 2) MOPOE_CUDA(cudaEventRecord(g_ev1, stream));
   // 4. second level
-  const int64_t nstat = (int64_t)daa->n_val * cx.C * cx.R;
+  // (the pipelined path honours the unit range; the other two compute every unit of the call)
+  const int64_t stat0 = impl == 2 ? (int64_t)unit_begin * cx.R : 0;
+  const int64_t nstat = impl == 2 ? (int64_t)(unit_end - unit_begin) * cx.R : (int64_t)daa->n_val * cx.C * cx.R;
   if (impl != 2) {
     daa_stats_kernel<<<(unsigned)((nstat + 127) / 128), 128, 0, stream>>>(daa->n_val, N, cx.C, cx.J, cx.R, daa->reg_method, ws.betas,
                                                                          ws.ybar, ws.syy, ws.xstat, reconstructions, coefs, pvalues);
@@ -1094,7 +1102,7 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   }
   if (impl != 0) {
     // p-values of the pipelined path (its slopes kernel leaves the t statistics in `pvalues`) + error poisoning
-    daa_pvalue_kernel<<<(unsigned)((nstat + 127) / 128), 128, 0, stream>>>(ws.err, coefs, pvalues, nstat, (double)(N - 1),
+    daa_pvalue_kernel<<<(unsigned)((nstat + 127) / 128), 128, 0, stream>>>(ws.err, coefs + stat0, pvalues + stat0, nstat, (double)(N - 1),
                                                                             lgamma(0.5 * (N - 1) + 0.5) - lgamma(0.5 * (N - 1)) - lgamma(0.5), impl == 2 ? 1 : 0);
     MOPOE_CUDA(cudaGetLastError());
   }

@@ -685,15 +685,35 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
         pk_arrive(bar_cache + (i & 1));
       }
     };
-    int gt_cur = (int)blockIdx.x < total_tiles ? (int)blockIdx.x : -1, gt_prev = -1, n_done = 0;
+    // shard units (mopoe_daa_desc.unit_begin / unit_end): a tile is run iff one of its (<= 2) series belongs to an
+    // owned (validation, score) unit; tiles of the other scores of a shared validation are skipped (another rank
+    // runs them).  Lane 0 only: draws from the global counter until it holds an owned tile.
+    const int own0 = cx.q.unit_begin, own1 = cx.q.unit_end;
+    const bool own_all = own0 == 0 && own1 == cx.q.n_val * C;
+    auto claim = [&](int gt) -> int {
+      while (gt < total_tiles && !own_all) {
+        int uA, uB;
+        tile_units(gt, uA, uB);
+        bool mine = false;
+        for (int u = uA; u <= uB; ++u) {
+          const int unit = (u / (N * C)) * C + u % C;
+          mine = mine || (unit >= own0 && unit < own1);
+        }
+        if (mine) break;
+        gt = (int)gridDim.x + atomicAdd(ws.counter, 1);
+      }
+      return gt < total_tiles ? gt : -1;
+    };
+    int gt_cur = 0, gt_prev = -1, n_done = 0;
+    if (lane == 0) gt_cur = claim((int)blockIdx.x);
+    gt_cur = __shfl_sync(0xffffffffu, gt_cur, 0);
     publish(0, gt_cur);
 #pragma unroll 1
     for (int i = 0; gt_cur >= 0; ++i) {
       // the next tile of this CTA: the round trip of the atomic overlaps the wait below
       int gt_next = 0;
       if (lane == 0) {
-        gt_next = (int)gridDim.x + atomicAdd(ws.counter, 1);
-        if (gt_next >= total_tiles) gt_next = -1;
+        gt_next = claim((int)gridDim.x + atomicAdd(ws.counter, 1));
       }
       gt_next = __shfl_sync(0xffffffffu, gt_next, 0);
       PK_T(1);
@@ -751,13 +771,14 @@ constexpr int BS_ROIS = BS_ROIS_, BS_GB = 25, BS_GP = 28;    // ROIs per CTA, su
 
 __device__ double two_sided_t_pvalue(double tval, double nu);
 
-__global__ void __launch_bounds__(256) daa_beta_stats_kernel(ModelView mv, int dst, int R, int C, int N, int J, UmmaDims dm,
+__global__ void __launch_bounds__(256) daa_beta_stats_kernel(ModelView mv, int dst, int R, int C, int N, int J, UmmaDims dm, int unit0,
                                                               const double* sacc, const double* xstat, double* betas,
                                                               double* coefs, double* tvals) {
   extern __shared__ __align__(16) float s_dyn[];
   const ModView& md = mv.mod[dst];
   const int t = threadIdx.x, nt = blockDim.x;
-  const int v = blockIdx.x / C, c = blockIdx.x % C;
+  const int vc = unit0 + blockIdx.x;                       // (validation, score) unit of this CTA
+  const int v = vc / C, c = vc % C;
   const int c0 = blockIdx.y * BS_ROIS, nc = min(BS_ROIS, R - c0);
   const int tpu = pipe_tiles_per_unit(J), KZ = dm.KZ;
   const int RP = nc | 1;                                   // odd row stride

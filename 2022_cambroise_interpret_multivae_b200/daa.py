@@ -24,7 +24,7 @@ class DaaResult:
 def daa_sweep(spec: PathSpec, flat_params, src, dst, n_samples, n_base, *, src_mod=0, dst_mod=1,
               sample_latents=True, reg_method="hierarchical", seed=1037, val_begin=0, n_val_total=None,
               eps_base=None, eps_score=None, eps_av=None, materialize=True, want_betas=True,
-              others=None, workspace=None, out=None, base_mean="draws"):
+              others=None, workspace=None, out=None, base_mean="draws", unit_begin=None, unit_end=None):
     """src: (n_val, N, C) drawn test batches of the perturbed modality, dst: (n_val, N, R).
     others: optional {modality index: (n_val, N, D_m)} for models with more than two modalities.
     base_mean: how the mean over the M stochastic reconstructions (workflow.py:388-398) gets its noise --
@@ -32,6 +32,9 @@ def daa_sweep(spec: PathSpec, flat_params, src, dst, n_samples, n_base, *, src_m
       "direct" draw the mean row itself, N(0, 1/M): the default decoders are affine in z, so the mean of the M
                decodes is the decode of mu + sd * eps_mean.  Same distribution of every output, 1/M of the
                draws (in-kernel generator only).
+    unit_begin, unit_end: the OWNED (validation, score) units of this call, u = v_local * C + score (SURVEY.md 8e,
+      `shard_units`): only their rows of coefs / pvalues / betas and their avatars are produced, the other scores of
+      a shared first / last validation are another rank's.  Default: every unit.
     Returns a DaaResult with CUDA tensors avatars (or None), sampled_scores, reconstructions,
     betas (or None), coefs, pvalues."""
     if base_mean not in ("draws", "direct"):
@@ -69,7 +72,8 @@ def daa_sweep(spec: PathSpec, flat_params, src, dst, n_samples, n_base, *, src_m
     q = _lib.DaaDesc(n_val=n_val, val_begin=val_begin, n_val_total=n_val_total or n_val, n_subjects=N,
                      n_samples=n_samples, n_base=n_base, src_mod=src_mod, dst_mod=dst_mod,
                      sample_latents=int(bool(sample_latents)), reg_method=REG_METHODS[reg_method],
-                     base_mode=1 if base_mean == "direct" else 0)
+                     base_mode=1 if base_mean == "direct" else 0,
+                     unit_begin=0 if unit_end is None else int(unit_begin or 0), unit_end=0 if unit_end is None else int(unit_end))
     bd = spec.batch_desc(N, (1 << spec.n_mods) - 1)
     lib = _lib.lib()
     nbytes = lib.mopoe_daa_workspace_bytes(C.byref(spec.desc), C.byref(q))
@@ -146,6 +150,19 @@ def shard_validations(n_validation, rank, world_size):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+def shard_units(n_validation, n_scores, rank, world_size):
+    """contiguous block split of the n_validation * n_scores (validation, score) units (140 for the
+    HBN sweep: 18 / 17 per rank on 8 GPUs, 97 % balance, where whole validations give 3 / 2 = 83 %).
+    -> dict(unit_begin, unit_end: global units of this rank; val_begin, val_end: the validations it touches (their
+    base passes are run by every rank that shares them); local_begin, local_end: the same units relative to
+    val_begin, the values `daa_sweep(unit_begin=, unit_end=)` takes)."""
+    ub, ue = shard_validations(n_validation * n_scores, rank, world_size)
+    if ue == ub:
+        return dict(unit_begin=ub, unit_end=ue, val_begin=0, val_end=0, local_begin=0, local_end=0)
+    vb, ve = ub // n_scores, (ue + n_scores - 1) // n_scores
+    return dict(unit_begin=ub, unit_end=ue, val_begin=vb, val_end=ve, local_begin=ub - vb * n_scores, local_end=ue - vb * n_scores)
+
+
 def gather_tables(local, n_validation, group=None, out=None):
     """all_gather the per-validation fp64 tables of every rank into the full (n_validation, ...) table.
     `local` is this rank's (n_local, ...) block.  Equal shards (the usual case) are gathered straight into
@@ -163,7 +180,16 @@ def gather_tables(local, n_validation, group=None, out=None):
             out = torch.empty(shape, dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(out, local.contiguous(), group=group)
         return out
-    n_max = max(sizes)
+    return gather_rows(local, sizes, group)
+
+
+def gather_rows(local, sizes, group=None):
+    """all_gather of per-rank blocks of leading sizes `sizes` (known on every rank; zero allowed), padded to the
+    largest: -> the concatenation in rank order."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    assert len(sizes) == world and local.shape[0] == sizes[dist.get_rank(group)]
+    n_max = max(max(sizes), 1)
     pad = torch.zeros((n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     bufs = [torch.empty_like(pad) for _ in range(world)]
@@ -244,6 +270,22 @@ class TableExchange:
             d.peer_base[r] = ptr
         _lib.check(_lib.lib().mopoe_daa_exchange_tables(C.byref(d), _ptr(c), _ptr(p), _stream()))
         self._keep = (c, p)
+        self.calls += 1
+        return self.calls
+
+    def exchange_units(self, coefs_local, pvalues_local, local_begin, local_end, unit_begin):
+        """`exchange` for (validation, score) shard units (`shard_units`): rows [local_begin, local_end) of this rank's
+        (n_val_local * C, R) tables are global units [unit_begin, unit_begin + local_end - local_begin)."""
+        assert coefs_local.is_contiguous() and pvalues_local.is_contiguous() and coefs_local.dtype == torch.float64
+        R = self.shape[2]
+        c = coefs_local.view(-1, R)[local_begin:local_end]
+        p = pvalues_local.view(-1, R)[local_begin:local_end]
+        d = _lib.TableExchangeDesc(world=self.world, rank=self.rank, root=self.root, reserved=0, elems_local=c.shape[0] * R,
+                                   elem_offset=int(unit_begin) * R, elems_total=self.elems_total)
+        for r, ptr in enumerate(self.peer_ptrs):
+            d.peer_base[r] = ptr
+        _lib.check(_lib.lib().mopoe_daa_exchange_tables(C.byref(d), _ptr(c), _ptr(p), _stream()))
+        self._keep = (coefs_local, pvalues_local)
         self.calls += 1
         return self.calls
 

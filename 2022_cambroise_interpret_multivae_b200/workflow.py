@@ -276,8 +276,8 @@ def daa_exp(dataset, datasetdir, outdir, run, sampling_strategy="likelihood", n_
     n_test_min = min(exp.resident_of(i)["n_test"] for i in range(n_models))
     if n_subjects > n_test_min:
         raise ValueError("n_subjects=%d exceeds the %d test subjects with every block" % (n_subjects, n_test_min))
-    if world > n_validation:
-        raise ValueError("world size %d exceeds n_validation=%d (validations are the sharding unit)" % (world, n_validation))
+    if world > n_validation * n_scores:
+        raise ValueError("world size %d exceeds the %d (validation, score) shard units" % (world, n_validation * n_scores))
     # draw n_validation batches of test subjects per model on the host (workflow.py:362-372): rank 0 draws, every
     # rank uses the same draws (with seed=None each rank would otherwise draw its own)
     if seed is None:
@@ -290,7 +290,16 @@ def daa_exp(dataset, datasetdir, outdir, run, sampling_strategy="likelihood", n_
     else:
         draw_seed = int(seed)
     rs = np.random.RandomState(draw_seed)
-    begin, end = daa.shard_validations(n_validation, rank, world)
+    # the shard unit is the (validation, score) pair; a rank runs the base passes of every validation
+    # it touches and the avatars / statistics of its own units only
+    shards = [daa.shard_units(n_validation, n_scores, q, world) for q in range(world)]
+    sh = shards[rank]
+    begin, end = sh["val_begin"], sh["val_end"]
+    unit_sizes = [q["unit_end"] - q["unit_begin"] for q in shards]
+    # per-validation arrays (scores, reconstructions) are identical on every rank that shares the validation: the
+    # owner of its first unit contributes them
+    lead_of = lambda q: [v for v in range(q["val_begin"], q["val_end"]) if q["unit_begin"] <= v * n_scores < q["unit_end"]]
+    lead_sizes = [len(lead_of(q)) for q in shards]
     all_draws, tabs = [], {k: [] for k in ("coefs", "pvalues", "betas", "scores", "recons")}
     if materialize_avatars:
         from numpy.lib.format import open_memmap
@@ -314,22 +323,33 @@ def daa_exp(dataset, datasetdir, outdir, run, sampling_strategy="likelihood", n_
         dst = res["test"][1][idx]
         r = daa.daa_sweep(model.spec, flat, src, dst, n_samples, M, sample_latents=sample_latents, reg_method=reg_method,
                           seed=draw_seed + 7919 * model_idx, val_begin=begin, n_val_total=n_validation,
-                          materialize=materialize_avatars, workspace=model._ws)
+                          materialize=materialize_avatars, workspace=model._ws,
+                          unit_begin=sh["local_begin"] if world > 1 else None, unit_end=sh["local_end"] if world > 1 else None)
         daa.check_status(model.spec, r)           # a device-side protocol error must not end up in result files
-        got = daa.gather_tables_many([r.coefs, r.pvalues, r.betas, r.sampled_scores, r.reconstructions], n_validation)
+        if world > 1:
+            lb, le = sh["local_begin"], sh["local_end"]
+            mine = [v - begin for v in lead_of(sh)]
+            rows = lambda t: t.reshape((t.shape[0] * t.shape[1],) + tuple(t.shape[2:]))[lb:le]
+            unrows = lambda t: t.reshape((n_validation, n_scores) + tuple(t.shape[1:]))
+            got = [unrows(daa.gather_rows(rows(t), unit_sizes)) for t in (r.coefs, r.pvalues, r.betas)]
+            got += [daa.gather_rows(t[mine], lead_sizes) for t in (r.sampled_scores, r.reconstructions)]
+        else:
+            got = [r.coefs, r.pvalues, r.betas, r.sampled_scores, r.reconstructions]
         torch.cuda.synchronize()
         for k, t in zip(("coefs", "pvalues", "betas", "scores", "recons"), got):
             tabs[k].append(t.cpu().numpy())
         if materialize_avatars:
             mm = np.load(da_file, mmap_mode="r+")
-            host = torch.empty(r.avatars.shape, dtype=torch.float32).pin_memory()      # pinned: the 1.9 GB copy runs at link speed
-            host.copy_(r.avatars)
-            if n_models > 1:
-                mm[model_idx, begin:end] = host.numpy()          # disjoint slices per rank
-            else:
-                mm[begin:end] = host.numpy()
+            out = mm[model_idx] if n_models > 1 else mm
+            for v in range(begin, end):                          # disjoint (validation, :, score range) slices per rank
+                c0 = max(sh["unit_begin"], v * n_scores) - v * n_scores
+                c1 = min(sh["unit_end"], (v + 1) * n_scores) - v * n_scores
+                part = r.avatars[v - begin, :, c0:c1]
+                host = torch.empty(part.shape, dtype=torch.float32).pin_memory()   # pinned: the copy runs at link speed
+                host.copy_(part)
+                out[v, :, c0:c1] = host.numpy()
             mm.flush()
-            del mm, host
+            del mm, out, host
     stack = lambda k: np.stack(tabs[k]) if n_models > 1 else tabs[k][0]
     coefs, pvalues, betas = stack("coefs"), stack("pvalues"), stack("betas")
     if rank == 0:

@@ -359,8 +359,9 @@ def run_ours(args, rank, world, local_rank):
     class Runner:
         """One shard of a sweep on this rank: sweep + exchange of the association tables, replayed from a CUDA graph."""
 
-        def __init__(self, src, dst, val_begin, n_val_total, base_mean="direct"):
+        def __init__(self, src, dst, val_begin, n_val_total, base_mean="direct", units=None):
             self.src, self.dst, self.val_begin, self.n_val_total, self.base_mean = src, dst, val_begin, n_val_total, base_mean
+            self.units = units                          # daa.shard_units(...) of this rank: (validation, score) shard units
             self.ex, self.full, self.graph, self.replays = None, {}, None, 0
             self.exchange_note = "single GPU: nothing to exchange"
             if world > 1:
@@ -386,11 +387,19 @@ def run_ours(args, rank, world, local_rank):
         def sweep(self, src=None, dst=None, out=None):
             return daa.daa_sweep(spec, flat, self.src if src is None else src, self.dst if dst is None else dst, J, Mb,
                                  seed=DAA["seed"], val_begin=self.val_begin, n_val_total=self.n_val_total, workspace=ws, out=out,
-                                 base_mean=self.base_mean)
+                                 base_mean=self.base_mean,
+                                 unit_begin=self.units["local_begin"] if self.units else None,
+                                 unit_end=self.units["local_end"] if self.units else None)
 
         def gather(self, r=None):
             r = r or self.r
-            if self.ex is not None:
+            if self.ex is not None and self.units:
+                self.ex.exchange_units(r.coefs, r.pvalues, self.units["local_begin"], self.units["local_end"], self.units["unit_begin"])
+            elif self.units and world > 1:
+                u = self.units
+                self.full["t"] = [daa.gather_tables(t.view(-1, R)[u["local_begin"]:u["local_end"]], self.n_val_total * C_).view(-1, C_, R)
+                                  for t in (r.coefs, r.pvalues)]
+            elif self.ex is not None:
                 self.ex.exchange(r.coefs, r.pvalues, self.val_begin)
             elif world > 1:   # both tables in one coalesced NCCL launch, straight into reused full-size tensors
                 self.full["t"] = daa.gather_tables_many([r.coefs, r.pvalues], self.n_val_total, outs=self.full.get("t"))
@@ -407,7 +416,12 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
             dist.barrier()
             cf, pv = self.tables()
-            ref = [daa.gather_tables(t, self.n_val_total) for t in (self.r.coefs, self.r.pvalues)]
+            if self.units:
+                u = self.units
+                ref = [daa.gather_tables(t.view(-1, R)[u["local_begin"]:u["local_end"]], self.n_val_total * C_).view(-1, C_, R)
+                       for t in (self.r.coefs, self.r.pvalues)]
+            else:
+                ref = [daa.gather_tables(t, self.n_val_total) for t in (self.r.coefs, self.r.pvalues)]
             torch.cuda.synchronize()
             ok = torch.ones(1, device=device)
             if rank == 0 and not (torch.equal(cf, ref[0]) and torch.equal(pv, ref[1])):     # the root holds the gathered tables
@@ -422,7 +436,8 @@ def run_ours(args, rank, world, local_rank):
             if os.environ.get("MOPOE_BENCH_NO_GRAPH"):
                 return note
             try:
-                want = (self.r.coefs.clone(), self.r.pvalues.clone())
+                own = (lambda t: t.view(-1, R)[self.units["local_begin"]:self.units["local_end"]]) if self.units else (lambda t: t)
+                want = (own(self.r.coefs).clone(), own(self.r.pvalues).clone())
                 _lib.check(lib.mopoe_profile_enable(0))
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
@@ -443,7 +458,7 @@ def run_ours(args, rank, world, local_rank):
                 if self.ex is not None:
                     self.ex.calls += 1
                 torch.cuda.synchronize()
-                if torch.equal(self.r.coefs, want[0]) and torch.equal(self.r.pvalues, want[1]):
+                if torch.equal(own(self.r.coefs), want[0]) and torch.equal(own(self.r.pvalues), want[1]):
                     self.graph = g
                     note = "CUDA graph replay of the sweep%s (verified bit-identical to direct launches)" % (
                         " + table exchange" if self.ex is not None else "")
@@ -582,11 +597,12 @@ def run_ours(args, rank, world, local_rank):
     # ---- strong scaling (N > 1): the SAME 20 validations of configs[3] split over the ranks ----
     strong = None
     if world > 1:
-        sb, se = daa.shard_validations(n_val, rank, world)
+        su = daa.shard_units(n_val, C_, rank, world)      # (validation, score) units, 140 for configs[3]
+        sb, se = su["val_begin"], su["val_end"]
         s_src, s_dst = draw_validation_batches(n_val, DAA["seed"], offset=0)
         del run, r, host_out
         torch.cuda.empty_cache()
-        srun = Runner(s_src[sb:se].to(device), s_dst[sb:se].to(device), sb, n_val)
+        srun = Runner(s_src[sb:se].to(device), s_dst[sb:se].to(device), sb, n_val, units=su)
         for _ in range(2):
             srun.step()
         s_ok = srun.verify_exchange()
@@ -596,13 +612,16 @@ def run_ours(args, rank, world, local_rank):
         ms_strong = srun.timed(args.steps)
         tms = torch.tensor([ms_strong], dtype=torch.float64, device=device)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        sizes = [e - b for b, e in (daa.shard_validations(n_val, q, world) for q in range(world))]
-        strong = {"scaling": "strong", "n_validation_total": n_val, "validations_per_rank": sizes,
+        shards = [daa.shard_units(n_val, C_, q, world) for q in range(world)]
+        sizes = [q["unit_end"] - q["unit_begin"] for q in shards]
+        strong = {"scaling": "strong", "n_validation_total": n_val, "shard_unit": "(validation, score)", "units_total": n_val * C_,
+                  "units_per_rank": sizes, "validations_touched_per_rank": [q["val_end"] - q["val_begin"] for q in shards],
                   "ms_per_step": tms.item() / args.steps, "value": n_val * N * C_ * J * args.steps / (tms.item() * 1e-3), "unit": UNIT,
-                  "balance_bound": n_val / (world * max(sizes)), "launch": s_note, "exchange": srun.exchange_note,
+                  "balance_bound": n_val * C_ / (world * max(sizes)), "launch": s_note, "exchange": srun.exchange_note,
                   "exchange_verified_vs_nccl": bool(s_ok),
-                  "note": "sharding unit = validation (the C-ABI sweep runs whole validations); with 20 validations the largest shard bounds "
-                          "the speed-up at balance_bound x N; (validation, score) units (140) would lift it to 0.97 at N = 8"}
+                  "note": "sharding unit = (validation, score) pair (SURVEY.md 8e): avatar tiles and statistics of the owned units only; "
+                          "the base passes / encoder heads of a validation are run by every rank that shares it (they do not shrink "
+                          "with the shard); the largest shard bounds the speed-up at balance_bound x N"}
     clocks = sampler.stop()
     times = torch.tensor([ms, ms_e2e, ms_tab, d2h_best], dtype=torch.float64, device=device)
     if world > 1:

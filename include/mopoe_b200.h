@@ -207,6 +207,12 @@ typedef struct mopoe_daa_desc {
                          *     is the decode of mu + sd * eps_mean -- same distribution, 1/M of the draws; only with the
                          *     in-kernel generator (eps_base == NULL).  Equivalent to base_mode 0 with n_base = 1 and
                          *     eps_base = that row / sqrt(M) (tests/test_gpu_parity.py). */
+  int32_t unit_begin;   /* shard units: unit u = v_local * n_scores + score, the regression of a (validation, */
+  int32_t unit_end;     /* score) pair needs nothing outside it.  [unit_begin, unit_end) of the n_val * n_scores units of this
+                         * call are OWNED: their rows of coefs / pvalues / betas and their avatars are produced; the other units
+                         * of the first and last validation belong to another rank -- their table rows are NOT written (avatar
+                         * tiles shared with an owned series are, with the values the owner computes: the noise is keyed
+                         * globally).  0, 0 = every unit.  Base passes and scores cover whole validations either way. */
 } mopoe_daa_desc;
 
 /* Bytes of scratch mopoe_daa_sweep needs. */

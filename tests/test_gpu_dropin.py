@@ -180,6 +180,24 @@ def test_train_exp_then_daa_exp_end_to_end(tmp_path):
     assert len(sig) - 1 == int(want.sum())
     meta = np.load(os.path.join(resdir, "metadatas.npy"), allow_pickle=True)
     assert meta.shape[:2] == (3, 20)
+    # the files through the reference's own reader expressions (workflow.py:611-630 anova_exp, analyze_avatars.py:59-78)
+    import pandas as pd
+    rois_names = np.load(os.path.join(ds, "rois_names.npy"), allow_pickle=True)
+    clinical_names = np.load(os.path.join(ds, "clinical_names.npy"), allow_pickle=True)
+    modified = [n.replace("&", "_").replace("-", "_") for n in rois_names]
+    all_coefs = np.load(os.path.join(resdir, "all_coefs.npy"), allow_pickle=True)[np.newaxis]
+    idx_sign = ((p < 0.05 / len(rois_names) / len(clinical_names)).sum(axis=0) >= 3 * 0.7)
+    assert np.array_equal(idx_sign, want)
+    for val_idx in range(3):
+        for score_idx in range(len(clinical_names)):
+            coefs_df = pd.DataFrame(all_coefs[0][val_idx][score_idx], columns=["participant_id", "site"] + modified)
+            coefs_df[modified] = coefs_df[modified].astype(float)
+            assert coefs_df.shape == (20, 2 + 444)
+            assert np.allclose(coefs_df[modified].to_numpy().mean(0), c[val_idx, score_idx], rtol=1e-9, atol=1e-12)
+            assert list(coefs_df["participant_id"]) == list(meta[val_idx][:, 0])
+    da = np.load(os.path.join(resdir, "rois_digital_avatars.npy"), mmap_mode="r")[1]
+    scores, metadata = sc[1], meta[1]
+    assert da.shape == (20, 7, 12, 444) and scores[5].shape == (12, 7) and metadata.shape[0] == 20
 
 
 def test_ensemble_train_and_daa_with_vote_prop(tmp_path):
@@ -210,3 +228,50 @@ def test_ensemble_train_and_daa_with_vote_prop(tmp_path):
     want = workflow.significant_votes(p, 0.5, 2, 0.5)
     sig = open(os.path.join(resdir, "significant_rois.tsv")).read().splitlines()
     assert len(sig) - 1 == int(want.sum())
+
+
+_TWO_RANKS = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+import mopoe_b200
+from mopoe_b200 import workflow
+rank = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+ds, out, run, J = sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4])
+workflow.daa_exp("hbn", ds, out, run, n_validation=3, n_samples=J, n_subjects=20, M=30, trust_level=0.7)
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+@pytest.mark.parametrize("J", [130, 12])
+def test_daa_exp_two_ranks_write_the_same_files_as_one(tmp_path, J):
+    """SURVEY.md 8e through the workflow: two ranks split the 21 (validation, score) units 11 / 10 (validation 1 is
+    shared), each writes its slices of the avatar memmap, rank 0 the tables: every file equals the one-rank run
+    (J = 130: pipelined tcgen05 kernel with unit ranges; J = 12: CUDA-core kernel)."""
+    import shutil, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from mopoe_b200 import data, workflow
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ds, out1, out2 = str(tmp_path / "data"), str(tmp_path / "out1"), str(tmp_path / "out2")
+    os.makedirs(out1)
+    data.write_dataset(ds, data.make_cohort(n_both=640, n_clinical_only=128, n_rois_only=64, standardize=False))
+    run = workflow.train_exp("hbn", ds, out1, [7, 444], num_epochs=3, batch_size=128, method="joint_elbo", data_seed=3)
+    shutil.copytree(out1, out2)
+    res1 = workflow.daa_exp("hbn", ds, out1, run, n_validation=3, n_samples=J, n_subjects=20, M=30, trust_level=0.7)
+    script = tmp_path / "two.py"
+    script.write_text(_TWO_RANKS % root)
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29537", str(script), ds, out2, run, str(J)],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    res2 = res1.replace(out1, out2)
+    for f in ("rois_digital_avatars.npy", "sampled_scores.npy", "rois_reconstructions.npy", "pvalues.npy", "coefs.npy"):
+        a, b = np.load(os.path.join(res1, f)), np.load(os.path.join(res2, f))
+        assert a.shape == b.shape and np.array_equal(a, b), f
+    assert open(os.path.join(res1, "significant_rois.tsv")).read() == open(os.path.join(res2, "significant_rois.tsv")).read()
+    a = np.load(os.path.join(res1, "all_coefs.npy"), allow_pickle=True)
+    b = np.load(os.path.join(res2, "all_coefs.npy"), allow_pickle=True)
+    assert a.shape == b.shape and bool((a == b).all())

@@ -555,6 +555,42 @@ def test_daa_full_hbn_sweep_properties():
     assert float(sc.mean(dim=2).std()) > 0 and bool(torch.isfinite(sc).all())
 
 
+@pytest.mark.parametrize("world", [3, 8])
+def test_daa_validation_score_units_equal_the_whole_sweep(world):
+    """the sharding unit is the (validation, score) pair.  Every simulated rank runs only the
+    validations it touches with its unit range; the owned rows of the tables, the per-subject slopes and the owned
+    avatar series are bit-identical to the unsharded sweep (noise keyed globally, per-(series, tile) sums)."""
+    import bench
+    from mopoe_b200 import daa, engine, _lib
+    import mopoe_b200
+    spec = mopoe_b200.PathSpec(bench.HBN["dims"], bench.HBN["style_dims"], 20, "joint_elbo", bench.HBN["mod_names"])
+    flat = engine.pack_params(spec, mo.init_params(mo.ModelSpec(**bench.HBN), seed=3), torch.device("cuda"))
+    n_val, C, J, Mb = 5, 7, 150, 40
+    src, dst = bench.draw_validation_batches(n_val, 1037)
+    src, dst = src.cuda(), dst.cuda()
+    kw = dict(seed=77, n_val_total=n_val)
+    full = daa.daa_sweep(spec, flat, src, dst, J, Mb, **kw)
+    torch.cuda.synchronize()
+    assert _lib.lib().mopoe_daa_last_impl() == 2
+    covered = torch.zeros(n_val * C, dtype=torch.bool)
+    for rank in range(world):
+        sh = daa.shard_units(n_val, C, rank, world)
+        vb, ve = sh["val_begin"], sh["val_end"]
+        part = daa.daa_sweep(spec, flat, src[vb:ve], dst[vb:ve], J, Mb, val_begin=vb, unit_begin=sh["local_begin"],
+                             unit_end=sh["local_end"], **kw)
+        torch.cuda.synchronize()
+        for u in range(sh["unit_begin"], sh["unit_end"]):
+            v, c = divmod(u, C)
+            assert not covered[u]
+            covered[u] = True
+            assert torch.equal(part.coefs[v - vb, c], full.coefs[v, c]), (rank, u)
+            assert torch.equal(part.pvalues[v - vb, c], full.pvalues[v, c]), (rank, u)
+            assert torch.equal(part.betas[v - vb, c], full.betas[v, c]), (rank, u)
+            assert torch.equal(part.avatars[v - vb, :, c], full.avatars[v, :, c]), (rank, u)
+        assert torch.equal(part.sampled_scores, full.sampled_scores[vb:ve])
+    assert bool(covered.all())
+
+
 def test_daa_four_modalities_pipelined_vs_cuda_core(monkeypatch):
     """Stress shape (BASELINE.json configs[4]: 4 modalities, 15 PoE subsets): the perturbed / read-out pair
     is (clinical, rois) as in daa_exp, the two extra blocks enter every subset posterior.  The reference

@@ -134,9 +134,43 @@ for n_val in (5, 6, 6):          # unequal shards (padded path), equal shards (o
     out = full
     a, b = daa.gather_tables_many([local, 2 * local], n_val)
     assert torch.equal(a, want) and torch.equal(b, 2 * want)
+# (validation, score) shard units as daa_exp gathers them: unit rows + the per-validation arrays of the lead rank
+for n_val, C in ((3, 7), (1, 3), (4, 1)):
+    shards = [daa.shard_units(n_val, C, q, world) for q in range(world)]
+    sh = shards[rank]
+    sizes = [q["unit_end"] - q["unit_begin"] for q in shards]
+    table = torch.arange(n_val * C * 5, dtype=torch.float64).view(n_val, C, 5)
+    local = table[sh["val_begin"]:sh["val_end"]].reshape(-1, 5)[sh["local_begin"]:sh["local_end"]].clone()
+    full = daa.gather_rows(local, sizes).view(n_val, C, 5)
+    assert torch.equal(full, table), (rank, n_val, C)
+    lead = lambda q: [v for v in range(q["val_begin"], q["val_end"]) if q["unit_begin"] <= v * C < q["unit_end"]]
+    per_val = torch.arange(n_val * 3, dtype=torch.float32).view(n_val, 3)
+    got = daa.gather_rows(per_val[lead(sh)], [len(lead(q)) for q in shards])
+    assert torch.equal(got, per_val), (rank, n_val, C)
 dist.destroy_process_group()
 print("ok", rank)
 '''
+
+
+@pytest.mark.parametrize("n_val,C,world", [(20, 7, 8), (20, 7, 3), (2, 7, 8), (1, 3, 8), (5, 1, 2)])
+def test_shard_units_partition_and_balance(n_val, C, world):
+    """SURVEY.md 8e: (validation, score) units, contiguous block split; at most one unit of imbalance."""
+    from mopoe_b200 import daa
+    seen, sizes = [], []
+    for r in range(world):
+        sh = daa.shard_units(n_val, C, r, world)
+        n = sh["unit_end"] - sh["unit_begin"]
+        sizes.append(n)
+        seen += list(range(sh["unit_begin"], sh["unit_end"]))
+        if n:
+            assert sh["val_begin"] * C <= sh["unit_begin"] and sh["unit_end"] <= sh["val_end"] * C
+            assert sh["val_begin"] == sh["unit_begin"] // C and sh["val_end"] == (sh["unit_end"] - 1) // C + 1
+            assert sh["local_begin"] == sh["unit_begin"] - sh["val_begin"] * C
+            assert sh["local_end"] - sh["local_begin"] == n
+    assert seen == list(range(n_val * C))
+    assert max(sizes) - min(sizes) <= 1
+    if (n_val, C, world) == (20, 7, 8):
+        assert sorted(sizes) == [17] * 4 + [18] * 4          # 97 % balance (whole validations: 3 / 2 = 83 %)
 
 
 def test_gather_tables_world_size_2_gloo(tmp_path):
