@@ -121,6 +121,12 @@ def lib():
     L.mopoe_profile_enable.restype = C.c_int
     L.mopoe_daa_last_kernel_ms.argtypes = [C.POINTER(C.c_float)]
     L.mopoe_daa_last_kernel_ms.restype = C.c_int
+    L.mopoe_rsa_cmat.argtypes = [i32, i32, vp, i32, vp, vp]
+    L.mopoe_rsa_cmat.restype = C.c_int
+    L.mopoe_rsa_kendall_workspace_bytes.argtypes = [i32, i32]
+    L.mopoe_rsa_kendall_workspace_bytes.restype = i64
+    L.mopoe_rsa_kendall.argtypes = [i32, i32, vp, vp, vp, vp, i64, vp]
+    L.mopoe_rsa_kendall.restype = C.c_int
     for fn in ("mopoe_param_layout_of", "mopoe_forward", "mopoe_train_steps", "mopoe_daa_sweep",
                "mopoe_daa_regression", "mopoe_philox_normal"):
         getattr(L, fn).restype = C.c_int
@@ -137,4 +143,5 @@ EXPORTED = ["mopoe_last_error", "mopoe_version", "mopoe_device_count", "mopoe_pa
             "mopoe_workspace_bytes", "mopoe_forward", "mopoe_train_steps", "mopoe_daa_workspace_bytes",
             "mopoe_daa_sweep", "mopoe_daa_regression", "mopoe_philox_normal", "mopoe_profile_enable",
             "mopoe_daa_last_kernel_ms", "mopoe_umma_selftest", "mopoe_daa_last_impl", "mopoe_daa_read_phases",
-            "mopoe_daa_status", "mopoe_train_last_impl", "mopoe_table_exchange_bytes", "mopoe_daa_exchange_tables"]
+            "mopoe_daa_status", "mopoe_train_last_impl", "mopoe_table_exchange_bytes", "mopoe_daa_exchange_tables",
+            "mopoe_rsa_cmat", "mopoe_rsa_kendall_workspace_bytes", "mopoe_rsa_kendall"]

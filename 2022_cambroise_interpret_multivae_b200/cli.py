@@ -1,7 +1,8 @@
 """Command line mirroring experiments/experiments.py:21-34 (`fire` is replaced by a tiny parser):
     python -m mopoe_b200.cli train --dataset hbn --datasetdir D --outdir O --input_dims 7,444 ...
     python -m mopoe_b200.cli daa   --dataset hbn --datasetdir D --outdir O --run hbn_2026_... ...
-Every `--key value` becomes a keyword argument of workflow.train_exp / workflow.daa_exp."""
+    python -m mopoe_b200.cli rsa   --dataset hbn --datasetdir D --outdir O --run hbn_2026_... ...
+Every `--key value` becomes a keyword argument of workflow.train_exp / daa_exp / rsa_exp."""
 import ast
 import sys
 
@@ -26,9 +27,9 @@ def _parse(argv):
 def main(argv=None):
     from . import workflow
     argv = list(sys.argv[1:] if argv is None else argv)
-    commands = {"train": workflow.train_exp, "daa": workflow.daa_exp}
+    commands = {"train": workflow.train_exp, "daa": workflow.daa_exp, "rsa": workflow.rsa_exp}
     if not argv or argv[0] not in commands:
-        raise SystemExit("usage: cli.py {train|daa} --key value ...   (the other reference commands are out of scope)")
+        raise SystemExit("usage: cli.py {train|daa|rsa} --key value ...   (the other reference commands are out of scope)")
     kw = _parse(argv[1:])
     if isinstance(kw.get("input_dims"), tuple):
         kw["input_dims"] = list(kw["input_dims"])

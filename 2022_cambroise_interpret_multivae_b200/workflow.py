@@ -25,6 +25,7 @@ import pandas as pd
 import torch
 
 from . import daa, run_epochs as re_
+from .engine import Workspace
 from .model import VAE
 
 MODALITIES = ["clinical", "rois"]
@@ -388,3 +389,72 @@ def daa_exp(dataset, datasetdir, outdir, run, sampling_strategy="likelihood", n_
     if world > 1:
         dist.barrier()
     return resdir
+
+
+def rsa_exp(dataset, datasetdir, outdir, run, n_validation=1, n_subjects=301, sample_latents=False, seed=None):
+    """Representational similarity analysis of the latent spaces (workflow.py:656-820): per model, validation and
+    latent block (joint, the clinical_rois subset posterior, the two style posteriors) the Euclidean dissimilarity
+    matrix of `n_subjects` test subjects is compared with the dissimilarity matrix of every clinical score and
+    covariate (age, sex, site[, fsiq]) by Kendall's tau-b.  Matrices and the P^2 pair counts run on the GPU
+    (rsa.py / csrc/mopoe_rsa.cu).  `seed` (ours): subject draws; the reference shuffles with the global torch RNG.
+    Returns the rsa directory; writes kendalltau_stats.npy (n_models, 4, n_validation, n_scores + n_cov, 2),
+    latent_dissimilarity.npy, scores_dissimilarity.npy and kendalltau_<latent>.tsv like the reference."""
+    from . import rsa
+    expdir = os.path.join(outdir, run)
+    rsadir = os.path.join(expdir, "rsa")
+    flags_file = os.path.join(expdir, "flags.rar")
+    if not os.path.isfile(flags_file):
+        raise ValueError("You need first to train the model.")
+    exp, flags = Experiment.get_experiment(flags_file, os.path.join(expdir, "checkpoints"))
+    os.makedirs(rsadir, exist_ok=True)
+    clinical_names = np.load(os.path.join(datasetdir, "clinical_names.npy"), allow_pickle=True)
+    cov_names = ["age", "sex", "site"] + (["fsiq"] if dataset == "euaims" else [])
+    categorical_covs = ["sex", "site"]
+    latent_names = ["joint", "clinical_rois", "clinical_style", "rois_style"]
+    n_models, n_scores = exp.num_models, len(clinical_names)
+    kendalltaus = np.zeros((n_models, len(latent_names), n_validation, n_scores + len(cov_names), 2))
+    latent_dis, scores_dis = [], []
+    rs = np.random.RandomState(seed)
+    ws = Workspace()
+    for model_idx in range(n_models):
+        model = exp.model_of(model_idx)
+        model.eval()
+        res = exp.resident_of(model_idx)
+        test_idx = exp.test_idx if n_models == 1 else exp.test_idx[model_idx]
+        meta = exp.metadata.iloc[test_idx].reset_index(drop=True)
+        latent_dis.append([])
+        scores_dis.append([])
+        for val_idx in range(n_validation):
+            take = rs.permutation(res["n_test"])[:n_subjects]              # workflow.py:733-741: one shuffled batch
+            idx = torch.from_numpy(take).to(exp.device)
+            data = {"clinical": res["test"][0][idx], "rois": res["test"][1][idx]}
+            # the reference matrices do not depend on the latent block: built once per validation
+            refs = [rsa.vec2cmat(data["clinical"][:, c].contiguous()) for c in range(n_scores)]
+            refs += [rsa.vec2cmat(meta[name].to_numpy()[take], categorical=name in categorical_covs) for name in cov_names]
+            refs = torch.stack(refs)
+            for latent_idx, latent_name in enumerate(latent_names):
+                latents = model(data, sample_latents=sample_latents)["latents"]       # workflow.py:751-758
+                if latent_name == "joint":
+                    latents = latents["joint"]
+                elif "style" in latent_name:
+                    latents = latents["modalities"][latent_name]
+                else:
+                    latents = latents["subsets"][latent_name]
+                latents = model.reparameterize(latents[0], latents[1]) if sample_latents and latents[0] is not None else latents[0]
+                if latents is not None:
+                    cmat = rsa.data2cmat(latents)
+                    taus, pvals = rsa.fit_rsa(cmat, refs, workspace=ws)
+                    kendalltaus[model_idx, latent_idx, val_idx, :, 0] = taus
+                    kendalltaus[model_idx, latent_idx, val_idx, :, 1] = pvals
+                    latent_dis[model_idx].append(cmat.cpu().numpy())
+                scores_dis[model_idx].append(refs.cpu().numpy())
+    np.save(os.path.join(rsadir, "kendalltau_stats.npy"), kendalltaus)
+    np.save(os.path.join(rsadir, "latent_dissimilarity.npy"), np.asarray(latent_dis))
+    np.save(os.path.join(rsadir, "scores_dissimilarity.npy"), np.asarray(scores_dis))
+    for latent_idx, latent_name in enumerate(latent_names):                          # workflow.py:797-815
+        names = list(clinical_names) + cov_names
+        k = kendalltaus[:, latent_idx]
+        df = pd.DataFrame({"score": names, "pval": k[..., 1].mean((0, 1)), "pval_std": k[..., 1].std((0, 1)),
+                           "r": k[..., 0].mean((0, 1)), "r_std": k[..., 0].std((0, 1))})
+        df.to_csv(os.path.join(rsadir, "kendalltau_%s.tsv" % latent_name), sep="\t", index=False)
+    return rsadir

@@ -303,6 +303,21 @@ int mopoe_philox_normal(uint64_t seed, uint64_t stream_id, int64_t start, int64_
 int mopoe_umma_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t variant,
                         int32_t* err_flag, void* stream);
 
+/* ---- representational similarity analysis (experiments/workflow.py:656-789 rsa_exp) ----
+ * mopoe_rsa_cmat: stat_utils.py:25-33 data2cmat (categorical = 0: Euclidean distances of the n rows of `data` (n, d),
+ *   fp64, summed in column order like scipy's pdist) or stat_utils.py:46-53 vec2cmat (d = 1; categorical = 1: the
+ *   0 / 1 "differs" matrix).  cmat (n, n) fp64. */
+int mopoe_rsa_cmat(int32_t n, int32_t d, const float* data, int32_t categorical, double* cmat, void* stream);
+/* mopoe_rsa_kendall: stat_utils.py:81-95 fit_rsa for ONE matrix against n_ref reference matrices (n_ref, n, n): the
+ *   upper triangles (stat_utils.py:36-43 cmat2triu, P = n (n - 1) / 2 entries) are compared entry pair by entry pair.
+ *   counts (n_ref, 7) int64, exact:  [0] sum_{i != j} sign(x_i - x_j) sign(y_i - y_j) = 2 (concordant - discordant),
+ *   [1..3] sum_i c_i, sum_i c_i (c_i - 1), sum_i c_i (2 c_i + 7) with c_i = #{j != i: x_j == x_i} (i.e. the sums over
+ *   tie groups of t (t - 1), t (t - 1)(t - 2), t (t - 1)(2 t + 5) that scipy.stats.kendalltau uses), [4..6] the same
+ *   for y.  tau-b and the asymptotic p-value follow on the host (rsa.py: kendall_from_counts). */
+int64_t mopoe_rsa_kendall_workspace_bytes(int32_t n, int32_t n_ref);
+int mopoe_rsa_kendall(int32_t n, int32_t n_ref, const double* cmat, const double* ref_cmats, int64_t* counts,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
 enum {
   MOPOE_STREAM_DAA_BASE = 1, MOPOE_STREAM_DAA_SCORE = 2, MOPOE_STREAM_DAA_AVATAR = 3,
   MOPOE_STREAM_TRAIN = 4, MOPOE_STREAM_FORWARD = 5

@@ -198,6 +198,20 @@ def test_train_exp_then_daa_exp_end_to_end(tmp_path):
     da = np.load(os.path.join(resdir, "rois_digital_avatars.npy"), mmap_mode="r")[1]
     scores, metadata = sc[1], meta[1]
     assert da.shape == (20, 7, 12, 444) and scores[5].shape == (12, 7) and metadata.shape[0] == 20
+    # rsa_exp (workflow.py:656-820) on the same run: files, shapes, and the statistics recomputed with scipy
+    from oracle import rsa_oracle as ro
+    rsadir = workflow.rsa_exp("hbn", ds, out, run, n_validation=2, n_subjects=40, seed=5)
+    kt = np.load(os.path.join(rsadir, "kendalltau_stats.npy"))
+    ld = np.load(os.path.join(rsadir, "latent_dissimilarity.npy"))
+    sd_ = np.load(os.path.join(rsadir, "scores_dissimilarity.npy"))
+    assert kt.shape == (1, 4, 2, 10, 2) and ld.shape == (1, 8, 40, 40) and sd_.shape == (1, 8, 10, 40, 40)
+    for k in range(8):                       # entry k = (validation k // 4, latent k % 4)
+        for r in range(10):
+            tau, pval = ro.fit_rsa(ld[0, k], sd_[0, k, r])
+            assert abs(kt[0, k % 4, k // 4, r, 0] - tau) <= 1e-13 and abs(kt[0, k % 4, k // 4, r, 1] - pval) <= 1e-9 * max(pval, 1e-300)
+    tsv = pd.read_table(os.path.join(rsadir, "kendalltau_joint.tsv"))
+    assert list(tsv.columns) == ["score", "pval", "pval_std", "r", "r_std"] and len(tsv) == 10
+    assert list(tsv["score"][-3:]) == ["age", "sex", "site"]
 
 
 def test_ensemble_train_and_daa_with_vote_prop(tmp_path):

@@ -684,3 +684,34 @@ def test_daa_full_sweep_trained_model_vs_oracle():
     differs = (gp < thr) != (p_or < thr)
     assert np.all(np.abs(np.log(np.maximum(p_or[differs], 1e-300)) - np.log(thr)) <= 1e-3 * abs(np.log(thr)))
     assert np.array_equal(sig_g, sig_o)
+
+
+# ---- representational similarity analysis ---------------------------------------------------
+@pytest.mark.parametrize("n,d", [(12, 3), (60, 20), (301, 20)])
+def test_rsa_matrices_and_kendall_vs_scipy(n, d):
+    """csrc/mopoe_rsa.cu through the C-ABI against oracle/rsa_oracle.py (scipy's pdist / kendalltau, the calls of
+    experiments/stat_utils.py:25-53,81-95): distance matrices bit-exact, tau-b exact to rounding, p-values 1e-9;
+    n = 301 is rsa_exp's default size (45 150 entries per triangle, 2e9 entry pairs per reference)."""
+    from mopoe_b200 import rsa
+    from oracle import rsa_oracle as ro
+    rng = np.random.default_rng(n)
+    lat = rng.standard_normal((n, d)).astype(np.float32)
+    scores = np.stack([np.round(rng.standard_normal(n) * 3) / 3, lat[:, 0] + 0.5 * rng.standard_normal(n),
+                       rng.standard_normal(n)], axis=1).astype(np.float32)
+    cov = {"age": rng.random(n).astype(np.float32), "sex": rng.integers(0, 2, n), "site": rng.integers(0, 4, n)}
+    cm_w, mats_w, kt_w = ro.rsa_table(lat, scores, cov, ["sex", "site"])
+    cm = rsa.data2cmat(torch.from_numpy(lat).cuda())
+    assert np.array_equal(cm.cpu().numpy(), cm_w)
+    refs = [rsa.vec2cmat(torch.from_numpy(scores[:, c].copy()).cuda()) for c in range(3)]
+    refs += [rsa.vec2cmat(v, categorical=k in ("sex", "site")) for k, v in cov.items()]
+    refs = torch.stack(refs)
+    assert np.array_equal(refs.cpu().numpy(), mats_w)
+    taus, pvals = rsa.fit_rsa(cm, refs)
+    assert np.abs(taus - kt_w[:, 0]).max() <= 1e-13
+    assert np.all(np.abs(pvals - kt_w[:, 1]) <= 1e-9 * np.maximum(kt_w[:, 1], 1e-300))
+    tau1, p1 = rsa.fit_rsa(cm, refs[1])                                   # the reference's two-matrix signature
+    assert abs(tau1 - kt_w[1, 0]) <= 1e-13 and abs(p1 - kt_w[1, 1]) <= 1e-9 * kt_w[1, 1]
+    if n == 12:
+        counts = rsa.kendall_counts(cm, refs).cpu().numpy()
+        for r in range(refs.shape[0]):
+            assert np.array_equal(counts[r], ro.brute_counts(ro.cmat2triu(cm_w), ro.cmat2triu(mats_w[r])))

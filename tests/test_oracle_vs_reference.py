@@ -33,3 +33,22 @@ def test_basic_routine_epoch_live(method, present):
             assert not used[k]
         else:
             assert (gr[k] - p.grad).abs().max() <= 1e-5 * p.grad.abs().max() + 1e-9, k
+
+
+def test_rsa_oracle_equals_the_reference_stat_utils():
+    """oracle/rsa_oracle.py against the unmodified experiments/stat_utils.py (data2cmat, vec2cmat, cmat2triu, fit_rsa)."""
+    import numpy as np
+    rh.install()
+    import stat_utils as ref
+    from oracle import rsa_oracle as ro
+    rng = np.random.default_rng(5)
+    lat = rng.standard_normal((40, 20)).astype(np.float32)
+    score = np.round(rng.standard_normal(40) * 2).astype(np.float32)          # discrete: ties
+    sex = rng.integers(0, 2, 40)
+    assert np.array_equal(ro.data2cmat(lat), ref.data2cmat(lat))
+    assert np.array_equal(ro.vec2cmat(score), ref.vec2cmat(score))
+    assert np.array_equal(ro.vec2cmat(sex, categorical=True), ref.vec2cmat(sex, categorical=True))
+    cm = ref.data2cmat(lat)
+    assert np.array_equal(ro.cmat2triu(cm), ref.cmat2triu(cm))
+    for other in (ref.vec2cmat(score), ref.vec2cmat(sex, categorical=True)):
+        assert ro.fit_rsa(cm, other) == tuple(ref.fit_rsa(cm, other))
