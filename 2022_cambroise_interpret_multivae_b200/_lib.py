@@ -12,11 +12,11 @@ MAX_MODS = 4
 MAX_SUBSETS = 15
 HIDDEN = 256
 N_SCALARS = 64
-METHODS = {"poe": 0, "moe": 1, "joint_elbo": 2}
+METHODS = {"poe": 0, "moe": 1, "joint_elbo": 2, "jsd": 3}
 
 # mopoe_scalar_index
 S_TOTAL_LOSS, S_JOINT_DIV, S_NLL, S_NLL_UNI, S_KLD_SUBSET, S_KLD_STYLE, S_MEAN_HEAD = 0, 1, 2, 6, 10, 25, 29
-S_N_ROWS, S_PRESENT = 45, 46
+S_N_ROWS, S_PRESENT, S_JSD_DIV = 45, 46, 47
 STREAM_DAA_BASE, STREAM_DAA_SCORE, STREAM_DAA_AVATAR, STREAM_TRAIN, STREAM_FORWARD = 1, 2, 3, 4, 5
 
 

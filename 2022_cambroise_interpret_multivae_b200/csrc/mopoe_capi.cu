@@ -42,8 +42,8 @@ int check_desc(const mopoe_model_desc* d) {
   if (d->hidden != MOPOE_HIDDEN) { set_error("hidden=%d unsupported (reference hard-codes 256)", d->hidden); return MOPOE_EINVAL; }
   if (d->n_hidden_enc != 1) { set_error("num_hidden_layer_encoder=%d unsupported (only 1)", d->n_hidden_enc); return MOPOE_EINVAL; }
   if (d->n_hidden_dec != 0) { set_error("num_hidden_layer_decoder=%d unsupported (only 0)", d->n_hidden_dec); return MOPOE_EINVAL; }
-  if (d->method < MOPOE_METHOD_POE || d->method > MOPOE_METHOD_JOINT_ELBO) {
-    set_error("method=%d unsupported (poe, moe, joint_elbo; jsd is not on this path)", d->method); return MOPOE_EINVAL; }
+  if (d->method < MOPOE_METHOD_POE || d->method > MOPOE_METHOD_JSD) {
+    set_error("method=%d unsupported (poe, moe, joint_elbo, jsd)", d->method); return MOPOE_EINVAL; }
   if (d->likelihood != 0) { set_error("likelihood=%d unsupported (only normal)", d->likelihood); return MOPOE_EINVAL; }
   if (d->scale_mode != 0) { set_error("learn_output_sample_scale is unsupported (per-feature logvar only)"); return MOPOE_EINVAL; }
   if (d->latent_dim < 1 || d->latent_dim > 32) { set_error("latent_dim=%d not in 1..32", d->latent_dim); return MOPOE_EINVAL; }

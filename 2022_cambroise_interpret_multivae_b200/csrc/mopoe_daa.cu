@@ -136,7 +136,7 @@ __device__ bool series_owner(const ModelView& mv, const DaaCtx& cx, int g, int& 
     if (kidx == owner) s_own = s;
     ++kidx;
   }
-  return ((mv.sub.mask[s_own] >> cx.q.src_mod) & 1) || (mv.method == MOPOE_METHOD_MOE && mv.sub.n_members[s_own] > 1);
+  return ((mv.sub.mask[s_own] >> cx.q.src_mod) & 1) || (moe_like(mv) && mv.sub.n_members[s_own] > 1);
 }
 
 __device__ void series_records(const ModelView& mv, const DaaCtx& cx, const DaaWs& ws, int64_t row, int g, int t, int nthreads,
@@ -455,9 +455,11 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_kernel(ModelView 
       if (kidx == owner) s_own = s;
       ++kidx;
     }
+    const bool own_prior = prior_component(mv, cx.b, owner);   // jsd: the row samples z from the prior N(0, I)
     if (cx.q.sample_latents) {
       need_src = (mv.sub.mask[s_own] >> src) & 1;
-      if (mv.method == MOPOE_METHOD_MOE && mv.sub.n_members[s_own] > 1) need_src = true;
+      if (moe_like(mv) && mv.sub.n_members[s_own] > 1) need_src = true;
+      if (own_prior) need_src = false;
     }
     {  // hidden pre-activation without the perturbed column, and that column of W1
       const float* w = ms.w1 + (int64_t)t * C;
@@ -569,7 +571,9 @@ __global__ void __launch_bounds__(MOPOE_THREADS, 1) daa_avatar_kernel(ModelView 
         }
         if (need_src) { mu_e[src] = s_e[jj * HO + l]; lv_e[src] = s_e[jj * HO + L + l]; }
         float z;
-        if (cx.q.sample_latents) {
+        if (cx.q.sample_latents && own_prior) {
+          z = s_eps[jj * E + l];
+        } else if (cx.q.sample_latents) {
           const SubsetEval ev = eval_subset(mv, cx.b, s_own, g, mu_e, lv_e);
           z = s_eps[jj * E + l] * expf(0.5f * ev.lv) + ev.mu;
         } else {
@@ -995,8 +999,10 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   const bool pipe_ok = umma_ok && daa->reg_method == 0 && daa->sample_latents && ud0.bias_slot >= 0 && ud0.KZ - ud0.KC <= 32 &&
                        pk_smem <= 227 * 1024 && (int64_t)n_units * cx.J < ((int64_t)1 << 31);
   int impl = pipe_ok ? 2 : (umma_ok ? 1 : 0);
+  if (desc->method == MOPOE_METHOD_JSD) impl = 0;     // prior-owned rows are handled by the CUDA-core kernel only
   const char* force = getenv("MOPOE_DAA_IMPL");
   if (force && !strcmp(force, "ffma")) impl = 0;
+  if (force && desc->method == MOPOE_METHOD_JSD && strcmp(force, "ffma")) { set_error("MOPOE_DAA_IMPL=%s: method jsd runs on the CUDA-core avatar kernel only", force); return MOPOE_EINVAL; }
   if (force && !strcmp(force, "umma")) { if (!umma_ok) { set_error("MOPOE_DAA_IMPL=umma but the shapes do not fit the tcgen05 tiling"); return MOPOE_EINVAL; } impl = 1; }
   if (force && !strcmp(force, "pipe")) { if (!pipe_ok) { set_error("MOPOE_DAA_IMPL=pipe but the configuration does not fit the pipelined kernel"); return MOPOE_EINVAL; } impl = 2; }
   g_last_impl = impl;

@@ -7,6 +7,13 @@
 
 namespace mopoe {
 
+// moe and jsd fuse the members of a subset by selection (BaseMMVae.py:46-54) and put the unimodal experts in the mixture
+__device__ __forceinline__ bool moe_like(const ModelView& mv) { return mv.method == MOPOE_METHOD_MOE || mv.method == MOPOE_METHOD_JSD; }
+// jsd: the last mixture component is the prior N(0, I) (BaseMMVae.py:217-223), which is no subset of the table
+__device__ __forceinline__ bool prior_component(const ModelView& mv, const mopoe_batch_desc& b, int k) {
+  return mv.method == MOPOE_METHOD_JSD && k == b.n_mix - 1;
+}
+
 // posterior of subset s at one (row, latent) element from the experts (mu_e, lv_e)
 struct SubsetEval {
   float mu, lv, sumT;
@@ -18,7 +25,7 @@ __device__ __forceinline__ SubsetEval eval_subset(const ModelView& mv, const mop
   SubsetEval r;
   const int nm = mv.sub.n_members[s];
   r.sel = 0; r.sumT = 1.f;
-  if (mv.method == MOPOE_METHOD_MOE) {  // moe_fusion -> mixture_component_selection
+  if (moe_like(mv)) {  // moe_fusion -> mixture_component_selection
     for (int i = 0; i < nm; ++i)
       if (n >= b.moe_bounds[nm][i] && n < b.moe_bounds[nm][i + 1]) r.sel = i;
     const int m = mv.sub.members[s][r.sel];
@@ -41,7 +48,7 @@ __device__ __forceinline__ SubsetEval eval_subset(const ModelView& mv, const mop
 }
 
 __device__ __forceinline__ bool in_mixture(const ModelView& mv, const mopoe_batch_desc& b, int s) {
-  if (mv.method == MOPOE_METHOD_MOE) return mv.sub.n_members[s] == 1;       // fusion_condition_moe
+  if (moe_like(mv)) return mv.sub.n_members[s] == 1;                          // fusion_condition_moe
   if (mv.method == MOPOE_METHOD_POE) return mv.sub.mask[s] == b.present_mask;  // fusion_condition_poe
   return true;                                                                // fusion_condition_joint
 }

@@ -295,7 +295,7 @@ __device__ __forceinline__ SubPost sub_post(const ModelView& mv, const mopoe_bat
   SubPost r;
   const int mask = mv.sub.mask[s], nm = mv.sub.n_members[s];
   r.sel_m = 0;
-  if (mv.method == MOPOE_METHOD_MOE) {
+  if (moe_like(mv)) {
     int sel = 0;
     for (int i = 0; i < nm; ++i)
       if (n >= b.moe_bounds[nm][i] && n < b.moe_bounds[nm][i + 1]) sel = i;
@@ -391,6 +391,26 @@ __device__ void lat_forward(const ModelView& mv, const StepCtx& cx, const mopoe_
       if (cx.use_expert == s) { jmu = ev.mu; jlv = ev.lv; }
     }
     LTP(2);
+    if (mv.method == MOPOE_METHOD_JSD) {
+      // divergence to the dynamic prior (BaseMMVae.py:81-93, mm_div.py:23-35,69-89): weighted PoE of the mixture
+      // components (present unimodal experts, then the prior N(0, I); weights 1 / n_mix), KL of each component to
+      // it.  (Rows owned by the prior component keep jmu = jlv = 0: no subset matches their owner index.)
+      const float wj = 1.f / (float)b.n_mix;
+      float A = 1.f / (1.f + MOPOE_POE_EPS), B = 0.f;
+#pragma unroll
+      for (int m = 0; m < MOPOE_MAX_MODS; ++m)
+        if (m < M && (present >> m & 1)) { A += T[m]; B += muT[m]; }
+      const float P = wj * A, mu_a = B / A, lv_a = -logf(P);
+      int kc = 0;
+#pragma unroll
+      for (int m = 0; m < MOPOE_MAX_MODS; ++m)
+        if (m < M && (present >> m & 1)) {
+          const float dm = mu_e[m] - mu_a;
+          block_add(sh.red, MOPOE_S_JSD_DIV + kc, valid ? -0.5f * (1.f - ex[m] * P - dm * dm * P + lv_e[m] - lv_a) : 0.f);
+          ++kc;
+        }
+      block_add(sh.red, MOPOE_S_JSD_DIV + kc, valid ? -0.5f * (1.f - P - mu_a * mu_a * P - lv_a) : 0.f);
+    }
     if (cx.use_expert < 0 && !cx.sample_latents) { jmu /= (float)b.n_mix; jlv /= (float)b.n_mix; }
     if (valid) {
       float z = jmu, rp = 0.f;
@@ -509,8 +529,10 @@ __device__ void lat_backward(const ModelView& mv, const StepCtx& cx, const mopoe
         float umu = 0.f, ulv = 0.f;
         const float dkl_lv = 0.5f * (ev.var - 1.f);
         if (in_mixture(mv, b, s)) {
-          umu += ckl * wmix * ev.mu;
-          ulv += ckl * wmix * dkl_lv;
+          if (mv.method != MOPOE_METHOD_JSD) {   // static prior; the dynamic-prior divergence of jsd follows the loop
+            umu += ckl * wmix * ev.mu;
+            ulv += ckl * wmix * dkl_lv;
+          }
           if (kidx == owner) { umu += gz; ulv += gz * sh.rp[r * L + l]; }
           ++kidx;
         }
@@ -524,7 +546,7 @@ __device__ void lat_backward(const ModelView& mv, const StepCtx& cx, const mopoe
           }
         }
         if (umu == 0.f && ulv == 0.f) continue;
-        if (mv.method == MOPOE_METHOD_MOE) {
+        if (moe_like(mv)) {
 #pragma unroll
           for (int m = 0; m < MOPOE_MAX_MODS; ++m)
             if (m == ev.sel_m) { dmu[m] += umu; dlv[m] += ulv; }
@@ -538,6 +560,29 @@ __device__ void lat_backward(const ModelView& mv, const StepCtx& cx, const mopoe
               dlv[m] += dT * (-T[m] * T[m] * ex[m]);
             }
         }
+      }
+      if (mv.method == MOPOE_METHOD_JSD) {
+        // d/d(expert) of D = sum_k w KL(component k || dynamic prior), components = present experts + prior:
+        // with A = sum T_k, mu_a = sum mu_k T_k / A, P = w A = 1 / var_a, Q = sum var_k, Sd = sum (mu_k - mu_a),
+        // S2 = sum (mu_k - mu_a)^2 and a_m = dT_m / dlv_m = -T_m^2 var_m:
+        //   dD/dmu_m = w P ((mu_m - mu_a) - T_m Sd / A)
+        //   dD/dlv_m = -w/2 (1 - P var_m - w a_m (Q + S2) + a_m / P + 2 P a_m (mu_m - mu_a) Sd / A)
+        float A = 1.f / (1.f + MOPOE_POE_EPS), B = 0.f, Q = 1.f;
+#pragma unroll
+        for (int m = 0; m < MOPOE_MAX_MODS; ++m)
+          if (m < M && (present >> m & 1)) { A += T[m]; B += muT[m]; Q += ex[m]; }
+        const float P = wmix * A, mu_a = B / A;
+        float Sd = -mu_a, S2 = mu_a * mu_a;
+#pragma unroll
+        for (int m = 0; m < MOPOE_MAX_MODS; ++m)
+          if (m < M && (present >> m & 1)) { const float dm = mu_e[m] - mu_a; Sd += dm; S2 += dm * dm; }
+#pragma unroll
+        for (int m = 0; m < MOPOE_MAX_MODS; ++m)
+          if (m < M && (present >> m & 1)) {
+            const float dm = mu_e[m] - mu_a, am = -T[m] * T[m] * ex[m];
+            dmu[m] += ckl * wmix * P * (dm - T[m] * Sd / A);
+            dlv[m] += ckl * -0.5f * wmix * (1.f - P * ex[m] - wmix * am * (Q + S2) + am / P + 2.f * P * am * dm * Sd / A);
+          }
       }
 #pragma unroll
       for (int m = 0; m < MOPOE_MAX_MODS; ++m)
@@ -870,6 +915,14 @@ __device__ void finalize_scalars(const ModelView& mv, const StepCtx& cx, const m
     kls += mv.beta_style * ks;  // calc_style_kld: style_weights[m] = beta_style
     if (mv.method == MOPOE_METHOD_POE)  // unimodal ELBO (utils.calc_elbo, modality != 'joint')
       uni += nu + mv.beta * (mv.beta_content * (acc[MOPOE_S_KLD_SUBSET + m] / N) + mv.beta_style * (mv.beta_style * ks));
+  }
+  if (mv.method == MOPOE_METHOD_JSD) {      // divergence_dynamic_prior: sum_k (1 / n_mix) KL(component k || dynamic prior) / N
+    jd = 0.0;
+    for (int k = 0; k < b.n_mix; ++k) {
+      const double kl = acc[MOPOE_S_JSD_DIV + k] / N;
+      s[MOPOE_S_JSD_DIV + k] = (float)kl;
+      jd += kl / (double)b.n_mix;
+    }
   }
   s[MOPOE_S_JOINT_DIV] = (float)jd;
   s[MOPOE_S_TOTAL_LOSS] = (float)(nll + mv.beta * (mv.beta_style * kls + mv.beta_content * jd) + uni);

@@ -155,15 +155,23 @@ class VAE(nn.Module):
             enc[name] = [h[:, :L], h[:, L:2 * L]]
             enc[name + "_style"] = [h[:, 2 * L:2 * L + S], h[:, 2 * L + S:]] if S > 0 else [None, None]
         idx = torch.tensor(mix, device=res.subset_mu.device)
-        latents = {"modalities": enc, "mus": res.subset_mu.index_select(0, idx),
-                   "logvars": res.subset_logvar.index_select(0, idx),
-                   "weights": (1 / float(len(mix))) * torch.ones(len(mix), device=idx.device),
+        mus, logvars = res.subset_mu.index_select(0, idx), res.subset_logvar.index_select(0, idx)
+        sc = res.scalars
+        ind, dyn_prior = sc[_lib.S_KLD_SUBSET:_lib.S_KLD_SUBSET + len(keys)].index_select(0, idx), None
+        if spec.method == "jsd":                   # the prior is one more mixture component (BaseMMVae.py:217-223)
+            zeros = torch.zeros_like(mus[:1])
+            mus, logvars = torch.cat((mus, zeros)), torch.cat((logvars, zeros))
+            ind = sc[_lib.S_JSD_DIV:_lib.S_JSD_DIV + len(mix) + 1]
+            T = 1.0 / (logvars.exp() + 1e-8)       # results["dyn_prior"]: alpha_poe of the components (mm_div.py:23-35);
+            pd_var = 1.0 / (T.mean(0))             # host-side view of what the kernel's divergence is measured against
+            dyn_prior = [pd_var * (mus * T).mean(0), pd_var.log()]
+        K = mus.shape[0]
+        latents = {"modalities": enc, "mus": mus, "logvars": logvars,
+                   "weights": (1 / float(K)) * torch.ones(K, device=idx.device),
                    "joint": [res.joint_mu, res.joint_logvar],
                    "subsets": {keys[s]: [res.subset_mu[s], res.subset_logvar[s]] for s in avail}}
-        sc = res.scalars
         results = {"latents": latents, "group_distr": latents["joint"], "joint_divergence": sc[_lib.S_JOINT_DIV],
-                   "individual_divs": sc[_lib.S_KLD_SUBSET:_lib.S_KLD_SUBSET + len(keys)].index_select(0, idx),
-                   "dyn_prior": None}
+                   "individual_divs": ind, "dyn_prior": dyn_prior}
         rec = {}
         for m, name in enumerate(spec.mod_names):
             if res.rec_loc[m] is not None:

@@ -45,7 +45,7 @@ class PathSpec:
         self.learn_output_sample_scale = bool(learn_output_sample_scale)
         self.initial_out_logvar = float(initial_out_logvar)
         if method not in _lib.METHODS:
-            raise NotImplementedError("method=%r is not on the B200 path (poe, moe, joint_elbo)" % (method,))
+            raise NotImplementedError("method=%r is not on the B200 path (poe, moe, joint_elbo, jsd)" % (method,))
         if likelihood != "normal":
             raise NotImplementedError("likelihood=%r is not on the B200 path (normal only)" % (likelihood,))
         if dropout_rate:
@@ -124,7 +124,7 @@ class PathSpec:
             if any(not (present_mask >> m & 1) for m in members):
                 continue
             avail.append(s)
-            if self.method == "moe":
+            if self.method in ("moe", "jsd"):
                 cond = len(members) == 1
             elif self.method == "poe":
                 cond = len(members) == n_present
@@ -166,8 +166,8 @@ class PathSpec:
         b.n_rows = int(n_rows)
         b.present_mask = int(present_mask)
         _, mix = self.mixture_subsets(present_mask)
-        b.n_mix = len(mix)
-        for i, v in enumerate(selection_bounds(n_rows, len(mix))):
+        b.n_mix = len(mix) + (1 if self.method == "jsd" else 0)     # jsd: + the prior component (BaseMMVae.py:217-223)
+        for i, v in enumerate(selection_bounds(n_rows, b.n_mix)):
             b.joint_bounds[i] = v
         for k in range(1, self.n_mods + 1):
             for i, v in enumerate(selection_bounds(n_rows, k)):

@@ -184,7 +184,7 @@ def _make_flags(dataset, datasetdir, outdir, input_dims, num_models, latent_dim,
     elif method == "joint_elbo":
         flags.joint_elbo = True
     elif method == "jsd":
-        raise NotImplementedError("method='jsd' is not on the B200 path")
+        flags.modality_jsd = True
     else:
         print("Method not implemented...exit!")                  # workflow.py:134-136
         return None

@@ -42,7 +42,9 @@ extern "C" {
 #define MOPOE_HIDDEN 256     /* networks.py:15,50 hard-code the hidden width */
 #define MOPOE_N_SCALARS 64
 
-enum { MOPOE_METHOD_POE = 0, MOPOE_METHOD_MOE = 1, MOPOE_METHOD_JOINT_ELBO = 2 };
+enum { MOPOE_METHOD_POE = 0, MOPOE_METHOD_MOE = 1, MOPOE_METHOD_JOINT_ELBO = 2,
+       MOPOE_METHOD_JSD = 3 /* BaseMMVae.py:51-54: MoE subset posteriors, unimodal experts + the prior N(0, I) in the
+                             * mixture (:217-223), divergence to the dynamic prior (:81-93, mm_div.py:23-35,69-89) */ };
 
 enum {
   MOPOE_OK = 0,
@@ -63,7 +65,7 @@ typedef struct mopoe_model_desc {
   int32_t hidden;                       /* must be 256 */
   int32_t n_hidden_enc;                 /* flags.num_hidden_layer_encoder, must be 1 */
   int32_t n_hidden_dec;                 /* flags.num_hidden_layer_decoder, must be 0 */
-  int32_t method;                       /* MOPOE_METHOD_* (flags.modality_poe/moe/joint_elbo) */
+  int32_t method;                       /* MOPOE_METHOD_* (flags.modality_poe/moe/jsd/joint_elbo) */
   int32_t likelihood;                   /* 0 = normal (modality.py:18-30); others rejected */
   int32_t scale_mode;                   /* 0 = per-feature logvar Parameter (networks.py:61-64) */
   int32_t learn_output_scale;           /* flags.learn_output_scale */
@@ -130,7 +132,9 @@ enum mopoe_scalar_index {
   MOPOE_S_KLD_STYLE = 25,   /* +m: klds_style[m]                run_epochs.py:51-59 */
   MOPOE_S_MEAN_HEAD = 29,   /* +4m+{0,1,2,3}: mean class_mu, class_logvar, style_mu, style_logvar */
   MOPOE_S_N_ROWS = 45,
-  MOPOE_S_PRESENT = 46
+  MOPOE_S_PRESENT = 46,
+  MOPOE_S_JSD_DIV = 47      /* +k: results['individual_divs'][k] of method jsd (k-th present modality, then the prior):
+                             * KL(component k || dynamic prior) / N                 mm_div.py:69-89 */
 };
 
 const char* mopoe_last_error(void);

@@ -35,6 +35,13 @@ for _i, (_m, _p) in enumerate(itertools.product(["joint_elbo", "moe", "poe"],
                                                 [(0, 1, 2, 3), (1, 3), (0, 2, 3)])):
     ELBO_CASES["stress_%s_%s" % (_m, "".join(map(str, _p)))] = _case(STRESS, _m, True, _p, 96, 50 + _i, 150 + _i)
 
+# method="jsd" (BaseMMVae.py:51-54,81-93,217-223, mm_div.py:23-35,69-89)
+for _i, (_f, _p) in enumerate(itertools.product([True, False], [(0, 1), (0,), (1,)])):
+    ELBO_CASES["hbn_jsd_%s_%s" % ("fact" if _f else "nofact", "".join(map(str, _p)))] = _case(
+        HBN, "jsd", _f, _p, 256, 80 + _i, 180 + _i)
+for _i, _p in enumerate([(0, 1, 2, 3), (1, 3), (0, 2, 3)]):
+    ELBO_CASES["stress_jsd_%s" % "".join(map(str, _p))] = _case(STRESS, "jsd", True, _p, 96, 90 + _i, 190 + _i)
+
 FORWARD_CASES = {
     "hbn_n50_sampled": _case(HBN, "joint_elbo", True, (0, 1), 50, 60, 160),
     "hbn_n50_mean": _case(HBN, "joint_elbo", True, (0, 1), 50, 61, 161, sample_latents=False),
@@ -42,6 +49,8 @@ FORWARD_CASES = {
     "hbn_n50_moe": _case(HBN, "moe", True, (0, 1), 50, 63, 163),
     "hbn_n50_poe_clinical_only": _case(HBN, "poe", False, (0,), 50, 64, 164),
     "stress_n33": _case(STRESS, "joint_elbo", True, (0, 1, 2, 3), 33, 65, 165),
+    "hbn_n50_jsd": _case(HBN, "jsd", True, (0, 1), 50, 66, 166),
+    "hbn_n50_jsd_mean": _case(HBN, "jsd", True, (0, 1), 50, 67, 167, sample_latents=False),
 }
 
 DAA_ROI_STRIDE = 16
@@ -53,6 +62,8 @@ DAA_CASES = {
                        n_samples=4, sample_latents=True),
     "poe_mean": dict(_case(HBN, "poe", True, (0, 1), 20, 72, 172), n_val=1, n_base=3,
                      n_samples=4, sample_latents=False),
+    "jsd": dict(_case(HBN, "jsd", True, (0, 1), 30, 73, 173), n_val=1, n_base=3,
+                n_samples=4, sample_latents=True),
 }
 
 

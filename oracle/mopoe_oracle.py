@@ -33,7 +33,7 @@ class ModelSpec:
     dims: Sequence[int] = (7, 444)
     style_dims: Sequence[int] = (3, 20)      # already zeroed when not factorised (workflow.py:148-149)
     latent_dim: int = 20
-    method: str = "joint_elbo"               # poe | moe | joint_elbo  (BaseMMVae.py:43-61)
+    method: str = "joint_elbo"               # poe | moe | joint_elbo | jsd  (BaseMMVae.py:43-61)
     mod_names: Sequence[str] = ("clinical", "rois")
     learn_output_scale: bool = True
     beta: float = 1.0
@@ -46,7 +46,7 @@ class ModelSpec:
         self.style_dims = list(self.style_dims)
         self.mod_names = list(self.mod_names)[: len(self.dims)]
         assert len(self.style_dims) == len(self.dims) == len(self.mod_names)
-        assert self.method in ("poe", "moe", "joint_elbo")
+        assert self.method in ("poe", "moe", "joint_elbo", "jsd")
 
     @property
     def n_mods(self):
@@ -185,6 +185,22 @@ def kl_std_normal(mu, logvar, norm):
     return -0.5 * torch.sum(1 - logvar.exp() - mu.pow(2) + logvar) / float(norm)
 
 
+def kl_two_normals(mu0, logvar0, mu1, logvar1, norm):
+    """divergence_measures/kl_div.py:7-14 with a second distribution."""
+    return -0.5 * torch.sum(1 - logvar0.exp() / logvar1.exp() - (mu0 - mu1).pow(2) / logvar1.exp()
+                            + logvar0 - logvar1) / float(norm)
+
+
+def alpha_poe(alpha, mus, logvars):
+    """divergence_measures/mm_div.py:23-35: weighted product of experts (the dynamic prior of the JSD objective)."""
+    var = torch.exp(logvars) + POE_EPS
+    a = alpha.view(-1, 1, 1).to(var.dtype)
+    T = 1.0 / var
+    pd_var = 1.0 / torch.sum(a * T, dim=0)
+    pd_mu = pd_var * torch.sum(a * mus * T, dim=0)
+    return pd_mu, torch.log(pd_var)
+
+
 def normal_nll(x, loc, scale, norm):
     """-Normal(loc, scale).log_prob(x).sum()/norm  (modalities/modality.py:42-45,
     torch.distributions.Normal.log_prob)."""
@@ -216,7 +232,7 @@ def inference(params, spec: ModelSpec, batch, sample=True, use_expert=None):
             continue
         s_mus = torch.stack([enc[spec.mod_names[m]][0] for m in members])
         s_lvs = torch.stack([enc[spec.mod_names[m]][1] for m in members])
-        if spec.method == "moe":                                    # moe_fusion :96-106
+        if spec.method in ("moe", "jsd"):                           # moe_fusion :96-106 (jsd: :51-54)
             s_mu, s_lv = mixture_select(s_mus, s_lvs)
         else:                                                       # poe_fusion :109-122
             if spec.method == "poe" or len(members) == spec.n_mods:
@@ -225,7 +241,7 @@ def inference(params, spec: ModelSpec, batch, sample=True, use_expert=None):
                 s_lvs = torch.cat((s_lvs, zeros), dim=0)
             s_mu, s_lv = poe(s_mus, s_lvs)
         distr_subsets[key] = [s_mu, s_lv]
-        if spec.method == "moe":                                    # fusion_condition_* :125-134
+        if spec.method in ("moe", "jsd"):                           # fusion_condition_* :125-134
             cond = len(members) == 1
         elif spec.method == "poe":
             cond = len(members) == len(present)
@@ -237,6 +253,11 @@ def inference(params, spec: ModelSpec, batch, sample=True, use_expert=None):
             mix_keys.append(key)
     mus = torch.stack(mus)
     logvars = torch.stack(logvars)
+    if spec.method == "jsd":                                        # :217-223: the prior N(0, I) is one more component
+        zeros = torch.zeros(1, N, L, dtype=mus.dtype)
+        mus = torch.cat((mus, zeros), dim=0)
+        logvars = torch.cat((logvars, zeros), dim=0)
+        mix_keys.append("prior")
     K = mus.shape[0]
     weights = (1 / float(K)) * torch.ones(K)                        # :225
     if sample and use_expert is None:
@@ -260,11 +281,18 @@ def forward(params, spec: ModelSpec, batch, eps=None, sample_latents=True, use_e
         z = jmu
     mus, logvars = latents["mus"], latents["logvars"]
     K, N = mus.shape[0], mus.shape[1]
-    w = latents["weights"] / latents["weights"].sum()               # divergence_static_prior :64-78
-    ind = torch.stack([kl_std_normal(mus[k], logvars[k], N) for k in range(K)])  # mm_div.py:92-111
+    dyn_prior = None
+    if spec.method == "jsd":                                        # divergence_dynamic_prior :81-93
+        w = latents["weights"]                                      # (not reweighted: already 1/K each)
+        a_mu, a_lv = alpha_poe(w, mus, logvars)                     # calc_alphaJSD_modalities, mm_div.py:69-89
+        ind = torch.stack([kl_two_normals(mus[k], logvars[k], a_mu, a_lv, N) for k in range(K)])
+        dyn_prior = [a_mu, a_lv]
+    else:
+        w = latents["weights"] / latents["weights"].sum()           # divergence_static_prior :64-78
+        ind = torch.stack([kl_std_normal(mus[k], logvars[k], N) for k in range(K)])  # mm_div.py:92-111
     results = {"latents": latents, "group_distr": latents["joint"],
                "joint_divergence": (w.to(ind.dtype) * ind).sum(), "individual_divs": ind,
-               "dyn_prior": None, "z": z, "z_style": {}}
+               "dyn_prior": dyn_prior, "z": z, "z_style": {}}
     rec = {}
     for m, name in enumerate(spec.mod_names):                       # :155-163
         if name not in batch:
@@ -298,7 +326,7 @@ def elbo(params, spec: ModelSpec, batch, eps):
         if smu is not None:
             klds_style[n + "_style"] = kl_std_normal(smu, slv, N)
     jd = res["joint_divergence"]
-    if spec.method in ("moe", "joint_elbo"):                                      # :95-103
+    if spec.method in ("moe", "joint_elbo", "jsd"):                               # :95-103
         kld_style = sum((spec.beta_style * klds_style[n + "_style"] for n in names
                          if n + "_style" in klds_style), 0.0)                     # calc_style_kld :62-69
         total = sum(log_probs.values()) + spec.beta * (spec.beta_style * kld_style

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 def _flags(method="joint_elbo", factorized=True):
     f = SimpleNamespace(input_dim=[7, 444], style_dim=[3, 20], class_dim=20, factorized_representation=factorized,
-                        modality_poe=method == "poe", modality_moe=method == "moe", modality_jsd=False,
+                        modality_poe=method == "poe", modality_moe=method == "moe", modality_jsd=method == "jsd",
                         joint_elbo=method == "joint_elbo", learn_output_scale=True, learn_output_sample_scale=False,
                         beta=1.0, beta_style=1.0, beta_content=1.0, num_hidden_layer_encoder=1,
                         num_hidden_layer_decoder=0, likelihood="normal", initial_out_logvar=-3.0, dropout_rate=0.0,
@@ -69,6 +69,29 @@ def test_forward_results_structure_and_values():
         model(batch)          # CPU tensors: no fallback
 
 
+def test_forward_results_of_the_jsd_model():
+    """method="jsd" through the drop-in model: mixture = unimodal experts + the prior, individual_divs and dyn_prior
+    as divergence_dynamic_prior returns them (BaseMMVae.py:81-93,217-223)."""
+    model, ospec, params = _model("jsd")
+    g = torch.Generator().manual_seed(4)
+    batch = {"clinical": torch.randn(50, 7, generator=g), "rois": torch.randn(50, 444, generator=g)}
+    eps = torch.randn(50, ospec.eps_width, generator=g)
+    model.inject_noise(eps)
+    res = model({k: v.cuda() for k, v in batch.items()}, sample_latents=True)
+    with torch.no_grad():
+        want = mo.forward(params, ospec, batch, eps)
+    assert res["latents"]["mus"].shape == (3, 50, 20) and float(res["latents"]["mus"][2].abs().max()) == 0.0
+    assert torch.allclose(res["latents"]["weights"].cpu(), want["latents"]["weights"])
+    tol = lambda t: RTOL * float(t.abs().max())
+    assert torch.allclose(res["latents"]["joint"][0].cpu(), want["latents"]["joint"][0], rtol=0, atol=tol(want["latents"]["joint"][0]))
+    assert float(res["latents"]["joint"][0][32:].abs().max()) == 0.0          # rows [32, 50) sample from the prior
+    assert torch.allclose(res["individual_divs"].cpu(), want["individual_divs"], rtol=RTOL)
+    assert abs(float(res["joint_divergence"]) - float(want["joint_divergence"])) <= RTOL * abs(float(want["joint_divergence"]))
+    for a, w in zip(res["dyn_prior"], want["dyn_prior"]):
+        assert torch.allclose(a.cpu(), w, rtol=0, atol=tol(w))
+    assert torch.allclose(res["rec"]["rois"].loc.cpu(), want["rec"]["rois"][0], rtol=0, atol=tol(want["rec"]["rois"][0]))
+
+
 def test_philox_seed_draws_fresh_noise_per_call():
     """In-kernel generator through the drop-in interface: every call draws new noise (the reference draws from
     the advancing global generator, BaseMMVae.py:37-40), reproducibly for a given philox_seed; seed 0 is a seed."""
@@ -94,7 +117,7 @@ def test_philox_seed_draws_fresh_noise_per_call():
     assert not torch.equal(model(batch)["class_embeddings"], z0)
 
 
-@pytest.mark.parametrize("method", ["joint_elbo", "poe", "moe"])
+@pytest.mark.parametrize("method", ["joint_elbo", "poe", "moe", "jsd"])
 def test_basic_routine_epoch_backward_and_torch_adam(method):
     from mopoe_b200 import run_epochs
     model, ospec, params = _model(method)

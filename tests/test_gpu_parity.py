@@ -140,6 +140,9 @@ def test_elbo_terms_and_gradients(name, train_impl):
         assert abs(sc[_lib.S_KLD_SUBSET + keys.index(k)] - v) <= RTOL * abs(v), k
     for k, v in want["log_probs"].items():
         assert abs(sc[_lib.S_NLL + spec.mod_names.index(k)] - v) <= RTOL * abs(v), k
+    if spec.method == "jsd":          # KL of every mixture component (present experts, prior) to the dynamic prior
+        for k, v in enumerate(want["individual_divs"]):
+            assert abs(sc[_lib.S_JSD_DIV + k] - v) <= RTOL * abs(v), k
     got = engine.unpack_params(spec, grads)
     skip = _relu_kink_units(spec, params, batch)
     for k in g:
@@ -163,6 +166,8 @@ for _base, _bn in ((cases.HBN, "hbn"), (cases.STRESS, "stress")):
                 continue
             _full = tuple(range(len(_base["dims"])))
             LARGE_CASES["%s_%s_%d" % (_bn, _method, _n)] = cases._case(_base, _method, True, _full, _n, 300 + _n % 97, 400 + _n % 89)
+LARGE_CASES["hbn_jsd_4097"] = cases._case(cases.HBN, "jsd", True, (0, 1), 4097, 312, 412)
+LARGE_CASES["stress_jsd_65536"] = cases._case(cases.STRESS, "jsd", True, (0, 1, 2, 3), 65536, 313, 413)
 LARGE_CASES["stress_joint_elbo_13_4097"] = cases._case(cases.STRESS, "joint_elbo", True, (1, 3), 4097, 310, 410)
 LARGE_CASES["hbn_joint_elbo_nofact_1_1500"] = cases._case(cases.HBN, "joint_elbo", False, (1,), 1500, 311, 411)
 
@@ -194,7 +199,7 @@ def test_elbo_large_batches(name, train_impl):
     assert np.allclose(sc0[:_lib.S_MEAN_HEAD], sc[:_lib.S_MEAN_HEAD], rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("name", ["hbn_joint_elbo_fact_01", "hbn_poe_fact_01", "hbn_moe_nofact_1",
+@pytest.mark.parametrize("name", ["hbn_joint_elbo_fact_01", "hbn_poe_fact_01", "hbn_moe_nofact_1", "hbn_jsd_fact_01",
                                   "stress_joint_elbo_13", "hbn_joint_elbo_fact_01_fixedscale",
                                   "hbn_joint_elbo_4097", "stress_joint_elbo_1024", "hbn_poe_512"])
 def test_fused_adam_steps(name, train_impl):

@@ -61,9 +61,19 @@ def test_unsupported_configurations_are_rejected(kw):
 
 def test_unsupported_method_and_likelihood():
     with pytest.raises(NotImplementedError):
-        mopoe_b200.PathSpec([7, 444], [3, 20], method="jsd")
+        mopoe_b200.PathSpec([7, 444], [3, 20], method="mvae")
     with pytest.raises(NotImplementedError):
         mopoe_b200.PathSpec([7, 444], [3, 20], likelihood="laplace")
+
+
+def test_jsd_mixture_has_the_prior_component():
+    """BaseMMVae.py:217-223: unimodal experts + the prior N(0, I); the last row range of the selection is the prior's."""
+    spec = mopoe_b200.PathSpec([7, 444], [3, 20], method="jsd")
+    assert spec.mixture_subsets(0b11)[1] == [0, 1]
+    b = spec.batch_desc(256, 0b11)
+    assert b.n_mix == 3 and list(b.joint_bounds[:4]) == [0, 85, 170, 256]
+    b1 = spec.batch_desc(50, 0b10)
+    assert b1.n_mix == 2 and list(b1.joint_bounds[:3]) == [0, 25, 50]
 
 
 @pytest.mark.parametrize("names", [["clinical", "rois"], ["clinical", "rois", "modc", "modd"], ["zeta", "alpha", "mid"]])

@@ -9,7 +9,7 @@ from oracle import mopoe_oracle as mo, ref_harness as rh
 pytestmark = pytest.mark.skipif(not rh.available(), reason="reference tree not present")
 
 
-@pytest.mark.parametrize("method", ["joint_elbo", "moe", "poe"])
+@pytest.mark.parametrize("method", ["joint_elbo", "moe", "poe", "jsd"])
 @pytest.mark.parametrize("present", [(0, 1), (0,), (1,)])
 def test_basic_routine_epoch_live(method, present):
     rh.install()
