@@ -49,7 +49,7 @@ class ForwardOut(C.Structure):
 class DaaDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_val", "val_begin", "n_val_total", "n_subjects", "n_samples", "n_base",
                                          "src_mod", "dst_mod", "sample_latents", "reg_method", "base_mode",
-                                         "unit_begin", "unit_end")]
+                                         "unit_begin", "unit_end", "score_mode")]
 
 
 MAX_PEERS = 8

@@ -335,7 +335,8 @@ __global__ void __launch_bounds__(BASE_THREADS) daa_base_kernel(ModelView mv, Da
   for (int i = t; i < cx.J * cx.C; i += BASE_THREADS) {
     const int j = i / cx.C, c = i % cx.C;
     const int64_t idx = (((int64_t)(cx.v_score_off + v) * cx.J + j) * cx.N + g) * cx.C + c;
-    const float s = s_loc[c] + expf(0.5f * ms.lv[c]) * cx.nz_score.at(idx);
+    const float e = cx.nz_score.at(idx);
+    const float s = cx.q.score_mode ? e : s_loc[c] + expf(0.5f * ms.lv[c]) * e;      // given values | Normal sample
     ws.scores[(row * cx.C + c) * cx.J + j] = s;
     if (sc_smem) s_sc[c * cx.J + j] = s;
     if (cx.sampled_scores) cx.sampled_scores[(row * cx.J + j) * cx.C + c] = s;
@@ -957,6 +958,7 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   const int M = desc->n_mods, N = daa->n_subjects;
   if (batch->n_rows != N || batch->present_mask != (1 << M) - 1) { set_error("batch desc must describe n_subjects rows with every modality present"); return MOPOE_EINVAL; }
   if (daa->reg_method == 1 && !reconstructions) { set_error("reg_method fixed needs the reconstructions buffer"); return MOPOE_EINVAL; }
+  if (daa->score_mode < 0 || daa->score_mode > 1 || (daa->score_mode == 1 && !eps_score)) { set_error("score_mode=%d invalid (1 needs the score values in eps_score)", daa->score_mode); return MOPOE_EINVAL; }
   if (daa->base_mode == 1 && eps_base) { set_error("base_mode 1 (mean noise row drawn directly) needs the in-kernel generator: eps_base must be NULL"); return MOPOE_EINVAL; }
   const int64_t need = daa_carve(desc, daa, nullptr, nullptr);
   if (workspace_bytes < need) { set_error("workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need); return MOPOE_ENOSPC; }

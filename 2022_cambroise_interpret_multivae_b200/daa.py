@@ -24,7 +24,7 @@ class DaaResult:
 def daa_sweep(spec: PathSpec, flat_params, src, dst, n_samples, n_base, *, src_mod=0, dst_mod=1,
               sample_latents=True, reg_method="hierarchical", seed=1037, val_begin=0, n_val_total=None,
               eps_base=None, eps_score=None, eps_av=None, materialize=True, want_betas=True,
-              others=None, workspace=None, out=None, base_mean="draws", unit_begin=None, unit_end=None):
+              others=None, workspace=None, out=None, base_mean="draws", unit_begin=None, unit_end=None, scores=None):
     """src: (n_val, N, C) drawn test batches of the perturbed modality, dst: (n_val, N, R).
     others: optional {modality index: (n_val, N, D_m)} for models with more than two modalities.
     base_mean: how the mean over the M stochastic reconstructions (workflow.py:388-398) gets its noise --
@@ -32,6 +32,8 @@ def daa_sweep(spec: PathSpec, flat_params, src, dst, n_samples, n_base, *, src_m
       "direct" draw the mean row itself, N(0, 1/M): the default decoders are affine in z, so the mean of the M
                decodes is the decode of mu + sd * eps_mean.  Same distribution of every output, 1/M of the
                draws (in-kernel generator only).
+    scores: (n_val, n_samples, N, C) artificial score values used as they are instead of draws around the base
+      reconstruction (sampling_strategy "linear", workflow.py:337-346); exclusive with eps_score.
     unit_begin, unit_end: the OWNED (validation, score) units of this call, u = v_local * C + score (SURVEY.md 8e,
       `shard_units`): only their rows of coefs / pvalues / betas and their avatars are produced, the other scores of
       a shared first / last validation are another rank's.  Default: every unit.
@@ -65,15 +67,21 @@ def daa_sweep(spec: PathSpec, flat_params, src, dst, n_samples, n_base, *, src_m
     E = spec.eps_width
     if eps_base is not None:
         eps_base = _f32(eps_base); assert eps_base.shape == (n_val, n_base, N, E)
+    if scores is not None:
+        if eps_score is not None:
+            raise ValueError("scores and eps_score are exclusive")
+        eps_score = scores
     if eps_score is not None:
         eps_score = _f32(eps_score); assert eps_score.shape == (n_val, n_samples, N, Cc)
+        _require_cuda(eps_score, "scores" if scores is not None else "eps_score")
     if eps_av is not None:
         eps_av = _f32(eps_av); assert eps_av.shape == (n_val, n_samples, Cc, N, E)
     q = _lib.DaaDesc(n_val=n_val, val_begin=val_begin, n_val_total=n_val_total or n_val, n_subjects=N,
                      n_samples=n_samples, n_base=n_base, src_mod=src_mod, dst_mod=dst_mod,
                      sample_latents=int(bool(sample_latents)), reg_method=REG_METHODS[reg_method],
                      base_mode=1 if base_mean == "direct" else 0,
-                     unit_begin=0 if unit_end is None else int(unit_begin or 0), unit_end=0 if unit_end is None else int(unit_end))
+                     unit_begin=0 if unit_end is None else int(unit_begin or 0), unit_end=0 if unit_end is None else int(unit_end),
+                     score_mode=0 if scores is None else 1)
     bd = spec.batch_desc(N, (1 << spec.n_mods) - 1)
     lib = _lib.lib()
     nbytes = lib.mopoe_daa_workspace_bytes(C.byref(spec.desc), C.byref(q))

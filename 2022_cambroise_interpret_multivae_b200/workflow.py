@@ -253,8 +253,10 @@ def daa_exp(dataset, datasetdir, outdir, run, sampling_strategy="likelihood", n_
             n_subjects=50, M=1000, trust_level=0.75, seed=1037, reg_method="hierarchical", sample_latents=True,
             vote_prop=1, materialize_avatars=True):
     """Digital avatars analysis (workflow.py:185-539).  Returns the results directory."""
-    if sampling_strategy != "likelihood":
-        raise NotImplementedError("sampling_strategy=%r is not on the B200 path (likelihood)" % (sampling_strategy,))
+    if sampling_strategy not in ("likelihood", "linear"):
+        # "uniform" indexes the wrong axis of its (N, n_scores, n_samples) array in the reference (workflow.py:347-350
+        # vs :411-412) and "gaussian" is named (:220-222) but never built
+        raise NotImplementedError("sampling_strategy=%r is not on the B200 path (likelihood, linear)" % (sampling_strategy,))
     import torch.distributed as dist
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
     expdir = os.path.join(outdir, run)
@@ -322,9 +324,15 @@ def daa_exp(dataset, datasetdir, outdir, run, sampling_strategy="likelihood", n_
         idx = torch.from_numpy(draws[begin:end]).to(flat.device)
         src = res["test"][0][idx]
         dst = res["test"][1][idx]
+        given = None
+        if sampling_strategy == "linear":         # workflow.py:337-346: the same ramp for every subject, between the
+            complete = torch.from_numpy(res["has_train"].all(0)).to(flat.device)   # 5 % / 95 % quantiles of the train
+            lo_hi = np.quantile(res["train"][0][complete].cpu().numpy(), [0.05, 0.95], 0)     # subjects with every block
+            ramp = torch.from_numpy(np.linspace(lo_hi[0], lo_hi[1], n_samples).astype(np.float32)).to(flat.device)
+            given = ramp[None, :, None, :].expand(end - begin, n_samples, n_subjects, n_scores).contiguous()
         r = daa.daa_sweep(model.spec, flat, src, dst, n_samples, M, sample_latents=sample_latents, reg_method=reg_method,
                           seed=draw_seed + 7919 * model_idx, val_begin=begin, n_val_total=n_validation,
-                          materialize=materialize_avatars, workspace=model._ws,
+                          materialize=materialize_avatars, workspace=model._ws, scores=given,
                           unit_begin=sh["local_begin"] if world > 1 else None, unit_end=sh["local_end"] if world > 1 else None)
         daa.check_status(model.spec, r)           # a device-side protocol error must not end up in result files
         if world > 1:

@@ -325,6 +325,42 @@ def bench_train(device, peaks, steps=300, warmup=60):
             del dd, ws
     except Exception as exc:
         out["stress_error"] = repr(exc)
+    # stress shape (configs[4], DAA half): 4 modalities / 15 PoE subsets, 20 validations x 1 000 subjects x 7 scores x
+    # 150 samples = 21 M avatars, 37.3 GB avatar tensor materialised in HBM (sized for 180 GB), pipelined tcgen05 kernel
+    try:
+        from mopoe_b200 import daa
+        import ctypes as C
+        spec = mopoe_b200.PathSpec(STRESS["dims"], STRESS["style_dims"], 20, "joint_elbo", STRESS["mod_names"])
+        flat = engine.pack_params(spec, engine.init_params(spec, seed=0), device)
+        g = torch.Generator().manual_seed(1)
+        nv, ns, J, Mb = 20, 1000, 150, 1000
+        xs = [torch.randn(nv, ns, d, generator=g).to(device) for d in spec.dims]
+        ws = engine.Workspace()
+        lib = _lib.lib()
+        _lib.check(lib.mopoe_profile_enable(1))
+        r = None
+        go = lambda r: daa.daa_sweep(spec, flat, xs[0], xs[1], J, Mb, seed=3, others={2: xs[2], 3: xs[3]}, workspace=ws, out=r,
+                                     base_mean="direct", want_betas=False)
+        r = go(r); torch.cuda.synchronize()
+        impl = int(lib.mopoe_daa_last_impl())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            r = go(r)
+        e1.record(); torch.cuda.synchronize()
+        kms = C.c_float()
+        _lib.check(lib.mopoe_daa_last_kernel_ms(C.byref(kms)))
+        ms = e0.elapsed_time(e1) / 3
+        n_av = nv * ns * spec.dims[0] * J
+        nbytes = n_av * (spec.dims[1] * 4 + 4)
+        out["stress_daa"] = {"avatars_per_s": n_av / (ms * 1e-3), "ms_per_sweep": ms, "avatars": n_av, "n_subjects": ns, "n_validation": nv,
+                             "avatar_tensor_gb": n_av * spec.dims[1] * 4 / 1e9, "impl": {2: "pipelined tcgen05 kernel", 1: "tcgen05 kernel", 0: "cuda-core kernel"}[impl],
+                             "kernel_ms": kms.value, "kernel_gbs": nbytes / (kms.value * 1e-3) / 1e9,
+                             "finite": bool(torch.isfinite(r.pvalues).all())}
+        del r, xs, ws
+        torch.cuda.empty_cache()
+    except Exception as exc:
+        out["stress_daa_error"] = repr(exc)
     return out
 
 

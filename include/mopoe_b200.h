@@ -217,6 +217,9 @@ typedef struct mopoe_daa_desc {
                          * of the first and last validation belong to another rank -- their table rows are NOT written (avatar
                          * tiles shared with an owned series are, with the values the owner computes: the noise is keyed
                          * globally).  0, 0 = every unit.  Base passes and scores cover whole validations either way. */
+  int32_t score_mode;   /* 0 = sampling_strategy "likelihood" (workflow.py:401-405): scores = loc_hat + scale_hat * noise;
+                         * 1 = the caller provides the artificial score VALUES in `eps_score` (n_val, n_samples, N, C), e.g.
+                         *     sampling_strategy "linear" (workflow.py:337-346: a linspace between population quantiles) */
 } mopoe_daa_desc;
 
 /* Bytes of scratch mopoe_daa_sweep needs. */

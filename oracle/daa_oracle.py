@@ -24,7 +24,7 @@ from . import mopoe_oracle as mo
 
 
 def daa_generate(params, spec, src, dst, eps_base, eps_score, eps_av, sample_latents=True,
-                 src_mod=0, dst_mod=1):
+                 src_mod=0, dst_mod=1, given_scores=False):
     """src: (n_val, N, C) perturbed modality ("clinical"); dst: (n_val, N, R) read-out modality
     ("rois").  Returns float32 numpy arrays shaped like the reference's output files:
       avatars (n_val, N, C, J, R)   rois_digital_avatars.npy  (workflow.py:280-288,423-427)
@@ -52,6 +52,8 @@ def daa_generate(params, spec, src, dst, eps_base, eps_score, eps_av, sample_lat
             scale_hat = scale_s.expand_as(loc_hat)                      # mean of identical scales
             recons[v] = torch.stack(loc_d).mean(0).numpy()
             scores = loc_hat + scale_hat * eps_score[v]                 # (J, N, C)  workflow.py:401-405
+            if given_scores:                                            # sampling_strategy != "likelihood" (:337-346,
+                scores = eps_score[v]                                   # :411-412): the values themselves
             for j in range(J):                                          # workflow.py:406-419
                 for c in range(C):
                     cdata = src[v].clone()

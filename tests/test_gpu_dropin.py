@@ -221,6 +221,14 @@ def test_train_exp_then_daa_exp_end_to_end(tmp_path):
     da = np.load(os.path.join(resdir, "rois_digital_avatars.npy"), mmap_mode="r")[1]
     scores, metadata = sc[1], meta[1]
     assert da.shape == (20, 7, 12, 444) and scores[5].shape == (12, 7) and metadata.shape[0] == 20
+    # sampling_strategy "linear" (workflow.py:337-346): the same ramp between train-set quantiles for every subject
+    lin = workflow.daa_exp("hbn", ds, out, run, sampling_strategy="linear", n_validation=2, n_samples=10, n_subjects=20, M=30)
+    assert "sampling_linear" in lin
+    sl = np.load(os.path.join(lin, "sampled_scores.npy"))
+    assert sl.shape == (2, 20, 10, 7) and np.array_equal(sl[0, 0], sl[1, 7]) and np.all(np.diff(sl[0, 0], axis=0) > 0)
+    avl = np.load(os.path.join(lin, "rois_digital_avatars.npy"))
+    pl_, cl_, _ = daa_oracle.hierarchical_regression(avl, sl)
+    assert np.allclose(np.load(os.path.join(lin, "coefs.npy")), cl_, rtol=1e-9, atol=1e-12)
     # rsa_exp (workflow.py:656-820) on the same run: files, shapes, and the statistics recomputed with scipy
     from oracle import rsa_oracle as ro
     rsadir = workflow.rsa_exp("hbn", ds, out, run, n_validation=2, n_subjects=40, seed=5)

@@ -720,3 +720,24 @@ def test_rsa_matrices_and_kendall_vs_scipy(n, d):
         counts = rsa.kendall_counts(cm, refs).cpu().numpy()
         for r in range(refs.shape[0]):
             assert np.array_equal(counts[r], ro.brute_counts(ro.cmat2triu(cm_w), ro.cmat2triu(mats_w[r])))
+
+
+def test_daa_given_score_values_linear_sampling():
+    """sampling_strategy "linear" (workflow.py:337-346,411-412): the artificial scores are given values, the same
+    ramp for every subject, instead of draws around the base reconstruction.  Pipelined tcgen05 kernel vs the oracle."""
+    from mopoe_b200 import daa, engine, _lib
+    case = dict(cases._case(cases.HBN, "joint_elbo", True, (0, 1), 9, 75, 175), n_val=2, n_base=3, n_samples=128, sample_latents=True)
+    ospec, spec, params, flat = _setup(case)
+    src, dst, eb, es, ea = cases.daa_inputs_of(case, ospec)
+    lo, hi = np.quantile(src.numpy().reshape(-1, 7), [0.05, 0.95], 0)
+    ramp = torch.from_numpy(np.linspace(lo, hi, 128).astype(np.float32))
+    scores = ramp[None, :, None, :].expand(2, 128, 9, 7).contiguous()
+    r = daa.daa_sweep(spec, flat, src.cuda(), dst.cuda(), 128, 3, eps_base=eb.cuda(), scores=scores.cuda(), eps_av=ea.cuda())
+    torch.cuda.synchronize()
+    assert _lib.lib().mopoe_daa_last_impl() == 2
+    av, sc, rec = daa_oracle.daa_generate(params, ospec, src, dst, eb, scores, ea, given_scores=True)
+    assert np.array_equal(r.sampled_scores.cpu().numpy(), sc)
+    assert np.array_equal(sc[0, 0], ramp.numpy()) and np.array_equal(sc[1, 5], ramp.numpy())
+    _close(r.avatars, av, "avatars")
+    p, coef, _ = daa_oracle.hierarchical_regression(av, sc)
+    _close(r.coefs, coef, "coefs")
