@@ -13,6 +13,7 @@ MAX_SUBSETS = 15
 HIDDEN = 256
 N_SCALARS = 64
 METHODS = {"poe": 0, "moe": 1, "joint_elbo": 2, "jsd": 3}
+LIKELIHOODS = {"normal": 0, "laplace": 1}
 
 # mopoe_scalar_index
 S_TOTAL_LOSS, S_JOINT_DIV, S_NLL, S_NLL_UNI, S_KLD_SUBSET, S_KLD_STYLE, S_MEAN_HEAD = 0, 1, 2, 6, 10, 25, 29
@@ -29,9 +30,15 @@ class ModelDesc(C.Structure):
                 ("beta_content", C.c_float)]
 
 
+MAX_LAYERS = 4
+
+
 class ParamLayout(C.Structure):
-    _fields_ = [(n, C.c_int64 * MAX_MODS) for n in
-                ("enc_w1", "enc_b1", "enc_wh", "enc_bh", "dec_w", "dec_b", "dec_lv")] + [("total", C.c_int64)]
+    _fields_ = ([(n, C.c_int64 * MAX_MODS) for n in
+                 ("enc_w1", "enc_b1", "enc_wh", "enc_bh", "dec_w", "dec_b", "dec_lv")] + [("total", C.c_int64)] +
+                [(n, (C.c_int64 * (MAX_LAYERS - 1)) * MAX_MODS) for n in ("enc_wx", "enc_bx")] +
+                [(n, (C.c_int64 * MAX_LAYERS) * MAX_MODS) for n in ("dec_hw", "dec_hb")] +
+                [(n, C.c_int64 * MAX_MODS) for n in ("dec_lvw", "dec_lvb")])
 
 
 class BatchDesc(C.Structure):
@@ -43,7 +50,8 @@ class BatchDesc(C.Structure):
 class ForwardOut(C.Structure):
     _fields_ = [("enc_heads", C.c_void_p * MAX_MODS), ("subset_mu", C.c_void_p), ("subset_logvar", C.c_void_p),
                 ("joint_mu", C.c_void_p), ("joint_logvar", C.c_void_p), ("z", C.c_void_p),
-                ("z_style", C.c_void_p * MAX_MODS), ("rec_loc", C.c_void_p * MAX_MODS), ("scalars", C.c_void_p)]
+                ("z_style", C.c_void_p * MAX_MODS), ("rec_loc", C.c_void_p * MAX_MODS), ("scalars", C.c_void_p),
+                ("rec_logvar", C.c_void_p * MAX_MODS)]
 
 
 class DaaDesc(C.Structure):

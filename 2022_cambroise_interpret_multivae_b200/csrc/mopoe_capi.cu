@@ -40,12 +40,12 @@ int check_desc(const mopoe_model_desc* d) {
   if (d->n_mods < 1 || d->n_mods > MOPOE_MAX_MODS) {
     set_error("n_mods=%d not in 1..%d", d->n_mods, MOPOE_MAX_MODS); return MOPOE_EINVAL; }
   if (d->hidden != MOPOE_HIDDEN) { set_error("hidden=%d unsupported (reference hard-codes 256)", d->hidden); return MOPOE_EINVAL; }
-  if (d->n_hidden_enc != 1) { set_error("num_hidden_layer_encoder=%d unsupported (only 1)", d->n_hidden_enc); return MOPOE_EINVAL; }
-  if (d->n_hidden_dec != 0) { set_error("num_hidden_layer_decoder=%d unsupported (only 0)", d->n_hidden_dec); return MOPOE_EINVAL; }
+  if (d->n_hidden_enc < 0 || d->n_hidden_enc > MOPOE_MAX_LAYERS) { set_error("num_hidden_layer_encoder=%d not in 0..%d", d->n_hidden_enc, MOPOE_MAX_LAYERS); return MOPOE_EINVAL; }
+  if (d->n_hidden_dec < 0 || d->n_hidden_dec > MOPOE_MAX_LAYERS) { set_error("num_hidden_layer_decoder=%d not in 0..%d", d->n_hidden_dec, MOPOE_MAX_LAYERS); return MOPOE_EINVAL; }
   if (d->method < MOPOE_METHOD_POE || d->method > MOPOE_METHOD_JSD) {
     set_error("method=%d unsupported (poe, moe, joint_elbo, jsd)", d->method); return MOPOE_EINVAL; }
-  if (d->likelihood != 0) { set_error("likelihood=%d unsupported (only normal)", d->likelihood); return MOPOE_EINVAL; }
-  if (d->scale_mode != 0) { set_error("learn_output_sample_scale is unsupported (per-feature logvar only)"); return MOPOE_EINVAL; }
+  if (d->likelihood < 0 || d->likelihood > 1) { set_error("likelihood=%d unsupported (0 normal, 1 laplace)", d->likelihood); return MOPOE_EINVAL; }
+  if (d->scale_mode < 0 || d->scale_mode > 1) { set_error("scale_mode=%d invalid", d->scale_mode); return MOPOE_EINVAL; }
   if (d->latent_dim < 1 || d->latent_dim > 32) { set_error("latent_dim=%d not in 1..32", d->latent_dim); return MOPOE_EINVAL; }
   for (int m = 0; m < d->n_mods; ++m) {
     if (d->dims[m] < 1 || d->dims[m] > 8192) { set_error("dims[%d]=%d not in 1..8192", m, d->dims[m]); return MOPOE_EINVAL; }
@@ -104,6 +104,7 @@ void build_view(const mopoe_model_desc* d, const mopoe_param_layout* lay, float*
     off += mv.S;
     mv.peps_off = poff;
     poff += (mv.S + 3) & ~3;
+    // (weight pointers are used by the fused kernels only: default architecture, where every offset exists)
     mv.w1 = base + lay->enc_w1[m];
     mv.b1 = base + lay->enc_b1[m];
     mv.wh = base + lay->enc_wh[m];
@@ -143,19 +144,31 @@ int mopoe_param_layout_of(const mopoe_model_desc* d, mopoe_param_layout* out) {
   if (!out) { set_error("out is NULL"); return MOPOE_EINVAL; }
   memset(out, 0, sizeof(*out));
   int64_t off = 0;
-  const int L = d->latent_dim, H = MOPOE_HIDDEN;
+  const int L = d->latent_dim, H = MOPOE_HIDDEN, He = d->n_hidden_enc, Hd = d->n_hidden_dec;
+  auto take = [&](int64_t n) { const int64_t o = off; off = align32(off + n); return o; };
   for (int m = 0; m < d->n_mods; ++m) {
     const int D = d->dims[m], S = d->style_dims[m];
-    out->enc_w1[m] = off; off = align32(off + (int64_t)H * D);
-    out->enc_b1[m] = off; off = align32(off + H);
-    out->enc_wh[m] = off; off = align32(off + (int64_t)(2 * L + 2 * S) * H);
-    out->enc_bh[m] = off; off = align32(off + 2 * L + 2 * S);
+    out->enc_w1[m] = He >= 1 ? take((int64_t)H * D) : -1;
+    out->enc_b1[m] = He >= 1 ? take(H) : -1;
+    for (int l = 1; l < MOPOE_MAX_LAYERS; ++l) {
+      out->enc_wx[m][l - 1] = l < He ? take((int64_t)H * H) : -1;
+      out->enc_bx[m][l - 1] = l < He ? take(H) : -1;
+    }
+    out->enc_wh[m] = take((int64_t)(2 * L + 2 * S) * (He >= 1 ? H : D));
+    out->enc_bh[m] = take(2 * L + 2 * S);
   }
   for (int m = 0; m < d->n_mods; ++m) {
     const int D = d->dims[m], S = d->style_dims[m];
-    out->dec_lv[m] = off; off = align32(off + D);
-    out->dec_w[m] = off; off = align32(off + (int64_t)D * (S + L));
-    out->dec_b[m] = off; off = align32(off + D);
+    const int in_o = Hd >= 1 ? H : S + L;
+    out->dec_lv[m] = d->scale_mode == 0 ? take(D) : -1;
+    for (int l = 0; l < MOPOE_MAX_LAYERS; ++l) {
+      out->dec_hw[m][l] = l < Hd ? take((int64_t)H * (l == 0 ? S + L : H)) : -1;
+      out->dec_hb[m][l] = l < Hd ? take(H) : -1;
+    }
+    out->dec_w[m] = take((int64_t)D * in_o);
+    out->dec_b[m] = take(D);
+    out->dec_lvw[m] = d->scale_mode == 1 ? take((int64_t)D * in_o) : -1;
+    out->dec_lvb[m] = d->scale_mode == 1 ? take(D) : -1;
   }
   out->total = off;
   return MOPOE_OK;

@@ -920,7 +920,14 @@ int mopoe_daa_last_kernel_ms(float* ms_out) {
   return MOPOE_OK;
 }
 
+// The sweep reads reconstruction locations and scales only: the likelihood family does not enter it
+// (workflow.py:388-419 samples the scores from a Normal whatever the training likelihood was).
+#define DAA_DESC_WITHOUT_LIKELIHOOD(desc)   \
+  mopoe_model_desc desc##_local;            \
+  if (desc) { desc##_local = *desc; desc##_local.likelihood = 0; desc = &desc##_local; }
+
 int64_t mopoe_daa_workspace_bytes(const mopoe_model_desc* desc, const mopoe_daa_desc* daa) {
+  DAA_DESC_WITHOUT_LIKELIHOOD(desc)
   if (check_desc(desc)) return MOPOE_EINVAL;
   if (!daa) { set_error("daa is NULL"); return MOPOE_EINVAL; }
   return daa_carve(desc, daa, nullptr, nullptr);
@@ -932,6 +939,9 @@ static int check_daa(const mopoe_model_desc* d, const mopoe_daa_desc* q) {
     return MOPOE_EINVAL; }
   if (q->src_mod < 0 || q->src_mod >= d->n_mods || q->dst_mod < 0 || q->dst_mod >= d->n_mods || q->src_mod == q->dst_mod) {
     set_error("src_mod=%d dst_mod=%d invalid", q->src_mod, q->dst_mod); return MOPOE_EINVAL; }
+  if (d->n_hidden_enc != 1 || d->n_hidden_dec != 0 || d->scale_mode != 0) {
+    set_error("the fused DAA sweep covers num_hidden_layer_encoder=1, num_hidden_layer_decoder=0, per-feature output scale "
+              "(its base passes use the affine decoder); other architectures go through daa.daa_sweep_layered"); return MOPOE_EINVAL; }
   if (q->base_mode < 0 || q->base_mode > 1) { set_error("base_mode=%d invalid", q->base_mode); return MOPOE_EINVAL; }
   if (q->reg_method < 0 || q->reg_method > 1) { set_error("reg_method=%d unsupported (hierarchical, fixed; mixed is not on this path)", q->reg_method); return MOPOE_EINVAL; }
   if (d->dims[q->src_mod] > 64) { set_error("src modality wider than 64 columns is unsupported in the DAA kernel"); return MOPOE_EINVAL; }
@@ -950,6 +960,7 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
                     const float* eps_score, const float* eps_av, uint64_t seed, float* avatars,
                     float* sampled_scores, float* reconstructions, double* betas, double* coefs, double* pvalues,
                     void* workspace, int64_t workspace_bytes, void* stream_) {
+  DAA_DESC_WITHOUT_LIKELIHOOD(desc)
   int rc = check_desc(desc);
   if (rc) return rc;
   if (mopoe_device_count() == 0) { set_error("no CUDA device: the DAA path has no CPU fallback"); return MOPOE_ENODEV; }
@@ -1231,6 +1242,7 @@ int mopoe_daa_exchange_tables(const mopoe_table_exchange* ex, const double* coef
 }
 
 int mopoe_daa_status(const mopoe_model_desc* desc, const mopoe_daa_desc* daa, void* workspace, void* stream_) {
+  DAA_DESC_WITHOUT_LIKELIHOOD(desc)
   if (check_desc(desc)) return MOPOE_EINVAL;
   if (!daa || !workspace) { set_error("NULL argument"); return MOPOE_EINVAL; }
   DaaWs ws;
@@ -1246,6 +1258,7 @@ int mopoe_daa_status(const mopoe_model_desc* desc, const mopoe_daa_desc* daa, vo
 }
 
 int mopoe_daa_read_phases(const mopoe_model_desc* desc, const mopoe_daa_desc* daa, void* workspace, int64_t* out32_host) {
+  DAA_DESC_WITHOUT_LIKELIHOOD(desc)
   if (check_desc(desc)) return MOPOE_EINVAL;
   DaaWs ws;
   daa_carve(desc, daa, (char*)workspace, &ws);

@@ -17,6 +17,7 @@
 //   utils.py:88-112 (calc_elbo), experiment.py:268-271 (Adam).
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <vector>
 
 #include "mopoe_common.cuh"
 #include "mopoe_latent.cuh"
@@ -1258,6 +1259,25 @@ static int pick_train_impl(const mopoe_model_desc* d, int64_t max_rows, tc::TcPl
   return ok ? 1 : 0;
 }
 
+#include "mopoe_generic.cuh"
+
+// architectures outside the train_exp defaults run on the layered path (mopoe_generic.cuh)
+static bool layered_path(const mopoe_model_desc* d) {
+  return d->n_hidden_enc != 1 || d->n_hidden_dec != 0 || d->scale_mode != 0 || d->likelihood != 0;
+}
+
+// build_view for the layered path: dims, subset table and loss weights only (the weight pointers of ModView belong
+// to the fused kernels; the layered path addresses the buffer through GModel offsets)
+static void build_view_layered(const mopoe_model_desc* d, const mopoe_param_layout* lay, float* base, ModelView* v) {
+  mopoe_param_layout tmp = *lay;
+  for (int m = 0; m < MOPOE_MAX_MODS; ++m) {
+    if (tmp.enc_w1[m] < 0) tmp.enc_w1[m] = 0;
+    if (tmp.enc_b1[m] < 0) tmp.enc_b1[m] = 0;
+    if (tmp.dec_lv[m] < 0) tmp.dec_lv[m] = 0;
+  }
+  build_view(d, &tmp, base, v);
+}
+
 }  // namespace mopoe
 
 using namespace mopoe;
@@ -1276,6 +1296,11 @@ int mopoe_debug_p2prof(float* out16_host) {
 int64_t mopoe_workspace_bytes(const mopoe_model_desc* desc, int64_t max_rows) {
   if (check_desc(desc)) return MOPOE_EINVAL;
   if (max_rows < 1) { set_error("max_rows=%lld", (long long)max_rows); return MOPOE_EINVAL; }
+  if (layered_path(desc)) {
+    mopoe_param_layout lay;
+    mopoe_param_layout_of(desc, &lay);
+    return gen::gen_carve(desc, &lay, max_rows, nullptr, nullptr);
+  }
   int64_t bytes = (carve(desc, max_rows, nullptr, nullptr) + 1023) & ~(int64_t)1023;
   tc::TcPlan plan;
   if (tc::make_plan(desc, max_rows, TC_SMEM_LIMIT, &plan)) bytes += plan.total;   // operand blobs of the tensor-core training step
@@ -1308,10 +1333,40 @@ int mopoe_forward(const mopoe_model_desc* desc, const float* params, const mopoe
   mopoe_param_layout lay;
   mopoe_param_layout_of(desc, &lay);
   ModelView mv;
-  build_view(desc, &lay, const_cast<float*>(params), &mv);
+  const bool layered = layered_path(desc);
+  if (layered) build_view_layered(desc, &lay, const_cast<float*>(params), &mv);
+  else build_view(desc, &lay, const_cast<float*>(params), &mv);
   if (use_expert >= mv.sub.n_subsets) { set_error("use_expert=%d out of range", use_expert); return MOPOE_EINVAL; }
   if (use_expert >= 0 && (mv.sub.mask[use_expert] & batch->present_mask) != mv.sub.mask[use_expert]) {
     set_error("use_expert subset %d is not available in this batch", use_expert); return MOPOE_EINVAL; }
+  if (layered) {
+    const int64_t gneed = gen::gen_carve(desc, &lay, batch->n_rows, nullptr, nullptr);
+    if (workspace_bytes < gneed) { set_error("workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)gneed); return MOPOE_ENOSPC; }
+    gen::GWs gws;
+    gen::gen_carve(desc, &lay, batch->n_rows, (char*)workspace, &gws);
+    gen::GModel gm;
+    gen::build_gmodel(desc, &lay, &gm);
+    StepCtx cx;
+    memset(&cx, 0, sizeof(cx));
+    for (int m = 0; m < desc->n_mods; ++m) {
+      cx.x[m] = (batch->present_mask >> m & 1) ? x[m] : nullptr;
+      if ((batch->present_mask >> m & 1) && !x[m]) { set_error("x[%d] is NULL but modality is present", m); return MOPOE_EINVAL; }
+    }
+    cx.noise = make_noise(eps, seed, MOPOE_STREAM_FORWARD);
+    cx.eps_pass_stride = (int64_t)batch->n_rows * mv.E;
+    cx.sample_latents = sample_latents; cx.use_expert = use_expert < 0 ? -1 : use_expert;
+    cx.with_nll = with_nll; cx.uni_pass = 0; cx.mode = 0;
+    cx.out = *out;
+    {
+      bool only = !with_nll && !out->scalars && !out->subset_mu && !out->subset_logvar && !out->joint_mu && !out->joint_logvar && !out->z;
+      for (int m = 0; m < MOPOE_MAX_MODS; ++m) only = only && !out->z_style[m] && !out->rec_loc[m] && !out->rec_logvar[m];
+      cx.heads_only = only ? 1 : 0;
+    }
+    cx.lay = lay;
+    mopoe_batch_desc b = *batch;
+    b.row_offset = 0;
+    return gen::gen_step(desc, gm, mv, cx, b, gws, const_cast<float*>(params), 0, out->scalars, (cudaStream_t)stream_);
+  }
   const int64_t need = carve(desc, batch->n_rows, nullptr, nullptr);
   if (workspace_bytes < need) { set_error("workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need); return MOPOE_ENOSPC; }
   Workspace ws;
@@ -1385,6 +1440,48 @@ int mopoe_train_steps(const mopoe_model_desc* desc, float* params, float* adam_m
   if (mode == 2 && (!adam_m || !adam_v || !adam_t)) { set_error("mode 2 needs Adam state"); return MOPOE_EINVAL; }
   if (out && n_steps != 1) { set_error("forward outputs need n_steps == 1"); return MOPOE_EINVAL; }
   if (n_steps < 1 || max_rows < 1) { set_error("n_steps=%d max_rows=%lld", n_steps, (long long)max_rows); return MOPOE_EINVAL; }
+  if (layered_path(desc)) {
+    // host-driven: the batch descriptors come back to the host once (one synchronisation per call; this path is not
+    // capturable in a CUDA graph), then every step is a sequence of launches
+    mopoe_param_layout glay;
+    mopoe_param_layout_of(desc, &glay);
+    const int64_t gneed = gen::gen_carve(desc, &glay, max_rows, nullptr, nullptr);
+    if (workspace_bytes < gneed) { set_error("workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)gneed); return MOPOE_ENOSPC; }
+    gen::GWs gws;
+    gen::gen_carve(desc, &glay, max_rows, (char*)workspace, &gws);
+    gen::GModel gm;
+    gen::build_gmodel(desc, &glay, &gm);
+    ModelView gmv;
+    build_view_layered(desc, &glay, params, &gmv);
+    cudaStream_t gstream = (cudaStream_t)stream_;
+    std::vector<mopoe_batch_desc> hb(n_steps);
+    MOPOE_CUDA(cudaMemcpyAsync(hb.data(), batches, sizeof(mopoe_batch_desc) * n_steps, cudaMemcpyDeviceToHost, gstream));
+    MOPOE_CUDA(cudaStreamSynchronize(gstream));
+    StepCtx gcx;
+    memset(&gcx, 0, sizeof(gcx));
+    for (int m = 0; m < desc->n_mods; ++m) { gcx.x[m] = data[m]; gcx.row_index[m] = row_index ? row_index[m] : nullptr; }
+    const int g_pass = desc->method == MOPOE_METHOD_POE ? 1 + desc->n_mods : 1;
+    gcx.noise = make_noise(eps, seed, MOPOE_STREAM_TRAIN);
+    gcx.eps_pass_stride = max_rows * gmv.E;
+    gcx.eps_step_stride = (int64_t)g_pass * max_rows * gmv.E;
+    gcx.sample_latents = 1; gcx.use_expert = -1; gcx.with_nll = 1;
+    gcx.uni_pass = desc->method == MOPOE_METHOD_POE; gcx.mode = mode;
+    gcx.lr = lr; gcx.b1 = b1; gcx.b2 = b2; gcx.adam_eps = adam_eps;
+    gcx.adam_m = adam_m; gcx.adam_v = adam_v; gcx.adam_t = adam_t; gcx.grads = grads; gcx.params = params;
+    gcx.lay = glay;
+    if (out) { gcx.out = *out; gcx.out.scalars = nullptr; }
+    if (mode == 1) MOPOE_CUDA(cudaMemsetAsync(grads, 0, glay.total * sizeof(float), gstream));
+    g_train_impl = 2;
+    for (int step = 0; step < n_steps; ++step) {
+      if ((rc = validate_batch(desc, &hb[step]))) return rc;
+      if (hb[step].n_rows > max_rows) { set_error("step %d: n_rows=%d > max_rows", step, hb[step].n_rows); return MOPOE_EINVAL; }
+      for (int m = 0; m < desc->n_mods; ++m)
+        if ((hb[step].present_mask >> m & 1) && !data[m]) { set_error("data[%d] is NULL but modality is present", m); return MOPOE_EINVAL; }
+      if ((rc = gen::gen_step(desc, gm, gmv, gcx, hb[step], gws, params, (int64_t)step * gcx.eps_step_stride,
+                              scalars + (int64_t)step * MOPOE_N_SCALARS, gstream))) return rc;
+    }
+    return MOPOE_OK;
+  }
   const int64_t need = carve(desc, max_rows, nullptr, nullptr);
   if (workspace_bytes < need) { set_error("workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need); return MOPOE_ENOSPC; }
   mopoe_param_layout lay;

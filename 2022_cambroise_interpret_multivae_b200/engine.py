@@ -91,6 +91,8 @@ class ForwardResult:
                         for m in range(spec.n_mods)]
         self.rec_loc = [f(n_rows, spec.dims[m]) if want_rec and (present_mask >> m & 1) else None
                         for m in range(spec.n_mods)]
+        self.rec_logvar = [f(n_rows, spec.dims[m]) if want_rec and spec.learn_output_sample_scale and (present_mask >> m & 1) else None
+                           for m in range(spec.n_mods)]          # per-sample output log-variance (networks.py:73-74)
         self.scalars = torch.zeros(_lib.N_SCALARS, dtype=torch.float32, device=device)
 
     def as_struct(self):
@@ -99,6 +101,7 @@ class ForwardResult:
             o.enc_heads[m] = _ptr(self.enc_heads[m]).value
             o.z_style[m] = _ptr(self.z_style[m]).value
             o.rec_loc[m] = _ptr(self.rec_loc[m]).value
+            o.rec_logvar[m] = _ptr(self.rec_logvar[m]).value
         o.subset_mu, o.subset_logvar = _ptr(self.subset_mu), _ptr(self.subset_logvar)
         o.joint_mu, o.joint_logvar, o.z = _ptr(self.joint_mu), _ptr(self.joint_logvar), _ptr(self.z)
         o.scalars = _ptr(self.scalars)

@@ -26,13 +26,19 @@ class Encoder(nn.Module):
     def __init__(self, spec: PathSpec, m):
         super().__init__()
         D, S, L = spec.dims[m], spec.style_dims[m], spec.latent_dim
-        self.shared_encoder = nn.Sequential(nn.Linear(D, _lib.HIDDEN), nn.ReLU(), nn.Dropout(0.0))
+        self.shared_encoder = nn.Sequential()
+        width = D
+        for _ in range(spec.n_hidden_enc):                       # networks.py:16-20
+            self.shared_encoder.append(nn.Linear(width, _lib.HIDDEN))
+            self.shared_encoder.append(nn.ReLU())
+            self.shared_encoder.append(nn.Dropout(0.0))
+            width = _lib.HIDDEN
         self.style_dim = S
-        self.class_mu = nn.Linear(_lib.HIDDEN, L)
-        self.class_logvar = nn.Linear(_lib.HIDDEN, L)
+        self.class_mu = nn.Linear(width, L)
+        self.class_logvar = nn.Linear(width, L)
         if S > 0:
-            self.style_mu = nn.Linear(_lib.HIDDEN, S)
-            self.style_logvar = nn.Linear(_lib.HIDDEN, S)
+            self.style_mu = nn.Linear(width, S)
+            self.style_logvar = nn.Linear(width, S)
 
 
 class Decoder(nn.Module):
@@ -42,8 +48,18 @@ class Decoder(nn.Module):
         super().__init__()
         D, S, L = spec.dims[m], spec.style_dims[m], spec.latent_dim
         self.style_dim = S
-        self.out_mu = nn.Linear(S + L, D)
-        self.logvar = nn.Parameter(torch.full((1, D), spec.initial_out_logvar), requires_grad=spec.learn_output_scale)
+        self.shared_decoder = nn.Sequential()
+        width = S + L
+        for _ in range(spec.n_hidden_dec):                       # networks.py:51-55
+            self.shared_decoder.append(nn.Linear(width, _lib.HIDDEN))
+            self.shared_decoder.append(nn.ReLU())
+            self.shared_decoder.append(nn.Dropout(0.0))
+            width = _lib.HIDDEN
+        self.out_mu = nn.Linear(width, D)
+        if spec.learn_output_sample_scale:                       # networks.py:58-59
+            self.logvar = nn.Linear(width, D)
+        else:
+            self.logvar = nn.Parameter(torch.full((1, D), spec.initial_out_logvar), requires_grad=spec.learn_output_scale)
 
 
 class VAE(nn.Module):
@@ -59,7 +75,8 @@ class VAE(nn.Module):
             encoders[key] = Encoder(self.spec, m)
             decoders[key] = Decoder(self.spec, m)
         self.encoders, self.decoders = encoders, decoders
-        self.lhoods = {k: torch.distributions.Normal for k in modalities}
+        lhood = {"normal": torch.distributions.Normal, "laplace": torch.distributions.Laplace}[self.spec.likelihood]
+        self.lhoods = {k: lhood for k in modalities}             # modalities/modality.py:18-30
         self._flat = None
         self._noise = None
         self._ws = engine.Workspace()
@@ -175,8 +192,8 @@ class VAE(nn.Module):
         rec = {}
         for m, name in enumerate(spec.mod_names):
             if res.rec_loc[m] is not None:
-                scale = (self.decoders[name].logvar.detach() * 0.5).exp()
-                rec[name] = torch.distributions.Normal(res.rec_loc[m], scale)
+                lv = res.rec_logvar[m] if spec.learn_output_sample_scale else self.decoders[name].logvar.detach()
+                rec[name] = self.lhoods[name](res.rec_loc[m], (lv * 0.5).exp())
         results["rec"] = rec
         results["class_embeddings"] = res.z
         return results

@@ -46,8 +46,8 @@ class PathSpec:
         self.initial_out_logvar = float(initial_out_logvar)
         if method not in _lib.METHODS:
             raise NotImplementedError("method=%r is not on the B200 path (poe, moe, joint_elbo, jsd)" % (method,))
-        if likelihood != "normal":
-            raise NotImplementedError("likelihood=%r is not on the B200 path (normal only)" % (likelihood,))
+        if likelihood not in _lib.LIKELIHOODS:
+            raise NotImplementedError("likelihood=%r is not on the B200 path (normal, laplace)" % (likelihood,))
         if dropout_rate:
             raise NotImplementedError("dropout_rate != 0 is not on the B200 path")
         if len(self.style_dims) != len(self.dims) or len(self.mod_names) != len(self.dims):
@@ -147,7 +147,7 @@ class PathSpec:
         d.n_hidden_enc = self.n_hidden_enc
         d.n_hidden_dec = self.n_hidden_dec
         d.method = _lib.METHODS[self.method]
-        d.likelihood = 0
+        d.likelihood = _lib.LIKELIHOODS[self.likelihood]
         d.scale_mode = 1 if self.learn_output_sample_scale else 0
         d.learn_output_scale = int(self.learn_output_scale)
         d.beta, d.beta_style, d.beta_content = self.beta, self.beta_style, self.beta_content
@@ -175,30 +175,49 @@ class PathSpec:
         b.row_offset = int(row_offset)
         return b
 
+    @property
+    def layered(self):
+        """True for the architectures that run on the layered path (csrc/mopoe_generic.cuh) instead of the fused
+        kernels: hidden-layer counts other than (1, 0), per-sample output scale, non-normal likelihood."""
+        return (self.n_hidden_enc != 1 or self.n_hidden_dec != 0 or self.learn_output_sample_scale
+                or self.likelihood != "normal")
+
     def param_slices(self):
-        """state-dict name -> (offset, shape) inside the flat parameter buffer."""
-        lay, L, out = self._layout, self.latent_dim, {}
+        """state-dict name -> (offset, shape) inside the flat parameter buffer, in the reference's own state-dict order
+        (networks.py:9-28,44-64: Sequential index 3 l for the l-th hidden Linear, heads, out_mu, logvar)."""
+        lay, L, H, out = self._layout, self.latent_dim, _lib.HIDDEN, {}
+        He, Hd = self.n_hidden_enc, self.n_hidden_dec
         for m, name in enumerate(self.mod_names):
             D, S = self.dims[m], self.style_dims[m]
             e = "encoders.%s." % name
-            out[e + "shared_encoder.0.weight"] = (lay.enc_w1[m], (_lib.HIDDEN, D))
-            out[e + "shared_encoder.0.bias"] = (lay.enc_b1[m], (_lib.HIDDEN,))
-            wh, bh = lay.enc_wh[m], lay.enc_bh[m]
-            out[e + "class_mu.weight"] = (wh, (L, _lib.HIDDEN))
+            for l in range(He):
+                w, b = (lay.enc_w1[m], lay.enc_b1[m]) if l == 0 else (lay.enc_wx[m][l - 1], lay.enc_bx[m][l - 1])
+                out[e + "shared_encoder.%d.weight" % (3 * l)] = (w, (H, D if l == 0 else H))
+                out[e + "shared_encoder.%d.bias" % (3 * l)] = (b, (H,))
+            wh, bh, K = lay.enc_wh[m], lay.enc_bh[m], (H if He >= 1 else D)
+            out[e + "class_mu.weight"] = (wh, (L, K))
             out[e + "class_mu.bias"] = (bh, (L,))
-            out[e + "class_logvar.weight"] = (wh + L * _lib.HIDDEN, (L, _lib.HIDDEN))
+            out[e + "class_logvar.weight"] = (wh + L * K, (L, K))
             out[e + "class_logvar.bias"] = (bh + L, (L,))
             if S > 0:
-                out[e + "style_mu.weight"] = (wh + 2 * L * _lib.HIDDEN, (S, _lib.HIDDEN))
+                out[e + "style_mu.weight"] = (wh + 2 * L * K, (S, K))
                 out[e + "style_mu.bias"] = (bh + 2 * L, (S,))
-                out[e + "style_logvar.weight"] = (wh + (2 * L + S) * _lib.HIDDEN, (S, _lib.HIDDEN))
+                out[e + "style_logvar.weight"] = (wh + (2 * L + S) * K, (S, K))
                 out[e + "style_logvar.bias"] = (bh + 2 * L + S, (S,))
         for m, name in enumerate(self.mod_names):
             D, S = self.dims[m], self.style_dims[m]
             d = "decoders.%s." % name
-            out[d + "logvar"] = (lay.dec_lv[m], (1, D))
-            out[d + "out_mu.weight"] = (lay.dec_w[m], (D, S + L))
+            K = H if Hd >= 1 else S + L
+            if not self.learn_output_sample_scale:
+                out[d + "logvar"] = (lay.dec_lv[m], (1, D))
+            for l in range(Hd):
+                out[d + "shared_decoder.%d.weight" % (3 * l)] = (lay.dec_hw[m][l], (H, S + L if l == 0 else H))
+                out[d + "shared_decoder.%d.bias" % (3 * l)] = (lay.dec_hb[m][l], (H,))
+            out[d + "out_mu.weight"] = (lay.dec_w[m], (D, K))
             out[d + "out_mu.bias"] = (lay.dec_b[m], (D,))
+            if self.learn_output_sample_scale:
+                out[d + "logvar.weight"] = (lay.dec_lvw[m], (D, K))
+                out[d + "logvar.bias"] = (lay.dec_lvb[m], (D,))
         return out
 
     def modality_of_param(self, name):

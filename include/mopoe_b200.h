@@ -63,11 +63,12 @@ typedef struct mopoe_model_desc {
   int32_t style_dims[MOPOE_MAX_MODS];   /* flags.style_dim, zeros when not factorised (workflow.py:148) */
   int32_t latent_dim;                   /* flags.class_dim, 1..32 */
   int32_t hidden;                       /* must be 256 */
-  int32_t n_hidden_enc;                 /* flags.num_hidden_layer_encoder, must be 1 */
-  int32_t n_hidden_dec;                 /* flags.num_hidden_layer_decoder, must be 0 */
+  int32_t n_hidden_enc;                 /* flags.num_hidden_layer_encoder, 0..4 (1 = the fused kernels, else the layered path) */
+  int32_t n_hidden_dec;                 /* flags.num_hidden_layer_decoder, 0..4 (0 = the fused kernels, else the layered path) */
   int32_t method;                       /* MOPOE_METHOD_* (flags.modality_poe/moe/jsd/joint_elbo) */
-  int32_t likelihood;                   /* 0 = normal (modality.py:18-30); others rejected */
-  int32_t scale_mode;                   /* 0 = per-feature logvar Parameter (networks.py:61-64) */
+  int32_t likelihood;                   /* 0 = normal, 1 = laplace (modality.py:18-30; layered path); others rejected */
+  int32_t scale_mode;                   /* 0 = per-feature logvar Parameter (networks.py:61-64), 1 = learn_output_sample_scale:
+                                           logvar = Linear(decoder features) per sample (networks.py:58-59,73-74; layered path) */
   int32_t learn_output_scale;           /* flags.learn_output_scale */
   int32_t name_rank[MOPOE_MAX_MODS];    /* rank of modality m's NAME in sorted order: fusion order
                                            inside a subset (BaseExperiment.py:72-77) */
@@ -83,11 +84,22 @@ typedef struct mopoe_model_desc {
  *   dec_w   = decoders.<m>.out_mu.weight (D, S + L)              dec_b = ....bias (D)
  *   dec_lv  = decoders.<m>.logvar (1, D)
  * Adam moments and gradient buffers use the same layout. */
+#define MOPOE_MAX_LAYERS 4
 typedef struct mopoe_param_layout {
   int64_t enc_w1[MOPOE_MAX_MODS], enc_b1[MOPOE_MAX_MODS];
   int64_t enc_wh[MOPOE_MAX_MODS], enc_bh[MOPOE_MAX_MODS];
   int64_t dec_w[MOPOE_MAX_MODS], dec_b[MOPOE_MAX_MODS], dec_lv[MOPOE_MAX_MODS];
   int64_t total; /* floats */
+  /* non-default architectures (networks.py:16-20,51-59), -1 where a block does not exist:
+   *   enc_wx[m][l-1] / enc_bx = encoders.<m>.shared_encoder.<3l>.weight (256, 256) / bias, hidden layers l = 1 ..
+   *     (with num_hidden_layer_encoder = 0 enc_w1 / enc_b1 are -1 and the heads enc_wh are (2L+2S, D))
+   *   dec_hw[m][l] / dec_hb    = decoders.<m>.shared_decoder.<3l>.weight (256, S+L | 256) / bias
+   *     (out_mu dec_w is then (D, 256))
+   *   dec_lvw[m] / dec_lvb[m]  = decoders.<m>.logvar.weight (D, in) / bias when learn_output_sample_scale
+   *     (dec_lv is -1: the per-feature Parameter does not exist) */
+  int64_t enc_wx[MOPOE_MAX_MODS][MOPOE_MAX_LAYERS - 1], enc_bx[MOPOE_MAX_MODS][MOPOE_MAX_LAYERS - 1];
+  int64_t dec_hw[MOPOE_MAX_MODS][MOPOE_MAX_LAYERS], dec_hb[MOPOE_MAX_MODS][MOPOE_MAX_LAYERS];
+  int64_t dec_lvw[MOPOE_MAX_MODS], dec_lvb[MOPOE_MAX_MODS];
 } mopoe_param_layout;
 
 /* One batch of the path.  A batch is homogeneous in its set of present modalities
@@ -119,6 +131,7 @@ typedef struct mopoe_forward_out {
   float* z_style[MOPOE_MAX_MODS];   /* (N, S_m) */
   float* rec_loc[MOPOE_MAX_MODS];   /* (N, D_m)            results['rec'][m].loc  (scale = exp(.5*logvar)) */
   float* scalars;                   /* (MOPOE_N_SCALARS)   see mopoe_scalar_index */
+  float* rec_logvar[MOPOE_MAX_MODS];/* (N, D_m)            per-sample output log-variance (scale_mode 1 only) */
 } mopoe_forward_out;
 
 /* Index of each entry of a `scalars` row (all are means over rows, exactly the numbers

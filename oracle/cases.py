@@ -42,6 +42,20 @@ for _i, (_f, _p) in enumerate(itertools.product([True, False], [(0, 1), (0,), (1
 for _i, _p in enumerate([(0, 1, 2, 3), (1, 3), (0, 2, 3)]):
     ELBO_CASES["stress_jsd_%s" % "".join(map(str, _p))] = _case(STRESS, "jsd", True, _p, 96, 90 + _i, 190 + _i)
 
+# architectures outside the train_exp defaults (networks.py:16-20,51-59, modality.py:18-30): the layered path
+ARCH_CASES = {
+    "enc2": dict(n_hidden_enc=2), "enc0": dict(n_hidden_enc=0), "dec1": dict(n_hidden_dec=1),
+    "enc3_dec2": dict(n_hidden_enc=3, n_hidden_dec=2), "samplescale": dict(sample_scale=True),
+    "samplescale_dec1": dict(sample_scale=True, n_hidden_dec=1), "laplace": dict(likelihood="laplace"),
+    "enc0_dec1_samplescale_laplace": dict(n_hidden_enc=0, n_hidden_dec=1, sample_scale=True, likelihood="laplace"),
+}
+for _i, (_a, _kw) in enumerate(ARCH_CASES.items()):
+    _m = ["joint_elbo", "poe", "moe", "jsd"][_i % 4]
+    ELBO_CASES["hbn_%s_%s_01" % (_a, _m)] = _case(HBN, _m, True, (0, 1), 96, 200 + _i, 300 + _i, **_kw)
+    ELBO_CASES["hbn_%s_joint_elbo_1" % _a] = _case(HBN, "joint_elbo", _i % 2 == 0, (1,), 64, 220 + _i, 320 + _i, **_kw)
+ELBO_CASES["stress_enc2_dec1_samplescale_poe_023"] = _case(STRESS, "poe", True, (0, 2, 3), 48, 240, 340, n_hidden_enc=2,
+                                                            n_hidden_dec=1, sample_scale=True)
+
 FORWARD_CASES = {
     "hbn_n50_sampled": _case(HBN, "joint_elbo", True, (0, 1), 50, 60, 160),
     "hbn_n50_mean": _case(HBN, "joint_elbo", True, (0, 1), 50, 61, 161, sample_latents=False),
@@ -51,6 +65,8 @@ FORWARD_CASES = {
     "stress_n33": _case(STRESS, "joint_elbo", True, (0, 1, 2, 3), 33, 65, 165),
     "hbn_n50_jsd": _case(HBN, "jsd", True, (0, 1), 50, 66, 166),
     "hbn_n50_jsd_mean": _case(HBN, "jsd", True, (0, 1), 50, 67, 167, sample_latents=False),
+    "hbn_n50_enc2_dec1_samplescale": _case(HBN, "joint_elbo", True, (0, 1), 50, 68, 168, n_hidden_enc=2, n_hidden_dec=1,
+                                           sample_scale=True),
 }
 
 DAA_ROI_STRIDE = 16
@@ -71,7 +87,9 @@ def spec_kwargs(case):
     return dict(dims=case["dims"],
                 style_dims=case["style_dims"] if case["factorized"] else [0] * len(case["dims"]),
                 latent_dim=case["latent_dim"], method=case["method"], mod_names=case["mod_names"],
-                learn_output_scale=case.get("learn_output_scale", True))
+                learn_output_scale=case.get("learn_output_scale", True),
+                n_hidden_enc=case.get("n_hidden_enc", 1), n_hidden_dec=case.get("n_hidden_dec", 0),
+                sample_scale=case.get("sample_scale", False), likelihood=case.get("likelihood", "normal"))
 
 
 def spec_of(case):

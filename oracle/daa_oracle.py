@@ -42,14 +42,14 @@ def daa_generate(params, spec, src, dst, eps_base, eps_score, eps_av, sample_lat
     with torch.no_grad():
         for v in range(n_val):
             data = {sname: src[v], dname: dst[v]}
-            loc_s, loc_d = [], []
+            loc_s, loc_d, scale_s = [], [], []
             for p in range(Mb):                                         # workflow.py:388-398
                 rec = mo.forward(params, spec, data, eps_base[v, p], sample_latents=True)["rec"]
                 loc_s.append(rec[sname][0])
                 loc_d.append(rec[dname][0])
-                scale_s = rec[sname][1]
+                scale_s.append(rec[sname][1].expand_as(rec[sname][0]))
             loc_hat = torch.stack(loc_s).mean(0)
-            scale_hat = scale_s.expand_as(loc_hat)                      # mean of identical scales
+            scale_hat = torch.stack(scale_s).mean(0)                    # (identical scales unless learn_output_sample_scale)
             recons[v] = torch.stack(loc_d).mean(0).numpy()
             scores = loc_hat + scale_hat * eps_score[v]                 # (J, N, C)  workflow.py:401-405
             if given_scores:                                            # sampling_strategy != "likelihood" (:337-346,

@@ -28,7 +28,9 @@ def ref_model_for(case):
     flags = rh.make_flags(input_dims=spec.dims, latent_dim=spec.latent_dim,
                           style_dim=case["style_dims"] if case["factorized"] else [3] * len(spec.dims),
                           method=spec.method, factorized_representation=case["factorized"],
-                          learn_output_scale=spec.learn_output_scale)
+                          learn_output_scale=spec.learn_output_scale, num_hidden_layer_encoder=spec.n_hidden_enc,
+                          num_hidden_layer_decoder=spec.n_hidden_dec, likelihood=spec.likelihood,
+                          out_scale_per_subject=spec.sample_scale)
     model, exp = rh.build_reference_model(flags, seed=0, mod_names=spec.mod_names)
     params = mo.init_params(spec, seed=case["seed"])
     missing = model.load_state_dict(params, strict=True)

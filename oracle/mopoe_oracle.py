@@ -40,6 +40,10 @@ class ModelSpec:
     beta_style: float = 1.0
     beta_content: float = 1.0
     initial_out_logvar: float = -3.0
+    n_hidden_enc: int = 1                    # flags.num_hidden_layer_encoder (networks.py:16-20)
+    n_hidden_dec: int = 0                    # flags.num_hidden_layer_decoder (networks.py:51-55)
+    sample_scale: bool = False               # flags.learn_output_sample_scale (networks.py:58-59,73-74)
+    likelihood: str = "normal"               # normal | laplace (modalities/modality.py:18-30)
 
     def __post_init__(self):
         self.dims = list(self.dims)
@@ -78,23 +82,35 @@ def param_shapes(spec: ModelSpec):
     for m, name in enumerate(spec.mod_names):
         D, S = spec.dims[m], spec.style_dims[m]
         e = "encoders.%s." % name
-        shapes[e + "shared_encoder.0.weight"] = (HIDDEN, D)
-        shapes[e + "shared_encoder.0.bias"] = (HIDDEN,)
-        shapes[e + "class_mu.weight"] = (L, HIDDEN)
+        width = D
+        for l in range(spec.n_hidden_enc):                       # Sequential(Linear, ReLU, Dropout) per layer
+            shapes[e + "shared_encoder.%d.weight" % (3 * l)] = (HIDDEN, width)
+            shapes[e + "shared_encoder.%d.bias" % (3 * l)] = (HIDDEN,)
+            width = HIDDEN
+        shapes[e + "class_mu.weight"] = (L, width)
         shapes[e + "class_mu.bias"] = (L,)
-        shapes[e + "class_logvar.weight"] = (L, HIDDEN)
+        shapes[e + "class_logvar.weight"] = (L, width)
         shapes[e + "class_logvar.bias"] = (L,)
         if S > 0:
-            shapes[e + "style_mu.weight"] = (S, HIDDEN)
+            shapes[e + "style_mu.weight"] = (S, width)
             shapes[e + "style_mu.bias"] = (S,)
-            shapes[e + "style_logvar.weight"] = (S, HIDDEN)
+            shapes[e + "style_logvar.weight"] = (S, width)
             shapes[e + "style_logvar.bias"] = (S,)
     for m, name in enumerate(spec.mod_names):
         D, S = spec.dims[m], spec.style_dims[m]
         d = "decoders.%s." % name
-        shapes[d + "logvar"] = (1, D)
-        shapes[d + "out_mu.weight"] = (D, S + L)
+        if not spec.sample_scale:
+            shapes[d + "logvar"] = (1, D)
+        width = S + L
+        for l in range(spec.n_hidden_dec):
+            shapes[d + "shared_decoder.%d.weight" % (3 * l)] = (HIDDEN, width)
+            shapes[d + "shared_decoder.%d.bias" % (3 * l)] = (HIDDEN,)
+            width = HIDDEN
+        shapes[d + "out_mu.weight"] = (D, width)
         shapes[d + "out_mu.bias"] = (D,)
+        if spec.sample_scale:
+            shapes[d + "logvar.weight"] = (D, width)
+            shapes[d + "logvar.bias"] = (D,)
     return shapes
 
 
@@ -104,7 +120,7 @@ def init_params(spec: ModelSpec, seed=0, dtype=torch.float32):
     g = torch.Generator().manual_seed(seed)
     params = {}
     for name, shape in param_shapes(spec).items():
-        if name.endswith("logvar") and name.startswith("decoders."):
+        if name.endswith(".logvar") and name.startswith("decoders."):
             params[name] = torch.full(shape, spec.initial_out_logvar, dtype=dtype)
             continue
         if name.endswith(".weight"):
@@ -117,16 +133,18 @@ def init_params(spec: ModelSpec, seed=0, dtype=torch.float32):
 
 
 def trainable(spec: ModelSpec, name: str) -> bool:
-    return spec.learn_output_scale or not (name.startswith("decoders.") and name.endswith("logvar"))
+    return spec.learn_output_scale or not (name.startswith("decoders.") and name.endswith(".logvar"))
 
 
 # --------------------------------------------------------------------------------------------
 # primitives
 # --------------------------------------------------------------------------------------------
 def encoder(params, spec, m, x):
-    """Encoder.forward (networks.py:30-36), one hidden layer, dropout p=0."""
+    """Encoder.forward (networks.py:30-36), dropout p=0."""
     e = "encoders.%s." % spec.mod_names[m]
-    h = torch.relu(x @ params[e + "shared_encoder.0.weight"].T + params[e + "shared_encoder.0.bias"])
+    h = x
+    for l in range(spec.n_hidden_enc):
+        h = torch.relu(h @ params[e + "shared_encoder.%d.weight" % (3 * l)].T + params[e + "shared_encoder.%d.bias" % (3 * l)])
     mu = h @ params[e + "class_mu.weight"].T + params[e + "class_mu.bias"]
     lv = h @ params[e + "class_logvar.weight"].T + params[e + "class_logvar.bias"]
     if spec.style_dims[m] > 0:
@@ -138,12 +156,17 @@ def encoder(params, spec, m, x):
 
 
 def decoder(params, spec, m, z_style, z):
-    """Decoder.forward (networks.py:66-77), no hidden layer, per-feature logvar parameter."""
+    """Decoder.forward (networks.py:66-77)."""
     d = "decoders.%s." % spec.mod_names[m]
-    zz = torch.cat((z_style, z), dim=1) if spec.style_dims[m] > 0 else z
-    loc = zz @ params[d + "out_mu.weight"].T + params[d + "out_mu.bias"]
-    scale = (params[d + "logvar"] * 0.5).exp()
-    return loc, scale
+    h = torch.cat((z_style, z), dim=1) if spec.style_dims[m] > 0 else z
+    for l in range(spec.n_hidden_dec):
+        h = torch.relu(h @ params[d + "shared_decoder.%d.weight" % (3 * l)].T + params[d + "shared_decoder.%d.bias" % (3 * l)])
+    loc = h @ params[d + "out_mu.weight"].T + params[d + "out_mu.bias"]
+    if spec.sample_scale:
+        logvar = h @ params[d + "logvar.weight"].T + params[d + "logvar.bias"]
+    else:
+        logvar = params[d + "logvar"]
+    return loc, (logvar * 0.5).exp()
 
 
 def poe(mus, logvars):
@@ -201,9 +224,12 @@ def alpha_poe(alpha, mus, logvars):
     return pd_mu, torch.log(pd_var)
 
 
-def normal_nll(x, loc, scale, norm):
+def normal_nll(x, loc, scale, norm, likelihood="normal"):
     """-Normal(loc, scale).log_prob(x).sum()/norm  (modalities/modality.py:42-45,
-    torch.distributions.Normal.log_prob)."""
+    torch.distributions.Normal.log_prob); likelihood="laplace": torch.distributions.Laplace.log_prob."""
+    if likelihood == "laplace":
+        scale = scale.expand_as(loc)
+        return -((-torch.log(2 * scale) - torch.abs(x - loc) / scale).sum()) / float(norm)
     var = scale ** 2
     logp = -((x - loc) ** 2) / (2 * var) - scale.log() - math.log(math.sqrt(2 * math.pi))
     return -(logp.sum()) / float(norm)
@@ -318,7 +344,7 @@ def elbo(params, spec: ModelSpec, batch, eps):
     res = forward(params, spec, batch, eps[0])
     names = [n for n in spec.mod_names if n in batch]
     N = batch[names[0]].shape[0]
-    log_probs = {n: normal_nll(batch[n], *res["rec"][n], N) for n in names}       # calc_log_probs :27-38
+    log_probs = {n: normal_nll(batch[n], *res["rec"][n], N, spec.likelihood) for n in names}   # calc_log_probs :27-38
     klds = {k: kl_std_normal(mu, lv, N) for k, (mu, lv) in res["latents"]["subsets"].items()}  # :41-48
     klds_style = {}
     for n in names:                                                               # :51-59
@@ -340,7 +366,7 @@ def elbo(params, spec: ModelSpec, batch, eps):
             m = spec.mod_names.index(n)
             ks = klds_style.get(n + "_style", 0.0)
             r_mod = forward(params, spec, {n: batch[n]}, eps[1 + m])
-            lp = normal_nll(batch[n], *r_mod["rec"][n], N)
+            lp = normal_nll(batch[n], *r_mod["rec"][n], N, spec.likelihood)
             uni[n] = lp
             div = spec.beta_content * klds[n] + spec.beta_style * (spec.beta_style * ks)
             total = total + lp + spec.beta * div

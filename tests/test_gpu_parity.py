@@ -24,8 +24,10 @@ def train_impl(request, monkeypatch):
     return {"tc": 1, "ffma": 0, "ffma_smem": 0}[request.param]
 
 
-def _ran(impl):
+def _ran(impl, spec=None):
     from mopoe_b200 import _lib
+    if spec is not None and spec.layered:
+        impl = 2          # architectures outside the train_exp defaults: the layered path (csrc/mopoe_generic.cuh)
     assert _lib.lib().mopoe_train_last_impl() == impl, "the forced training implementation did not run"
 
 
@@ -34,7 +36,9 @@ def _setup(case):
     from mopoe_b200 import engine
     ospec = cases.spec_of(case)
     spec = mopoe_b200.PathSpec(ospec.dims, ospec.style_dims, ospec.latent_dim, ospec.method, ospec.mod_names,
-                               learn_output_scale=ospec.learn_output_scale)
+                               learn_output_scale=ospec.learn_output_scale, num_hidden_layer_encoder=ospec.n_hidden_enc,
+                               num_hidden_layer_decoder=ospec.n_hidden_dec, likelihood=ospec.likelihood,
+                               learn_output_sample_scale=ospec.sample_scale)
     params = mo.init_params(ospec, seed=case["seed"])
     flat = engine.pack_params(spec, params, torch.device("cuda"))
     return ospec, spec, params, flat
@@ -50,6 +54,9 @@ def _relu_kink_units(spec, params, batch):
         if n not in batch:
             continue
         e = "encoders.%s.shared_encoder.0." % n
+        if e + "weight" not in params:           # num_hidden_layer_encoder = 0: no ReLU in the encoder
+            skip[n] = torch.zeros(0, dtype=torch.long)
+            continue
         pre = batch[n] @ params[e + "weight"].T + params[e + "bias"]
         scale = batch[n].abs() @ params[e + "weight"].abs().T
         skip[n] = torch.nonzero(((pre.abs() <= 4e-6 * scale).sum(0) > 0)).reshape(-1)
@@ -96,6 +103,8 @@ def test_forward(name):
     for m, n in enumerate(spec.mod_names):
         if n in batch:
             _close(res.rec_loc[m], want["rec"][n][0], "loc " + n)
+            if spec.learn_output_sample_scale:
+                _close((0.5 * res.rec_logvar[m]).exp(), want["rec"][n][1], "per-sample scale " + n)
             smu, slv, mu, lv = mo.encoder(params, ospec, m, batch[n])
             _close(res.enc_heads[m][:, :spec.latent_dim], mu, "class_mu " + n)
             _close(res.enc_heads[m][:, spec.latent_dim:2 * spec.latent_dim], lv, "class_logvar " + n)
@@ -128,7 +137,7 @@ def test_elbo_terms_and_gradients(name, train_impl):
     grads = torch.zeros_like(flat)
     sc = _run_step(spec, flat, batch, eps, 1, grads=grads)[0].cpu().numpy()
     torch.cuda.synchronize()
-    _ran(train_impl)
+    _ran(train_impl, spec)
     out, g, used = mo.elbo_and_grads(params, ospec, batch, eps)
     want = GOLD["elbo"][name]
     from mopoe_b200 import _lib
@@ -168,6 +177,8 @@ for _base, _bn in ((cases.HBN, "hbn"), (cases.STRESS, "stress")):
             LARGE_CASES["%s_%s_%d" % (_bn, _method, _n)] = cases._case(_base, _method, True, _full, _n, 300 + _n % 97, 400 + _n % 89)
 LARGE_CASES["hbn_jsd_4097"] = cases._case(cases.HBN, "jsd", True, (0, 1), 4097, 312, 412)
 LARGE_CASES["stress_jsd_65536"] = cases._case(cases.STRESS, "jsd", True, (0, 1, 2, 3), 65536, 313, 413)
+LARGE_CASES["hbn_enc2_dec1_samplescale_4097"] = cases._case(cases.HBN, "joint_elbo", True, (0, 1), 4097, 314, 414, n_hidden_enc=2,
+                                                             n_hidden_dec=1, sample_scale=True)
 LARGE_CASES["stress_joint_elbo_13_4097"] = cases._case(cases.STRESS, "joint_elbo", True, (1, 3), 4097, 310, 410)
 LARGE_CASES["hbn_joint_elbo_nofact_1_1500"] = cases._case(cases.HBN, "joint_elbo", False, (1,), 1500, 311, 411)
 
@@ -181,7 +192,7 @@ def test_elbo_large_batches(name, train_impl):
     grads = torch.zeros_like(flat)
     sc = _run_step(spec, flat, batch, eps, 1, grads=grads)[0].cpu().numpy()
     torch.cuda.synchronize()
-    _ran(train_impl)
+    _ran(train_impl, spec)
     out, g, used = mo.elbo_and_grads(params, ospec, batch, eps)
     assert abs(sc[_lib.S_TOTAL_LOSS] - float(out["total_loss"])) <= RTOL * abs(float(out["total_loss"]))
     assert abs(sc[_lib.S_JOINT_DIV] - float(out["joint_divergence"])) <= RTOL * abs(float(out["joint_divergence"]))
@@ -200,6 +211,7 @@ def test_elbo_large_batches(name, train_impl):
 
 
 @pytest.mark.parametrize("name", ["hbn_joint_elbo_fact_01", "hbn_poe_fact_01", "hbn_moe_nofact_1", "hbn_jsd_fact_01",
+                                  "hbn_enc3_dec2_jsd_01", "hbn_samplescale_dec1_poe_01", "hbn_enc0_dec1_samplescale_laplace_jsd_01",
                                   "stress_joint_elbo_13", "hbn_joint_elbo_fact_01_fixedscale",
                                   "hbn_joint_elbo_4097", "stress_joint_elbo_1024", "hbn_poe_512"])
 def test_fused_adam_steps(name, train_impl):
@@ -241,7 +253,7 @@ def test_fused_adam_steps(name, train_impl):
     sc = engine.train_steps(spec, flat, data, bdev, steps, N, 2, row_index=row_index, eps=eps, adam_m=m_,
                             adam_v=v_, adam_t=t_, lr=lr).cpu().numpy()
     torch.cuda.synchronize()
-    _ran(train_impl)
+    _ran(train_impl, spec)
     got = engine.unpack_params(spec, flat)
     # (a) replay with the kernel's own gradients through the oracle Adam
     cur = flat0.clone()
@@ -255,8 +267,11 @@ def test_fused_adam_steps(name, train_impl):
         used = {k: (spec.mod_names[spec.modality_of_param(k)] in batches[s]) and mo.trainable(ospec, k) for k in oparams}
         oparams = oadam.step(oparams, gd, used)
         cur = engine.pack_params(spec, oparams, dev)
+    # (deeper networks: the replayed parameters differ from the kernel's own by rounding, and a hidden unit whose
+    # pre-activation sits within that rounding of zero flips relu' for a row -- Adam turns the resulting ~1e-8 gradient
+    # difference into ~1e-5 of a parameter through 1 / sqrt(v): layered architectures get 1e-4)
     for k in oparams:
-        _close(got[k], oparams[k], "adam replay " + k, rtol=1e-5)
+        _close(got[k], oparams[k], "adam replay " + k, rtol=1e-4 if spec.layered else 1e-5)
     assert t_.cpu().tolist()[:spec.n_mods] == [sum(n in b for b in batches) for n in spec.mod_names]
     # (b) independent oracle trajectory
     for s in range(steps):

@@ -52,8 +52,7 @@ def test_no_device_is_a_loud_error():
     assert b"no CUDA device" in _lib.lib().mopoe_last_error()
 
 
-@pytest.mark.parametrize("kw", [dict(num_hidden_layer_decoder=1), dict(num_hidden_layer_encoder=2),
-                                dict(learn_output_sample_scale=True), dict(latent_dim=64)])
+@pytest.mark.parametrize("kw", [dict(num_hidden_layer_decoder=5), dict(num_hidden_layer_encoder=-1), dict(latent_dim=64)])
 def test_unsupported_configurations_are_rejected(kw):
     with pytest.raises(_lib.MopoeError):
         mopoe_b200.PathSpec([7, 444], [3, 20], **kw)
@@ -63,7 +62,27 @@ def test_unsupported_method_and_likelihood():
     with pytest.raises(NotImplementedError):
         mopoe_b200.PathSpec([7, 444], [3, 20], method="mvae")
     with pytest.raises(NotImplementedError):
-        mopoe_b200.PathSpec([7, 444], [3, 20], likelihood="laplace")
+        mopoe_b200.PathSpec([7, 444], [3, 20], likelihood="bernoulli")
+
+
+def test_layered_architectures_keep_the_reference_state_dict_names():
+    """networks.py:9-28,44-64 with hidden-layer counts other than (1, 0) and learn_output_sample_scale: parameter names,
+    shapes and order equal the oracle's (pinned to the reference's state_dict by load_state_dict(strict=True) in
+    oracle/make_golden.py), blocks are disjoint."""
+    from oracle import mopoe_oracle as mo
+    for kw, okw in ((dict(num_hidden_layer_encoder=0, num_hidden_layer_decoder=2, learn_output_sample_scale=True),
+                     dict(n_hidden_enc=0, n_hidden_dec=2, sample_scale=True)),
+                    (dict(num_hidden_layer_encoder=3), dict(n_hidden_enc=3)),
+                    (dict(likelihood="laplace"), dict(likelihood="laplace"))):
+        spec = mopoe_b200.PathSpec([7, 444], [3, 20], **kw)
+        assert spec.layered
+        want = mo.param_shapes(mo.ModelSpec(**okw))
+        got = spec.param_slices()
+        assert list(got) == list(want)
+        assert all(tuple(got[k][1]) == tuple(want[k]) for k in want)
+        spans = sorted((off, off + int(np.prod(shape))) for off, shape in got.values())
+        assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] <= spec.layout.total
+    assert not mopoe_b200.PathSpec([7, 444], [3, 20]).layered
 
 
 def test_jsd_mixture_has_the_prior_component():
