@@ -44,7 +44,8 @@ class ParamLayout(C.Structure):
 class BatchDesc(C.Structure):
     _fields_ = [("n_rows", C.c_int32), ("present_mask", C.c_int32), ("n_mix", C.c_int32),
                 ("joint_bounds", C.c_int32 * (MAX_SUBSETS + 1)),
-                ("moe_bounds", (C.c_int32 * (MAX_MODS + 1)) * (MAX_MODS + 1)), ("row_offset", C.c_int64)]
+                ("moe_bounds", (C.c_int32 * (MAX_MODS + 1)) * (MAX_MODS + 1)), ("row_offset", C.c_int64),
+                ("owner_div", C.c_int32), ("owner_mod", C.c_int32)]
 
 
 class ForwardOut(C.Structure):

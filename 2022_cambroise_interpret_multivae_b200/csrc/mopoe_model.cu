@@ -362,15 +362,16 @@ __device__ void lat_forward(const ModelView& mv, const StepCtx& cx, const mopoe_
     float smu[MOPOE_MAX_MODS], slv[MOPOE_MAX_MODS];  // singleton posteriors (poe unimodal passes)
 #pragma unroll
     for (int m = 0; m < MOPOE_MAX_MODS; ++m) smu[m] = slv[m] = 0.f;
+    const int no = b.owner_mod ? (n / b.owner_div) % b.owner_mod : n;   // row of the selection pattern (mopoe_batch_desc)
     int kidx = 0, owner = 0;
     for (int k = 0; k < b.n_mix; ++k)
-      if (n >= b.joint_bounds[k] && n < b.joint_bounds[k + 1]) owner = k;
+      if (no >= b.joint_bounds[k] && no < b.joint_bounds[k + 1]) owner = k;
     LTP(1);
 #pragma unroll 1
     for (int s = 0; s < mv.sub.n_subsets; ++s) {
       const int mask = mv.sub.mask[s];
       if ((mask & present) != mask) continue;
-      const SubPost ev = sub_post(mv, b, s, n, mu_e, lv_e, ex, T, muT);
+      const SubPost ev = sub_post(mv, b, s, no, mu_e, lv_e, ex, T, muT);
       if (valid) {
         if (cx.out.subset_mu) cx.out.subset_mu[((int64_t)s * N + n) * L + l] = ev.mu;
         if (cx.out.subset_logvar) cx.out.subset_logvar[((int64_t)s * N + n) * L + l] = ev.lv;
@@ -516,16 +517,17 @@ __device__ void lat_backward(const ModelView& mv, const StepCtx& cx, const mopoe
         dmu[m] = dlv[m] = 0.f;
         if (on) gz += sh.dzz[((m * sh.NP + 0) * sh.R + r) * sh.ZDM + mv.mod[m].S + l];
       }
+      const int no = b.owner_mod ? (n / b.owner_div) % b.owner_mod : n;
       int kidx = 0, owner = 0;
       for (int k = 0; k < b.n_mix; ++k)
-        if (n >= b.joint_bounds[k] && n < b.joint_bounds[k + 1]) owner = k;
+        if (no >= b.joint_bounds[k] && no < b.joint_bounds[k + 1]) owner = k;
       // upstream gradients of each subset posterior (mixture KL share, reparameterised z of the owner rows,
       // unimodal ELBO in poe mode) distributed to the experts (hand-derived)
 #pragma unroll 1
       for (int s = 0; s < mv.sub.n_subsets; ++s) {
         const int mask = mv.sub.mask[s];
         if ((mask & present) != mask) continue;
-        const SubPost ev = sub_post(mv, b, s, n, mu_e, lv_e, ex, T, muT);
+        const SubPost ev = sub_post(mv, b, s, no, mu_e, lv_e, ex, T, muT);
         const int nm = mv.sub.n_members[s];
         float umu = 0.f, ulv = 0.f;
         const float dkl_lv = 0.5f * (ev.var - 1.f);
@@ -1233,7 +1235,8 @@ static int validate_batch(const mopoe_model_desc* d, const mopoe_batch_desc* b) 
   if (b->n_rows < 1) { set_error("n_rows=%d", b->n_rows); return MOPOE_EINVAL; }
   if (b->present_mask <= 0 || b->present_mask >= (1 << d->n_mods)) { set_error("present_mask=%d invalid", b->present_mask); return MOPOE_EINVAL; }
   if (b->n_mix < 1 || b->n_mix > MOPOE_MAX_SUBSETS) { set_error("n_mix=%d invalid", b->n_mix); return MOPOE_EINVAL; }
-  if (b->joint_bounds[0] != 0 || b->joint_bounds[b->n_mix] != b->n_rows) { set_error("joint_bounds do not span the batch"); return MOPOE_EINVAL; }
+  if (b->owner_mod < 0 || (b->owner_mod > 0 && b->owner_div < 1)) { set_error("owner_div=%d owner_mod=%d invalid", b->owner_div, b->owner_mod); return MOPOE_EINVAL; }
+  if (b->joint_bounds[0] != 0 || b->joint_bounds[b->n_mix] != (b->owner_mod ? b->owner_mod : b->n_rows)) { set_error("joint_bounds do not span the batch"); return MOPOE_EINVAL; }
   return MOPOE_OK;
 }
 

@@ -39,6 +39,13 @@ def daa_sweep(spec: PathSpec, flat_params, src, dst, n_samples, n_base, *, src_m
       a shared first / last validation are another rank's.  Default: every unit.
     Returns a DaaResult with CUDA tensors avatars (or None), sampled_scores, reconstructions,
     betas (or None), coefs, pvalues."""
+    if spec.n_hidden_enc != 1 or spec.n_hidden_dec != 0 or spec.learn_output_sample_scale:
+        if base_mean != "draws" or unit_end is not None or others is not None:
+            raise NotImplementedError("layered architectures: base_mean='draws', whole validations, two modalities")
+        return daa_sweep_layered(spec, flat_params, src, dst, n_samples, n_base, src_mod=src_mod, dst_mod=dst_mod,
+                                 sample_latents=sample_latents, reg_method=reg_method, seed=seed, val_begin=val_begin,
+                                 eps_base=eps_base, eps_score=eps_score, eps_av=eps_av, scores=scores,
+                                 materialize=materialize, workspace=workspace)
     if base_mean not in ("draws", "direct"):
         raise ValueError("base_mean=%r (draws, direct)" % (base_mean,))
     if base_mean == "direct" and eps_base is not None:
@@ -107,10 +114,85 @@ def daa_sweep(spec: PathSpec, flat_params, src, dst, n_samples, n_base, *, src_m
     return r
 
 
+def daa_sweep_layered(spec: PathSpec, flat_params, src, dst, n_samples, n_base, *, src_mod=0, dst_mod=1,
+                      sample_latents=True, reg_method="hierarchical", seed=1037, val_begin=0, eps_base=None,
+                      eps_score=None, eps_av=None, scores=None, materialize=True, workspace=None):
+    """The DAA sweep for the architectures of the layered path (hidden decoder layers make the decoder non-affine and
+    a per-sample output scale is not a constant: the shortcuts of the fused sweep -- mean noise row of the base passes,
+    slopes by linearity from z -- do not apply).  Per validation TWO forward launches of the C-ABI forward:
+      * the M base passes as one batch of M * N rows (workflow.py:388-398), then their mean over M;
+      * the n_samples x n_scores perturbed forwards as one batch of N * C * J rows in the avatar tensor's own
+        (subject, score, sample) order (workflow.py:406-419),
+    each row selecting its mixture component like the row of the N-subject batch it stands for (batch desc
+    owner_div / owner_mod); then the regression kernels read the materialised tensor (`daa_regression`).
+    Same arguments / result as `daa_sweep`; the generator noise is keyed by (seed, global validation, stage)."""
+    from . import engine
+    if reg_method not in REG_METHODS:
+        raise NotImplementedError("reg_method=%r is not on the B200 path (hierarchical, fixed)" % (reg_method,))
+    if not materialize:
+        raise NotImplementedError("the layered sweep regresses on the materialised avatar tensor")
+    if spec.n_mods != 2:
+        raise NotImplementedError("the layered sweep covers the reference's two-modality cohorts")
+    _require_cuda(flat_params, "parameters")
+    src, dst = _f32(src), _f32(dst)
+    _require_cuda(src, "src")
+    _require_cuda(dst, "dst")
+    device = flat_params.device
+    n_val, N, Cc = src.shape
+    R, J, M, E = dst.shape[2], int(n_samples), int(n_base), spec.eps_width
+    sname, dname = spec.mod_names[src_mod], spec.mod_names[dst_mod]
+    if scores is not None and eps_score is not None:
+        raise ValueError("scores and eps_score are exclusive")
+    ws = workspace or Workspace()
+    f = lambda dt, *s: torch.empty(*s, dtype=dt, device=device)
+    r = DaaResult()
+    r.avatars = f(torch.float32, n_val, N, Cc, J, R)
+    r.sampled_scores = f(torch.float32, n_val, N, J, Cc)
+    r.reconstructions = f(torch.float32, n_val, N, R)
+    for v in range(n_val):
+        key = (int(seed) * 1000003 + (val_begin + v)) & 0x7FFFFFFFFFFFFFFF
+        # ---- M stochastic reconstructions (rows (pass, subject)) and their mean ----
+        base = {sname: src[v].repeat(M, 1), dname: dst[v].repeat(M, 1)}
+        eb = _f32(eps_base[v]).reshape(M * N, E) if eps_base is not None else None
+        res = engine.forward(spec, flat_params, base, eps=eb, seed=3 * key, sample_latents=True, workspace=ws, owner=(1, N))
+        loc_hat = res.rec_loc[src_mod].view(M, N, Cc).mean(0)
+        lv = res.rec_logvar[src_mod] if spec.learn_output_sample_scale else flat_params[spec.layout.dec_lv[src_mod]:][:Cc].expand(M * N, Cc)
+        scale_hat = (0.5 * lv).exp().view(M, N, Cc).mean(0)
+        r.reconstructions[v] = res.rec_loc[dst_mod].view(M, N, R).mean(0)
+        # ---- artificial scores (J, N, C) ----
+        if scores is not None:
+            sc = _f32(scores[v])
+        else:
+            if eps_score is not None:
+                es = _f32(eps_score[v])
+            else:
+                es = f(torch.float32, J, N, Cc)
+                _lib.check(_lib.lib().mopoe_philox_normal(3 * key + 1, _lib.STREAM_DAA_SCORE, 0, es.numel(), _ptr(es), _stream()))
+            sc = loc_hat + scale_hat * es                                   # Normal(loc_hat, scale_hat).sample, workflow.py:401-405
+        r.sampled_scores[v] = sc.permute(1, 0, 2)
+        # ---- one perturbed forward per (subject, score, sample), rows in that order ----
+        cdata = src[v][:, None, None, :].expand(N, Cc, J, Cc).clone()
+        idx = torch.arange(Cc, device=device)
+        cdata[:, idx, :, idx] = sc.permute(2, 1, 0)                          # [c, n, j] -> column c of rows (n, c, j)
+        pert = {sname: cdata.view(N * Cc * J, Cc), dname: dst[v][:, None, :].expand(N, Cc * J, R).reshape(N * Cc * J, R)}
+        ea = None
+        if sample_latents and eps_av is not None:
+            ea = _f32(eps_av[v]).permute(2, 1, 0, 3).reshape(N * Cc * J, E)   # (J, C, N, E) -> rows (n, c, j)
+        res = engine.forward(spec, flat_params, pert, eps=ea, seed=3 * key + 2, sample_latents=sample_latents, workspace=ws,
+                             owner=(Cc * J, N))
+        r.avatars[v] = res.rec_loc[dst_mod].view(N, Cc, J, R)
+    r.pvalues, r.coefs, r.betas = daa_regression(r.avatars, r.sampled_scores, r.reconstructions, reg_method=reg_method)
+    r._keep, r._desc = (ws,), None
+    return r
+
+
 def check_status(spec: PathSpec, result):
     """Synchronise and raise MopoeError if the sweep that produced `result` flagged a device-side protocol error
     (a bounded tcgen05 / mbarrier wait timed out; the kernels then poison the tables with NaN rather than hang).
     Callers that persist results (workflow.daa_exp) call this before writing anything."""
+    if result._desc is None:          # layered sweep: no bounded device-side waits to report on
+        torch.cuda.synchronize()
+        return result
     _lib.check(_lib.lib().mopoe_daa_status(C.byref(spec.desc), C.byref(result._desc), _ptr(result._keep[-1]), _stream()))
     return result
 

@@ -109,8 +109,9 @@ class ForwardResult:
 
 
 def forward(spec: PathSpec, flat_params, batch, eps=None, seed=0, sample_latents=True, use_expert=None,
-            with_nll=False, workspace=None):
-    """BaseMMVae.forward on the GPU.  batch: dict name -> (N, D_m) CUDA tensor (present only)."""
+            with_nll=False, workspace=None, owner=None):
+    """BaseMMVae.forward on the GPU.  batch: dict name -> (N, D_m) CUDA tensor (present only).
+    owner=(div, P): the N rows are P-row reference batches laid out side by side (see PathSpec.batch_desc)."""
     _require_cuda(flat_params, "parameters")
     device = flat_params.device
     mask = spec.present_mask(batch.keys())
@@ -119,7 +120,7 @@ def forward(spec: PathSpec, flat_params, batch, eps=None, seed=0, sample_latents
         if x is not None:
             _require_cuda(x, "input batch")
     n_rows = next(x for x in xs if x is not None).shape[0]
-    bd = spec.batch_desc(n_rows, mask)
+    bd = spec.batch_desc(n_rows, mask, owner=owner)
     if eps is not None:
         eps = _f32(eps)
         assert eps.shape == (n_rows, spec.eps_width), (eps.shape, (n_rows, spec.eps_width))

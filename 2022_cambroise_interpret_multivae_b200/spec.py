@@ -161,18 +161,22 @@ class PathSpec:
     def layout(self):
         return self._layout
 
-    def batch_desc(self, n_rows, present_mask, row_offset=0):
+    def batch_desc(self, n_rows, present_mask, row_offset=0, owner=None):
+        """owner=(div, P): the rows are P-row reference batches side by side, row n selects its mixture component like
+        row (n // div) % P of a P-row batch (include/mopoe_b200.h: mopoe_batch_desc.owner_div / owner_mod)."""
         b = _lib.BatchDesc()
         b.n_rows = int(n_rows)
         b.present_mask = int(present_mask)
         _, mix = self.mixture_subsets(present_mask)
         b.n_mix = len(mix) + (1 if self.method == "jsd" else 0)     # jsd: + the prior component (BaseMMVae.py:217-223)
-        for i, v in enumerate(selection_bounds(n_rows, b.n_mix)):
+        n_sel = int(owner[1]) if owner else int(n_rows)
+        for i, v in enumerate(selection_bounds(n_sel, b.n_mix)):
             b.joint_bounds[i] = v
         for k in range(1, self.n_mods + 1):
-            for i, v in enumerate(selection_bounds(n_rows, k)):
+            for i, v in enumerate(selection_bounds(n_sel, k)):
                 b.moe_bounds[k][i] = v
         b.row_offset = int(row_offset)
+        b.owner_div, b.owner_mod = (int(owner[0]), int(owner[1])) if owner else (0, 0)
         return b
 
     @property

@@ -115,6 +115,12 @@ typedef struct mopoe_batch_desc {
   int32_t moe_bounds[MOPOE_MAX_MODS + 1][MOPOE_MAX_MODS + 1]; /* [k][0..k]: selection inside a
                                                k-member subset (method = moe only) */
   int64_t row_offset;                       /* first entry of this batch in `row_index` */
+  int32_t owner_div, owner_mod;             /* 0, 0: row n selects its mixture component by its own index (the reference's
+                                               batches).  owner_mod = P > 0: the rows are P-row batches of the reference laid
+                                               out side by side -- row n behaves like row (n / owner_div) % P of a P-row batch
+                                               (the bounds then span P rows).  One launch can so carry the M base passes or the
+                                               n_samples x n_scores perturbed forwards of a DAA validation (daa.py:
+                                               daa_sweep_layered).  Noise and outputs stay indexed by n. */
 } mopoe_batch_desc;
 
 /* Outputs of one forward pass == the `results` dict of BaseMMVae.forward (BaseMMVae.py:137-165).

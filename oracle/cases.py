@@ -80,6 +80,10 @@ DAA_CASES = {
                      n_samples=4, sample_latents=False),
     "jsd": dict(_case(HBN, "jsd", True, (0, 1), 30, 73, 173), n_val=1, n_base=3,
                 n_samples=4, sample_latents=True),
+    "dec1_samplescale": dict(_case(HBN, "joint_elbo", True, (0, 1), 18, 74, 174, n_hidden_dec=1, sample_scale=True),
+                             n_val=2, n_base=4, n_samples=5, sample_latents=True),
+    "enc2_moe_mean": dict(_case(HBN, "moe", True, (0, 1), 16, 75, 175, n_hidden_enc=2), n_val=1, n_base=3,
+                          n_samples=4, sample_latents=False),
 }
 
 

@@ -320,3 +320,54 @@ def test_daa_exp_two_ranks_write_the_same_files_as_one(tmp_path, J):
     a = np.load(os.path.join(res1, "all_coefs.npy"), allow_pickle=True)
     b = np.load(os.path.join(res2, "all_coefs.npy"), allow_pickle=True)
     assert a.shape == b.shape and bool((a == b).all())
+
+
+def test_layered_architecture_through_the_drop_in_model_and_workflow(tmp_path):
+    """num_hidden_layer_decoder=1 + out_scale_per_subject (networks.py:51-59) end to end: state-dict names of the
+    reference, per-sample scales in results['rec'], basic_routine_epoch gradients vs the oracle, then train_exp -> daa_exp
+    (layered sweep: hidden decoder layers make the decoder non-affine) with the statistics recomputed from the files."""
+    from mopoe_b200 import data, run_epochs, workflow
+    from mopoe_b200.model import VAE
+    flags = _flags("joint_elbo")
+    flags.num_hidden_layer_decoder, flags.learn_output_sample_scale = 1, True
+    mods = {"clinical": SimpleNamespace(name="clinical"), "rois": SimpleNamespace(name="rois")}
+    model = VAE(flags, mods).cuda()
+    ospec = mo.ModelSpec(method="joint_elbo", n_hidden_dec=1, sample_scale=True)
+    params = mo.init_params(ospec, seed=21)
+    assert list(model.state_dict().keys()) == list(params.keys())
+    model.load_state_dict(params, strict=True)
+    g = torch.Generator().manual_seed(6)
+    batch = {"clinical": torch.randn(80, 7, generator=g), "rois": torch.randn(80, 444, generator=g)}
+    eps = torch.randn(1, 80, ospec.eps_width, generator=g)
+    model.inject_noise(eps[0])
+    res = model({k: v.cuda() for k, v in batch.items()})
+    with torch.no_grad():
+        want = mo.forward(params, ospec, batch, eps[0])
+    assert res["rec"]["rois"].scale.shape == (80, 444)
+    assert torch.allclose(res["rec"]["rois"].scale.cpu(), want["rec"]["rois"][1], rtol=1e-4)
+    assert torch.allclose(res["rec"]["clinical"].loc.cpu(), want["rec"]["clinical"][0], rtol=0, atol=RTOL * float(want["rec"]["clinical"][0].abs().max()))
+    exp = SimpleNamespace(models=model, flags=model.flags)
+    model.inject_noise(eps)
+    out = run_epochs.basic_routine_epoch(exp, 0, ({k: v.clone() for k, v in batch.items()}, None, None))
+    out["total_loss"].backward()
+    w, grads, used = mo.elbo_and_grads(params, ospec, batch, eps)
+    assert abs(float(out["total_loss"]) - float(w["total_loss"])) <= RTOL * abs(float(w["total_loss"]))
+    for k, p in model.named_parameters():
+        err = float((p.grad.cpu() - grads[k]).abs().max() / (grads[k].abs().max() + 1e-30))
+        assert err <= RTOL, (k, err)
+    # workflow
+    ds, out_dir = str(tmp_path / "data"), str(tmp_path / "out")
+    os.makedirs(out_dir)
+    data.write_dataset(ds, data.make_cohort(n_both=480, n_clinical_only=64, n_rois_only=32, standardize=False))
+    run = workflow.train_exp("hbn", ds, out_dir, [7, 444], num_epochs=5, batch_size=128, num_hidden_layer_decoder=1,
+                             out_scale_per_subject=True, data_seed=4)
+    tr = np.load(os.path.join(out_dir, run, "logs", "scalars_train_model0.npy"))
+    assert np.isfinite(tr).all() and tr[-1, 0] < tr[0, 0]
+    sd = torch.load(os.path.join(out_dir, run, "checkpoints", "0004", "model"))
+    assert list(sd.keys()) == list(params.keys())
+    resdir = workflow.daa_exp("hbn", ds, out_dir, run, n_validation=2, n_samples=8, n_subjects=16, M=12, trust_level=0.5)
+    av = np.load(os.path.join(resdir, "rois_digital_avatars.npy"))
+    sc = np.load(os.path.join(resdir, "sampled_scores.npy"))
+    assert av.shape == (2, 16, 7, 8, 444) and np.isfinite(av).all()
+    pw, cw, _ = daa_oracle.hierarchical_regression(av, sc)
+    assert np.allclose(np.load(os.path.join(resdir, "coefs.npy")), cw, rtol=1e-9, atol=1e-12)
