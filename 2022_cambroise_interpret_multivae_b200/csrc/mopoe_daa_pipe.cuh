@@ -486,7 +486,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
             // to the copy engine (3-D map (column, row inside the validation, validation): rows past the end of a
             // validation and columns past R are clipped by the hardware).  No LDS / STG on the LSU path that the
             // producers' shared-memory traffic uses.
+#ifndef PK_EXP_NOWAIT   // experiment (WRONG results): the gain an unbounded stage ring could give at most
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous box has left the stage
+#endif
             __syncwarp();
             {
               unsigned char* rowp = reinterpret_cast<unsigned char*>(s_stage) + lane * 128;

@@ -40,8 +40,9 @@ def daa_sweep(spec: PathSpec, flat_params, src, dst, n_samples, n_base, *, src_m
     Returns a DaaResult with CUDA tensors avatars (or None), sampled_scores, reconstructions,
     betas (or None), coefs, pvalues."""
     if spec.n_hidden_enc != 1 or spec.n_hidden_dec != 0 or spec.learn_output_sample_scale:
-        if base_mean != "draws" or unit_end is not None or others is not None:
-            raise NotImplementedError("layered architectures: base_mean='draws', whole validations, two modalities")
+        if base_mean != "draws" or others is not None:
+            raise NotImplementedError("layered architectures: base_mean='draws', two modalities")
+        # (a unit range is honoured trivially: the layered sweep computes whole validations, the owned rows are among them)
         return daa_sweep_layered(spec, flat_params, src, dst, n_samples, n_base, src_mod=src_mod, dst_mod=dst_mod,
                                  sample_latents=sample_latents, reg_method=reg_method, seed=seed, val_begin=val_begin,
                                  eps_base=eps_base, eps_score=eps_score, eps_av=eps_av, scores=scores,
