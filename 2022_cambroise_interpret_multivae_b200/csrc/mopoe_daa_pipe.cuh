@@ -372,8 +372,13 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
           } else {
             // two independent Philox chains (draws past the end of the section are unused)
             const uint64_t blk = (uint64_t)(ridx * nbrow + ((content ? 0 : mdst.peps_off) + l0) / 4);
+#ifdef PK_EXP_NONOISE    // experiment (WRONG results): what the generator costs on the kernel's critical path
+#pragma unroll
+            for (int k = 0; k < 8; ++k) e[k] = __uint_as_float(0x3e000000u | (((uint32_t)blk + k) & 0xffffu));
+#else
             philox_normal4(cx.nz_av, blk, e);
             philox_normal4(cx.nz_av, blk + 1, e + 4);
+#endif
           }
           const bool heads = content && tile_need;
           float hm[8], hl[8];
