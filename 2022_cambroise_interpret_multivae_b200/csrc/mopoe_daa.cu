@@ -131,6 +131,7 @@ __device__ bool series_owner(const ModelView& mv, const DaaCtx& cx, int g, int& 
   s_own = 0;
   for (int k = 0; k < cx.b.n_mix; ++k)
     if (g >= cx.b.joint_bounds[k] && g < cx.b.joint_bounds[k + 1]) owner = k;
+  if (prior_component(mv, cx.b, owner)) { s_own = -1; return false; }   // jsd: the row samples z from the prior N(0, I)
   for (int s = 0; s < mv.sub.n_subsets; ++s) {
     if (!in_mixture(mv, cx.b, s)) continue;
     if (kidx == owner) s_own = s;
@@ -178,7 +179,9 @@ __device__ void series_records(const ModelView& mv, const DaaCtx& cx, const DaaW
     const int sec = i >> 5, k = i & 31;                 // sections: other precisions | other mu*T | style mu | style sd
     if (sec < 2 && k < L) {
       float A = 0.f, B = 0.f;
-      if (mv.method == MOPOE_METHOD_MOE) {
+      if (so < 0) {                                     // owned by the prior component (jsd): finished posterior (0, 1)
+        A = 0.f; B = 1.f;
+      } else if (moe_like(mv)) {
         const int m = mv.sub.members[so][0];
         A = ws.enc[m][row * mv.mod[m].HC + k];
         B = expf(0.5f * ws.enc[m][row * mv.mod[m].HC + L + k]);
@@ -1012,10 +1015,10 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
   const bool pipe_ok = umma_ok && daa->reg_method == 0 && daa->sample_latents && ud0.bias_slot >= 0 && ud0.KZ - ud0.KC <= 32 &&
                        pk_smem <= 227 * 1024 && (int64_t)n_units * cx.J < ((int64_t)1 << 31);
   int impl = pipe_ok ? 2 : (umma_ok ? 1 : 0);
-  if (desc->method == MOPOE_METHOD_JSD) impl = 0;     // prior-owned rows are handled by the CUDA-core kernel only
+  if (desc->method == MOPOE_METHOD_JSD) impl = pipe_ok ? 2 : 0;   // prior-owned rows: pipelined and CUDA-core kernels only
   const char* force = getenv("MOPOE_DAA_IMPL");
   if (force && !strcmp(force, "ffma")) impl = 0;
-  if (force && desc->method == MOPOE_METHOD_JSD && strcmp(force, "ffma")) { set_error("MOPOE_DAA_IMPL=%s: method jsd runs on the CUDA-core avatar kernel only", force); return MOPOE_EINVAL; }
+  if (force && desc->method == MOPOE_METHOD_JSD && !strcmp(force, "umma")) { set_error("MOPOE_DAA_IMPL=umma: method jsd runs on the pipelined and the CUDA-core avatar kernels"); return MOPOE_EINVAL; }
   if (force && !strcmp(force, "umma")) { if (!umma_ok) { set_error("MOPOE_DAA_IMPL=umma but the shapes do not fit the tcgen05 tiling"); return MOPOE_EINVAL; } impl = 1; }
   if (force && !strcmp(force, "pipe")) { if (!pipe_ok) { set_error("MOPOE_DAA_IMPL=pipe but the configuration does not fit the pipelined kernel"); return MOPOE_EINVAL; } impl = 2; }
   g_last_impl = impl;

@@ -153,12 +153,13 @@ __device__ __forceinline__ int pk_owner_subset(const ModelView& mv, const DaaCtx
   int owner = 0, kidx = 0, s_own = 0;
   for (int k = 0; k < cx.b.n_mix; ++k)
     if (g >= cx.b.joint_bounds[k] && g < cx.b.joint_bounds[k + 1]) owner = k;
+  if (prior_component(mv, cx.b, owner)) { need_src = false; return 0x7f; }   // jsd: z from the prior, cached posterior (0, 1)
   for (int s = 0; s < mv.sub.n_subsets; ++s) {
     if (!in_mixture(mv, cx.b, s)) continue;
     if (kidx == owner) s_own = s;
     ++kidx;
   }
-  need_src = ((mv.sub.mask[s_own] >> cx.q.src_mod) & 1) || (mv.method == MOPOE_METHOD_MOE && mv.sub.n_members[s_own] > 1);
+  need_src = ((mv.sub.mask[s_own] >> cx.q.src_mod) & 1) || (moe_like(mv) && mv.sub.n_members[s_own] > 1);
   return s_own;
 }
 
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
             if (heads) {        // warp-uniform; rows that do not need the src expert keep the cached posterior
               const float m_ = hm[k] + s_biash[l0 + k], lv = hl[k] + s_biash[L + l0 + k];
               float mu2, sd2;
-              if (mv.method == MOPOE_METHOD_MOE) { mu2 = m_; sd2 = pk_ex2(0.5f * 1.4426950408889634f * lv); }
+              if (moe_like(mv)) { mu2 = m_; sd2 = pk_ex2(0.5f * 1.4426950408889634f * lv); }
               else {
                 // poe (mm_div.py:13-20) in MUFU arithmetic: T = 1/(exp(lv)+eps), var = 1/sum T
                 const float T = pk_rcp(pk_ex2(1.4426950408889634f * lv) + MOPOE_POE_EPS);

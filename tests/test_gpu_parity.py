@@ -484,6 +484,7 @@ def test_daa_tensor_core_kernel_vs_oracle_and_cuda_core_kernel(kw, monkeypatch):
 
 
 @pytest.mark.parametrize("kw", [dict(), dict(method="moe", factorized=False), dict(method="poe", n_samples=131),
+                                dict(method="jsd", n_rows=10, n_samples=130), dict(method="jsd", factorized=False, n_rows=50, n_val=2),
                                 dict(n_rows=50, n_val=3, n_samples=150), dict(dims=(7, 445), n_rows=9),
                                 dict(dims=(5, 900), n_rows=7, n_val=1, n_samples=140), dict(n_rows=3, n_val=1, n_samples=128)])
 def test_daa_pipelined_kernel_vs_oracle_and_cuda_core_kernel(kw, monkeypatch):
