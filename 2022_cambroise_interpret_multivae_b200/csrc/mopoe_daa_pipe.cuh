@@ -36,8 +36,15 @@
 namespace mopoe {
 
 constexpr int PK_ROWS = 128;
-constexpr int PK_NCH = 96;             // decoder columns per accumulator buffer
-constexpr int PK_MAXCH = 5;            // chunks per launch
+#ifndef PK_NCH_
+#define PK_NCH_ 96
+#define PK_MAXCH_ 5
+#define PK_ACC_BUFS_ 2
+#endif
+constexpr int PK_NCH = PK_NCH_;        // decoder columns per accumulator buffer (a multiple of 32, <= 256)
+constexpr int PK_MAXCH = PK_MAXCH_;    // chunks per launch
+constexpr int PK_ACC_BUFS = PK_ACC_BUFS_;   // accumulator buffers in TMEM: 2 = ping-pong between the decoder MMAs and the epilogue
+static_assert(PK_NCH % 32 == 0 && PK_NCH <= 256 && 320 + PK_ACC_BUFS * PK_NCH <= 512, "accumulators do not fit the TMEM plan");
 constexpr int PK_CBP = PK_NCH * PK_MAXCH;   // 480 decoder columns per launch
 #ifndef PK_NPW_
 #define PK_NPW_ 3
@@ -469,12 +476,12 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
       const int tile_v = tile_row / rpv, row_in_val = tile_row - tile_v * rpv + q4 * 32;
 #pragma unroll 1
       for (int ch = 0; ch < n_chunks; ++ch, ++q) {
-        const int b = q & 1;
+        const int b = PK_ACC_BUFS == 2 ? (q & 1) : 0;
         PK_T(1);
-        pk_wait(bar_acc_full + b, (q >> 1) & 1, s_abort);
+        pk_wait(bar_acc_full + b, (PK_ACC_BUFS == 2 ? (q >> 1) : q) & 1, s_abort);
         PK_T(0);
         tc_fence_after();
-        const int nsub = min(3, (ncol - ch * PK_NCH + 31) >> 5);
+        const int nsub = min(PK_NCH / 32, (ncol - ch * PK_NCH + 31) >> 5);
 #pragma unroll 1
         for (int sub = 0; sub < nsub; ++sub) {
           const int cb0 = ch * PK_NCH + sub * 32;
@@ -598,9 +605,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
         const uint32_t az_hi = smem_u32(s_az + (i & 1) * 2 * AZ_PLANE), az_lo = az_hi + AZ_PLANE;
 #pragma unroll 1
         for (int ch = 0; ch < n_chunks; ++ch, ++q) {
-          const int b = q & 1;
+          const int b = PK_ACC_BUFS == 2 ? (q & 1) : 0;
           PK_T(2);
-          pk_wait(bar_acc_empty + b, ((q >> 1) & 1) ^ 1, s_abort);
+          pk_wait(bar_acc_empty + b, ((PK_ACC_BUFS == 2 ? (q >> 1) : q) & 1) ^ 1, s_abort);
           PK_T(1);
           tc_fence_after();
           const uint32_t dcol = tmem + PK_TM_ACC + b * PK_NCH;
