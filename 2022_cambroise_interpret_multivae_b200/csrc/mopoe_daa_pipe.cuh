@@ -44,7 +44,12 @@ constexpr int PK_ROWS = 128;
 constexpr int PK_NCH = PK_NCH_;        // decoder columns per accumulator buffer (a multiple of 32, <= 256)
 constexpr int PK_MAXCH = PK_MAXCH_;    // chunks per launch
 constexpr int PK_ACC_BUFS = PK_ACC_BUFS_;   // accumulator buffers in TMEM: 2 = ping-pong between the decoder MMAs and the epilogue
-static_assert(PK_NCH % 32 == 0 && PK_NCH <= 256 && 320 + PK_ACC_BUFS * PK_NCH <= 512, "accumulators do not fit the TMEM plan");
+#ifndef PK_Z_TMEM
+#define PK_Z_TMEM 0                    // 1: the hi plane of z (A operand of the decoder GEMM) lives in TMEM, double buffered
+#endif                                 //    (needs 48 free columns behind the accumulators: 64-column chunks)
+constexpr int PK_TM_AZ = 320 + PK_ACC_BUFS * PK_NCH;   // [2][KZ / 2] packed fp16 pairs of z_hi (PK_Z_TMEM)
+static_assert(PK_NCH % 32 == 0 && PK_NCH <= 256 && 320 + PK_ACC_BUFS * PK_NCH + (PK_Z_TMEM ? 64 : 0) <= 512,
+              "accumulators (and the z operand) do not fit the TMEM plan");
 constexpr int PK_CBP = PK_NCH * PK_MAXCH;   // 480 decoder columns per launch
 #ifndef PK_NPW_
 #define PK_NPW_ 3
@@ -434,7 +439,13 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
               zq[k] = __half2float(h8[k]) + __half2float(l8[k]);
             }
             const uint32_t off = core_off(r, ci, PK_ROWS);
+#if PK_Z_TMEM
+            // hi plane -> TMEM (lane = row, 32-bit column = 2 consecutive latents): read by two of the three MMA passes
+            // of every chunk without touching shared memory
+            tmem_st4(lane_addr + PK_TM_AZ + (i & 1) * 32 + ci * 4, reinterpret_cast<const uint32_t*>(h8));
+#else
             *reinterpret_cast<uint4*>(az_hi + off) = *reinterpret_cast<const uint4*>(h8);
+#endif
             *reinterpret_cast<uint4*>(az_lo + off) = *reinterpret_cast<const uint4*>(l8);
           }
           // regression sums of this warp's 32 rows (series uA and, past a boundary, uA + 1)
@@ -452,6 +463,10 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
         if (tile_need && !waited) { pk_wait(bar_heads_done, heads_waits & 1, s_abort); ++heads_waits; }
       }
       PK_T(4);
+#if PK_Z_TMEM
+      tmem_st_wait();
+      tc_fence_before();
+#endif
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) pk_arrive(bar_z_full + (i & 1));
@@ -615,8 +630,15 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
             const uint32_t oa = ks * 2 * LBO_A, ob = ks * 2 * LBO_BD + ch * (PK_NCH / 8) * 128;
             const uint64_t dah = smem_desc(az_hi + oa, LBO_A, 128), dal = smem_desc(az_lo + oa, LBO_A, 128);
             const uint64_t dbh = smem_desc(smem_u32(s_bd_hi) + ob, LBO_BD, 128), dbl = smem_desc(smem_u32(s_bd_lo) + ob, LBO_BD, 128);
+#if PK_Z_TMEM
+            const uint32_t tah = tmem + PK_TM_AZ + (i & 1) * 32 + ks * 8;
+            mma_f16_ts(dcol, tah, dbh, idesc_d, ks ? 1u : 0u);
+            mma_f16_ts(dcol, tah, dbl, idesc_d, 1u);
+            (void)dah;
+#else
             mma_f16(dcol, dah, dbh, idesc_d, ks ? 1u : 0u);
             mma_f16(dcol, dah, dbl, idesc_d, 1u);
+#endif
             mma_f16(dcol, dal, dbh, idesc_d, 1u);
           }
           mma_commit(bar_acc_full + b);
