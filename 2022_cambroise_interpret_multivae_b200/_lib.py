@@ -114,8 +114,6 @@ def lib():
                                   vp, vp, vp, u64, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     L.mopoe_daa_regression.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.mopoe_philox_normal.argtypes = [u64, u64, i64, i64, vp, vp]
-    L.mopoe_umma_selftest.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
-    L.mopoe_umma_selftest.restype = C.c_int
     L.mopoe_daa_last_impl.restype = C.c_int
     L.mopoe_table_exchange_bytes.argtypes = [i64]
     L.mopoe_table_exchange_bytes.restype = i64
@@ -143,6 +141,24 @@ def lib():
     return L
 
 
+SELFTEST_LIB_PATH = os.path.join(os.path.dirname(LIB_PATH), "libmopoe_b200_selftest.so")
+_selftest = None
+
+
+def selftest_lib():
+    """libmopoe_b200_selftest.so: the tcgen05 building-block self-test (test-only, not part of the product library)."""
+    global _selftest
+    if _selftest is None:
+        if not os.path.isfile(SELFTEST_LIB_PATH):
+            raise MopoeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % SELFTEST_LIB_PATH)
+        T = C.CDLL(SELFTEST_LIB_PATH)
+        T.mopoe_umma_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        T.mopoe_umma_selftest.restype = C.c_int
+        T.mopoe_last_error.restype = C.c_char_p
+        _selftest = T
+    return _selftest
+
+
 def check(rc):
     if rc != 0:
         raise MopoeError("libmopoe_b200: error %d: %s" % (rc, lib().mopoe_last_error().decode()))
@@ -151,6 +167,6 @@ def check(rc):
 EXPORTED = ["mopoe_last_error", "mopoe_version", "mopoe_device_count", "mopoe_param_layout_of",
             "mopoe_workspace_bytes", "mopoe_forward", "mopoe_train_steps", "mopoe_daa_workspace_bytes",
             "mopoe_daa_sweep", "mopoe_daa_regression", "mopoe_philox_normal", "mopoe_profile_enable",
-            "mopoe_daa_last_kernel_ms", "mopoe_umma_selftest", "mopoe_daa_last_impl", "mopoe_daa_read_phases",
+            "mopoe_daa_last_kernel_ms", "mopoe_daa_last_impl", "mopoe_daa_read_phases",
             "mopoe_daa_status", "mopoe_train_last_impl", "mopoe_table_exchange_bytes", "mopoe_daa_exchange_tables",
             "mopoe_rsa_cmat", "mopoe_rsa_kendall_workspace_bytes", "mopoe_rsa_kendall"]

@@ -324,11 +324,6 @@ int mopoe_daa_last_kernel_ms(float* ms_out);
 int mopoe_philox_normal(uint64_t seed, uint64_t stream_id, int64_t start, int64_t n, float* out,
                         void* stream);
 
-/* Self-test of the tcgen05 building blocks: one CTA computes D[128][N] = A[128][K] * B[N][K]^T on
- * the tensor cores with the 3xFP16 split the DAA kernel uses (N%16==0, K%16==0). */
-int mopoe_umma_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t variant,
-                        int32_t* err_flag, void* stream);
-
 /* ---- representational similarity analysis (experiments/workflow.py:656-789 rsa_exp) ----
  * mopoe_rsa_cmat: stat_utils.py:25-33 data2cmat (categorical = 0: Euclidean distances of the n rows of `data` (n, d),
  *   fp64, summed in column order like scipy's pdist) or stat_utils.py:46-53 vec2cmat (d = 1; categorical = 1: the

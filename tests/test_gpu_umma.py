@@ -15,7 +15,9 @@ def _run(N, K, variant=0, seed=0):
     D = torch.zeros(128, N, device="cuda")
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
     p = lambda t: C.c_void_p(t.data_ptr())
-    _lib.check(_lib.lib().mopoe_umma_selftest(p(A), p(B), p(D), N, K, variant, p(err), None))
+    T = _lib.selftest_lib()                  # test-only library, not part of libmopoe_b200.so
+    rc = T.mopoe_umma_selftest(p(A), p(B), p(D), N, K, variant, p(err), None)
+    assert rc == 0, T.mopoe_last_error().decode()
     torch.cuda.synchronize()
     want = A.double() @ B.double().T
     scale = (A.double().abs() @ B.double().abs().T).max()

@@ -25,6 +25,11 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), name
     assert set(_lib.EXPORTED) == declared
+    assert not hasattr(L, "mopoe_umma_selftest")          # test code stays out of the product library
+    T = ctypes.CDLL(_lib.SELFTEST_LIB_PATH)
+    thdr = open(os.path.join(ROOT, "include", "mopoe_b200_selftest.h")).read()
+    for name in set(re.findall(r"\b(mopoe_[a-z_0-9]+)\s*\(", thdr)):
+        assert hasattr(T, name), name
 
 
 def test_package_init_params_equal_the_oracle_init():
