@@ -223,6 +223,9 @@ __global__ void __launch_bounds__(BASE_THREADS) daa_base_kernel(ModelView mv, Da
   const bool sc_smem = cx.J * cx.C <= DAA_BASE_SC_MAX;
   // records of the pipelined avatar kernel first: they depend on the encoder heads and the inputs only, and
   // their load -> store chains then overlap the Philox loop of the co-resident CTAs
+  // (the error flag and the tile counter of the sweep are reset here rather than by memset nodes: each node on the
+  // stream is a couple of microseconds of the sweep's critical path)
+  if (blockIdx.x == 0 && t == 0 && phase != 1) *ws.err = 0;
   if (cx.make_rec) {
     if (blockIdx.x == 0 && t == 0) *ws.counter = 0;    // tile counter of the pipelined kernel's dynamic schedule
     series_records(mv, cx, ws, row, g, t, BASE_THREADS, phase == 0 ? 3 : phase);
@@ -1067,7 +1070,6 @@ int mopoe_daa_sweep(const mopoe_model_desc* desc, const float* params, const mop
     daa_base_kernel<<<daa->n_val * N, BASE_THREADS, base_smem, stream>>>(mv, cx, ws, 0);
   }
   MOPOE_CUDA(cudaGetLastError());
-  MOPOE_CUDA(cudaMemsetAsync(ws.err, 0, sizeof(int), stream));
   if (impl == 2) {
     MOPOE_CUDA(cudaFuncSetAttribute((void*)daa_avatar_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pk_smem));
     CUtensorMap tmap;

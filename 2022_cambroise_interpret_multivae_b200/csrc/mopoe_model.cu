@@ -1394,7 +1394,7 @@ int mopoe_forward(const mopoe_model_desc* desc, const float* params, const mopoe
   cx.lay = lay;
   mopoe_batch_desc b = *batch;
   b.row_offset = 0;
-  MOPOE_CUDA(cudaMemsetAsync(ws.acc, 0, MOPOE_N_SCALARS * sizeof(double), stream));
+  if (!cx.heads_only) MOPOE_CUDA(cudaMemsetAsync(ws.acc, 0, MOPOE_N_SCALARS * sizeof(double), stream));   // (the heads-only pass of the DAA sweep accumulates no scalars)
   const int tn = (b.n_rows + TILE - 1) / TILE;
   int nu1 = 0;
   for (int m = 0; m < desc->n_mods; ++m)
