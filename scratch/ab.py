@@ -8,10 +8,10 @@ sys.path.insert(0, %r)
 import mopoe_b200
 from mopoe_b200 import daa, engine, _lib
 if sys.argv[1]: _lib.LIB_PATH = sys.argv[1]
-from oracle import mopoe_oracle as mo
+
 import bench
 spec = mopoe_b200.PathSpec(bench.HBN["dims"], bench.HBN["style_dims"], 20, "joint_elbo", bench.HBN["mod_names"])
-flat = engine.pack_params(spec, mo.init_params(mo.ModelSpec(**bench.HBN), seed=0), torch.device("cuda"))
+flat = engine.pack_params(spec, engine.init_params(spec, seed=0), torch.device("cuda"))
 src, dst = bench.draw_validation_batches(20, 1037)
 src, dst = src.cuda(), dst.cuda()
 L = _lib.lib(); L.mopoe_profile_enable(1)

@@ -3,10 +3,10 @@ sys.path.insert(0, "/root/repo")
 import mopoe_b200
 from mopoe_b200 import daa, engine, _lib
 _lib.LIB_PATH = "/root/repo/scratch/variants/lib_prof.so"
-from oracle import mopoe_oracle as mo
+
 import bench, numpy as np, ctypes as C
 spec = mopoe_b200.PathSpec(bench.HBN["dims"], bench.HBN["style_dims"], 20, "joint_elbo", bench.HBN["mod_names"])
-flat = engine.pack_params(spec, mo.init_params(mo.ModelSpec(**bench.HBN), seed=0), torch.device("cuda"))
+flat = engine.pack_params(spec, engine.init_params(spec, seed=0), torch.device("cuda"))
 src, dst = bench.draw_validation_batches(20, 1037)
 ws = engine.Workspace()
 L = _lib.lib(); L.mopoe_profile_enable(1)
