@@ -804,6 +804,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) daa_avatar_pipe_kernel(ModelVie
 // enter the product; accumulation error ~1e-7 of the absolute term sum, the same order as the rounding already
 // in the sums); the sum over tiles, the division by Sxx, the subject statistics (shifted sums) and the t
 // statistic are fp64.
+#ifndef BS_SPLIT_LO
+#define BS_SPLIT_LO 0
+#endif
 constexpr int BS_ROIS = BS_ROIS_, BS_GB = 25, BS_GP = 28;    // ROIs per CTA, subjects per batch, padded batch stride
 
 __device__ double two_sided_t_pvalue(double tval, double nu);
@@ -882,31 +885,50 @@ __global__ void __launch_bounds__(256) daa_beta_stats_kernel(ModelView mv, int d
           const double a = ((part[q][0] + part[q][1]) + part[q][2]) + part[q][3];
           const float hi = (float)a;
           s_hi[k * BS_GP + gb] = hi;
+#if BS_SPLIT_LO
           s_lo[k * BS_GP + gb] = (float)(a - (double)hi);
+#endif
         }
       }
     }
     // 1 / Sxx once per subject: an fp64 division per slope would cost as much as the whole contraction
     if (t < BS_GB) s_sxx[t] = t < ng ? 1.0 / xstat[(((int64_t)v * C + c) * N + g0 + t) * 2 + 1] : 1.0;
     __syncthreads();
-    float ah0[BS_GB], al0[BS_GB], ah1[BS_GB], al1[BS_GB];
+    // fp32 contraction of the fp32-rounded sums: the 48-term fp32 accumulation rounds at ~3e-7 of the slope, which a lo
+    // part of the sums (BS_SPLIT_LO: 6e-8 each) cannot improve -- it only doubled the FMAs and the accumulator registers
+    float ah0[BS_GB], ah1[BS_GB];
+#if BS_SPLIT_LO
+    float al0[BS_GB], al1[BS_GB];
 #pragma unroll
-    for (int gb = 0; gb < BS_GB; ++gb) ah0[gb] = al0[gb] = ah1[gb] = al1[gb] = 0.f;
+    for (int gb = 0; gb < BS_GB; ++gb) al0[gb] = al1[gb] = 0.f;
+#endif
+#pragma unroll
+    for (int gb = 0; gb < BS_GB; ++gb) ah0[gb] = ah1[gb] = 0.f;
 #pragma unroll 2
     for (int k = 0; k < KZ; ++k) {
       const float w0 = s_wf[k * RP + q0], w1 = s_wf[k * RP + q1];
       const float4* hp = reinterpret_cast<const float4*>(s_hi + k * BS_GP);
+#if BS_SPLIT_LO
       const float4* lp = reinterpret_cast<const float4*>(s_lo + k * BS_GP);
+#endif
 #pragma unroll
       for (int q = 0; q < BS_GP / 4; ++q) {
-        const float4 h = hp[q], l = lp[q];
-        const float hv[4] = {h.x, h.y, h.z, h.w}, lv[4] = {l.x, l.y, l.z, l.w};
+        const float4 h = hp[q];
+        const float hv[4] = {h.x, h.y, h.z, h.w};
+#if BS_SPLIT_LO
+        const float4 l = lp[q];
+        const float lv[4] = {l.x, l.y, l.z, l.w};
+#endif
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int gb = 4 * q + e;
           if (gb < BS_GB) {
-            ah0[gb] = fmaf(hv[e], w0, ah0[gb]); al0[gb] = fmaf(lv[e], w0, al0[gb]);
-            ah1[gb] = fmaf(hv[e], w1, ah1[gb]); al1[gb] = fmaf(lv[e], w1, al1[gb]);
+            ah0[gb] = fmaf(hv[e], w0, ah0[gb]);
+            ah1[gb] = fmaf(hv[e], w1, ah1[gb]);
+#if BS_SPLIT_LO
+            al0[gb] = fmaf(lv[e], w0, al0[gb]);
+            al1[gb] = fmaf(lv[e], w1, al1[gb]);
+#endif
           }
         }
       }
@@ -917,14 +939,22 @@ __global__ void __launch_bounds__(256) daa_beta_stats_kernel(ModelView mv, int d
         const double isx = s_sxx[gb];
         double* brow = betas + (((int64_t)v * C + c) * N + g0 + gb) * R + c0;
         if (act0) {
+#if BS_SPLIT_LO
           const double beta = ((double)ah0[gb] + (double)al0[gb]) * isx;
+#else
+          const double beta = (double)ah0[gb] * isx;
+#endif
           brow[r0] = beta;
           if (g0 + gb == 0) b0[0] = beta;
           const double d = beta - b0[0];                  // shifted sums: no cancellation in the variance
           sd1[0] += d; sd2[0] = fma(d, d, sd2[0]);
         }
         if (act1) {
+#if BS_SPLIT_LO
           const double beta = ((double)ah1[gb] + (double)al1[gb]) * isx;
+#else
+          const double beta = (double)ah1[gb] * isx;
+#endif
           brow[r1] = beta;
           if (g0 + gb == 0) b0[1] = beta;
           const double d = beta - b0[1];
