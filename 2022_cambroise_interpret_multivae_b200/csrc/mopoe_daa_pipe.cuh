@@ -848,7 +848,16 @@ __global__ void __launch_bounds__(256) daa_beta_stats_kernel(ModelView mv, int d
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int i = i0 + q * nt + t;
-          if (i < n4) { put(4 * i, buf[q].x); put(4 * i + 1, buf[q].y); put(4 * i + 2, buf[q].z); put(4 * i + 3, buf[q].w); }
+          if (i < n4) {      // one division per float4: (column, latent) of its first element, then stepped
+            int col = (4 * i) / md.ZD, zd = 4 * i - col * md.ZD;
+            const float wv[4] = {buf[q].x, buf[q].y, buf[q].z, buf[q].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int kz = zd < md.S ? dm.KC + zd : zd - md.S;
+              s_wf[kz * RP + col] = wv[e];
+              if (++zd == md.ZD) { zd = 0; ++col; }
+            }
+          }
         }
       }
     } else {
