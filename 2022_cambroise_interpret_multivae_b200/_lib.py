@@ -120,7 +120,6 @@ def lib():
     L.mopoe_daa_exchange_tables.argtypes = [C.POINTER(TableExchangeDesc), vp, vp, vp]
     L.mopoe_daa_exchange_tables.restype = C.c_int
     L.mopoe_train_last_impl.restype = C.c_int
-    L.mopoe_forward_last_heads_impl.restype = C.c_int
     L.mopoe_daa_read_phases.argtypes = [C.POINTER(ModelDesc), C.POINTER(DaaDesc), vp, C.POINTER(C.c_int64)]
     L.mopoe_daa_read_phases.restype = C.c_int
     L.mopoe_daa_status.argtypes = [C.POINTER(ModelDesc), C.POINTER(DaaDesc), vp, vp]
@@ -169,5 +168,5 @@ EXPORTED = ["mopoe_last_error", "mopoe_version", "mopoe_device_count", "mopoe_pa
             "mopoe_workspace_bytes", "mopoe_forward", "mopoe_train_steps", "mopoe_daa_workspace_bytes",
             "mopoe_daa_sweep", "mopoe_daa_regression", "mopoe_philox_normal", "mopoe_profile_enable",
             "mopoe_daa_last_kernel_ms", "mopoe_daa_last_impl", "mopoe_daa_read_phases",
-            "mopoe_daa_status", "mopoe_train_last_impl", "mopoe_forward_last_heads_impl", "mopoe_table_exchange_bytes", "mopoe_daa_exchange_tables",
+            "mopoe_daa_status", "mopoe_train_last_impl", "mopoe_table_exchange_bytes", "mopoe_daa_exchange_tables",
             "mopoe_rsa_cmat", "mopoe_rsa_kendall_workspace_bytes", "mopoe_rsa_kendall"]

@@ -1246,7 +1246,6 @@ static int validate_batch(const mopoe_model_desc* d, const mopoe_batch_desc* b) 
 constexpr int TC_SMEM_LIMIT = 227 * 1024 - 2048;
 static float* g_tc_prof = nullptr;   // device address of the TC_PROF counters of the last tensor-core launch
 static int g_train_impl = 0;   // implementation of the last mopoe_train_steps call: 0 CUDA cores, 1 tensor cores
-static int g_fwd_heads_impl = 0;   // last heads-only mopoe_forward: 1 = tensor-core tiles, 0 = CUDA-core kernels
 
 // MOPOE_TRAIN_IMPL=tc|ffma forces one implementation (the tests cross-check both).  Default: the tensor-core
 // kernel for batches of TC_MIN_ROWS rows and more (measured on B200: 4 096 rows 0.61 vs 0.82 ms, 65 536 rows
@@ -1312,7 +1311,6 @@ int64_t mopoe_workspace_bytes(const mopoe_model_desc* desc, int64_t max_rows) {
 }
 
 int mopoe_train_last_impl(void) { return g_train_impl; }
-int mopoe_forward_last_heads_impl(void) { return g_fwd_heads_impl; }
 
 #ifdef TC_PROF
 // profiling builds only: copy out and clear the 64 per-stage cycle counters of the tensor-core training kernel
@@ -1396,32 +1394,6 @@ int mopoe_forward(const mopoe_model_desc* desc, const float* params, const mopoe
   cx.lay = lay;
   mopoe_batch_desc b = *batch;
   b.row_offset = 0;
-  // heads-only pass (the encoder sweep of the DAA) on the tensor-core training kernel's tile up to the encoder heads, as
-  // two plain launches (operand preparation, tiles): OPT-IN (MOPOE_FWD_HEADS=tc).  Measured on B200 for the 1 000 rows of
-  // the HBN sweep: preparation 31 us + tiles 57 us against 22 + 12 us of the CUDA-core kernels (sweep 0.572 vs 0.521 ms):
-  // the kernel's per-tile hand-overs and its all-blob preparation are built for large training batches.
-  g_fwd_heads_impl = 0;
-  if (cx.heads_only && b.owner_mod == 0) {
-    const char* fh = getenv("MOPOE_FWD_HEADS");
-    tc::TcPlan plan;
-    if (fh && !strcmp(fh, "tc") && tc::make_plan(desc, b.n_rows, TC_SMEM_LIMIT, &plan)) {
-      const int64_t base_off = (need + 1023) & ~(int64_t)1023;
-      if (workspace_bytes >= base_off + plan.total) {
-        plan.base = (unsigned char*)workspace + base_off;
-        MOPOE_CUDA(cudaMemsetAsync(plan.base + plan.err, 0, 256, stream));
-        void (*fn)(ModelView, StepCtx, const mopoe_batch_desc*, int, float*, Workspace, tc::TcPlan, int, mopoe_batch_desc) =
-            plan.R == 32 ? tc::train_tc_kernel<32> : tc::train_tc_kernel<16>;
-        MOPOE_CUDA(cudaFuncSetAttribute((void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.s_total));
-        const int nt = (b.n_rows + plan.R - 1) / plan.R;
-        fn<<<num_sms(), tc::THREADS, plan.s_total, stream>>>(mv, cx, nullptr, 0, nullptr, ws, plan, 1, b);
-        MOPOE_CUDA(cudaGetLastError());
-        fn<<<nt < num_sms() ? nt : num_sms(), tc::THREADS, plan.s_total, stream>>>(mv, cx, nullptr, 0, nullptr, ws, plan, 2, b);
-        MOPOE_CUDA(cudaGetLastError());
-        g_fwd_heads_impl = 1;
-        return MOPOE_OK;
-      }
-    }
-  }
   if (!cx.heads_only) MOPOE_CUDA(cudaMemsetAsync(ws.acc, 0, MOPOE_N_SCALARS * sizeof(double), stream));   // (the heads-only pass of the DAA sweep accumulates no scalars)
   const int tn = (b.n_rows + TILE - 1) / TILE;
   int nu1 = 0;
@@ -1558,10 +1530,7 @@ int mopoe_train_steps(const mopoe_model_desc* desc, float* params, float* adam_m
     if (per_sm < 1) { set_error("tensor-core train kernel does not fit on an SM (smem %d)", plan.s_total); return MOPOE_EINVAL; }
     const mopoe_batch_desc* bptr = batches;
     float* sptr = scalars;
-    int fwd_mode = 0;
-    mopoe_batch_desc b0;
-    memset(&b0, 0, sizeof(b0));
-    void* args[] = {&mv, &cx, &bptr, &n_steps, &sptr, &ws, &plan, &fwd_mode, &b0};
+    void* args[] = {&mv, &cx, &bptr, &n_steps, &sptr, &ws, &plan};
     MOPOE_CUDA(cudaLaunchCooperativeKernel(fn, dim3(num_sms()), dim3(tc::THREADS), args, plan.s_total, stream));
     return MOPOE_OK;
   }

@@ -340,7 +340,6 @@ struct TileCtx {
   const ModelView* mv; const StepCtx* cx; const mopoe_batch_desc* b; const Workspace* ws; const TcPlan* pl;
   unsigned char* sm; Bars* bars; int* gerr;
   int tile, r0, nr; int64_t eps_base; bool bwd;
-  bool heads_only;    // encoder sweep of the DAA (mopoe_forward asked for the heads only): the tile ends after P1 + S1
 };
 
 template <int R>
@@ -355,7 +354,6 @@ __device__ void tile_loader(const TileCtx& c, Ring& rg) {
       for (int mt = 0; mt < 2; ++mt) load_chunk(rg, pl, c.bars, ring, pl.base + t.w1 + (int64_t)(mt * t.NCx + cc) * CHUNK, c.gerr);
     for (int cc = 0; cc < 8; ++cc) load_chunk(rg, pl, c.bars, ring, pl.base + t.wh + (int64_t)cc * CHUNK, c.gerr);
   }
-  if (c.heads_only) return;
   for (int m = 0; m < mv.M; ++m) {
     if (!(present >> m & 1)) continue;
     const TcMod& t = pl.mod[m];
@@ -419,7 +417,6 @@ __device__ void tile_mma(const TileCtx& c, Ring& rg, Sync& sy, uint32_t tmem) {
       mma_chunk(rg, pl, bars, ring, c.gerr, acc2, hbuf + cc * 4 * SF, 512u * R, SF, 128, 2 * SF, id_mn, 2, a2);
     mma_commit(&bars->acc_done); ++sy.na;
   }
-  if (c.heads_only) return;
   for (int m = 0; m < mv.M; ++m) {
     if (!(present >> m & 1)) continue;
     const TcMod& t = pl.mod[m];
@@ -620,7 +617,6 @@ __device__ void tile_compute(const TileCtx& c, Sync& sy, uint32_t tmem) {
     bar_compute();
     TCP(5);
   }
-  if (c.heads_only) return;                                 // (the next tile of this CTA starts with a barrier)
   // ================= latent forward =================
   for (int i = t; i < M * pl.np * R * pl.zdm; i += 256) sh.dzz[i] = 0.f;
   lat_forward(mv, cx, b, c.eps_base, r0, nr, sh);
@@ -1050,23 +1046,14 @@ __device__ void p3_columns(const ModelView& mv, const StepCtx& cx, const mopoe_b
 // -------------------------------------------------------------------------------------------
 // the persistent kernel
 // -------------------------------------------------------------------------------------------
-// fwd_mode 0: the training loop below (cooperative launch).  The encoder sweep of the DAA (mopoe_forward, heads only) uses
-// the same kernel in two ordinary launches: fwd_mode 1 = operand preparation only, fwd_mode 2 = the tiles of ONE batch
-// (`b0`, passed by value) up to the encoder heads -- no grid barrier inside either, so both are plain, graph-capturable
-// launches and the kernel boundary orders the blobs before the bulk copies that read them.
 template <int R>
 __global__ void __launch_bounds__(THREADS, 1) train_tc_kernel(ModelView mv, StepCtx cx, const mopoe_batch_desc* batches,
-                                                              int n_steps, float* scalars, Workspace ws, TcPlan pl,
-                                                              int fwd_mode, mopoe_batch_desc b0) {
+                                                              int n_steps, float* scalars, Workspace ws, TcPlan pl) {
   extern __shared__ __align__(1024) unsigned char sm[];
   __shared__ mopoe_batch_desc sb;
   Bars* bars = reinterpret_cast<Bars*>(sm + pl.s_bar);
   int* gerr = reinterpret_cast<int*>(pl.base + pl.err);
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  if (fwd_mode == 1) {
-    tc_prep(mv, pl, reinterpret_cast<PrepBlob*>(sm + pl.s_e));
-    return;
-  }
   const int tmem_cols = 256;   // P2 uses 3 R columns, a P3 output tile up to 256
   if (t == 0) {
     for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(&bars->ring_full[s], 1); mbar_init(&bars->ring_empty[s], 1); }
@@ -1085,19 +1072,6 @@ __global__ void __launch_bounds__(THREADS, 1) train_tc_kernel(ModelView mv, Step
   Sync sy = {0, 0, 0, 0};
   Ring rg3 = {0, 0};
   unsigned int target = 0;
-  if (fwd_mode == 2) {
-    const int nt = (b0.n_rows + R - 1) / R;
-    for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
-      TileCtx c;
-      c.mv = &mv; c.cx = &cx; c.b = &b0; c.ws = &ws; c.pl = &pl; c.sm = sm; c.bars = bars; c.gerr = gerr;
-      c.tile = tile; c.r0 = tile * R; c.nr = min(R, b0.n_rows - tile * R);
-      c.eps_base = 0; c.bwd = false; c.heads_only = true;
-      if (warp == 8) { if (lane == 0) tile_loader<R>(c, rg); }
-      else if (warp == 9) { if (lane == 0) tile_mma<R>(c, rg, sy, tmem); }
-      else tile_compute<R>(c, sy, tmem);
-    }
-    n_steps = 0;                                            // fall through to the teardown
-  }
   for (int step = 0; step < n_steps; ++step) {
     __syncthreads();
     if (t == 0) sb = batches[step];
@@ -1120,7 +1094,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_tc_kernel(ModelView mv, Step
       TileCtx c;
       c.mv = &mv; c.cx = &cx; c.b = &b; c.ws = &ws; c.pl = &pl; c.sm = sm; c.bars = bars; c.gerr = gerr;
       c.tile = tile; c.r0 = tile * R; c.nr = min(R, b.n_rows - tile * R);
-      c.eps_base = (int64_t)step * cx.eps_step_stride; c.bwd = bwd; c.heads_only = false;
+      c.eps_base = (int64_t)step * cx.eps_step_stride; c.bwd = bwd;
       if (warp == 8) { if (lane == 0) tile_loader<R>(c, rg); }
       else if (warp == 9) { if (lane == 0) tile_mma<R>(c, rg, sy, tmem); }
       else tile_compute<R>(c, sy, tmem);
@@ -1166,8 +1140,7 @@ __global__ void __launch_bounds__(THREADS, 1) train_tc_kernel(ModelView mv, Step
     }
   }
   __syncthreads();
-  if (bars->dead && t == 0 && scalars) scalars[0] = __int_as_float(0x7fc00000);
-  if (bars->dead && t == 0 && fwd_mode == 2 && cx.out.enc_heads[0]) cx.out.enc_heads[0][0] = __int_as_float(0x7fc00000);   // poison: a bounded wait timed out
+  if (bars->dead && t == 0) scalars[0] = __int_as_float(0x7fc00000);
   tc_fence_before();
   __syncthreads();
   if (warp == 9) tmem_dealloc(tmem, tmem_cols);

@@ -209,9 +209,6 @@ int mopoe_train_steps(const mopoe_model_desc* desc, float* params, float* adam_m
  * csrc/mopoe_train_tc.cuh; the default whenever the configuration fits its tiling), 0 = CUDA-core kernel.
  * MOPOE_TRAIN_IMPL=tc|ffma in the environment forces one (the tests cross-check both). */
 int mopoe_train_last_impl(void);
-/* which kernels the last heads-only mopoe_forward (the encoder sweep of the DAA) used: 0 = CUDA-core kernels (default),
- * 1 = the tensor-core training kernel's tile up to the encoder heads (opt-in: MOPOE_FWD_HEADS=tc; measured slower) */
-int mopoe_forward_last_heads_impl(void);
 
 /* ---- Digital Avatars Analysis  (workflow.daa_exp, workflow.py:361-537) ----------------------- */
 

@@ -757,41 +757,3 @@ def test_daa_given_score_values_linear_sampling():
     _close(r.avatars, av, "avatars")
     p, coef, _ = daa_oracle.hierarchical_regression(av, sc)
     _close(r.coefs, coef, "coefs")
-
-
-def test_forward_heads_on_the_tensor_core_tile(monkeypatch):
-    """Opt-in encoder sweep (MOPOE_FWD_HEADS=tc): the tensor-core training kernel's tile up to the encoder heads equals
-    the CUDA-core heads (3xFP16 split: 2e-6 of the tensor scale) -- measured slower at the sweep's 1 000 rows, kept as a
-    switch."""
-    from mopoe_b200 import engine
-    case = cases._case(cases.HBN, "joint_elbo", True, (0, 1), 1000, 95, 195)
-    ospec, spec, params, flat = _setup(case)
-    batch, _ = cases.inputs_of(case, ospec)
-    dev = {k: v.cuda() for k, v in batch.items()}
-
-    def heads(impl):
-        monkeypatch.setenv("MOPOE_FWD_HEADS", impl)
-        res = engine.ForwardResult(spec, 1000, 3, flat.device, want_rec=False)
-        # ask for the encoder heads only, as mopoe_daa_sweep does
-        import ctypes as C
-        from mopoe_b200 import _lib
-        o = _lib.ForwardOut()
-        for m in range(2):
-            o.enc_heads[m] = res.enc_heads[m].data_ptr()
-        lib = _lib.lib()
-        ws = engine.Workspace().get(lib.mopoe_workspace_bytes(C.byref(spec.desc), 1000), flat.device)
-        xp = (C.c_void_p * _lib.MAX_MODS)(dev["clinical"].data_ptr(), dev["rois"].data_ptr(), None, None)
-        bd = spec.batch_desc(1000, 3)
-        _lib.check(lib.mopoe_forward(C.byref(spec.desc), C.c_void_p(flat.data_ptr()), C.byref(bd), xp, None, 0, 1, -1, 0, C.byref(o),
-                                     C.c_void_p(ws.data_ptr()), ws.numel(), None))
-        torch.cuda.synchronize()
-        assert lib.mopoe_forward_last_heads_impl() == (1 if impl == "tc" else 0)
-        return [h.clone() for h in res.enc_heads]
-
-    a, b = heads("tc"), heads("ffma")
-    for m in range(2):
-        smu, slv, mu, lv = mo.encoder(params, ospec, m, batch[spec.mod_names[m]])
-        want = torch.cat([mu, lv, smu, slv], dim=1)
-        _close(a[m], want, "tensor-core heads vs oracle")
-        _close(b[m], want, "cuda-core heads vs oracle")
-        _close(a[m], b[m], "tensor-core vs cuda-core heads", rtol=5e-6)
