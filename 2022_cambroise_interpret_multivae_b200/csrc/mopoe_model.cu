@@ -704,6 +704,35 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
         wa[u] = wrow[lane]; wb[u] = wrow[lane + 32];
         bjs[u] = md.bh[j < md.HC ? j : jb];
       }
+      if constexpr (R <= 4) {
+        // small tiles: the 4 R dot products of the warp are reduced TOGETHER, round by round (independent shuffles back
+        // to back instead of 4 R dependent five-shuffle chains)
+        float accs[4][R];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float4* hr = reinterpret_cast<const float4*>(sh_h + (m * R + r) * MOPOE_HIDDEN);
+            const float4 ha = hr[lane], hb = hr[lane + 32];
+            accs[u][r] = wa[u].x * ha.x + wa[u].y * ha.y + wa[u].z * ha.z + wa[u].w * ha.w + wb[u].x * hb.x + wb[u].y * hb.y +
+                         wb[u].z * hb.z + wb[u].w * hb.w;
+          }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int r = 0; r < R; ++r) accs[u][r] += __shfl_xor_sync(0xffffffffu, accs[u][r], o);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = jb + u * (MOPOE_THREADS / 32);
+          if (j < md.HC) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+              if (lane == r % 32) sh_e[(m * R + r) * HCM + j] = accs[u][r] + bjs[u];
+          }
+        }
+      } else {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int j = jb + u * (MOPOE_THREADS / 32);
@@ -723,6 +752,7 @@ __device__ void p2_tile(const ModelView& mv, const StepCtx& cx, const mopoe_batc
           for (int r = 0; r < R; ++r)
             if (lane == r % 32) sh_e[(m * R + r) * HCM + j] = acc[r] + bj;
         }
+      }
       }
     }
   }
