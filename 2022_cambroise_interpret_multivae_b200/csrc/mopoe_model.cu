@@ -455,8 +455,11 @@ __device__ void lat_forward(const ModelView& mv, const StepCtx& cx, const mopoe_
     const int S = md.S;
     if (S == 0) continue;
     float a_kl = 0.f, a_mu = 0.f, a_lv = 0.f;
+    // (thread index rotated by one warp per modality: for small tiles the content items above occupy warp 0 only, so
+    // the style items of modality m go to warp 1 + m and the three sections run side by side)
+    const int ts = (t + MOPOE_THREADS - 32 * (1 + m)) & (MOPOE_THREADS - 1);
     for (int base = 0; base < sh.R * S; base += MOPOE_THREADS) {
-      const int idx = base + t;
+      const int idx = base + ts;
       const int r = idx / S, s = idx % S;
       const bool valid = idx < sh.R * S && r < nr;
       const int n = r0 + r;
@@ -601,7 +604,8 @@ __device__ void lat_backward(const ModelView& mv, const StepCtx& cx, const mopoe
     const int S = mv.mod[m].S;
     // style KL enters the joint ELBO and (poe) the unimodal ELBO of m, each with beta*beta_style^2
     const float cks = mv.beta * mv.beta_style * mv.beta_style * invN * (mv.method == MOPOE_METHOD_POE ? 2.f : 1.f);
-    for (int idx = t; idx < sh.R * S; idx += MOPOE_THREADS) {
+    const int ts = (t + MOPOE_THREADS - 32 * (1 + m)) & (MOPOE_THREADS - 1);   // as in lat_forward: one warp per modality
+    for (int idx = ts; idx < sh.R * S; idx += MOPOE_THREADS) {
       const int r = idx / S, s = idx % S;
       if (r >= nr) continue;
       const float mu = sh.e[(m * sh.R + r) * sh.HCM + 2 * L + s];
